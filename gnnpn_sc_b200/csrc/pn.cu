@@ -1,0 +1,349 @@
+// Pointer-network entry points: weight packing, encoder scan, fused greedy decode,
+// interface-faithful logits materialisation, composition objective / reward.
+#include <math.h>
+#include "lstm_step.cuh"
+
+namespace gnnpn {
+namespace {
+
+// ---------------------------------------------------------------------------
+// weight packing (fp64 accumulate, once per model)
+// ---------------------------------------------------------------------------
+__global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                 const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                 const float* __restrict__ w_e, const float* __restrict__ b_e,
+                                 const float* __restrict__ start, int H, int F, int Fpad,
+                                 float* __restrict__ packed) {
+  const int G = 4 * H;
+  const int rows = H + Fpad + 2;  // + bias row + start row
+  const int64_t total = (int64_t)rows * G;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e / G), nn = (int)(e % G);
+    const int j = nn >> 2, g = nn & 3;
+    const int r = g * H + j;                       // torch row: gate-major
+    float out = 0.f;
+    if (k < H) {
+      out = w_hh[(int64_t)r * H + k];
+    } else if (k < H + Fpad) {
+      const int f = k - H;
+      if (f < F) {
+        double s = 0.0;
+        for (int i = 0; i < H; ++i) s += (double)w_ih[(int64_t)r * H + i] * (double)w_e[(int64_t)i * F + f];
+        out = (float)s;
+      }
+    } else if (k == H + Fpad) {                    // bias = b_ih + b_hh + W_ih . b_e
+      double s = (double)b_ih[r] + (double)b_hh[r];
+      for (int i = 0; i < H; ++i) s += (double)w_ih[(int64_t)r * H + i] * (double)b_e[i];
+      out = (float)s;
+    } else {                                       // start = b_ih + b_hh + W_ih . start_input
+      if (start) {
+        double s = (double)b_ih[r] + (double)b_hh[r];
+        for (int i = 0; i < H; ++i) s += (double)w_ih[(int64_t)r * H + i] * (double)start[i];
+        out = (float)s;
+      }
+    }
+    packed[e] = out;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pointer step (Dot attention): one warp per instance
+//   u_j   = <enc_out[b, kN+j, :], q[b,:]>            j in [0,N)
+//   l_j   = use_tanh ? C*tanh(u_j) : u_j            -> win_logits[b, kN+j]
+//   w_j   = l_j + alpha*latent[b, kN+j]
+//   p     = softmax_j(w)  (exp(w-max)/sum, fp32)    -> win_probs[b, kN+j]
+//   pick  = first j with maximal p                  -> idx_out[b] = kN + j
+// Positions outside the window carry -inf after modelPN.py:220-222 and contribute exp(-inf)=0.
+// ---------------------------------------------------------------------------
+constexpr int kMaxWindow = 32;
+
+// <row, q> over the 8 elements a lane owns, explicit fma chain so every kernel that forms a
+// pointer logit rounds identically (window logits == the same entries of the full logits).
+__device__ __forceinline__ float dot8(const float4 r0, const float4 r1, const float4 q0, const float4 q1) {
+  float s = r0.x * q0.x;
+  s = fmaf(r0.y, q0.y, s); s = fmaf(r0.z, q0.z, s); s = fmaf(r0.w, q0.w, s);
+  s = fmaf(r1.x, q1.x, s); s = fmaf(r1.y, q1.y, s); s = fmaf(r1.z, q1.z, s); s = fmaf(r1.w, q1.w, s);
+  return s;
+}
+
+__global__ void __launch_bounds__(256) pointer_step_dot_kernel(
+    const float* __restrict__ enc_out, int64_t enc_inst_ld, const float* __restrict__ q, int64_t q_ld,
+    const float* __restrict__ latent_win, float alpha, int use_tanh, float C, int64_t n, int L, int k,
+    int N, int32_t* __restrict__ idx_out, float* __restrict__ win_logits, float* __restrict__ win_probs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= n) return;
+  const float4* qp = reinterpret_cast<const float4*>(q + b * q_ld);
+  const float4 q0 = __ldg(qp + lane), q1 = __ldg(qp + 32 + lane);
+  const float* base = enc_out + b * enc_inst_ld + (int64_t)k * N * kH;
+
+  float my_w = -INFINITY, my_l = 0.f;          // lane j holds candidate j
+  for (int j0 = 0; j0 < N; j0 += 4) {          // 4 rows in flight per iteration
+    float part[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      part[u] = 0.f;
+      if (j0 + u < N) {
+        const float4* rp = reinterpret_cast<const float4*>(base + (int64_t)(j0 + u) * kH);
+        const float4 r0 = ldg_stream(rp + lane), r1 = ldg_stream(rp + 32 + lane);
+        part[u] = dot8(r0, r1, q0, q1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float d = warp_sum(part[u]);
+      if (j0 + u < N && lane == j0 + u) {
+        my_l = use_tanh ? C * tanhf(d) : d;
+        my_w = my_l;
+      }
+    }
+  }
+  const int64_t wpos = b * L + (int64_t)k * N + lane;
+  if (lane < N) {
+    if (latent_win) my_w = my_l + alpha * __ldg(latent_win + wpos);
+    win_logits[wpos] = my_l;
+  }
+  float mx = my_w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float e = lane < N ? expf(my_w - mx) : 0.f;
+  // sequential sum in candidate order (deterministic, independent of warp shuffles' tree)
+  float s = 0.f;
+  for (int j = 0; j < N; ++j) s += __shfl_sync(0xffffffffu, e, j);
+  const float p = e / s;
+  if (lane < N) win_probs[wpos] = p;
+  // first maximal probability (torch.max tie rule, modelPN.py:225-226)
+  float best = p;
+  int best_j = lane < N ? lane : 0x7fffffff;
+  if (lane >= N) best = -1.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+    if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+  }
+  if (lane == 0) idx_out[b] = k * N + best_j;
+}
+
+// ---------------------------------------------------------------------------
+// full logits: one CTA per (instance, 32-row slab of L); queries of the instance in smem
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) full_logits_dot_kernel(
+    const float* __restrict__ enc_out, const float* __restrict__ dec_h, const int32_t* __restrict__ idx,
+    int use_tanh, float C, int64_t n, int L, int K, float* __restrict__ out) {
+  extern __shared__ float sq[];                // [K][kH]
+  const int64_t b = blockIdx.x;
+  const int l0 = blockIdx.y * 32;
+  const float4* qsrc = reinterpret_cast<const float4*>(dec_h + b * (int64_t)K * kH);
+  for (int i = threadIdx.x; i < K * kH / 4; i += blockDim.x) reinterpret_cast<float4*>(sq)[i] = __ldg(qsrc + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int l = l0 + warp; l < min(L, l0 + 32); l += 8) {
+    const float4* rp = reinterpret_cast<const float4*>(enc_out + (b * L + l) * (int64_t)kH);
+    const float4 r0 = __ldg(rp + lane), r1 = __ldg(rp + 32 + lane);
+    for (int k = 0; k < K; ++k) {
+      const float4 a0 = reinterpret_cast<const float4*>(sq + k * kH)[lane];
+      const float4 a1 = reinterpret_cast<const float4*>(sq + k * kH)[32 + lane];
+      const float d = warp_sum(dot8(r0, r1, a0, a1));
+      if (lane == 0) out[((int64_t)k * n + b) * L + l] = use_tanh ? C * tanhf(d) : d;
+    }
+  }
+  // cumulative visited mask: step k sees -inf at the picks of steps 0..k-1 (modelPN.py:165-173)
+  __syncthreads();
+  for (int pair = threadIdx.x; pair < K * K; pair += blockDim.x) {
+    const int k = pair / K, jprev = pair % K;
+    if (jprev >= k) continue;
+    const int pos = idx[(int64_t)jprev * n + b];
+    if (pos >= l0 && pos < l0 + 32 && pos < L) out[((int64_t)k * n + b) * L + pos] = -INFINITY;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// composition objective (calc / reward): one thread per instance, fp32 sequential products
+// and numpy's float32 pairwise-sum order for sum(q0) so results are bit-identical to the CPU path
+// ---------------------------------------------------------------------------
+__device__ float numpy_pairwise_sum_f32(const float* v, int n) {
+  // numpy pairwise_sum for n < 128 (PW_BLOCKSIZE): 8 accumulators, then the tail in order.
+  if (n < 8) {
+    float r = 0.f;
+    for (int i = 0; i < n; ++i) r = __fadd_rn(r, v[i]);
+    return r;
+  }
+  float r[8];
+  for (int j = 0; j < 8; ++j) r[j] = v[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], v[i + j]);
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __fadd_rn(res, v[i]);
+  return res;
+}
+
+__device__ float numpy_sum_f32(const float* v, int n) {
+  if (n <= 128) return numpy_pairwise_sum_f32(v, n);
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return __fadd_rn(numpy_sum_f32(v, n2), numpy_sum_f32(v + n2, n - n2));
+}
+
+constexpr int kMaxTasks = 512;
+
+__global__ void reward_kernel(const float* __restrict__ inputs, const int32_t* __restrict__ idx, int64_t n,
+                              int L, int F, int K, int tag, int32_t* __restrict__ viol_out,
+                              float* __restrict__ obj_out, float* __restrict__ rew_out) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  float q0s[kMaxTasks];
+  float prod[2] = {1.f, 1.f};
+  float min_q1 = INFINITY;
+  int used = 0;
+  float lo[2] = {0, 0}, hi[2] = {0, 0};
+  for (int k = 0; k < K; ++k) {
+    const float* row = inputs + (b * L + idx[(int64_t)k * n + b]) * (int64_t)F + tag;
+    const float q0 = row[0], q1 = row[1];
+    q0s[k] = q0;
+    used += q0 > 0.f;
+    min_q1 = fminf(min_q1, q1);
+    prod[0] = k == 0 ? row[2] : __fmul_rn(prod[0], row[2]);
+    prod[1] = k == 0 ? row[3] : __fmul_rn(prod[1], row[3]);
+    if (k == 0) { lo[0] = row[4]; hi[0] = row[5]; lo[1] = row[6]; hi[1] = row[7]; }
+  }
+  int viol = 0;
+  for (int i = 0; i < 2; ++i) viol += (prod[i] < lo[i] || prod[i] > hi[i]) ? 1 : 0;
+  const float s = numpy_sum_f32(q0s, K);
+  float obj = __fdiv_rn(s, (float)used);
+  obj = __fadd_rn(obj, 1.0f);
+  obj = __fsub_rn(obj, min_q1);
+  obj = __fdiv_rn(obj, 2.0f);
+  if (viol_out) viol_out[b] = viol;
+  if (obj_out) obj_out[b] = obj;
+  if (rew_out) {
+    const double v = (double)viol + (double)obj;          // python: round(violate + objFunc, 5)
+    rew_out[b] = (float)(rint(v * 1e5) / 1e5);
+  }
+}
+
+}  // namespace
+}  // namespace gnnpn
+
+using namespace gnnpn;
+
+extern "C" {
+
+size_t gnnpn_pn_packed_lstm_floats(int hidden, int in_features) {
+  return (size_t)(hidden + round_up(in_features, kXPad) + 2) * 4 * hidden;
+}
+
+int gnnpn_pn_pack_lstm_f32(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                           const float* w_embed, const float* b_embed, const float* start_input,
+                           int hidden, int in_features, float* packed, void* stream) {
+  GNNPN_REQUIRE(w_ih && w_hh && b_ih && b_hh && w_embed && b_embed && packed, GNNPN_ENULL);
+  GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= kXPad, GNNPN_ESHAPE);
+  pack_lstm_kernel<<<kNumSMs * 2, 256, 0, (cudaStream_t)stream>>>(w_ih, w_hh, b_ih, b_hh, w_embed, b_embed,
+                                                                  start_input, hidden, in_features, kXPad,
+                                                                  packed);
+  return after_launch();
+}
+
+int gnnpn_lstm_encode_f32(const float* inputs, int64_t n, int L, int in_features, int hidden,
+                          const float* packed, float* enc_out, float* c_state, void* stream) {
+  GNNPN_REQUIRE(inputs && packed && enc_out && c_state, GNNPN_ENULL);
+  GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= kXPad && L >= 1 && n >= 0, GNNPN_ESHAPE);
+  GNNPN_REQUIRE(n < (1ll << 31), GNNPN_ERANGE);
+  GNNPN_REQUIRE(aligned16(enc_out) && aligned16(c_state) && aligned16(packed), GNNPN_EALIGN);
+  LstmStepArgs a{};
+  a.x = inputs; a.x_inst_ld = (int64_t)L * in_features; a.F = in_features; a.use_x = 1; a.gather = nullptr;
+  a.P = packed; a.bias = packed + (size_t)(kH + kXPad) * kG;
+  a.c = c_state; a.M = (int)n;
+  a.h_in_ld = a.h_out_ld = (int64_t)L * kH;
+  for (int t = 0; t < L; ++t) {
+    a.first = t == 0;
+    a.h_in = t == 0 ? nullptr : enc_out + (int64_t)(t - 1) * kH;
+    a.h_out = enc_out + (int64_t)t * kH;
+    a.x_row = t;
+    int rc = launch_lstm_step(a, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return GNNPN_OK;
+}
+
+int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float* c_state,
+                               const float* latent_win, float alpha, const float* packed,
+                               int attention, const float* att_params, int use_tanh, float C,
+                               int64_t n, int L, int in_features, int hidden, int K, int N,
+                               float* dec_h, int32_t* idx_out, float* win_logits, float* win_probs,
+                               const int32_t* forced_idx, void* stream) {
+  GNNPN_REQUIRE(inputs && enc_out && c_state && packed && dec_h && idx_out && win_logits && win_probs,
+                GNNPN_ENULL);
+  GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= kXPad, GNNPN_ESHAPE);
+  GNNPN_REQUIRE(K >= 1 && N >= 1 && N <= kMaxWindow && (int64_t)K * N == L, GNNPN_ESHAPE);
+  GNNPN_REQUIRE(n >= 0 && n < (1ll << 31), GNNPN_ERANGE);
+  GNNPN_REQUIRE(attention == GNNPN_ATT_DOT, GNNPN_EUNSUPPORTED);
+  (void)att_params;
+  GNNPN_REQUIRE(aligned16(enc_out) && aligned16(dec_h) && aligned16(c_state) && aligned16(packed), GNNPN_EALIGN);
+  cudaStream_t st = (cudaStream_t)stream;
+  LstmStepArgs a{};
+  a.x = inputs; a.x_inst_ld = (int64_t)L * in_features; a.F = in_features; a.x_row = -1;
+  a.P = packed; a.c = c_state; a.M = (int)n; a.first = 0;
+  a.h_out_ld = (int64_t)K * kH;
+  const float* bias = packed + (size_t)(kH + kXPad) * kG;
+  const float* start = bias + kG;
+  const unsigned att_blocks = (unsigned)ceil_div(n, 8);
+  for (int k = 0; k < K; ++k) {
+    if (k == 0) {
+      a.h_in = enc_out + (int64_t)(L - 1) * kH; a.h_in_ld = (int64_t)L * kH;
+      a.use_x = 0; a.bias = start; a.gather = nullptr;
+    } else {
+      a.h_in = dec_h + (int64_t)(k - 1) * kH; a.h_in_ld = (int64_t)K * kH;
+      a.use_x = 1; a.bias = bias;
+      a.gather = (forced_idx ? forced_idx : idx_out) + (int64_t)(k - 1) * n;
+    }
+    a.h_out = dec_h + (int64_t)k * kH;
+    int rc = launch_lstm_step(a, st);
+    if (rc) return rc;
+    if (n > 0) {
+      pointer_step_dot_kernel<<<att_blocks, 256, 0, st>>>(enc_out, (int64_t)L * kH, dec_h + (int64_t)k * kH,
+                                                          (int64_t)K * kH, latent_win, alpha, use_tanh, C, n,
+                                                          L, k, N, idx_out + (int64_t)k * n, win_logits,
+                                                          win_probs);
+      rc = after_launch();
+      if (rc) return rc;
+    }
+  }
+  return GNNPN_OK;
+}
+
+int gnnpn_pn_full_logits_f32(const float* enc_out, const float* dec_h, const int32_t* idx,
+                             int attention, const float* att_params, int use_tanh, float C,
+                             int64_t n, int L, int hidden, int K, float* logits_full, void* stream) {
+  GNNPN_REQUIRE(enc_out && dec_h && idx && logits_full, GNNPN_ENULL);
+  GNNPN_REQUIRE(hidden == kH && K >= 1 && L >= 1, GNNPN_ESHAPE);
+  GNNPN_REQUIRE(attention == GNNPN_ATT_DOT, GNNPN_EUNSUPPORTED);
+  (void)att_params;
+  const size_t smem = (size_t)K * kH * sizeof(float);
+  GNNPN_REQUIRE(smem <= 200 * 1024, GNNPN_ESHAPE);
+  GNNPN_REQUIRE(n < 65536ll * 32768ll, GNNPN_ERANGE);
+  if (n == 0) return GNNPN_OK;
+  cudaError_t e = cudaFuncSetAttribute(full_logits_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((unsigned)n, (unsigned)ceil_div(L, 32));
+  full_logits_dot_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(enc_out, dec_h, idx, use_tanh, C, n, L, K,
+                                                                  logits_full);
+  return after_launch();
+}
+
+int gnnpn_pn_reward_f32(const float* inputs, const int32_t* idx, int64_t n, int L, int in_features,
+                        int K, int tag, int32_t* viol_out, float* obj_out, float* reward_high_out,
+                        void* stream) {
+  GNNPN_REQUIRE(inputs && idx, GNNPN_ENULL);
+  GNNPN_REQUIRE(K >= 1 && K <= kMaxTasks && (tag == 0 || tag == 1) && in_features >= tag + 8, GNNPN_ESHAPE);
+  if (n == 0) return GNNPN_OK;
+  reward_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
+      inputs, idx, n, L, in_features, K, tag, viol_out, obj_out, reward_high_out);
+  return after_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+"""Drop-in replacement for the reference's ``src/models/modelPN.py`` on B200.
+
+Same public names, constructor signatures, ``forward`` signatures, return tuples
+and ``state_dict`` keys as the reference (modelPN.py:75-306) -- the
+trainers and ``main.py`` call it unchanged -- but ``forward`` runs the
+hand-written sm_100a kernels of ``libgnnpn_b200.so``:
+
+* encoder  : ``gnnpn_lstm_encode_f32``  (embedding2 folded into the LSTM input weights)
+* decode   : ``gnnpn_pn_decode_greedy_f32`` (LSTM cell + window logits + C*tanh + latent +
+             mask + softmax + first-max pick + next-input gather, K steps, whole batch)
+* reward   : ``gnnpn_pn_reward_f32``
+
+The reference returns K-long python lists of dense ``[B, L]`` tensors
+(``prev_probs``, ``prev_logits``).  Only the window slice ``[k*N,(k+1)*N)`` of
+step k ever influences a pick (modelPN.py:220-222), so the kernels keep the
+compact ``[B, L]`` "window" form and the lists handed back are *lazy*: indexing
+one materialises the reference's dense tensors (``gnnpn_pn_full_logits_f32``),
+while passing one on as ``latent`` to the next network stays compact.
+
+No CPU fallback: CUDA tensors only, and a missing extension raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+qosandcons = 8      # modelPN.py:10-12
+qosNum = 4
+consNum = 2
+
+VERBOSE_REWARD = False     # the reference prints every batch's reward list (modelPN.py:67)
+
+
+# --------------------------------------------------------------------------- lazy step lists
+class _StepList(Sequence):
+    """K-long, read-only, list-like view whose dense ``[K, B, L]`` backing tensor is built on first use."""
+
+    def __init__(self, K: int, make_dense):
+        self._K = K
+        self._make = make_dense
+        self._dense: Optional[torch.Tensor] = None
+
+    def dense(self) -> torch.Tensor:
+        if self._dense is None:
+            self._dense = self._make()
+        return self._dense
+
+    def __len__(self):
+        return self._K
+
+    def __bool__(self):
+        return self._K > 0
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self.dense()[i] for i in range(*k.indices(self._K))]
+        if k < 0:
+            k += self._K
+        if not 0 <= k < self._K:
+            raise IndexError(k)
+        return self.dense()[k]
+
+    def copy(self):
+        return self
+
+
+class WindowLogits(_StepList):
+    """``prev_logits`` / ``latent_p``.  ``.window`` is the compact ``[B, L]`` tensor the decode kernel consumes."""
+
+    def __init__(self, K, window: torch.Tensor, make_dense):
+        super().__init__(K, make_dense)
+        self.window = window
+
+
+def _window_of(latent, K: int, N: int) -> torch.Tensor:
+    """Compact ``[B, L]`` latent from whatever the caller passed (our lazy list or the reference's dense list)."""
+    if isinstance(latent, WindowLogits):
+        return latent.window
+    dense = torch.stack([t for t in latent])                       # [K, B, L]
+    Kk, B, L = dense.shape
+    assert Kk == K and L == K * N
+    return dense.view(K, B, K, N).diagonal(dim1=0, dim2=2).permute(0, 2, 1).reshape(B, L).contiguous()
+
+
+# --------------------------------------------------------------------------- reward
+def reward(sample_solution, optSolutions, sCategory, USE_CUDA=False, level="Low", embedding_size=20):
+    """modelPN.py:35-72 on the GPU: ``sample_solution`` is the K-list of chosen rows ``[B, F]``.
+
+    Low -> number of violated global constraints; High -> round(violations + objFunc, 5).
+    """
+    acts = sample_solution if torch.is_tensor(sample_solution) else torch.stack(list(sample_solution))
+    K, B, _ = acts.shape
+    rows = acts.permute(1, 0, 2).contiguous()                      # [B, K, F]: pick k is row k
+    idx = torch.arange(K, device=rows.device, dtype=torch.int32).view(K, 1).expand(K, B).contiguous()
+    viol, _obj, rew = ops.pn_reward(rows, idx, tag=0 if embedding_size == 0 else 1)
+    out = viol.float() if level == "Low" else rew
+    if VERBOSE_REWARD:
+        lst = out.tolist()
+        print(f"{level}, {sum(1 for v in lst if v >= 1)}, {sum(lst) / max(len(lst), 1)}: ", lst)
+    return out if USE_CUDA else out.cpu()
+
+
+# --------------------------------------------------------------------------- Attention
+class Attention(nn.Module):
+    """modelPN.py:75-123.  Parameters exist exactly as in the reference (Bahdanau only)."""
+
+    def __init__(self, hidden_size, use_tanh=False, C=10, name='Bahdanau', use_cuda=True):
+        super().__init__()
+        self.use_tanh = use_tanh
+        self.C = C
+        self.name = name
+        if name == 'Bahdanau':
+            self.W_query = nn.Linear(hidden_size, hidden_size)
+            self.W_ref = nn.Conv1d(hidden_size, hidden_size, 1, 1)
+            bound = 1.0 / math.sqrt(hidden_size)
+            self.V = nn.Parameter(torch.empty(hidden_size).uniform_(-bound, bound))
+
+    def forward(self, query, ref):
+        """query [B,H], ref [B,L,H] -> (ref as [B,H,L], logits [B,L])."""
+        if self.name != 'Dot':
+            raise NotImplementedError(f"attention {self.name!r}: only 'Dot' has a CUDA kernel so far")
+        B, L, H = ref.shape
+        refc = ref.contiguous()
+        none_picked = torch.zeros(1, B, device=ref.device, dtype=torch.int32)
+        logits = ops.pn_full_logits(refc, query.contiguous().view(B, 1, H), none_picked, "Dot", None,
+                                    bool(self.use_tanh), float(self.C))[0]
+        return ref.permute(0, 2, 1), logits
+
+
+# --------------------------------------------------------------------------- PointerNet
+class PointerNet(nn.Module):
+    """modelPN.py:126-241."""
+
+    def __init__(self, embedding_size, hidden_size, seq_len, n_glimpses, tanh_exploration, use_tanh,
+                 attention, sNumber, sCategory, use_cuda=True, level="low", mask=False):
+        super().__init__()
+        self.embedding_size = embedding_size
+        self.hidden_size = hidden_size
+        self.n_glimpses = n_glimpses
+        self.seq_len = seq_len
+        self.use_cuda = use_cuda
+        self.level = level
+        self.serNumber = sNumber
+        self.serCategory = sCategory
+        self.alpha = torch.ones(1)                # plain tensor, not in state_dict (modelPN.py:151)
+        self.mask = mask
+        if embedding_size != 0:
+            self.embedding1 = nn.Embedding(sCategory, embedding_size)
+        self.embedding2 = nn.Linear(embedding_size + qosandcons, hidden_size)
+        self.encoder = nn.LSTM(hidden_size, hidden_size, batch_first=True)
+        self.decoder = nn.LSTM(hidden_size, hidden_size, batch_first=True)
+        self.pointer = Attention(hidden_size, use_tanh=use_tanh, C=tanh_exploration, name=attention, use_cuda=use_cuda)
+        self.glimpse = Attention(hidden_size, use_tanh=False, name=attention, use_cuda=use_cuda)
+        bound = 1.0 / math.sqrt(hidden_size)
+        self.decoder_start_input = nn.Parameter(torch.empty(hidden_size).uniform_(-bound, bound))
+        self._pack_key = None
+        self._packed = None
+        self.last = None                          # device-side results of the most recent forward
+
+    # -- packed weights are a cache over the parameters; rebuilt when any of them changes
+    def _packed_weights(self):
+        ps = [self.embedding2.weight, self.embedding2.bias, self.decoder_start_input]
+        for rnn in (self.encoder, self.decoder):
+            ps += [rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._pack_key:
+            with torch.no_grad():
+                e, d = self.encoder, self.decoder
+                we, be = self.embedding2.weight, self.embedding2.bias
+                enc = ops.pack_lstm(e.weight_ih_l0, e.weight_hh_l0, e.bias_ih_l0, e.bias_hh_l0, we, be, None)
+                dec = ops.pack_lstm(d.weight_ih_l0, d.weight_hh_l0, d.bias_ih_l0, d.bias_hh_l0, we, be,
+                                    self.decoder_start_input)
+            self._packed, self._pack_key = (enc, dec), key
+        return self._packed
+
+    def forward(self, inputs, latent, sample="sample", forced_idxs=None):
+        """inputs [B, L, F] -> (prev_probs, prev_idxs, prev_logits), K-long each (modelPN.py:241)."""
+        B, L, _ = inputs.shape
+        assert L == self.seq_len
+        if sample != "greedy":
+            raise NotImplementedError("sampled decoding is provided by gnnpn_sc_b200.trainPN (REINFORCE replay)")
+        if self.embedding_size != 0 or self.n_glimpses != 0 or self.pointer.name != "Dot":
+            raise NotImplementedError("CUDA path covers embedding_size=0, n_glimpses=0, attention='Dot' "
+                                      "(every PN section of environment.ini)")
+        if not inputs.is_cuda:
+            raise RuntimeError("PointerNet.forward needs CUDA tensors: the B200 path has no CPU fallback")
+        K, N = self.serCategory, self.serNumber
+        x = inputs.detach().float().contiguous()
+        enc_w, dec_w = self._packed_weights()
+        with torch.no_grad():
+            enc_out, c = ops.lstm_encode(x, enc_w, self.hidden_size)
+            lat = _window_of(latent, K, N) if latent else None
+            forced = None if forced_idxs is None else torch.stack([t.to(torch.int32) for t in forced_idxs])
+            use_tanh, C = bool(self.pointer.use_tanh), float(self.pointer.C)
+            dec_h, idx, win_logits, win_probs = ops.pn_decode_greedy(
+                x, enc_out, c, dec_w, K, N, latent_win=lat, alpha=float(self.alpha), attention="Dot",
+                use_tanh=use_tanh, C=C, forced_idx=forced)
+        idx64 = idx.long()
+        self.last = {"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "enc_out": enc_out, "dec_h": dec_h}
+
+        def dense_logits():
+            return ops.pn_full_logits(enc_out, dec_h, idx, "Dot", None, use_tanh, C)
+
+        def dense_probs():      # exactly zero outside window k
+            out = torch.zeros(K, B, L, device=x.device, dtype=torch.float32)
+            out.view(K, B, K, N).diagonal(dim1=0, dim2=2).copy_(win_probs.view(B, K, N).permute(0, 2, 1))
+            return out
+
+        prev_probs = _StepList(K, dense_probs)
+        prev_probs.window = win_probs
+        prev_logits = WindowLogits(K, win_logits, dense_logits)
+        return prev_probs, list(idx64.unbind(0)), prev_logits
+
+
+# --------------------------------------------------------------------------- CombinatorialRL
+class CombinatorialRL(nn.Module):
+    """modelPN.py:244-306."""
+
+    def __init__(self, embedding_size, hidden_size, seq_len, n_glimpses, tanh_exploration, use_tanh, reward,
+                 attention, sNumber, sCategory, use_cuda=True, level="Low", mask=False):
+        super().__init__()
+        self.reward = reward
+        self.use_cuda = use_cuda
+        self.level = level
+        self.embedding_size = embedding_size
+        self.sNumber = sNumber
+        self.serCategory = sCategory
+        self.actor = PointerNet(embedding_size, hidden_size, seq_len, n_glimpses, tanh_exploration, use_tanh,
+                                attention, sNumber, sCategory, use_cuda, level=level, mask=mask)
+
+    def forward(self, inputs, labs, latent=None, sample="sample", training="RL"):
+        """-> (R | probs, action_probs, actions, action_idxs, latent_p), lists of length K (modelPN.py:282-306)."""
+        probs, action_idxs, logits = self.actor(inputs, latent, sample=sample)
+        latent_p = logits.copy()
+        idx = torch.stack(action_idxs)                                              # [K, B] int64
+        B = inputs.shape[0]
+        rows = torch.arange(B, device=inputs.device)
+        actions = list(inputs[rows.unsqueeze(0), idx].unbind(0))                    # K x [B, F]
+        action_probs = list(probs.window.gather(1, idx.t()).t().unbind(0))          # K x [B]
+        if training == "RL":
+            R = self.reward(actions, labs, self.serCategory, USE_CUDA=self.use_cuda, level=self.level,
+                            embedding_size=self.embedding_size)
+            return R, action_probs, actions, action_idxs, latent_p
+        return probs, action_probs, actions, action_idxs, latent_p

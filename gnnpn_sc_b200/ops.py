@@ -1,0 +1,166 @@
+"""Torch-tensor front end of the C ABI: allocates outputs with torch, passes raw
+device pointers + the current CUDA stream.  Plumbing only -- all arithmetic
+happens in ``libgnnpn_b200.so``.  Every function requires CUDA tensors."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import check, lib
+
+ACT = {None: 0, "none": 0, "relu": 1, "sigmoid": 2}
+ATT = {"Dot": 0, "Bahdanau": 1}
+CSR_PLAIN, CSR_GCN_NORM = 0, 1
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------ pointer network
+def packed_lstm_floats(hidden: int, in_features: int) -> int:
+    return int(lib().gnnpn_pn_packed_lstm_floats(hidden, in_features))
+
+
+def pack_lstm(w_ih, w_hh, b_ih, b_hh, w_embed, b_embed, start_input=None) -> torch.Tensor:
+    """Folded + gate-interleaved LSTM block (see ``gnnpn_pn_pack_lstm_f32``)."""
+    H = w_hh.shape[1]
+    F = w_embed.shape[1]
+    args = [_f32(t, "weight") for t in (w_ih, w_hh, b_ih, b_hh, w_embed, b_embed)]
+    st = None if start_input is None else _f32(start_input, "start_input")
+    out = torch.empty(packed_lstm_floats(H, F), device=args[0].device, dtype=torch.float32)
+    check(lib().gnnpn_pn_pack_lstm_f32(*[a.data_ptr() for a in args], _ptr(st), H, F, out.data_ptr(), _stream()),
+          "pn_pack_lstm")
+    return out
+
+
+def lstm_encode(inputs: torch.Tensor, packed: torch.Tensor, hidden: int = 256,
+                enc_out: Optional[torch.Tensor] = None, c_state: Optional[torch.Tensor] = None):
+    x = _f32(inputs, "inputs")
+    n, L, F = x.shape
+    if enc_out is None:
+        enc_out = torch.empty(n, L, hidden, device=x.device, dtype=torch.float32)
+    if c_state is None:
+        c_state = torch.empty(n, hidden, device=x.device, dtype=torch.float32)
+    check(lib().gnnpn_lstm_encode_f32(x.data_ptr(), n, L, F, hidden, packed.data_ptr(), enc_out.data_ptr(),
+                                      c_state.data_ptr(), _stream()), "lstm_encode")
+    return enc_out, c_state
+
+
+def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, latent_win=None, alpha: float = 1.0,
+                     attention: str = "Dot", att_params=None, use_tanh: bool = True, C: float = 10.0,
+                     forced_idx=None, out=None):
+    """Returns (dec_h [n,K,H], idx int32 [K,n], win_logits [n,L], win_probs [n,L]).  ``c_state`` is updated in place."""
+    x = _f32(inputs, "inputs")
+    n, L, F = x.shape
+    H = enc_out.shape[2]
+    dev = x.device
+    if out is None:
+        dec_h = torch.empty(n, K, H, device=dev, dtype=torch.float32)
+        idx = torch.empty(K, n, device=dev, dtype=torch.int32)
+        wl = torch.empty(n, L, device=dev, dtype=torch.float32)
+        wp = torch.empty(n, L, device=dev, dtype=torch.float32)
+    else:
+        dec_h, idx, wl, wp = out
+    if latent_win is not None:
+        latent_win = _f32(latent_win, "latent_win")
+        assert latent_win.shape == (n, L)
+    if forced_idx is not None:
+        forced_idx = forced_idx.to(torch.int32).contiguous()
+        assert forced_idx.shape == (K, n)
+    check(lib().gnnpn_pn_decode_greedy_f32(
+        x.data_ptr(), enc_out.data_ptr(), c_state.data_ptr(), _ptr(latent_win), float(alpha),
+        packed_dec.data_ptr(), ATT[attention], _ptr(att_params), int(bool(use_tanh)), float(C),
+        n, L, F, H, K, N, dec_h.data_ptr(), idx.data_ptr(), wl.data_ptr(), wp.data_ptr(),
+        _ptr(forced_idx), _stream()), "pn_decode_greedy")
+    return dec_h, idx, wl, wp
+
+
+def pn_full_logits(enc_out, dec_h, idx, attention: str = "Dot", att_params=None, use_tanh: bool = True,
+                   C: float = 10.0) -> torch.Tensor:
+    n, L, H = enc_out.shape
+    K = dec_h.shape[1]
+    out = torch.empty(K, n, L, device=enc_out.device, dtype=torch.float32)
+    check(lib().gnnpn_pn_full_logits_f32(enc_out.data_ptr(), dec_h.data_ptr(), idx.data_ptr(), ATT[attention],
+                                         _ptr(att_params), int(bool(use_tanh)), float(C), n, L, H, K,
+                                         out.data_ptr(), _stream()), "pn_full_logits")
+    return out
+
+
+def pn_reward(inputs, idx, tag: int = 0):
+    """(violations int32 [n], objFunc fp32 [n], round(viol+obj,5) fp32 [n]) for picks ``idx`` int32 [K,n]."""
+    x = _f32(inputs, "inputs")
+    n, L, F = x.shape
+    idx = idx.to(torch.int32).contiguous()
+    K = idx.shape[0]
+    viol = torch.empty(n, device=x.device, dtype=torch.int32)
+    obj = torch.empty(n, device=x.device, dtype=torch.float32)
+    rew = torch.empty(n, device=x.device, dtype=torch.float32)
+    check(lib().gnnpn_pn_reward_f32(x.data_ptr(), idx.data_ptr(), n, L, F, K, tag, viol.data_ptr(),
+                                    obj.data_ptr(), rew.data_ptr(), _stream()), "pn_reward")
+    return viol, obj, rew
+
+
+# ------------------------------------------------------------------ graph ops
+def csr_build(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], n_nodes: int, mode: int = CSR_PLAIN):
+    """Destination-major CSR, stable in edge order.  Returns (rowptr int64 [n+1], col int32 [nnz], val fp32 [nnz] | None)."""
+    if not edge_index.is_cuda:
+        raise RuntimeError("csr_build: expected CUDA tensors")
+    ei = edge_index.to(torch.int64).contiguous()
+    E = ei.shape[1]
+    w = None if edge_weight is None else _f32(edge_weight, "edge_weight")
+    dev = ei.device
+    cap = E + (n_nodes if mode == CSR_GCN_NORM else 0)
+    rowptr = torch.empty(n_nodes + 1, device=dev, dtype=torch.int64)
+    col = torch.empty(max(cap, 1), device=dev, dtype=torch.int32)
+    need_val = mode == CSR_GCN_NORM or w is not None
+    val = torch.empty(max(cap, 1), device=dev, dtype=torch.float32) if need_val else None
+    nnz = torch.zeros(1, device=dev, dtype=torch.int64)
+    import ctypes
+    nbytes = ctypes.c_size_t(0)
+    check(lib().gnnpn_csr_build_workspace_bytes(n_nodes, E, mode, ctypes.byref(nbytes)), "csr_workspace")
+    ws = torch.empty(nbytes.value, device=dev, dtype=torch.uint8)
+    check(lib().gnnpn_csr_build(ei.data_ptr(), _ptr(w), E, n_nodes, mode, rowptr.data_ptr(), col.data_ptr(),
+                                _ptr(val), nnz.data_ptr(), ws.data_ptr(), nbytes.value, _stream()), "csr_build")
+    total = int(nnz.item())
+    return rowptr, col[:total], (None if val is None else val[:total])
+
+
+def spmm_csr(rowptr, col, val, x, n_rows: Optional[int] = None, self_scale: float = 0.0, mean: bool = False,
+             bias=None, scale=None, shift=None, act=None, out=None) -> torch.Tensor:
+    x = _f32(x, "x")
+    F = x.shape[1]
+    assert F % 4 == 0, "feature dim must be padded to a multiple of 4"
+    n_rows = rowptr.numel() - 1 if n_rows is None else n_rows
+    y = torch.empty(n_rows, F, device=x.device, dtype=torch.float32) if out is None else out
+    check(lib().gnnpn_spmm_csr_f32(rowptr.data_ptr(), col.data_ptr(), _ptr(val), x.data_ptr(), x.stride(0),
+                                   y.data_ptr(), y.stride(0), n_rows, F, float(self_scale), int(mean),
+                                   _ptr(bias), _ptr(scale), _ptr(shift), ACT[act], _stream()), "spmm_csr")
+    return y
+
+
+def gemm_bias_act(a, w, bias=None, scale=None, shift=None, act=None, out=None) -> torch.Tensor:
+    """``act((a @ w.T + bias) * scale + shift)`` with ``w`` in nn.Linear layout [N,K]."""
+    a = _f32(a, "a")
+    w = _f32(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    c = torch.empty(M, N, device=a.device, dtype=torch.float32) if out is None else out
+    check(lib().gnnpn_gemm_f32_bias_act(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+                                        _ptr(scale), _ptr(shift), ACT[act], c.data_ptr(), c.stride(0),
+                                        M, N, K, _stream()), "gemm_bias_act")
+    return c

@@ -1,0 +1,167 @@
+/*
+ * gnnpn_b200.h -- C ABI of libgnnpn_b200.so: the B200 (sm_100a) hot path of GNNPN-SC.
+ *
+ * The reference (wangxiaohit/GNNPN-SC) is pure Python and has no FFI of its own;
+ * each entry point below names the reference interface it replaces (file:line in
+ * the reference tree) -- these are the calls a maintainer binds with ctypes from
+ * the reference's src/models modules.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - tensors are caller-allocated, row-major, fp32 / int32 / int64 as declared;
+ *    the library never allocates, frees or retains a pointer past return;
+ *    scratch is sized by the matching *_workspace_bytes() query;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *    the call returns without synchronising (except *_host entry points);
+ *  - return 0 on success, a negative GNNPN_E* for an argument error detected
+ *    before any launch, or a positive cudaError_t from the launch.  Nothing
+ *    throws across the ABI.  There is no CPU fallback.
+ */
+#ifndef GNNPN_B200_H_
+#define GNNPN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNNPN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GNNPN_API __attribute__((visibility("default")))
+#else
+#define GNNPN_API
+#endif
+
+enum {
+  GNNPN_OK = 0,
+  GNNPN_ENULL = -1,      /* required pointer is NULL */
+  GNNPN_ESHAPE = -2,     /* unsupported size (e.g. hidden_size != 256) */
+  GNNPN_EALIGN = -3,     /* pointer / leading dimension not 16-byte aligned */
+  GNNPN_EWORKSPACE = -4, /* workspace too small */
+  GNNPN_ERANGE = -5,     /* size exceeds the int32 index range used internally */
+  GNNPN_EUNSUPPORTED = -6
+};
+
+enum { GNNPN_ATT_DOT = 0, GNNPN_ATT_BAHDANAU = 1 };
+enum { GNNPN_ACT_NONE = 0, GNNPN_ACT_RELU = 1, GNNPN_ACT_SIGMOID = 2 };
+enum { GNNPN_CSR_PLAIN = 0, GNNPN_CSR_GCN_NORM = 1 };
+
+GNNPN_API int gnnpn_abi_version(void);
+GNNPN_API const char* gnnpn_error_string(int code);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+GNNPN_API uint64_t gnnpn_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * Pointer network  (reference: src/models/modelPN.py)
+ * ------------------------------------------------------------------------- */
+
+/* Size in floats of one packed LSTM ("[h | x] -> 4H gates") weight block for hidden size H
+ * and `in_features` raw input columns: (H + round_up(in_features,16)) * 4H  +  2 * 4H. */
+GNNPN_API size_t gnnpn_pn_packed_lstm_floats(int hidden, int in_features);
+
+/* Fold nn.Linear(F,H) `embedding2` (modelPN.py:155,190) into an nn.LSTM's input weights
+ * (modelPN.py:157-158) and lay the result out for the step kernel:
+ *   packed[k][4*j+g]            k <  H : W_hh[g*H+j][k]
+ *   packed[H+f][4*j+g]          f <  F : sum_i W_ih[g*H+j][i] * W_e[i][f]      (fp64 accumulate)
+ *   bias[4*j+g]   = b_ih + b_hh + W_ih . b_e
+ *   start[4*j+g]  = b_ih + b_hh + W_ih . start_input   (decoder_start_input, modelPN.py:162,202; may be NULL)
+ * Gate order i,f,g,o as in torch.  All inputs fp32 device pointers. */
+GNNPN_API int gnnpn_pn_pack_lstm_f32(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                           const float* w_embed, const float* b_embed, const float* start_input,
+                           int hidden, int in_features, float* packed, void* stream);
+
+/* Encoder: embedding2 + nn.LSTM over L steps (modelPN.py:190-191).
+ *   inputs  fp32 [n, L, F]          (F = in_features, 8 when embedding_size == 0)
+ *   enc_out fp32 [n, L, H]          every hidden state
+ *   c_state fp32 [n, H]             final cell state (also scratch during the scan)
+ * The final hidden state is enc_out[:, L-1, :]. */
+GNNPN_API int gnnpn_lstm_encode_f32(const float* inputs, int64_t n, int L, int in_features, int hidden,
+                          const float* packed_encoder, float* enc_out, float* c_state, void* stream);
+
+/* Fused greedy pointer decode: K x { decoder LSTM cell -> pointer logits on window k ->
+ * C*tanh -> (+ alpha*latent) -> window/visited mask -> softmax -> first-max index -> gather
+ * next decoder input }  (modelPN.py:204-239 with sample="greedy"), batched over n instances.
+ *   enc_out      fp32 [n, L, H]     from gnnpn_lstm_encode_f32
+ *   c_state      fp32 [n, H]        in: encoder final cell state; out: decoder final cell state
+ *   latent_win   fp32 [n, L] or NULL   PNLow's step-(l/N) logit at position l (only the window
+ *                                   slice of latent[k] can influence a pick)
+ *   att_params   NULL for Dot; for Bahdanau a packed block, see gnnpn_pn_pack_bahdanau_f32
+ *   dec_h        fp32 [n, K, H]     out: decoder hidden state (= attention query) of every step
+ *   idx_out      int32 [K, n]       out: selected position in [k*N, (k+1)*N)
+ *   win_logits   fp32 [n, L]        out: this network's pointer logit at position l taken at step l/N
+ *   win_probs    fp32 [n, L]        out: softmax probability at position l at step l/N
+ *   forced_idx   int32 [K, n] or NULL: teacher forcing -- feed these picks to the next step
+ *                                   while idx_out still records the free choice
+ */
+GNNPN_API int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float* c_state,
+                               const float* latent_win, float alpha, const float* packed_decoder,
+                               int attention, const float* att_params, int use_tanh, float C,
+                               int64_t n, int L, int in_features, int hidden, int K, int N,
+                               float* dec_h, int32_t* idx_out, float* win_logits, float* win_probs,
+                               const int32_t* forced_idx, void* stream);
+
+/* Interface-faithful materialisation of PointerNet.forward's prev_logits (modelPN.py:213-214,239):
+ *   logits_full fp32 [K, n, L] = C*tanh(<enc_out[b,l,:], dec_h[b,k,:]>) with -inf at the positions
+ *   chosen at steps < k (the cumulative visited mask, modelPN.py:165-173). */
+GNNPN_API int gnnpn_pn_full_logits_f32(const float* enc_out, const float* dec_h, const int32_t* idx,
+                             int attention, const float* att_params, int use_tanh, float C,
+                             int64_t n, int L, int hidden, int K, float* logits_full, void* stream);
+
+/* reward()/calc() (modelPN.py:15-72; also src/ML2PN.py:6-12):
+ *   inputs fp32 [n, L, F], idx int32 [K, n]; tag = 1 if the rows carry a leading category column.
+ *   viol_out int32 [n]  number of violated global constraints (level "Low" reward)
+ *   obj_out  fp32 [n]   objFunc = (sum q0 / #(q0>0) + 1 - min q1) / 2
+ *   reward_high_out fp32 [n]  float32(round(viol + objFunc, 5))   (any out pointer may be NULL) */
+GNNPN_API int gnnpn_pn_reward_f32(const float* inputs, const int32_t* idx, int64_t n, int L, int in_features,
+                        int K, int tag, int32_t* viol_out, float* obj_out, float* reward_high_out,
+                        void* stream);
+
+/* Host-buffer convenience for non-torch callers: PNLow greedy -> latent -> PNHigh greedy
+ * (src/models/trainPNHigh.py:131-144) on pageable or pinned HOST memory; allocates its own device
+ * scratch, copies in and out, synchronises.  idx_high_host int32 [K, n]; reward_high_host fp32 [n]. */
+GNNPN_API int gnnpn_pn_greedy_low_high_host(const float* inputs_host, int64_t n, int L, int in_features, int hidden,
+                                  int K, int N, const float* packed_low_host, const float* packed_high_host,
+                                  int use_tanh, float C, float alpha,
+                                  int32_t* idx_low_host, int32_t* idx_high_host, float* reward_high_host);
+
+/* ---------------------------------------------------------------------------
+ * ML stage: graph message passing  (reference: src/models/modelML.py + PyG 1.7.0 ops)
+ * ------------------------------------------------------------------------- */
+
+/* edge_index -> destination-major CSR, stable in edge order (replaces the per-forward, per-layer
+ * re-normalisation inside GCNConv, modelML.py:153, and the scatter index handling of GINConv :140).
+ *   mode GNNPN_CSR_PLAIN   : rows = edge_index[1] (target), cols = edge_index[0] (source), val = weight or absent
+ *   mode GNNPN_CSR_GCN_NORM: add_remaining_self_loops(fill 1) then val = deg^-1/2[src] * w * deg^-1/2[dst]
+ *   rowptr int64 [n_nodes+1]; col int32 [nnz]; val fp32 [nnz] (NULL allowed for PLAIN without weights);
+ *   nnz_out int64 [1] device.  Capacity of col/val must be n_edges (PLAIN) or n_edges + n_nodes (GCN). */
+GNNPN_API int gnnpn_csr_build_workspace_bytes(int64_t n_nodes, int64_t n_edges, int mode, size_t* bytes);
+GNNPN_API int gnnpn_csr_build(const int64_t* edge_index, const float* edge_weight, int64_t n_edges, int64_t n_nodes,
+                    int mode, int64_t* rowptr, int32_t* col, float* val, int64_t* nnz_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Neighbour aggregation as CSR segment-reduce, one warp (or sub-warp) per destination row,
+ * sequential in CSR order per feature (deterministic; equals CPU index_add_ in edge order):
+ *   y[i,:] = act( ( self_scale * x[i,:] + sum_e val[e] * x[col[e],:] ) / (mean ? max(rowlen,1) : 1)
+ *                 [+ bias] [* scale + shift] )
+ * Covers GINConv's sum + (1+eps)*x (self_scale = 1+eps), GCNConv's normalised sum + bias with the
+ * following eval-mode BatchNorm + ReLU folded in, and scatter(reduce='mean') (modelML.py:166,172).
+ * F must be a multiple of 4; x, y 16-byte aligned with leading dimensions ldx, ldy (floats). */
+GNNPN_API int gnnpn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                       const float* x, int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int F,
+                       float self_scale, int mean, const float* bias, const float* scale,
+                       const float* shift, int act, void* stream);
+
+/* Node transform: C[M,N] = act( (A[M,K] . W[N,K]^T + bias[N]) * scale[N] + shift[N] )
+ * (nn.Linear / GCNConv's X.W, modelML.py:77-93,98-106,164-165; bias/scale/shift may be NULL).
+ * fp32 in/out; tensor-core path uses error-compensated 3xTF32 on tcgen05. */
+GNNPN_API int gnnpn_gemm_f32_bias_act(const float* A, int64_t lda, const float* W, int64_t ldw,
+                            const float* bias, const float* scale, const float* shift, int act,
+                            float* C, int64_t ldc, int64_t M, int N, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNPN_B200_H_ */

@@ -1,0 +1,72 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, product-side helpers agree with the oracle's, synthetic data has the reference's layout."""
+import os
+import re
+
+import numpy as np
+import torch
+
+from oracle import pn_oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gnnpn_sc_b200 import _lib
+    with open(os.path.join(ROOT, "include", "gnnpn_b200.h")) as f:
+        declared = set(re.findall(r"GNNPN_API\s+[\w\s\*]+?\b(gnnpn_\w+)\s*\(", f.read()))
+    assert declared, "header parse failed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    L = _lib.lib()                      # CDLL + getattr of every symbol; no compute without a GPU
+    assert L.gnnpn_abi_version() == 1
+    assert L.gnnpn_error_string(-2) == b"unsupported shape"
+    assert L.gnnpn_pn_packed_lstm_floats(256, 8) == (256 + 16 + 2) * 1024
+    # argument errors are detected before any CUDA call, so they are testable on a CPU box
+    assert L.gnnpn_lstm_encode_f32(None, 1, 1, 8, 256, None, None, None, None) == -1
+
+
+def test_product_weights_equal_oracle_weights():
+    from gnnpn_sc_b200.weights import reference_shaped_state_dict
+    cfg = po.PNConfig()
+    a, b = reference_shaped_state_dict(256, 8, 5, 3.0), po.make_state_dict(cfg, 5, 3.0)
+    assert a.keys() == b.keys()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_state_dict_keys_match_reference_layout():
+    from gnnpn_sc_b200 import modelPN as M
+    m = M.CombinatorialRL(0, 256, 235, 0, 10, 1, M.reward, "Dot", 5, 47)
+    assert set(m.state_dict()) == set(po.make_state_dict(po.PNConfig(), 0))
+    mb = M.CombinatorialRL(20, 256, 18, 1, 10, 1, M.reward, "Bahdanau", 3, 6)
+    cfgb = po.PNConfig(seq_len=18, s_number=3, s_category=6, embedding_size=20, attention="Bahdanau")
+    ref = po.make_state_dict(cfgb, 0)
+    assert set(mb.state_dict()) == set(ref)
+    assert all(mb.state_dict()[k].shape == ref[k].shape for k in ref)
+
+
+def test_no_cpu_fallback():
+    import pytest
+    from gnnpn_sc_b200 import modelPN as M
+    m = M.CombinatorialRL(0, 256, 6, 0, 10, 1, M.reward, "Dot", 2, 3)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 6, 8), None, sample="greedy", training="SL")
+
+
+def test_pn_instances_layout():
+    from gnnpn_sc_b200.synth import pn_instances
+    x = pn_instances(32, 47, 5, seed=1).view(32, 47, 5, 8).numpy()
+    assert (x[:, 1:, :, 4:] == 0).all()                       # global bounds only on category-0 rows
+    assert (x[:, 0, :, 5] == 1).all() and (x[:, 0, :, 4] > 0).all()
+    neutral = (x[..., :4] == np.array([0, 1, 1, 1], np.float32)).all(-1)
+    assert neutral.all(-1).sum() == neutral.any(-1).sum()     # neutral categories are neutral on all N rows
+    assert 0.05 < neutral.mean() < 0.4
+    assert torch.equal(pn_instances(8, 6, 3, seed=4), pn_instances(8, 6, 3, seed=4))
+
+
+def test_window_compaction_of_dense_latent():
+    from gnnpn_sc_b200.modelPN import _window_of
+    K, N, B = 5, 3, 4
+    dense = [torch.randn(B, K * N) for _ in range(K)]
+    w = _window_of(dense, K, N)
+    for k in range(K):
+        assert torch.equal(w[:, k * N:(k + 1) * N], dense[k][:, k * N:(k + 1) * N])

@@ -1,0 +1,203 @@
+"""GPU parity of the pointer-network path: CUDA kernels (through the drop-in modules and the C ABI)
+against (1) fixtures produced by the real reference and (2) the CPU oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): selected indices / masks / -inf pattern exact -- any index
+mismatch must be explained by a reference top-2 margin below LOGIT_TOL and is counted; fp32 logits and
+probabilities within 1e-5 relative (|a-b| <= 1e-5 * max(1, |ref|))."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import make_golden as mg
+from oracle import pn_oracle as po
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL = 1e-5
+CUDA_CASES = ["qws_b4", "normal_b2", "small_b16", "sharp_b4", "notanh_b3"]
+
+
+def _models(name, device="cuda"):
+    from gnnpn_sc_b200 import modelPN as M
+    kw, B, (s_lo, s_hi), s_in, gain, dist = mg.CASES[name]
+    cfg = mg.case_config(name)
+    x = mg.build_inputs(cfg, B, s_in, dist)
+    out = []
+    for level, seed in (("Low", s_lo), ("High", s_hi)):
+        m = M.CombinatorialRL(cfg.embedding_size, cfg.hidden_size, cfg.seq_len, cfg.n_glimpses,
+                              cfg.tanh_exploration, int(cfg.use_tanh), M.reward, cfg.attention,
+                              cfg.s_number, cfg.s_category, use_cuda=True, level=level)
+        m.load_state_dict(po.make_state_dict(cfg, seed, gain), strict=True)
+        out.append(m.to(device).eval())
+    return cfg, x, out[0], out[1]
+
+
+def _close(a, b, tol=LOGIT_TOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b))
+
+
+def _explain_flips(idx, ref_idx, ref_work_logits, N):
+    """Every differing pick must sit on a reference top-2 margin < LOGIT_TOL.  Returns the number of flips."""
+    K, B = ref_idx.shape
+    flips = 0
+    for k, b in zip(*np.nonzero(idx != ref_idx)):
+        win = np.sort(ref_work_logits[k, b, k * N:(k + 1) * N])[::-1]
+        margin = win[0] - win[1]
+        assert margin < LOGIT_TOL * max(1.0, abs(win[0])), f"pick (k={k}, b={b}) differs with margin {margin}"
+        flips += 1
+    return flips
+
+
+@pytest.mark.parametrize("name", CUDA_CASES)
+def test_greedy_low_high_matches_reference_fixture(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"pn_{name}.npz"))
+    cfg, x, low, high = _models(name)
+    xc = x.cuda()
+    with torch.no_grad():
+        _, ap_lo, _, idx_lo, latent = low(xc, None, sample="greedy", training="SL")
+        R_hi, ap_hi, act_hi, idx_hi, lg_hi = high(xc, None, latent, sample="greedy", training="RL")
+    N = cfg.s_number
+    idx_lo = torch.stack(idx_lo).cpu().numpy()
+    idx_hi = torch.stack(idx_hi).cpu().numpy()
+    flips = _explain_flips(idx_lo, g["idx_low"], g["logits_low"], N)
+    assert flips == 0, f"{flips} tolerance-limited picks in PNLow -- downstream comparison undefined for this fixture"
+    work_hi = g["logits_high"] + g["logits_low"]
+    flips += _explain_flips(idx_hi, g["idx_high"], work_hi, N)
+    assert flips == 0
+    for mine, ref in ((latent, g["logits_low"]), (lg_hi, g["logits_high"])):
+        dense = torch.stack([mine[k] for k in range(len(mine))]).cpu().numpy()
+        assert np.array_equal(np.isneginf(dense), np.isneginf(ref)), "visited-mask (-inf) pattern"
+        fin = np.isfinite(ref)
+        bad = ~_close(dense[fin], ref[fin])
+        assert not bad.any(), f"max logit err {np.abs(dense[fin] - ref[fin]).max()}"
+    assert _close(torch.stack(ap_lo).cpu().numpy(), g["action_probs_low"]).all()
+    assert _close(torch.stack(ap_hi).cpu().numpy(), g["action_probs_high"]).all()
+    assert np.array_equal(torch.stack(act_hi).cpu().numpy(), g["actions_high"])
+    assert np.array_equal(R_hi.cpu().numpy(), g["reward_high"])          # bit-exact objective evaluator
+    r_low = high.reward(act_hi, None, cfg.s_category, USE_CUDA=True, level="Low", embedding_size=0)
+    assert np.array_equal(r_low.cpu().numpy(), g["viol_high"])
+
+
+def test_dense_probs_structure(golden_dir):
+    g = np.load(os.path.join(golden_dir, "pn_qws_b4.npz"))
+    cfg, x, low, high = _models("qws_b4")
+    with torch.no_grad():
+        _, _, _, _, latent = low(x.cuda(), None, sample="greedy", training="SL")
+        probs, *_ = high(x.cuda(), None, latent, sample="greedy", training="SL")
+    p1 = probs[1].cpu().numpy()
+    assert np.array_equal(p1 == 0, g["probs_high_step1"] == 0)
+    assert _close(p1, g["probs_high_step1"]).all()
+    assert len(probs) == cfg.s_category
+
+
+def test_accepts_reference_style_dense_latent_list():
+    """A caller holding the reference's K-list of dense [B,L] tensors gets the same picks as the lazy form."""
+    cfg, x, low, high = _models("small_b16")
+    with torch.no_grad():
+        _, _, _, _, latent = low(x.cuda(), None, sample="greedy", training="SL")
+        dense = [latent[k].clone() for k in range(len(latent))]
+        a = high(x.cuda(), None, latent, sample="greedy", training="SL")[3]
+        b = high(x.cuda(), None, dense, sample="greedy", training="SL")[3]
+    assert all(torch.equal(u, v) for u, v in zip(a, b))
+
+
+@pytest.mark.parametrize("n,K,N,gain", [(300, 47, 5, 1.0), (129, 50, 10, 1.0), (64, 12, 5, 3.0), (1, 3, 2, 1.0)])
+def test_teacher_forced_steps_against_oracle(n, K, N, gain):
+    """Per-step comparison with the oracle's picks fed back, so one tolerance-limited pick cannot cascade."""
+    from gnnpn_sc_b200 import modelPN as M
+    from gnnpn_sc_b200.synth import pn_instances
+    cfg = po.PNConfig(seq_len=K * N, s_number=N, s_category=K)
+    sd = po.make_state_dict(cfg, 77, gain)
+    x = pn_instances(n, K, N, seed=5)
+    with torch.no_grad():
+        _, idx_ref, lg_ref = po.pointer_forward(sd, cfg, x, None, "greedy")
+    m = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level="Low")
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        probs, idx, lg = m.actor(x.cuda(), None, sample="greedy", forced_idxs=[t.cuda() for t in idx_ref])
+    idx = torch.stack(idx).cpu().numpy()
+    ref = torch.stack(idx_ref).numpy()
+    ref_lg = torch.stack(lg_ref).numpy()
+    flips = _explain_flips(idx, ref, ref_lg, N)
+    dense = torch.stack([lg[k] for k in range(K)]).cpu().numpy()
+    assert np.array_equal(np.isneginf(dense), np.isneginf(ref_lg))
+    fin = np.isfinite(ref_lg)
+    err = np.abs(dense[fin] - ref_lg[fin])
+    assert _close(dense[fin], ref_lg[fin]).all(), f"max err {err.max()}"
+    print(f"teacher-forced n={n} K={K} N={N}: {flips} tolerance-limited picks of {K * n}, max |dlogit| {err.max():.2e}")
+
+
+def test_free_running_full_size_properties():
+    """QWS shape at a batch the oracle cannot finish quickly: structural properties + reward vs oracle."""
+    from gnnpn_sc_b200 import modelPN as M
+    from gnnpn_sc_b200.synth import pn_instances
+    n, K, N = 4096, 47, 5
+    cfg = po.PNConfig(seq_len=K * N, s_number=N, s_category=K)
+    x = pn_instances(n, K, N, seed=9).cuda()
+    low = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level="Low")
+    high = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level="High")
+    low.load_state_dict(po.make_state_dict(cfg, 1))
+    high.load_state_dict(po.make_state_dict(cfg, 2))
+    low, high = low.cuda().eval(), high.cuda().eval()
+
+    def run(xs):
+        with torch.no_grad():
+            _, _, _, _, lat = low(xs, None, sample="greedy", training="SL")
+            R, ap, act, idx, _ = high(xs, None, lat, sample="greedy", training="RL")
+        return torch.stack(idx), R, torch.stack(act)
+
+    idx, R, act = run(x)
+    idx2, R2, _ = run(x)
+    assert torch.equal(idx, idx2) and torch.equal(R, R2)                      # deterministic
+    lo = torch.arange(K, device="cuda").view(K, 1) * N
+    assert bool(((idx >= lo) & (idx < lo + N)).all())                        # picks stay in their window
+    parts = [run(x[s:s + 1000]) for s in range(0, n, 1000)]                  # instance sharding == unsharded
+    assert torch.equal(torch.cat([p[0] for p in parts], dim=1), idx)
+    assert torch.equal(torch.cat([p[1] for p in parts]), R)
+    sub = slice(0, 256)                                                      # reward evaluator vs oracle, exact
+    R_ref = po.reward(list(act[:, sub].cpu()), None, K, "High", 0)
+    assert torch.equal(R[sub].cpu(), R_ref)
+
+
+def test_host_buffer_c_abi_matches_module_path():
+    import ctypes
+    from gnnpn_sc_b200 import modelPN as M, _lib
+    from gnnpn_sc_b200.synth import pn_instances
+    n, K, N = 200, 47, 5
+    cfg = po.PNConfig(seq_len=K * N, s_number=N, s_category=K)
+    x = pn_instances(n, K, N, seed=3)
+    low = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level="Low")
+    high = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level="High")
+    low.load_state_dict(po.make_state_dict(cfg, 1))
+    high.load_state_dict(po.make_state_dict(cfg, 2))
+    low, high = low.cuda().eval(), high.cuda().eval()
+    with torch.no_grad():
+        _, _, _, il, lat = low(x.cuda(), None, sample="greedy", training="SL")
+        R, _, _, ih, _ = high(x.cuda(), None, lat, sample="greedy", training="RL")
+    pk_lo = torch.cat(low.actor._packed_weights()).cpu().contiguous()
+    pk_hi = torch.cat(high.actor._packed_weights()).cpu().contiguous()
+    idx_lo = np.zeros((K, n), np.int32)
+    idx_hi = np.zeros((K, n), np.int32)
+    rew = np.zeros(n, np.float32)
+    xin = x.contiguous().numpy()
+    rc = _lib.lib().gnnpn_pn_greedy_low_high_host(
+        xin.ctypes.data, n, K * N, 8, 256, K, N, pk_lo.data_ptr(), pk_hi.data_ptr(), 1, 10.0, 1.0,
+        idx_lo.ctypes.data, idx_hi.ctypes.data, rew.ctypes.data)
+    assert rc == 0
+    assert np.array_equal(idx_lo, torch.stack(il).cpu().numpy())
+    assert np.array_equal(idx_hi, torch.stack(ih).cpu().numpy())
+    assert np.array_equal(rew, R.cpu().numpy())
+
+
+def test_argument_errors_are_reported_not_thrown():
+    from gnnpn_sc_b200 import _lib, modelPN as M
+    L = _lib.lib()
+    assert L.gnnpn_lstm_encode_f32(None, 1, 1, 8, 256, None, None, None, None) == -1       # GNNPN_ENULL
+    t = torch.zeros(16, device="cuda")
+    assert L.gnnpn_lstm_encode_f32(t.data_ptr(), 1, 1, 8, 128, t.data_ptr(), t.data_ptr(), t.data_ptr(), None) == -2
+    with pytest.raises(RuntimeError):
+        m = M.CombinatorialRL(0, 256, 6, 0, 10, 1, M.reward, "Dot", 2, 3).cuda()
+        m(torch.zeros(2, 6, 8), None, sample="greedy", training="SL")                       # CPU tensor -> loud error
