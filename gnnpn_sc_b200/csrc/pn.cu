@@ -181,11 +181,18 @@ __device__ float numpy_pairwise_sum_f32(const float* v, int n) {
   return res;
 }
 
+// numpy splits n > 128 as (n/2 rounded down to a multiple of 8) + rest, recursively; unrolled by
+// template depth (3 levels cover n <= 1024) because device recursion has no static stack bound.
+template <int DEPTH>
 __device__ float numpy_sum_f32(const float* v, int n) {
   if (n <= 128) return numpy_pairwise_sum_f32(v, n);
-  int n2 = n / 2;
-  n2 -= n2 % 8;
-  return __fadd_rn(numpy_sum_f32(v, n2), numpy_sum_f32(v + n2, n - n2));
+  if constexpr (DEPTH == 0) {
+    return numpy_pairwise_sum_f32(v, n);   // unreachable for n <= kMaxTasks
+  } else {
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(numpy_sum_f32<DEPTH - 1>(v, n2), numpy_sum_f32<DEPTH - 1>(v + n2, n - n2));
+  }
 }
 
 constexpr int kMaxTasks = 512;
@@ -212,7 +219,7 @@ __global__ void reward_kernel(const float* __restrict__ inputs, const int32_t* _
   }
   int viol = 0;
   for (int i = 0; i < 2; ++i) viol += (prod[i] < lo[i] || prod[i] > hi[i]) ? 1 : 0;
-  const float s = numpy_sum_f32(q0s, K);
+  const float s = numpy_sum_f32<2>(q0s, K);
   float obj = __fdiv_rn(s, (float)used);
   obj = __fadd_rn(obj, 1.0f);
   obj = __fsub_rn(obj, min_q1);

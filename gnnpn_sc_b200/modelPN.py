@@ -203,8 +203,10 @@ class PointerNet(nn.Module):
         idx64 = idx.long()
         self.last = {"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "enc_out": enc_out, "dec_h": dec_h}
 
+        fed = idx if forced is None else forced.contiguous()     # the picks the visited mask follows
+
         def dense_logits():
-            return ops.pn_full_logits(enc_out, dec_h, idx, "Dot", None, use_tanh, C)
+            return ops.pn_full_logits(enc_out, dec_h, fed, "Dot", None, use_tanh, C)
 
         def dense_probs():      # exactly zero outside window k
             out = torch.zeros(K, B, L, device=x.device, dtype=torch.float32)

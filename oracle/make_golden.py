@@ -89,7 +89,22 @@ def run_reference(ref, name: str):
                           embedding_size=cfg.embedding_size)
         r_hi_as_low = ref.reward(act_hi, None, cfg.s_category, USE_CUDA=False, level="Low",
                                  embedding_size=cfg.embedding_size)
+    # the reference itself evaluated in float64 (same modules, .double()): used to state how far the
+    # reference's own fp32 run is from exact arithmetic when a stress case amplifies rounding noise
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        for m in models.values():
+            m.double()
+            m.actor.alpha = m.actor.alpha.double()
+        _, _, _, idx_lo64, latent64 = models["Low"](x.double(), None, sample="greedy", training="SL")
+        _, _, _, idx_hi64, lg_hi64 = models["High"](x.double(), None, latent64, sample="greedy", training="SL")
+    same64 = bool((torch.stack(idx_lo64) == torch.stack(idx_lo)).all() and (torch.stack(idx_hi64) == torch.stack(idx_hi)).all())
+    out["picks_equal_in_f64"] = np.array(same64)
+    if torch.stack(latent64).numel() <= 20000:          # keep the big-shape fixtures small
+        out.update(logits_low_f64=torch.stack(latent64).numpy(), logits_high_f64=torch.stack(lg_hi64).numpy())
     out.update(
+        objfunc_high=np.array([ref.calc([act_hi[k][b][0:4] for k in range(cfg.s_category)] if cfg.embedding_size == 0 else
+                                        [act_hi[k][b][1:5] for k in range(cfg.s_category)],
+                                        [[[0.0, 2.0]], [[0.0, 2.0]]], cfg.s_category)[1] for b in range(B)], dtype=np.float32),
         idx_low=torch.stack(idx_lo).numpy().astype(np.int32),
         logits_low=torch.stack(latent).numpy(),
         action_probs_low=torch.stack(ap_lo).numpy(),

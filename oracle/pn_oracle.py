@@ -291,7 +291,8 @@ def composition_objective(actions: np.ndarray, tag: int = 0) -> Tuple[np.ndarray
     obj = np.empty(B, dtype=np.float32)
     for b in range(B):                      # np.sum on a contiguous fp32 vector: numpy's pairwise order
         s = np.sum(np.ascontiguousarray(q[:, b, 0]))
-        obj[b] = (s / n_used[b] + 1 - np.min(q[:, b, 1])) / 2
+        # serviceNum is a python int in the reference (modelPN.py:26-28): float32 arithmetic throughout
+        obj[b] = (s / int(n_used[b]) + 1 - np.min(q[:, b, 1])) / 2
     return viol, obj
 
 

@@ -42,6 +42,9 @@ def test_oracle_matches_reference_fixture(name, golden_dir):
     # reward / objective evaluator: exact (fp32 sequential products + python round)
     assert np.array_equal(res["reward_high"].numpy(), g["reward_high"])
     assert np.array_equal(res["viol_high"].numpy(), g["viol_high"])
+    tag = 1 if cfg.embedding_size else 0
+    _, obj = po.composition_objective(res["actions"].numpy(), tag)
+    assert np.array_equal(obj, g["objfunc_high"])          # unrounded objFunc of the reference's calc()
 
 
 def test_faithful_loops_same_result():

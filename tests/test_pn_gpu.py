@@ -33,9 +33,20 @@ def _models(name, device="cuda"):
     return cfg, x, out[0], out[1]
 
 
-def _close(a, b, tol=LOGIT_TOL):
+def _close(a, b, tol=LOGIT_TOL, floor=0.0):
+    """|a-b| <= max(tol * max(1,|b|), floor).  `floor` = 2x the reference's own fp32-vs-fp64 deviation on a
+    stress case whose weights amplify rounding noise beyond 1e-5 for ANY fp32 evaluation order."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    return np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b))
+    return np.abs(a - b) <= np.maximum(tol * np.maximum(1.0, np.abs(b)), floor)
+
+
+def _reference_noise(g, key):
+    """max |reference fp32 - reference fp64| on a fixture tensor (0 when the fixture has no fp64 run)."""
+    k64 = key + "_f64"
+    if k64 not in g.files or not bool(g["picks_equal_in_f64"]):
+        return 0.0
+    fin = np.isfinite(g[key])
+    return float(np.abs(g[key][fin] - g[k64][fin]).max())
 
 
 def _explain_flips(idx, ref_idx, ref_work_logits, N):
@@ -59,6 +70,7 @@ def test_greedy_low_high_matches_reference_fixture(name, golden_dir):
         _, ap_lo, _, idx_lo, latent = low(xc, None, sample="greedy", training="SL")
         R_hi, ap_hi, act_hi, idx_hi, lg_hi = high(xc, None, latent, sample="greedy", training="RL")
     N = cfg.s_number
+    idx_hi_t = idx_hi
     idx_lo = torch.stack(idx_lo).cpu().numpy()
     idx_hi = torch.stack(idx_hi).cpu().numpy()
     flips = _explain_flips(idx_lo, g["idx_low"], g["logits_low"], N)
@@ -66,16 +78,22 @@ def test_greedy_low_high_matches_reference_fixture(name, golden_dir):
     work_hi = g["logits_high"] + g["logits_low"]
     flips += _explain_flips(idx_hi, g["idx_high"], work_hi, N)
     assert flips == 0
-    for mine, ref in ((latent, g["logits_low"]), (lg_hi, g["logits_high"])):
+    for mine, key in ((latent, "logits_low"), (lg_hi, "logits_high")):
+        ref = g[key]
         dense = torch.stack([mine[k] for k in range(len(mine))]).cpu().numpy()
         assert np.array_equal(np.isneginf(dense), np.isneginf(ref)), "visited-mask (-inf) pattern"
         fin = np.isfinite(ref)
-        bad = ~_close(dense[fin], ref[fin])
-        assert not bad.any(), f"max logit err {np.abs(dense[fin] - ref[fin]).max()}"
+        noise = _reference_noise(g, key)
+        err = np.abs(dense[fin] - ref[fin]).max()
+        print(f"{name}/{key}: max |dlogit| {err:.2e} (reference's own fp32 noise vs its fp64 run: {noise:.2e})")
+        assert _close(dense[fin], ref[fin], floor=2 * noise if noise > LOGIT_TOL / 2 else 0.0).all(), err
     assert _close(torch.stack(ap_lo).cpu().numpy(), g["action_probs_low"]).all()
     assert _close(torch.stack(ap_hi).cpu().numpy(), g["action_probs_high"]).all()
     assert np.array_equal(torch.stack(act_hi).cpu().numpy(), g["actions_high"])
     assert np.array_equal(R_hi.cpu().numpy(), g["reward_high"])          # bit-exact objective evaluator
+    from gnnpn_sc_b200 import ops
+    _, obj, _ = ops.pn_reward(xc, torch.stack(idx_hi_t).to(torch.int32))
+    assert np.array_equal(obj.cpu().numpy(), g["objfunc_high"])          # unrounded objFunc, exact
     r_low = high.reward(act_hi, None, cfg.s_category, USE_CUDA=True, level="Low", embedding_size=0)
     assert np.array_equal(r_low.cpu().numpy(), g["viol_high"])
 
@@ -126,8 +144,14 @@ def test_teacher_forced_steps_against_oracle(n, K, N, gain):
     assert np.array_equal(np.isneginf(dense), np.isneginf(ref_lg))
     fin = np.isfinite(ref_lg)
     err = np.abs(dense[fin] - ref_lg[fin])
-    assert _close(dense[fin], ref_lg[fin]).all(), f"max err {err.max()}"
-    print(f"teacher-forced n={n} K={K} N={N}: {flips} tolerance-limited picks of {K * n}, max |dlogit| {err.max():.2e}")
+    # the oracle's own distance from exact arithmetic: same network in float64, same (forced) picks
+    sd64 = {k: v.double() for k, v in sd.items()}
+    with torch.no_grad():
+        _, _, lg64 = po.pointer_forward(sd64, cfg, x.double(), None, "greedy", forced_idxs=idx_ref)
+    noise = float(np.abs(torch.stack(lg64).numpy()[fin] - ref_lg[fin]).max())
+    print(f"teacher-forced n={n} K={K} N={N} gain={gain}: {flips} tolerance-limited picks of {K * n}, "
+          f"max |dlogit| {err.max():.2e}, oracle fp32-vs-fp64 noise {noise:.2e}")
+    assert _close(dense[fin], ref_lg[fin], floor=2 * noise if noise > LOGIT_TOL / 2 else 0.0).all(), err.max()
 
 
 def test_free_running_full_size_properties():
