@@ -28,16 +28,18 @@ SIGNATURES = {
     "gnnpn_launch_count": (C.c_uint64, []),
     "gnnpn_pn_packed_lstm_floats": (C.c_size_t, [_i, _i]),
     "gnnpn_pn_pack_lstm_f32": (_i, [_p] * 7 + [_i, _i, _p, _p]),
-    "gnnpn_lstm_encode_f32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p]),
+    "gnnpn_lstm_encode_f32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p, C.c_size_t, _p]),
+    "gnnpn_pn_workspace_bytes": (C.c_size_t, [_i64, _i]),
     "gnnpn_pn_decode_greedy_f32": (_i, [_p, _p, _p, _p, _f, _p, _i, _p, _i, _f, _i64, _i, _i, _i, _i, _i,
-                                        _p, _p, _p, _p, _p, _p]),
+                                        _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "gnnpn_pn_full_logits_f32": (_i, [_p, _p, _p, _i, _p, _i, _f, _i64, _i, _i, _i, _p, _p]),
     "gnnpn_pn_reward_f32": (_i, [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p]),
     "gnnpn_pn_greedy_low_high_host": (_i, [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _i, _f, _f, _p, _p, _p]),
     "gnnpn_csr_build_workspace_bytes": (_i, [_i64, _i64, _i, C.POINTER(C.c_size_t)]),
     "gnnpn_csr_build": (_i, [_p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "gnnpn_spmm_csr_f32": (_i, [_p, _p, _p, _p, _i64, _p, _i64, _i64, _i, _f, _i, _p, _p, _p, _i, _p]),
-    "gnnpn_gemm_f32_bias_act": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _p, _i64, _i64, _i, _i, _p]),
+    "gnnpn_gemm_workspace_bytes": (C.c_size_t, [_i64, _i, _i]),
+    "gnnpn_gemm_f32_bias_act": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _p, _i64, _i64, _i, _i, _p, C.c_size_t, _p]),
 }
 
 
@@ -61,7 +63,7 @@ def lib():
                 fn = getattr(h, name)          # AttributeError if the ABI lost a symbol
                 fn.restype = res
                 fn.argtypes = args
-            if h.gnnpn_abi_version() != 1:
+            if h.gnnpn_abi_version() != 2:
                 raise GnnpnError("libgnnpn_b200.so ABI version mismatch")
             _lib = h
     return _lib

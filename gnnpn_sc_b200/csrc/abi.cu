@@ -8,6 +8,10 @@ std::atomic<uint64_t> g_launch_count{0};
 int launch_gemm_ffma(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                      const float* scale, const float* shift, int act, float* C, int64_t ldc, int64_t M, int N,
                      int K, cudaStream_t st);
+size_t tc_gemm_workspace_bytes(int64_t M, int N, int K);
+int launch_gemm_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* scale,
+                   const float* shift, int act, float* C, int64_t ldc, int64_t M, int N, int K, void* workspace,
+                   cudaStream_t st);
 }  // namespace gnnpn
 
 using namespace gnnpn;
@@ -33,14 +37,24 @@ const char* gnnpn_error_string(int code) {
   return "unknown gnnpn error";
 }
 
+size_t gnnpn_gemm_workspace_bytes(int64_t M, int N, int K) {
+  return (M < 0 || N < 1 || K < 1) ? 0 : tc_gemm_workspace_bytes(M, N, K);
+}
+
 int gnnpn_gemm_f32_bias_act(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                             const float* scale, const float* shift, int act, float* C, int64_t ldc, int64_t M,
-                            int N, int K, void* stream) {
+                            int N, int K, void* workspace, size_t workspace_bytes, void* stream) {
   GNNPN_REQUIRE(A && W && C, GNNPN_ENULL);
   GNNPN_REQUIRE(M >= 0 && N >= 1 && K >= 1 && lda >= K && ldw >= K && ldc >= N, GNNPN_ESHAPE);
   GNNPN_REQUIRE((scale == nullptr) == (shift == nullptr), GNNPN_ENULL);
   GNNPN_REQUIRE(M < (1ll << 31) * 64, GNNPN_ERANGE);
   if (M == 0) return GNNPN_OK;
+  if (workspace) {
+    GNNPN_REQUIRE(workspace_bytes >= tc_gemm_workspace_bytes(M, N, K), GNNPN_EWORKSPACE);
+    GNNPN_REQUIRE(M < (1ll << 31), GNNPN_ERANGE);
+    return launch_gemm_tc(A, lda, W, ldw, bias, scale, shift, act, C, ldc, M, N, K, workspace,
+                          (cudaStream_t)stream);
+  }
   return launch_gemm_ffma(A, lda, W, ldw, bias, scale, shift, act, C, ldc, M, N, K, (cudaStream_t)stream);
 }
 
@@ -71,6 +85,8 @@ int gnnpn_pn_greedy_low_high_host(const float* inputs_host, int64_t n, int L, in
   const size_t pfloats = gnnpn_pn_packed_lstm_floats(H, F);
   float *d_in = nullptr, *d_enc = nullptr, *d_c = nullptr, *d_dech = nullptr, *d_wl_lo = nullptr, *d_wl_hi = nullptr,
         *d_wp = nullptr, *d_rew = nullptr, *d_pk = nullptr;
+  void* d_ws = nullptr;
+  const size_t ws_bytes = gnnpn_pn_workspace_bytes(chunk, H);
   int32_t *d_idx_lo = nullptr, *d_idx_hi = nullptr;
   cudaStream_t st = nullptr;
   if (n == 0) return GNNPN_OK;
@@ -86,6 +102,7 @@ int gnnpn_pn_greedy_low_high_host(const float* inputs_host, int64_t n, int L, in
   CUDA_TRY(cudaMalloc(&d_rew, chunk * sizeof(float)));
   CUDA_TRY(cudaMalloc(&d_idx_lo, chunk * K * sizeof(int32_t)));
   CUDA_TRY(cudaMalloc(&d_idx_hi, chunk * K * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&d_ws, ws_bytes));
   // packed_*_host = [encoder block | decoder block], each gnnpn_pn_packed_lstm_floats() long
   CUDA_TRY(cudaMemcpyAsync(d_pk, packed_low_host, 2 * pfloats * sizeof(float), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_pk + 2 * pfloats, packed_high_host, 2 * pfloats * sizeof(float),
@@ -95,10 +112,11 @@ int gnnpn_pn_greedy_low_high_host(const float* inputs_host, int64_t n, int L, in
     CUDA_TRY(cudaMemcpyAsync(d_in, inputs_host + s * L * F, m * L * F * sizeof(float), cudaMemcpyHostToDevice, st));
     for (int level = 0; level < 2; ++level) {
       const float* pk = d_pk + (size_t)level * 2 * pfloats;
-      RC_TRY(gnnpn_lstm_encode_f32(d_in, m, L, F, H, pk, d_enc, d_c, st));
+      RC_TRY(gnnpn_lstm_encode_f32(d_in, m, L, F, H, pk, d_enc, d_c, d_ws, ws_bytes, st));
       RC_TRY(gnnpn_pn_decode_greedy_f32(d_in, d_enc, d_c, level ? d_wl_lo : nullptr, alpha, pk + pfloats,
                                         GNNPN_ATT_DOT, nullptr, use_tanh, C, m, L, F, H, K, N, d_dech,
-                                        level ? d_idx_hi : d_idx_lo, level ? d_wl_hi : d_wl_lo, d_wp, nullptr, st));
+                                        level ? d_idx_hi : d_idx_lo, level ? d_wl_hi : d_wl_lo, d_wp, nullptr,
+                                        d_ws, ws_bytes, st));
     }
     RC_TRY(gnnpn_pn_reward_f32(d_in, d_idx_hi, m, L, F, K, 0, nullptr, nullptr, d_rew, st));
     // device layout is [K, m]; the host result is [K, n]: copy row by row
@@ -115,7 +133,7 @@ int gnnpn_pn_greedy_low_high_host(const float* inputs_host, int64_t n, int L, in
   }
 done:
   cudaFree(d_pk); cudaFree(d_in); cudaFree(d_enc); cudaFree(d_c); cudaFree(d_dech); cudaFree(d_wl_lo);
-  cudaFree(d_wl_hi); cudaFree(d_wp); cudaFree(d_rew); cudaFree(d_idx_lo); cudaFree(d_idx_hi);
+  cudaFree(d_ws); cudaFree(d_wl_hi); cudaFree(d_wp); cudaFree(d_rew); cudaFree(d_idx_lo); cudaFree(d_idx_hi);
   if (st) cudaStreamDestroy(st);
   return rc;
 }

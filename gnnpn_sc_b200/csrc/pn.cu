@@ -2,6 +2,7 @@
 // interface-faithful logits materialisation, composition objective / reward.
 #include <math.h>
 #include "lstm_step.cuh"
+#include "tc_lstm.cuh"
 
 namespace gnnpn {
 namespace {
@@ -9,29 +10,46 @@ namespace {
 // ---------------------------------------------------------------------------
 // weight packing (fp64 accumulate, once per model)
 // ---------------------------------------------------------------------------
+__device__ float folded_weight(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                               const float* __restrict__ w_e, int H, int F, int r, int k) {
+  // column k of the "[h | x]" operand for torch gate row r:  k < H -> W_hh ; H <= k < H+F -> (W_ih . W_e)[:, k-H]
+  if (k < H) return w_hh[(int64_t)r * H + k];
+  const int f = k - H;
+  if (f >= F) return 0.f;
+  double s = 0.0;
+  for (int i = 0; i < H; ++i) s += (double)w_ih[(int64_t)r * H + i] * (double)w_e[(int64_t)i * F + f];
+  return (float)s;
+}
+
 __global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                                  const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                                  const float* __restrict__ w_e, const float* __restrict__ b_e,
-                                 const float* __restrict__ start, int H, int F, int Fpad,
+                                 const float* __restrict__ start, int H, int F, int Fpad, int Kp,
                                  float* __restrict__ packed) {
   const int G = 4 * H;
   const int rows = H + Fpad + 2;  // + bias row + start row
-  const int64_t total = (int64_t)rows * G;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+  const int64_t ffma_total = (int64_t)rows * G;
+  const int64_t tc_total = (int64_t)G * Kp;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ffma_total + tc_total;
        e += (int64_t)gridDim.x * blockDim.x) {
+    if (e >= ffma_total) {                         // tcgen05 operand: [4H gate columns][Kp], K contiguous
+      const int64_t t = e - ffma_total;
+      const int nn = (int)(t / Kp), k = (int)(t % Kp);
+      const int r = (nn & 3) * H + (nn >> 2);
+      const float w = folded_weight(w_ih, w_hh, w_e, H, F, r, k);
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+      const float hi = __uint_as_float(hb);
+      packed[ffma_total + t] = hi;
+      packed[ffma_total + tc_total + t] = w - hi;
+      continue;
+    }
     const int k = (int)(e / G), nn = (int)(e % G);
     const int j = nn >> 2, g = nn & 3;
     const int r = g * H + j;                       // torch row: gate-major
     float out = 0.f;
-    if (k < H) {
-      out = w_hh[(int64_t)r * H + k];
-    } else if (k < H + Fpad) {
-      const int f = k - H;
-      if (f < F) {
-        double s = 0.0;
-        for (int i = 0; i < H; ++i) s += (double)w_ih[(int64_t)r * H + i] * (double)w_e[(int64_t)i * F + f];
-        out = (float)s;
-      }
+    if (k < H + Fpad) {
+      out = folded_weight(w_ih, w_hh, w_e, H, F, r, k);
     } else if (k == H + Fpad) {                    // bias = b_ih + b_hh + W_ih . b_e
       double s = (double)b_ih[r] + (double)b_hh[r];
       for (int i = 0; i < H; ++i) s += (double)w_ih[(int64_t)r * H + i] * (double)b_e[i];
@@ -70,7 +88,9 @@ __device__ __forceinline__ float dot8(const float4 r0, const float4 r1, const fl
 __global__ void __launch_bounds__(256) pointer_step_dot_kernel(
     const float* __restrict__ enc_out, int64_t enc_inst_ld, const float* __restrict__ q, int64_t q_ld,
     const float* __restrict__ latent_win, float alpha, int use_tanh, float C, int64_t n, int L, int k,
-    int N, int32_t* __restrict__ idx_out, float* __restrict__ win_logits, float* __restrict__ win_probs) {
+    int N, int32_t* __restrict__ idx_out, float* __restrict__ win_logits, float* __restrict__ win_probs,
+    const int32_t* __restrict__ forced, const float* __restrict__ inputs, int F, float* __restrict__ a_hi_next,
+    float* __restrict__ a_lo_next, int64_t a_ld) {
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= n) return;
@@ -124,6 +144,15 @@ __global__ void __launch_bounds__(256) pointer_step_dot_kernel(
     if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
   }
   if (lane == 0) idx_out[b] = k * N + best_j;
+  if (a_hi_next && lane < F) {
+    // tensor-core path: the chosen candidate's raw row becomes columns [H, H+F) of the next step's A operand
+    const int fed = forced ? forced[b] : k * N + best_j;   // the xor butterfly left best_j in every lane
+    const float v = __ldg(inputs + (b * L + fed) * (int64_t)F + lane);
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    a_hi_next[b * a_ld + kH + lane] = __uint_as_float(hb);
+    a_lo_next[b * a_ld + kH + lane] = v - __uint_as_float(hb);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -240,7 +269,12 @@ using namespace gnnpn;
 extern "C" {
 
 size_t gnnpn_pn_packed_lstm_floats(int hidden, int in_features) {
-  return (size_t)(hidden + round_up(in_features, kXPad) + 2) * 4 * hidden;
+  (void)in_features;
+  return hidden == kH ? kPackedFloats : 0;
+}
+
+size_t gnnpn_pn_workspace_bytes(int64_t n, int hidden) {
+  return hidden == kH && n >= 0 ? tc_lstm_workspace_bytes(n) : 0;
 }
 
 int gnnpn_pn_pack_lstm_f32(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
@@ -248,21 +282,41 @@ int gnnpn_pn_pack_lstm_f32(const float* w_ih, const float* w_hh, const float* b_
                            int hidden, int in_features, float* packed, void* stream) {
   GNNPN_REQUIRE(w_ih && w_hh && b_ih && b_hh && w_embed && b_embed && packed, GNNPN_ENULL);
   GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= kXPad, GNNPN_ESHAPE);
-  pack_lstm_kernel<<<kNumSMs * 2, 256, 0, (cudaStream_t)stream>>>(w_ih, w_hh, b_ih, b_hh, w_embed, b_embed,
-                                                                  start_input, hidden, in_features, kXPad,
+  pack_lstm_kernel<<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(w_ih, w_hh, b_ih, b_hh, w_embed, b_embed,
+                                                                  start_input, hidden, in_features, kXPad, kKp,
                                                                   packed);
   return after_launch();
 }
 
 int gnnpn_lstm_encode_f32(const float* inputs, int64_t n, int L, int in_features, int hidden,
-                          const float* packed, float* enc_out, float* c_state, void* stream) {
+                          const float* packed, float* enc_out, float* c_state, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   GNNPN_REQUIRE(inputs && packed && enc_out && c_state, GNNPN_ENULL);
   GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= kXPad && L >= 1 && n >= 0, GNNPN_ESHAPE);
   GNNPN_REQUIRE(n < (1ll << 31), GNNPN_ERANGE);
   GNNPN_REQUIRE(aligned16(enc_out) && aligned16(c_state) && aligned16(packed), GNNPN_EALIGN);
+  if (n == 0) return GNNPN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (workspace) {
+    // ---- tcgen05 recurrence: [h|x] kept as tf32 hi/lo pairs in two ping-pong buffers
+    TcLstmPlan plan;
+    int rc = tc_lstm_plan(&plan, workspace, workspace_bytes, n, packed);
+    if (rc) return rc;
+    if ((rc = tc_lstm_reset(plan, inputs, (int64_t)L * in_features, 0, in_features, st))) return rc;
+    TcLstmStep s{};
+    s.use_x = 1; s.bias = packed + kOffBias; s.c = c_state; s.h_out_ld = (int64_t)L * kH;
+    s.x_next = inputs; s.x_inst_ld = (int64_t)L * in_features; s.F = in_features;
+    for (int t = 0; t < L; ++t) {
+      s.cur = t & 1; s.first = t == 0;
+      s.h_out = enc_out + (int64_t)t * kH;
+      s.x_row_next = t + 1 < L ? t + 1 : -1;
+      if ((rc = tc_lstm_step(plan, s, st))) return rc;
+    }
+    return GNNPN_OK;
+  }
   LstmStepArgs a{};
   a.x = inputs; a.x_inst_ld = (int64_t)L * in_features; a.F = in_features; a.use_x = 1; a.gather = nullptr;
-  a.P = packed; a.bias = packed + (size_t)(kH + kXPad) * kG;
+  a.P = packed; a.bias = packed + kOffBias;
   a.c = c_state; a.M = (int)n;
   a.h_in_ld = a.h_out_ld = (int64_t)L * kH;
   for (int t = 0; t < L; ++t) {
@@ -270,7 +324,7 @@ int gnnpn_lstm_encode_f32(const float* inputs, int64_t n, int L, int in_features
     a.h_in = t == 0 ? nullptr : enc_out + (int64_t)(t - 1) * kH;
     a.h_out = enc_out + (int64_t)t * kH;
     a.x_row = t;
-    int rc = launch_lstm_step(a, (cudaStream_t)stream);
+    int rc = launch_lstm_step(a, st);
     if (rc) return rc;
   }
   return GNNPN_OK;
@@ -281,7 +335,8 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
                                int attention, const float* att_params, int use_tanh, float C,
                                int64_t n, int L, int in_features, int hidden, int K, int N,
                                float* dec_h, int32_t* idx_out, float* win_logits, float* win_probs,
-                               const int32_t* forced_idx, void* stream) {
+                               const int32_t* forced_idx, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   GNNPN_REQUIRE(inputs && enc_out && c_state && packed && dec_h && idx_out && win_logits && win_probs,
                 GNNPN_ENULL);
   GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= kXPad, GNNPN_ESHAPE);
@@ -290,34 +345,52 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
   GNNPN_REQUIRE(attention == GNNPN_ATT_DOT, GNNPN_EUNSUPPORTED);
   (void)att_params;
   GNNPN_REQUIRE(aligned16(enc_out) && aligned16(dec_h) && aligned16(c_state) && aligned16(packed), GNNPN_EALIGN);
+  if (n == 0) return GNNPN_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  LstmStepArgs a{};
-  a.x = inputs; a.x_inst_ld = (int64_t)L * in_features; a.F = in_features; a.x_row = -1;
-  a.P = packed; a.c = c_state; a.M = (int)n; a.first = 0;
-  a.h_out_ld = (int64_t)K * kH;
-  const float* bias = packed + (size_t)(kH + kXPad) * kG;
-  const float* start = bias + kG;
+  const float* bias = packed + kOffBias;
+  const float* start = packed + kOffStart;
   const unsigned att_blocks = (unsigned)ceil_div(n, 8);
+  const bool use_tc = workspace != nullptr;
+  TcLstmPlan plan;
+  TcLstmStep ts{};
+  LstmStepArgs a{};
+  int rc;
+  if (use_tc) {
+    if ((rc = tc_lstm_plan(&plan, workspace, workspace_bytes, n, packed))) return rc;
+    // decoder state starts from the encoder's last hidden state (modelPN.py:191,205)
+    if ((rc = tc_lstm_load_h(plan, 0, enc_out + (int64_t)(L - 1) * kH, (int64_t)L * kH, st))) return rc;
+    if ((rc = tc_lstm_zero(plan, 1, st))) return rc;
+    ts.c = c_state; ts.h_out_ld = (int64_t)K * kH; ts.x_next = nullptr; ts.x_row_next = -1;
+    ts.F = in_features; ts.first = 0;
+  } else {
+    a.x = inputs; a.x_inst_ld = (int64_t)L * in_features; a.F = in_features; a.x_row = -1;
+    a.P = packed; a.c = c_state; a.M = (int)n; a.first = 0;
+    a.h_out_ld = (int64_t)K * kH;
+  }
   for (int k = 0; k < K; ++k) {
-    if (k == 0) {
-      a.h_in = enc_out + (int64_t)(L - 1) * kH; a.h_in_ld = (int64_t)L * kH;
-      a.use_x = 0; a.bias = start; a.gather = nullptr;
+    const int32_t* fed_prev = k == 0 ? nullptr : (forced_idx ? forced_idx : idx_out) + (int64_t)(k - 1) * n;
+    if (use_tc) {
+      ts.cur = k & 1; ts.use_x = k != 0; ts.bias = k == 0 ? start : bias;
+      ts.h_out = dec_h + (int64_t)k * kH;
+      if ((rc = tc_lstm_step(plan, ts, st))) return rc;
     } else {
-      a.h_in = dec_h + (int64_t)(k - 1) * kH; a.h_in_ld = (int64_t)K * kH;
-      a.use_x = 1; a.bias = bias;
-      a.gather = (forced_idx ? forced_idx : idx_out) + (int64_t)(k - 1) * n;
+      if (k == 0) {
+        a.h_in = enc_out + (int64_t)(L - 1) * kH; a.h_in_ld = (int64_t)L * kH;
+        a.use_x = 0; a.bias = start; a.gather = nullptr;
+      } else {
+        a.h_in = dec_h + (int64_t)(k - 1) * kH; a.h_in_ld = (int64_t)K * kH;
+        a.use_x = 1; a.bias = bias; a.gather = fed_prev;
+      }
+      a.h_out = dec_h + (int64_t)k * kH;
+      if ((rc = launch_lstm_step(a, st))) return rc;
     }
-    a.h_out = dec_h + (int64_t)k * kH;
-    int rc = launch_lstm_step(a, st);
-    if (rc) return rc;
-    if (n > 0) {
-      pointer_step_dot_kernel<<<att_blocks, 256, 0, st>>>(enc_out, (int64_t)L * kH, dec_h + (int64_t)k * kH,
-                                                          (int64_t)K * kH, latent_win, alpha, use_tanh, C, n,
-                                                          L, k, N, idx_out + (int64_t)k * n, win_logits,
-                                                          win_probs);
-      rc = after_launch();
-      if (rc) return rc;
-    }
+    const int nxt = (k + 1) & 1;
+    pointer_step_dot_kernel<<<att_blocks, 256, 0, st>>>(
+        enc_out, (int64_t)L * kH, dec_h + (int64_t)k * kH, (int64_t)K * kH, latent_win, alpha, use_tanh, C, n, L,
+        k, N, idx_out + (int64_t)k * n, win_logits, win_probs,
+        forced_idx ? forced_idx + (int64_t)k * n : nullptr, inputs, in_features,
+        use_tc ? plan.hi[nxt] : nullptr, use_tc ? plan.lo[nxt] : nullptr, (int64_t)kKp);
+    if ((rc = after_launch())) return rc;
   }
   return GNNPN_OK;
 }

@@ -1,0 +1,412 @@
+// tcgen05 (5th-gen tensor core) kernels, fp32 results through error-compensated 3xTF32:
+//     A.B^T  ~=  A_hi.B_hi^T + A_lo.B_hi^T + A_hi.B_lo^T       (hi = tf32(a), lo = a - hi; the dropped
+//                                                                lo.lo term is ~2^-22 relative)
+// accumulated in fp32 in TMEM.  One mainloop, two epilogues:
+//   * node transform   C = act((A.W^T + bias)*scale + shift)                     (modelML.py linears / GCNConv X.W)
+//   * LSTM step        gates = [h|x].P^T + bias -> c', h'  (+ tf32 split of h' for the next step's A operand)
+//
+// CTA = one 128-row M tile; loops over `n_tiles` N tiles of BN <= 256 columns with two TMEM
+// accumulator buffers so the epilogue of tile j overlaps the MMAs of tile j+1.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM lane quarter = warp&3).
+// smem ring: STAGES x { A_hi, A_lo [128 x 32 f32], B_hi, B_lo [BN x 32 f32] }, 128B-swizzled K-major tiles
+// written by TMA and read by tcgen05.mma through UMMA descriptors.
+#include "tc_common.cuh"
+#include "common.cuh"
+#include "lstm_step.cuh"
+#include "tc_lstm.cuh"
+
+namespace gnnpn {
+namespace tc {
+
+constexpr int BM = 128;            // rows per CTA = UMMA M = TMEM lanes
+constexpr int BK = 32;             // fp32 per 128-byte swizzle row
+constexpr int BN_MAX = 256;        // UMMA N limit
+constexpr int STAGES = 2;
+constexpr int A_TILE_BYTES = BM * BK * 4;          // 16 KiB
+constexpr int B_TILE_BYTES = BN_MAX * BK * 4;      // 32 KiB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 256;
+constexpr int TMEM_COLS = 512;
+
+struct GemmEpilogueParams {
+  const float* bias; const float* scale; const float* shift; int act;
+  float* C; int64_t ldc; int N;
+};
+
+struct LstmEpilogueParams {
+  const float* bias;        // [1024] gate-interleaved
+  float* c;                 // [M,256] in/out
+  float* h_out;             // exact fp32 h' rows, h_out_ld apart
+  int64_t h_out_ld;
+  float* a_hi_next;         // [M, a_ld]  tf32 split of h' for the next step (+ x columns)
+  float* a_lo_next;
+  int64_t a_ld;
+  const float* x_next;      // raw inputs row of the NEXT step per instance (nullptr: none)
+  int64_t x_inst_ld;
+  int x_row_next;           // fixed row (encoder) ; <0 -> no x written here (decoder: pointer step writes it)
+  int F;
+  int first;                // c_old = 0
+};
+
+struct MainloopParams {
+  int M;                    // valid rows
+  int n_tiles;              // N tiles handled by each CTA
+  int bn;                   // columns per N tile (multiple of 16, <= 256)
+  int k_blocks;             // K / 32
+  int last_block_ksteps;    // k-steps (of 8) actually non-zero in the last k block (1..4)
+};
+
+// ------------------------------------------------------------------------------------------------
+template <class Epilogue, class EpiParams>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                   const MainloopParams mp, const EpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+    tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const uint32_t stage_tx = 2u * A_TILE_BYTES + 2u * (uint32_t)mp.bn * BK * 4u;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int nt = 0; nt < mp.n_tiles; ++nt) {
+        for (int kb = 0; kb < mp.k_blocks; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), stage_tx);
+          const uint32_t st = smem_base + s * STAGE_BYTES;
+          tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
+          tma_load_2d(st + A_TILE_BYTES, &map_a_lo, full_bar(s), kb * BK, m0);
+          tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, full_bar(s), kb * BK, nt * mp.bn);
+          tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, full_bar(s), kb * BK, nt * mp.bn);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(BM, mp.bn);
+      int s = 0; uint32_t ph = 0;
+      for (int nt = 0; nt < mp.n_tiles; ++nt) {
+        const int buf = nt & 1;
+        const uint32_t use = (uint32_t)(nt >> 1);            // how many times this buffer was used before
+        mbar_wait(tmem_empty_bar(buf), (use & 1u) ^ 1u);    // epilogue has drained it (passes on first use)
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * BN_MAX);
+        for (int kb = 0; kb < mp.k_blocks; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t st = smem_base + s * STAGE_BYTES;
+          const uint64_t a_hi = smem_desc_k_sw128(st), a_lo = smem_desc_k_sw128(st + A_TILE_BYTES);
+          const uint64_t b_hi = smem_desc_k_sw128(st + 2 * A_TILE_BYTES);
+          const uint64_t b_lo = smem_desc_k_sw128(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+          const int ksteps = (kb == mp.k_blocks - 1) ? mp.last_block_ksteps : BK / 8;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * 8 * 4 >> 4);   // +32 B per k-step inside the swizzle row
+            const uint32_t acc0 = (kb | ks) != 0;
+            mma_tf32_ss(d, a_lo + adv, b_hi + adv, idesc, acc0);
+            mma_tf32_ss(d, a_hi + adv, b_lo + adv, idesc, 1u);
+            mma_tf32_ss(d, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+          mma_commit(empty_bar(s));                 // smem slot reusable once these MMAs retire
+          if (kb == mp.k_blocks - 1) mma_commit(tmem_full_bar(buf));
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: thread = one accumulator row =================
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    Epilogue epi(ep, row, row < mp.M);
+    for (int nt = 0; nt < mp.n_tiles; ++nt) {
+      const int buf = nt & 1;
+      const uint32_t use = (uint32_t)(nt >> 1);
+      mbar_wait(tmem_full_bar(buf), use & 1u);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_MAX);
+      for (int c0 = 0; c0 < mp.bn; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(t0 + (uint32_t)c0, v);
+        epi.chunk(nt * mp.bn + c0, min(32, mp.bn - c0), v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct GemmEpilogue {
+  const GemmEpilogueParams& p; int64_t row; bool ok;
+  __device__ GemmEpilogue(const GemmEpilogueParams& p_, int row_, bool ok_) : p(p_), row(row_), ok(ok_) {}
+  __device__ void chunk(int col0, int ncols, const float* v) {
+    if (!ok) return;
+    float* out = p.C + row * p.ldc;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = col0 + j;
+      if (j < ncols && n < p.N) {
+        float r = v[j];
+        if (p.bias) r += __ldg(p.bias + n);
+        if (p.scale) r = fmaf(r, __ldg(p.scale + n), __ldg(p.shift + n));
+        if (p.act == GNNPN_ACT_RELU) r = fmaxf(r, 0.f);
+        else if (p.act == GNNPN_ACT_SIGMOID) r = sigmoid_accurate(r);
+        out[n] = r;
+      }
+    }
+  }
+};
+
+struct LstmEpilogue {
+  const LstmEpilogueParams& p; int64_t row; bool ok;
+  __device__ LstmEpilogue(const LstmEpilogueParams& p_, int row_, bool ok_) : p(p_), row(row_), ok(ok_) {
+    if (ok && p.x_next && p.x_row_next >= 0) {           // stage the next step's raw input as A columns 256..
+      const float* x = p.x_next + row * p.x_inst_ld + (int64_t)p.x_row_next * p.F;
+      for (int f = 0; f < p.F; ++f) {
+        float hi, lo;
+        split_tf32(__ldg(x + f), hi, lo);
+        p.a_hi_next[row * p.a_ld + kH + f] = hi;
+        p.a_lo_next[row * p.a_ld + kH + f] = lo;
+      }
+    }
+  }
+  // 32 gate columns = 8 hidden units x (i,f,g,o)
+  __device__ void chunk(int col0, int /*ncols*/, const float* v) {
+    if (!ok) return;
+    const int j0 = col0 >> 2;
+    float hv[8], hh[8], hl[8], cv[8];
+    const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col0);
+    float* crow = p.c + row * kH + j0;
+    if (!p.first) {
+      const float4 c0 = *reinterpret_cast<const float4*>(crow), c1 = *reinterpret_cast<const float4*>(crow + 4);
+      cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cv[u] = 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 b = __ldg(bias4 + u);
+      const float gi = v[4 * u + 0] + b.x, gf = v[4 * u + 1] + b.y, gg = v[4 * u + 2] + b.z, go = v[4 * u + 3] + b.w;
+      const float cn = sigmoid_accurate(gf) * cv[u] + sigmoid_accurate(gi) * tanhf(gg);
+      cv[u] = cn;
+      hv[u] = sigmoid_accurate(go) * tanhf(cn);
+      split_tf32(hv[u], hh[u], hl[u]);
+    }
+    auto st8 = [](float* dst, const float* s) {
+      *reinterpret_cast<float4*>(dst) = make_float4(s[0], s[1], s[2], s[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(s[4], s[5], s[6], s[7]);
+    };
+    st8(crow, cv);
+    st8(p.h_out + row * p.h_out_ld + j0, hv);
+    st8(p.a_hi_next + row * p.a_ld + j0, hh);
+    st8(p.a_lo_next + row * p.a_ld + j0, hl);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// elementwise tf32 split with zero padding of K up to Kpad (also used for the weights)
+__global__ void split_tf32_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int K, int Kpad,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t total = rows * Kpad;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / Kpad;
+    const int k = (int)(e % Kpad);
+    float h = 0.f, l = 0.f;
+    if (k < K) split_tf32(src[r * ld + k], h, l);
+    hi[e] = h;
+    lo[e] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// row-major fp32 [rows, cols] with leading dimension ld (floats); box = {32 cols, box_rows}; 128B swizzle
+int make_map_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return GNNPN_EUNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GNNPN_OK : GNNPN_ESHAPE;
+}
+
+template <class Epi, class EpiParams>
+int launch_mainloop(const CUtensorMap maps[4], const MainloopParams& mp, const EpiParams& ep, cudaStream_t st) {
+  auto kern = tc_mainloop_kernel<Epi, EpiParams>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const unsigned grid = (unsigned)ceil_div(mp.M, BM);
+  kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], mp, ep);
+  return after_launch();
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// node transform through tcgen05.  Workspace holds the tf32 splits of A and W.
+size_t tc_gemm_workspace_bytes(int64_t M, int N, int K) {
+  const int64_t Kp = round_up(K, tc::BK);
+  return (size_t)(2 * (M + N) * Kp) * sizeof(float) + 1024;
+}
+
+int launch_gemm_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* scale,
+                   const float* shift, int act, float* C, int64_t ldc, int64_t M, int N, int K, void* workspace,
+                   cudaStream_t st) {
+  using namespace tc;
+  const int Kp = round_up(K, BK);
+  float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  float* a_hi = ws;
+  float* a_lo = a_hi + M * Kp;
+  float* w_hi = a_lo + M * Kp;
+  float* w_lo = w_hi + (int64_t)N * Kp;
+  split_tf32_kernel<<<kNumSMs * 4, 256, 0, st>>>(A, lda, M, K, Kp, a_hi, a_lo);
+  int rc = after_launch();
+  if (rc) return rc;
+  split_tf32_kernel<<<kNumSMs * 4, 256, 0, st>>>(W, ldw, N, K, Kp, w_hi, w_lo);
+  if ((rc = after_launch())) return rc;
+  int bn = N >= BN_MAX ? BN_MAX : round_up(N, 16);
+  const int n_tiles = (int)ceil_div(N, bn);
+  CUtensorMap maps[4];
+  if ((rc = make_map_2d(&maps[0], a_hi, M, Kp, Kp, BM))) return rc;
+  if ((rc = make_map_2d(&maps[1], a_lo, M, Kp, Kp, BM))) return rc;
+  if ((rc = make_map_2d(&maps[2], w_hi, N, Kp, Kp, bn))) return rc;
+  if ((rc = make_map_2d(&maps[3], w_lo, N, Kp, Kp, bn))) return rc;
+  MainloopParams mp{(int)M, n_tiles, bn, Kp / BK, BK / 8};
+  GemmEpilogueParams ep{bias, scale, shift, act, C, ldc, N};
+  return launch_mainloop<GemmEpilogue, GemmEpilogueParams>(maps, mp, ep, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSTM recurrence on tcgen05
+namespace {
+
+__global__ void stage_x_kernel(const float* __restrict__ inputs, int64_t x_inst_ld, int row, int F, int64_t n,
+                               float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n * F) return;
+  const int64_t m = e / F;
+  const int f = (int)(e % F);
+  float h, l;
+  tc::split_tf32(inputs[m * x_inst_ld + (int64_t)row * F + f], h, l);
+  hi[m * kKp + kH + f] = h;
+  lo[m * kKp + kH + f] = l;
+}
+
+}  // namespace
+
+size_t tc_lstm_workspace_bytes(int64_t n) { return (size_t)4 * n * kKp * sizeof(float) + 1024; }
+
+int tc_lstm_plan(TcLstmPlan* plan, void* workspace, size_t workspace_bytes, int64_t n, const float* packed) {
+  if (workspace_bytes < tc_lstm_workspace_bytes(n)) return GNNPN_EWORKSPACE;
+  float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  const size_t one = (size_t)n * kKp;
+  plan->n = n;
+  plan->hi[0] = ws; plan->lo[0] = ws + one; plan->hi[1] = ws + 2 * one; plan->lo[1] = ws + 3 * one;
+  int rc;
+  for (int b = 0; b < 2; ++b) {
+    if ((rc = tc::make_map_2d(&plan->a_hi[b], plan->hi[b], n, kKp, kKp, tc::BM))) return rc;
+    if ((rc = tc::make_map_2d(&plan->a_lo[b], plan->lo[b], n, kKp, kKp, tc::BM))) return rc;
+  }
+  if ((rc = tc::make_map_2d(&plan->b_hi, packed + kOffTcHi, kG, kKp, kKp, tc::BN_MAX))) return rc;
+  if ((rc = tc::make_map_2d(&plan->b_lo, packed + kOffTcLo, kG, kKp, kKp, tc::BN_MAX))) return rc;
+  return GNNPN_OK;
+}
+
+int tc_lstm_zero(const TcLstmPlan& plan, int which, cudaStream_t st) {
+  // hi[which] and lo[which] are adjacent in the workspace
+  cudaError_t e = cudaMemsetAsync(plan.hi[which], 0, (size_t)2 * plan.n * kKp * sizeof(float), st);
+  return e == cudaSuccess ? GNNPN_OK : (int)e;
+}
+
+int tc_lstm_reset(const TcLstmPlan& plan, const float* inputs, int64_t x_inst_ld, int row0, int F,
+                  cudaStream_t st) {
+  int rc;
+  if ((rc = tc_lstm_zero(plan, 0, st))) return rc;
+  if ((rc = tc_lstm_zero(plan, 1, st))) return rc;
+  stage_x_kernel<<<(unsigned)ceil_div(plan.n * F, 256), 256, 0, st>>>(inputs, x_inst_ld, row0, F, plan.n,
+                                                                     plan.hi[0], plan.lo[0]);
+  return after_launch();
+}
+
+int tc_lstm_load_h(const TcLstmPlan& plan, int dst, const float* h, int64_t ld, cudaStream_t st) {
+  tc::split_tf32_kernel<<<kNumSMs * 4, 256, 0, st>>>(h, ld, plan.n, kH, kKp, plan.hi[dst], plan.lo[dst]);
+  return after_launch();
+}
+
+int tc_lstm_step(const TcLstmPlan& plan, const TcLstmStep& s, cudaStream_t st) {
+  using namespace tc;
+  const CUtensorMap maps[4] = {plan.a_hi[s.cur], plan.a_lo[s.cur], plan.b_hi, plan.b_lo};
+  MainloopParams mp;
+  mp.M = (int)plan.n;
+  mp.n_tiles = kG / BN_MAX;
+  mp.bn = BN_MAX;
+  mp.k_blocks = kH / BK + (s.use_x ? 1 : 0);
+  mp.last_block_ksteps = s.use_x ? (s.F + 7) / 8 : BK / 8;
+  LstmEpilogueParams ep;
+  ep.bias = s.bias; ep.c = s.c; ep.h_out = s.h_out; ep.h_out_ld = s.h_out_ld;
+  ep.a_hi_next = plan.hi[s.cur ^ 1]; ep.a_lo_next = plan.lo[s.cur ^ 1]; ep.a_ld = kKp;
+  ep.x_next = s.x_next; ep.x_inst_ld = s.x_inst_ld; ep.x_row_next = s.x_row_next; ep.F = s.F; ep.first = s.first;
+  return launch_mainloop<LstmEpilogue, LstmEpilogueParams>(maps, mp, ep, st);
+}
+
+}  // namespace gnnpn

@@ -161,6 +161,7 @@ class PointerNet(nn.Module):
         self._pack_key = None
         self._packed = None
         self.last = None                          # device-side results of the most recent forward
+        self.impl = None                          # None -> ops.DEFAULT_IMPL ("tc"); "ffma" = strict-fp32 kernels
 
     # -- packed weights are a cache over the parameters; rebuilt when any of them changes
     def _packed_weights(self):
@@ -193,13 +194,14 @@ class PointerNet(nn.Module):
         x = inputs.detach().float().contiguous()
         enc_w, dec_w = self._packed_weights()
         with torch.no_grad():
-            enc_out, c = ops.lstm_encode(x, enc_w, self.hidden_size)
+            ws = ops.pn_workspace(B, self.hidden_size, x.device, self.impl)
+            enc_out, c = ops.lstm_encode(x, enc_w, self.hidden_size, workspace=ws)
             lat = _window_of(latent, K, N) if latent else None
             forced = None if forced_idxs is None else torch.stack([t.to(torch.int32) for t in forced_idxs])
             use_tanh, C = bool(self.pointer.use_tanh), float(self.pointer.C)
             dec_h, idx, win_logits, win_probs = ops.pn_decode_greedy(
                 x, enc_out, c, dec_w, K, N, latent_win=lat, alpha=float(self.alpha), attention="Dot",
-                use_tanh=use_tanh, C=C, forced_idx=forced)
+                use_tanh=use_tanh, C=C, forced_idx=forced, workspace=ws)
         idx64 = idx.long()
         self.last = {"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "enc_out": enc_out, "dec_h": dec_h}
 

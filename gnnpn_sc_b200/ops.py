@@ -9,7 +9,12 @@ import torch
 
 from ._lib import check, lib
 
+import os
+
 ACT = {None: 0, "none": 0, "relu": 1, "sigmoid": 2}
+# "tc": tcgen05 3xTF32 recurrence / node transform (default);  "ffma": strict-fp32 CUDA-core kernels
+DEFAULT_IMPL = os.environ.get("GNNPN_IMPL", "tc")
+TC_GEMM_MIN_ROWS = 512          # below this the tile pipeline cannot fill; the FFMA kernel is used
 ATT = {"Dot": 0, "Bahdanau": 1}
 CSR_PLAIN, CSR_GCN_NORM = 0, 1
 
@@ -47,8 +52,21 @@ def pack_lstm(w_ih, w_hh, b_ih, b_hh, w_embed, b_embed, start_input=None) -> tor
     return out
 
 
+def pn_workspace(n: int, hidden: int = 256, device=None, impl: Optional[str] = None) -> Optional[torch.Tensor]:
+    """Scratch for the tensor-core recurrence, or None when the FFMA kernels are selected."""
+    if (impl or DEFAULT_IMPL) != "tc":
+        return None
+    nbytes = int(lib().gnnpn_pn_workspace_bytes(n, hidden))
+    return torch.empty(nbytes, device=device, dtype=torch.uint8)
+
+
+def _ws(ws):
+    return (None, 0) if ws is None else (ws.data_ptr(), ws.numel())
+
+
 def lstm_encode(inputs: torch.Tensor, packed: torch.Tensor, hidden: int = 256,
-                enc_out: Optional[torch.Tensor] = None, c_state: Optional[torch.Tensor] = None):
+                enc_out: Optional[torch.Tensor] = None, c_state: Optional[torch.Tensor] = None,
+                workspace: Optional[torch.Tensor] = None):
     x = _f32(inputs, "inputs")
     n, L, F = x.shape
     if enc_out is None:
@@ -56,13 +74,13 @@ def lstm_encode(inputs: torch.Tensor, packed: torch.Tensor, hidden: int = 256,
     if c_state is None:
         c_state = torch.empty(n, hidden, device=x.device, dtype=torch.float32)
     check(lib().gnnpn_lstm_encode_f32(x.data_ptr(), n, L, F, hidden, packed.data_ptr(), enc_out.data_ptr(),
-                                      c_state.data_ptr(), _stream()), "lstm_encode")
+                                      c_state.data_ptr(), *_ws(workspace), _stream()), "lstm_encode")
     return enc_out, c_state
 
 
 def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, latent_win=None, alpha: float = 1.0,
                      attention: str = "Dot", att_params=None, use_tanh: bool = True, C: float = 10.0,
-                     forced_idx=None, out=None):
+                     forced_idx=None, out=None, workspace: Optional[torch.Tensor] = None):
     """Returns (dec_h [n,K,H], idx int32 [K,n], win_logits [n,L], win_probs [n,L]).  ``c_state`` is updated in place."""
     x = _f32(inputs, "inputs")
     n, L, F = x.shape
@@ -85,7 +103,7 @@ def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, laten
         x.data_ptr(), enc_out.data_ptr(), c_state.data_ptr(), _ptr(latent_win), float(alpha),
         packed_dec.data_ptr(), ATT[attention], _ptr(att_params), int(bool(use_tanh)), float(C),
         n, L, F, H, K, N, dec_h.data_ptr(), idx.data_ptr(), wl.data_ptr(), wp.data_ptr(),
-        _ptr(forced_idx), _stream()), "pn_decode_greedy")
+        _ptr(forced_idx), *_ws(workspace), _stream()), "pn_decode_greedy")
     return dec_h, idx, wl, wp
 
 
@@ -152,15 +170,21 @@ def spmm_csr(rowptr, col, val, x, n_rows: Optional[int] = None, self_scale: floa
     return y
 
 
-def gemm_bias_act(a, w, bias=None, scale=None, shift=None, act=None, out=None) -> torch.Tensor:
-    """``act((a @ w.T + bias) * scale + shift)`` with ``w`` in nn.Linear layout [N,K]."""
+def gemm_bias_act(a, w, bias=None, scale=None, shift=None, act=None, out=None, impl: Optional[str] = None) -> torch.Tensor:
+    """``act((a @ w.T + bias) * scale + shift)`` with ``w`` in nn.Linear layout [N,K].
+
+    ``impl="tc"`` (default for M >= TC_GEMM_MIN_ROWS): tcgen05 3xTF32; ``"ffma"``: strict fp32 CUDA cores."""
     a = _f32(a, "a")
     w = _f32(w, "w")
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K
     c = torch.empty(M, N, device=a.device, dtype=torch.float32) if out is None else out
+    impl = impl or (DEFAULT_IMPL if M >= TC_GEMM_MIN_ROWS else "ffma")
+    ws = None
+    if impl == "tc":
+        ws = torch.empty(int(lib().gnnpn_gemm_workspace_bytes(M, N, K)), device=a.device, dtype=torch.uint8)
     check(lib().gnnpn_gemm_f32_bias_act(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
                                         _ptr(scale), _ptr(shift), ACT[act], c.data_ptr(), c.stride(0),
-                                        M, N, K, _stream()), "gemm_bias_act")
+                                        M, N, K, *_ws(ws), _stream()), "gemm_bias_act")
     return c

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNNPN_ABI_VERSION 1
+#define GNNPN_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GNNPN_API __attribute__((visibility("default")))
@@ -58,8 +58,12 @@ GNNPN_API uint64_t gnnpn_launch_count(void);
  * Pointer network  (reference: src/models/modelPN.py)
  * ------------------------------------------------------------------------- */
 
-/* Size in floats of one packed LSTM ("[h | x] -> 4H gates") weight block for hidden size H
- * and `in_features` raw input columns: (H + round_up(in_features,16)) * 4H  +  2 * 4H. */
+/* Size in floats of one packed LSTM ("[h | x] -> 4H gates") weight block for hidden size H and
+ * `in_features` raw input columns.  Layout (Kp = H + 32):
+ *   [ (H + 16) x 4H   k-major block for the strict-fp32 FFMA step kernel ]
+ *   [ 4H bias ] [ 4H start ]
+ *   [ 4H x Kp  tf32 "hi" part, gate-column-major (K contiguous) for the tcgen05 step kernel ]
+ *   [ 4H x Kp  tf32 "lo" part ( = w - hi ) ] */
 GNNPN_API size_t gnnpn_pn_packed_lstm_floats(int hidden, int in_features);
 
 /* Fold nn.Linear(F,H) `embedding2` (modelPN.py:155,190) into an nn.LSTM's input weights
@@ -79,7 +83,13 @@ GNNPN_API int gnnpn_pn_pack_lstm_f32(const float* w_ih, const float* w_hh, const
  *   c_state fp32 [n, H]             final cell state (also scratch during the scan)
  * The final hidden state is enc_out[:, L-1, :]. */
 GNNPN_API int gnnpn_lstm_encode_f32(const float* inputs, int64_t n, int L, int in_features, int hidden,
-                          const float* packed_encoder, float* enc_out, float* c_state, void* stream);
+                          const float* packed_encoder, float* enc_out, float* c_state,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Scratch for the tensor-core (tcgen05, 3xTF32) recurrence: the tf32 hi/lo split of [h | x] of the
+ * current and next step, 4 * n * (H + 32) floats.  Passing workspace == NULL to encode/decode selects
+ * the strict-fp32 FFMA step kernel instead (same results to ~1e-6, ~5x slower). */
+GNNPN_API size_t gnnpn_pn_workspace_bytes(int64_t n, int hidden);
 
 /* Fused greedy pointer decode: K x { decoder LSTM cell -> pointer logits on window k ->
  * C*tanh -> (+ alpha*latent) -> window/visited mask -> softmax -> first-max index -> gather
@@ -101,7 +111,8 @@ GNNPN_API int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_o
                                int attention, const float* att_params, int use_tanh, float C,
                                int64_t n, int L, int in_features, int hidden, int K, int N,
                                float* dec_h, int32_t* idx_out, float* win_logits, float* win_probs,
-                               const int32_t* forced_idx, void* stream);
+                               const int32_t* forced_idx, void* workspace, size_t workspace_bytes,
+                               void* stream);
 
 /* Interface-faithful materialisation of PointerNet.forward's prev_logits (modelPN.py:213-214,239):
  *   logits_full fp32 [K, n, L] = C*tanh(<enc_out[b,l,:], dec_h[b,k,:]>) with -inf at the positions
@@ -156,10 +167,14 @@ GNNPN_API int gnnpn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, cons
 
 /* Node transform: C[M,N] = act( (A[M,K] . W[N,K]^T + bias[N]) * scale[N] + shift[N] )
  * (nn.Linear / GCNConv's X.W, modelML.py:77-93,98-106,164-165; bias/scale/shift may be NULL).
- * fp32 in/out; tensor-core path uses error-compensated 3xTF32 on tcgen05. */
+ * fp32 in/out.  With a workspace of gnnpn_gemm_workspace_bytes() the contraction runs on tcgen05
+ * as error-compensated 3xTF32 (fp32 accumulate in TMEM); with workspace == NULL it runs as strict
+ * fp32 FFMA (the small request-graph shapes). */
+GNNPN_API size_t gnnpn_gemm_workspace_bytes(int64_t M, int N, int K);
 GNNPN_API int gnnpn_gemm_f32_bias_act(const float* A, int64_t lda, const float* W, int64_t ldw,
                             const float* bias, const float* scale, const float* shift, int act,
-                            float* C, int64_t ldc, int64_t M, int N, int K, void* stream);
+                            float* C, int64_t ldc, int64_t M, int N, int K,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

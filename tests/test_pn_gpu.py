@@ -219,9 +219,9 @@ def test_host_buffer_c_abi_matches_module_path():
 def test_argument_errors_are_reported_not_thrown():
     from gnnpn_sc_b200 import _lib, modelPN as M
     L = _lib.lib()
-    assert L.gnnpn_lstm_encode_f32(None, 1, 1, 8, 256, None, None, None, None) == -1       # GNNPN_ENULL
+    assert L.gnnpn_lstm_encode_f32(None, 1, 1, 8, 256, None, None, None, None, 0, None) == -1       # GNNPN_ENULL
     t = torch.zeros(16, device="cuda")
-    assert L.gnnpn_lstm_encode_f32(t.data_ptr(), 1, 1, 8, 128, t.data_ptr(), t.data_ptr(), t.data_ptr(), None) == -2
+    assert L.gnnpn_lstm_encode_f32(t.data_ptr(), 1, 1, 8, 128, t.data_ptr(), t.data_ptr(), t.data_ptr(), None, 0, None) == -2
     with pytest.raises(RuntimeError):
         m = M.CombinatorialRL(0, 256, 6, 0, 10, 1, M.reward, "Dot", 2, 3).cuda()
         m(torch.zeros(2, 6, 8), None, sample="greedy", training="SL")                       # CPU tensor -> loud error
