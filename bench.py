@@ -143,6 +143,7 @@ def run_ours(args):
         m.load_state_dict(reference_shaped_state_dict(HID, FEAT, seed))
         nets.append(m.to(dev).eval())
     low, high = nets
+    low.actor.impl = high.actor.impl = args.kernel
     enc_w_lo, dec_w_lo = low.actor._packed_weights()
     enc_w_hi, dec_w_hi = high.actor._packed_weights()
 
@@ -151,6 +152,7 @@ def run_ours(args):
     c = torch.empty(n, HID, device=dev)
     bufs = [(torch.empty(n, K_TASKS, HID, device=dev), torch.empty(K_TASKS, n, device=dev, dtype=torch.int32),
              torch.empty(n, L_SEQ, device=dev), torch.empty(n, L_SEQ, device=dev)) for _ in range(2)]
+    ws = ops.pn_workspace(n, HID, dev, args.kernel)
     enc_ev = []
 
     def device_step(record: bool):
@@ -159,11 +161,11 @@ def run_ours(args):
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            ops.lstm_encode(x, ew, HID, enc_out, c)
+            ops.lstm_encode(x, ew, HID, enc_out, c, workspace=ws)
             if record:
                 e1.record()
                 enc_ev.append((e0, e1))
-            _, idx, wl, _ = ops.pn_decode_greedy(x, enc_out, c, dw, K_TASKS, N_CAND, latent_win=lat, out=bufs[lvl])
+            _, idx, wl, _ = ops.pn_decode_greedy(x, enc_out, c, dw, K_TASKS, N_CAND, latent_win=lat, out=bufs[lvl], workspace=ws)
             lat = wl
         return ops.pn_reward(x, idx)[2], idx
 
@@ -229,9 +231,10 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "instances_per_gpu_per_step": n, "K": K_TASKS, "N": N_CAND,
-                       "L": L_SEQ, "hidden": HID, "parallelism": f"instance-sharded x{world}, no collective",
+                       "L": L_SEQ, "hidden": HID, "kernel": args.kernel, "parallelism": f"instance-sharded x{world}, no collective",
                        "l2": f"working set {(enc_out.numel() * 4) >> 20} MiB of encodings per step >> 126 MB L2"},
-            "roofline": {"kernel": "lstm_step (encoder/decoder recurrence GEMM + fused cell)", "bound": "tensor",
+            "roofline": {"kernel": ("tc_mainloop_kernel<LstmEpilogue> (tcgen05 3xTF32 recurrence GEMM + fused cell)"
+                                    if args.kernel == "tc" else "lstm_step_ffma_kernel (fp32 FFMA recurrence GEMM + fused cell)"), "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": None, "avg_launch_ms": enc_ms,
                          "peak_source": f"{pk['src']}: TF32 proxy = 1/2 bf16 sustained (SURVEY 8d)"},
@@ -254,6 +257,8 @@ def main():
     ap.add_argument("--instances", type=int, default=16384, help="composition instances per GPU per step")
     ap.add_argument("--cpu-batches", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel", default="tc", choices=["tc", "ffma"],
+                    help="recurrence kernel: tcgen05 3xTF32 (default) or strict-fp32 FFMA")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -78,7 +78,9 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 }
 
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = TMEM lane base+i).
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+// Split into issue + wait so independent global loads can be put in flight between the two; the wait
+// names the registers as read-write operands so no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -90,7 +92,50 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :
+      : "memory");
+}
+
+// ----------------------------------------------------------------- activations for the epilogue
+// MUFU-based, ~1e-7 absolute error (same order as fp32 rounding of O(1) values); the libm-accurate
+// expf/tanhf/IEEE-divide versions cost ~3x the instructions and made the epilogue the bottleneck.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_refined(float d) {        // MUFU.RCP + one Newton step
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  const float t = ex2_approx(fminf(-1.4426950408889634f * x, 80.0f));     // e^-x, clamped so 1+t stays finite
+  return rcp_refined(1.0f + t);
+}
+__device__ __forceinline__ float tanh_mufu(float x) {
+  const float ax = fabsf(x);
+  // |x| >= 0.55 : 1 - 2/(e^{2|x|} + 1)
+  const float t = ex2_approx(fminf(2.8853900817779268f * ax, 80.0f));
+  const float big = fmaf(-2.0f, rcp_refined(t + 1.0f), 1.0f);
+  // |x| <  0.55 : x + x^3 * P(x^2), degree-4 Chebyshev interpolant of (tanh(x)/x - 1)/x^2 (max rel err 7.3e-8)
+  const float u = ax * ax;
+  float p = -6.542542018e-03f;
+  p = fmaf(p, u, 2.127274871e-02f);
+  p = fmaf(p, u, -5.390334874e-02f);
+  p = fmaf(p, u, 1.333308220e-01f);
+  p = fmaf(p, u, -3.333333135e-01f);
+  const float small = fmaf(p * u, ax, ax);
+  return copysignf(ax < 0.55f ? small : big, x);
 }
 
 // ----------------------------------------------------------------- descriptors

@@ -7,9 +7,12 @@
 //
 // CTA = one 128-row M tile; loops over `n_tiles` N tiles of BN <= 256 columns with two TMEM
 // accumulator buffers so the epilogue of tile j overlaps the MMAs of tile j+1.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM lane quarter = warp&3).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..19 = epilogue (TMEM lane quarter = warp&3;
+// epilogue group g = (warp-4)/4 takes the 32-column chunks g, g+4, ... of a tile: four epilogue warps per SM
+// sub-partition, which is what hides the global-memory latency of the per-row state loads/stores).
 // smem ring: STAGES x { A_hi, A_lo [128 x 32 f32], B_hi, B_lo [BN x 32 f32] }, 128B-swizzled K-major tiles
 // written by TMA and read by tcgen05.mma through UMMA descriptors.
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "common.cuh"
 #include "lstm_step.cuh"
@@ -25,8 +28,11 @@ constexpr int STAGES = 2;
 constexpr int A_TILE_BYTES = BM * BK * 4;          // 16 KiB
 constexpr int B_TILE_BYTES = BN_MAX * BK * 4;      // 32 KiB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4096 /*epilogue*/;
+constexpr int EPI_GROUPS = 4;
+constexpr int EPI_WARPS = 4 * EPI_GROUPS;
+constexpr int THREADS = 128 + 32 * EPI_WARPS;
+constexpr int EPI_SMEM_BYTES = 4096;       // epilogue-owned scratch (LSTM: the 1024 gate biases)
 constexpr int TMEM_COLS = 512;
 
 struct GemmEpilogueParams {
@@ -55,6 +61,7 @@ struct MainloopParams {
   int bn;                   // columns per N tile (multiple of 16, <= 256)
   int k_blocks;             // K / 32
   int last_block_ksteps;    // k-steps (of 8) actually non-zero in the last k block (1..4)
+  int dbg;                  // profiling experiments only (GNNPN_TC_DBG): 1 = hi.hi MMA only, 2 = epilogue skips math
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -72,6 +79,7 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
   auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  float* epi_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM;
@@ -82,7 +90,7 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -133,9 +141,13 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t adv = (uint64_t)(ks * 8 * 4 >> 4);   // +32 B per k-step inside the swizzle row
             const uint32_t acc0 = (kb | ks) != 0;
-            mma_tf32_ss(d, a_lo + adv, b_hi + adv, idesc, acc0);
-            mma_tf32_ss(d, a_hi + adv, b_lo + adv, idesc, 1u);
-            mma_tf32_ss(d, a_hi + adv, b_hi + adv, idesc, 1u);
+            if (mp.dbg != 1) {
+              mma_tf32_ss(d, a_lo + adv, b_hi + adv, idesc, acc0);
+              mma_tf32_ss(d, a_hi + adv, b_lo + adv, idesc, 1u);
+              mma_tf32_ss(d, a_hi + adv, b_hi + adv, idesc, 1u);
+            } else {
+              mma_tf32_ss(d, a_hi + adv, b_hi + adv, idesc, acc0);
+            }
           }
           mma_commit(empty_bar(s));                 // smem slot reusable once these MMAs retire
           if (kb == mp.k_blocks - 1) mma_commit(tmem_full_bar(buf));
@@ -144,20 +156,36 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue: thread = one accumulator row =================
+    // ================= epilogue: thread = one accumulator row, 32-column chunks =================
     const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;                 // chunk phase of this warp
     const int row = m0 + q * 32 + lane;
-    Epilogue epi(ep, row, row < mp.M);
+    Epilogue::stage_smem(ep, epi_smem, threadIdx.x - 128, 32 * EPI_WARPS);
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");     // epilogue warps only
+    Epilogue epi(ep, epi_smem, row, row < mp.M, grp == 0);
+    constexpr int MAX_CHUNKS = BN_MAX / (32 * EPI_GROUPS);     // chunks of one tile owned by a thread
     for (int nt = 0; nt < mp.n_tiles; ++nt) {
       const int buf = nt & 1;
       const uint32_t use = (uint32_t)(nt >> 1);
+      // per-row state this thread needs for the tile does not depend on the accumulators: put those global
+      // loads in flight before blocking on the MMA warp
+#pragma unroll
+      for (int i = 0; i < MAX_CHUNKS; ++i) {
+        const int c0 = (grp + i * EPI_GROUPS) * 32;
+        if (c0 < mp.bn) epi.prefetch(i, nt * mp.bn + c0);
+      }
       mbar_wait(tmem_full_bar(buf), use & 1u);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN_MAX);
-      for (int c0 = 0; c0 < mp.bn; c0 += 32) {
-        float v[32];
-        tmem_ld_32x32(t0 + (uint32_t)c0, v);
-        epi.chunk(nt * mp.bn + c0, min(32, mp.bn - c0), v);
+#pragma unroll
+      for (int i = 0; i < MAX_CHUNKS; ++i) {
+        const int c0 = (grp + i * EPI_GROUPS) * 32;
+        if (c0 < mp.bn) {
+          float v[32];
+          tmem_ld_32x32_issue(t0 + (uint32_t)c0, v);
+          tmem_ld_wait(v);
+          if (mp.dbg != 2) epi.chunk(i, nt * mp.bn + c0, min(32, mp.bn - c0), v);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -172,8 +200,11 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 // ------------------------------------------------------------------------------------------------
 struct GemmEpilogue {
   const GemmEpilogueParams& p; int64_t row; bool ok;
-  __device__ GemmEpilogue(const GemmEpilogueParams& p_, int row_, bool ok_) : p(p_), row(row_), ok(ok_) {}
-  __device__ void chunk(int col0, int ncols, const float* v) {
+  __device__ static void stage_smem(const GemmEpilogueParams&, float*, int, int) {}
+  __device__ GemmEpilogue(const GemmEpilogueParams& p_, const float*, int row_, bool ok_, bool)
+      : p(p_), row(row_), ok(ok_) {}
+  __device__ void prefetch(int, int) {}
+  __device__ void chunk(int, int col0, int ncols, const float* v) {
     if (!ok) return;
     float* out = p.C + row * p.ldc;
 #pragma unroll
@@ -193,8 +224,14 @@ struct GemmEpilogue {
 
 struct LstmEpilogue {
   const LstmEpilogueParams& p; int64_t row; bool ok;
-  __device__ LstmEpilogue(const LstmEpilogueParams& p_, int row_, bool ok_) : p(p_), row(row_), ok(ok_) {
-    if (ok && p.x_next && p.x_row_next >= 0) {           // stage the next step's raw input as A columns 256..
+  const float* sbias;            // the 1024 gate biases, staged once per CTA
+  float4 c_pre[2 * (BN_MAX / (32 * EPI_GROUPS))];   // prefetched cell state: 8 hidden units per owned chunk
+  __device__ static void stage_smem(const LstmEpilogueParams& p, float* smem, int tid, int nthreads) {
+    for (int i = tid; i < kG; i += nthreads) smem[i] = __ldg(p.bias + i);
+  }
+  __device__ LstmEpilogue(const LstmEpilogueParams& p_, const float* smem, int row_, bool ok_, bool primary)
+      : p(p_), row(row_), ok(ok_), sbias(smem) {
+    if (ok && primary && p.x_next && p.x_row_next >= 0) {   // stage the next step's raw input as A columns 256..
       const float* x = p.x_next + row * p.x_inst_ld + (int64_t)p.x_row_next * p.F;
       for (int f = 0; f < p.F; ++f) {
         float hi, lo;
@@ -204,34 +241,37 @@ struct LstmEpilogue {
       }
     }
   }
+  __device__ void prefetch(int slot, int col0) {
+    if (ok && !p.first) {
+      const float4* cp = reinterpret_cast<const float4*>(p.c + row * kH + (col0 >> 2));
+      c_pre[2 * slot] = cp[0];
+      c_pre[2 * slot + 1] = cp[1];
+    } else {
+      c_pre[2 * slot] = c_pre[2 * slot + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   // 32 gate columns = 8 hidden units x (i,f,g,o)
-  __device__ void chunk(int col0, int /*ncols*/, const float* v) {
+  __device__ void chunk(int slot, int col0, int /*ncols*/, const float* v) {
     if (!ok) return;
     const int j0 = col0 >> 2;
-    float hv[8], hh[8], hl[8], cv[8];
-    const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col0);
-    float* crow = p.c + row * kH + j0;
-    if (!p.first) {
-      const float4 c0 = *reinterpret_cast<const float4*>(crow), c1 = *reinterpret_cast<const float4*>(crow + 4);
-      cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
-    } else {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) cv[u] = 0.f;
-    }
+    float hv[8], hh[8], hl[8];
+    const float4 c_lo = c_pre[2 * slot], c_hi = c_pre[2 * slot + 1];
+    float cv[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
+    const float4* bias4 = reinterpret_cast<const float4*>(sbias + col0);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float4 b = __ldg(bias4 + u);
+      const float4 b = bias4[u];
       const float gi = v[4 * u + 0] + b.x, gf = v[4 * u + 1] + b.y, gg = v[4 * u + 2] + b.z, go = v[4 * u + 3] + b.w;
-      const float cn = sigmoid_accurate(gf) * cv[u] + sigmoid_accurate(gi) * tanhf(gg);
+      const float cn = fmaf(sigmoid_mufu(gf), cv[u], sigmoid_mufu(gi) * tanh_mufu(gg));
       cv[u] = cn;
-      hv[u] = sigmoid_accurate(go) * tanhf(cn);
+      hv[u] = sigmoid_mufu(go) * tanh_mufu(cn);
       split_tf32(hv[u], hh[u], hl[u]);
     }
     auto st8 = [](float* dst, const float* s) {
       *reinterpret_cast<float4*>(dst) = make_float4(s[0], s[1], s[2], s[3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(s[4], s[5], s[6], s[7]);
     };
-    st8(crow, cv);
+    st8(p.c + row * kH + j0, cv);
     st8(p.h_out + row * p.h_out_ld + j0, hv);
     st8(p.a_hi_next + row * p.a_ld + j0, hh);
     st8(p.a_lo_next + row * p.a_ld + j0, hl);
@@ -296,7 +336,10 @@ int launch_mainloop(const CUtensorMap maps[4], const MainloopParams& mp, const E
     configured = true;
   }
   const unsigned grid = (unsigned)ceil_div(mp.M, BM);
-  kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], mp, ep);
+  static const int dbg = getenv("GNNPN_TC_DBG") ? atoi(getenv("GNNPN_TC_DBG")) : 0;
+  MainloopParams mpd = mp;
+  mpd.dbg = dbg;
+  kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], mpd, ep);
   return after_launch();
 }
 
@@ -331,7 +374,7 @@ int launch_gemm_tc(const float* A, int64_t lda, const float* W, int64_t ldw, con
   if ((rc = make_map_2d(&maps[1], a_lo, M, Kp, Kp, BM))) return rc;
   if ((rc = make_map_2d(&maps[2], w_hi, N, Kp, Kp, bn))) return rc;
   if ((rc = make_map_2d(&maps[3], w_lo, N, Kp, Kp, bn))) return rc;
-  MainloopParams mp{(int)M, n_tiles, bn, Kp / BK, BK / 8};
+  MainloopParams mp{(int)M, n_tiles, bn, Kp / BK, BK / 8, 0};
   GemmEpilogueParams ep{bias, scale, shift, act, C, ldc, N};
   return launch_mainloop<GemmEpilogue, GemmEpilogueParams>(maps, mp, ep, st);
 }
@@ -402,6 +445,7 @@ int tc_lstm_step(const TcLstmPlan& plan, const TcLstmStep& s, cudaStream_t st) {
   mp.bn = BN_MAX;
   mp.k_blocks = kH / BK + (s.use_x ? 1 : 0);
   mp.last_block_ksteps = s.use_x ? (s.F + 7) / 8 : BK / 8;
+  mp.dbg = 0;
   LstmEpilogueParams ep;
   ep.bias = s.bias; ep.c = s.c; ep.h_out = s.h_out; ep.h_out_ld = s.h_out_ld;
   ep.a_hi_next = plan.hi[s.cur ^ 1]; ep.a_lo_next = plan.lo[s.cur ^ 1]; ep.a_ld = kKp;

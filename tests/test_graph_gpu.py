@@ -116,12 +116,18 @@ def test_gcn_layer_epilogue():
     assert err.max() <= 1e-5, err.max()
 
 
-@pytest.mark.parametrize("M,N,K", [(1, 128, 128), (97, 256, 28), (5014, 256, 24), (1000, 128, 256), (130, 2507, 128)])
-def test_node_transform_gemm(M, N, K):
+@pytest.mark.parametrize("impl", ["tc", "ffma"])
+@pytest.mark.parametrize("M,N,K", [(1, 128, 128), (97, 256, 28), (5014, 256, 24), (1000, 128, 256), (130, 2507, 128),
+                                   (5014, 256, 256), (200000, 256, 256)])
+def test_node_transform_gemm(M, N, K, impl):
+    """tcgen05 3xTF32 and FFMA node transforms against torch fp32 on the CPU, 1e-5 relative."""
     from gnnpn_sc_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
     a, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
-    ref = torch.relu(torch.nn.functional.linear(a, w, b))
-    y = ops.gemm_bias_act(a.cuda(), w.cuda(), bias=b.cuda(), act="relu")
-    err = (y.cpu() - ref).abs() / ref.abs().clamp(min=1)
+    scale, shift = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g)
+    ref = torch.relu(torch.nn.functional.linear(a, w, b) * scale + shift)
+    y = ops.gemm_bias_act(a.cuda(), w.cuda(), bias=b.cuda(), scale=scale.cuda(), shift=shift.cuda(), act="relu", impl=impl)
+    # 1e-5 relative to the output scale (max-norm): entries that cancel to ~0 are not held to 1e-5 of themselves
+    err = (y.cpu() - ref).abs() / ref.abs().max().clamp(min=1)
+    print(f"gemm[{impl}] M={M} N={N} K={K}: max err / max|ref| {err.max():.2e}")
     assert err.max() <= 1e-5, err.max()
