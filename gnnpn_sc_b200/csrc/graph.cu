@@ -224,6 +224,27 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(
   }
 }
 
+// NodeEncoder (modelML.py:9-29, only table 0 is reachable) + concat of the remaining float columns:
+//   out[i, 0:E) = table[(int)x[i,0], :],  out[i, E:E+C-1) = x[i, 1:C),  zero padding up to ld_out
+__global__ void embed_concat_kernel(const float* __restrict__ x, int64_t n, int C, const float* __restrict__ table,
+                                    int rows, int E, float* __restrict__ out, int64_t ld_out) {
+  const int64_t total = n * ld_out;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / ld_out;
+    const int j = (int)(e % ld_out);
+    float v = 0.f;
+    if (j < E) {
+      int t = (int)x[i * C];
+      t = t < 0 ? 0 : (t >= rows ? rows - 1 : t);
+      v = table[(int64_t)t * E + j];
+    } else if (j < E + C - 1) {
+      v = x[i * C + 1 + (j - E)];
+    }
+    out[e] = v;
+  }
+}
+
 template <int GROUP, int VPL, int UNROLL>
 int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx,
                 float* y, int64_t ldy, int64_t n_rows, int F4, float self_scale, int mean, const float* bias,
@@ -301,6 +322,17 @@ int gnnpn_csr_build(const int64_t* edge_index, const float* edge_weight, int64_t
     if ((rc = after_launch())) return rc;
   }
   return GNNPN_OK;
+}
+
+int gnnpn_embed_concat_f32(const float* x, int64_t n, int n_cols, const float* table, int table_rows,
+                           int embed_dim, float* out, int64_t ld_out, void* stream) {
+  GNNPN_REQUIRE(x && table && out, GNNPN_ENULL);
+  GNNPN_REQUIRE(n >= 0 && n_cols >= 1 && table_rows >= 1 && embed_dim >= 1 && ld_out >= embed_dim + n_cols - 1,
+                GNNPN_ESHAPE);
+  if (n == 0) return GNNPN_OK;
+  embed_concat_kernel<<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(x, n, n_cols, table, table_rows, embed_dim,
+                                                                     out, ld_out);
+  return after_launch();
 }
 
 int gnnpn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val, const float* x,

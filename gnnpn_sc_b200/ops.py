@@ -157,6 +157,19 @@ def csr_build(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], n_n
     return rowptr, col[:total], (None if val is None else val[:total])
 
 
+def embed_concat(x: torch.Tensor, table: torch.Tensor, pad_to: int = 4) -> torch.Tensor:
+    """``cat(table[x[:,0].long()], x[:,1:])`` zero-padded to a multiple of ``pad_to`` columns."""
+    x = _f32(x, "x")
+    table = _f32(table, "table")
+    n, C = x.shape
+    rows, E = table.shape
+    ld = (E + C - 1 + pad_to - 1) // pad_to * pad_to
+    out = torch.empty(n, ld, device=x.device, dtype=torch.float32)
+    check(lib().gnnpn_embed_concat_f32(x.data_ptr(), n, C, table.data_ptr(), rows, E, out.data_ptr(), ld, _stream()),
+          "embed_concat")
+    return out
+
+
 def spmm_csr(rowptr, col, val, x, n_rows: Optional[int] = None, self_scale: float = 0.0, mean: bool = False,
              bias=None, scale=None, shift=None, act=None, out=None) -> torch.Tensor:
     x = _f32(x, "x")

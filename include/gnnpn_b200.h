@@ -153,6 +153,12 @@ GNNPN_API int gnnpn_csr_build(const int64_t* edge_index, const float* edge_weigh
                     int mode, int64_t* rowptr, int32_t* col, float* val, int64_t* nnz_out,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* NodeEncoder + concat (modelML.py:22-29,134-137,145-149): column 0 of x (a category id stored as float)
+ * selects a row of the [table_rows, embed_dim] embedding table, the remaining n_cols-1 float columns are
+ * appended, the row is zero-padded to ld_out (a multiple of 4 so the aggregation can use 128-bit loads). */
+GNNPN_API int gnnpn_embed_concat_f32(const float* x, int64_t n, int n_cols, const float* table, int table_rows,
+                           int embed_dim, float* out, int64_t ld_out, void* stream);
+
 /* Neighbour aggregation as CSR segment-reduce, one warp (or sub-warp) per destination row,
  * sequential in CSR order per feature (deterministic; equals CPU index_add_ in edge order):
  *   y[i,:] = act( ( self_scale * x[i,:] + sum_e val[e] * x[col[e],:] ) / (mean ? max(rowlen,1) : 1)
