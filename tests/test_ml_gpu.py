@@ -69,10 +69,12 @@ def test_net_train_step_gradients_match_oracle():
         if gr[name].grad is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0
             continue
-        d = (p.grad.cpu() - gr[name].grad).abs().max() / gr[name].grad.abs().max().clamp(min=1e-6)
+        # biases that feed a BatchNorm have an exactly-zero true gradient (1e-8 noise on both sides): compare on
+        # an absolute floor instead of dividing noise by noise
+        d = (p.grad.cpu() - gr[name].grad).abs().max() / gr[name].grad.abs().max().clamp(min=1e-3)
         worst = max(worst, float(d))
     print(f"train-mode gradient max relative deviation {worst:.2e}")
-    assert worst < 2e-3          # train-mode BatchNorm over ~25 nodes amplifies fp32 reduction-order noise
+    assert worst < 1e-4
 
 
 def test_trainml_smoke(tmp_path):
