@@ -116,7 +116,7 @@ int gnnpn_pn_greedy_low_high_host(const float* inputs_host, int64_t n, int L, in
       RC_TRY(gnnpn_pn_decode_greedy_f32(d_in, d_enc, d_c, level ? d_wl_lo : nullptr, alpha, pk + pfloats,
                                         GNNPN_ATT_DOT, nullptr, use_tanh, C, m, L, F, H, K, N, d_dech,
                                         level ? d_idx_hi : d_idx_lo, level ? d_wl_hi : d_wl_lo, d_wp, nullptr,
-                                        d_ws, ws_bytes, st));
+                                        nullptr, d_ws, ws_bytes, st));
     }
     RC_TRY(gnnpn_pn_reward_f32(d_in, d_idx_hi, m, L, F, K, 0, nullptr, nullptr, d_rew, st));
     // device layout is [K, m]; the host result is [K, n]: copy row by row

@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(256) pointer_step_dot_kernel(
     const float* __restrict__ enc_out, int64_t enc_inst_ld, const float* __restrict__ q, int64_t q_ld,
     const float* __restrict__ latent_win, float alpha, int use_tanh, float C, int64_t n, int L, int k,
     int N, int32_t* __restrict__ idx_out, float* __restrict__ win_logits, float* __restrict__ win_probs,
-    const int32_t* __restrict__ forced, const float* __restrict__ inputs, int F, float* __restrict__ a_hi_next,
-    float* __restrict__ a_lo_next, int64_t a_ld) {
+    const int32_t* __restrict__ forced, const float* __restrict__ uniform, const float* __restrict__ inputs, int F,
+    float* __restrict__ a_hi_next, float* __restrict__ a_lo_next, int64_t a_ld) {
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= n) return;
@@ -142,6 +142,20 @@ __global__ void __launch_bounds__(256) pointer_step_dot_kernel(
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
     const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
     if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+  }
+  if (uniform) {
+    // sample="sample" (modelPN.py:227-228): inverse-CDF draw from the window distribution with a caller-supplied
+    // uniform in [0,1); falls back to the last candidate with non-zero probability on round-off
+    const float u = __ldg(uniform + b);
+    float cum = 0.f;
+    int pick = -1, last_pos = 0;
+    for (int j = 0; j < N; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      cum += pj;
+      if (pj > 0.f) last_pos = j;
+      if (pick < 0 && u < cum) pick = j;
+    }
+    best_j = pick < 0 ? last_pos : pick;
   }
   if (lane == 0) idx_out[b] = k * N + best_j;
   if (a_hi_next && lane < F) {
@@ -335,8 +349,8 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
                                int attention, const float* att_params, int use_tanh, float C,
                                int64_t n, int L, int in_features, int hidden, int K, int N,
                                float* dec_h, int32_t* idx_out, float* win_logits, float* win_probs,
-                               const int32_t* forced_idx, void* workspace, size_t workspace_bytes,
-                               void* stream) {
+                               const int32_t* forced_idx, const float* sample_uniform, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   GNNPN_REQUIRE(inputs && enc_out && c_state && packed && dec_h && idx_out && win_logits && win_probs,
                 GNNPN_ENULL);
   GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= kXPad, GNNPN_ESHAPE);
@@ -388,7 +402,8 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
     pointer_step_dot_kernel<<<att_blocks, 256, 0, st>>>(
         enc_out, (int64_t)L * kH, dec_h + (int64_t)k * kH, (int64_t)K * kH, latent_win, alpha, use_tanh, C, n, L,
         k, N, idx_out + (int64_t)k * n, win_logits, win_probs,
-        forced_idx ? forced_idx + (int64_t)k * n : nullptr, inputs, in_features,
+        forced_idx ? forced_idx + (int64_t)k * n : nullptr,
+        sample_uniform ? sample_uniform + (int64_t)k * n : nullptr, inputs, in_features,
         use_tc ? plan.hi[nxt] : nullptr, use_tc ? plan.lo[nxt] : nullptr, (int64_t)kKp);
     if ((rc = after_launch())) return rc;
   }

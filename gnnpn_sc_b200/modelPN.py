@@ -162,6 +162,7 @@ class PointerNet(nn.Module):
         self._packed = None
         self.last = None                          # device-side results of the most recent forward
         self.impl = None                          # None -> ops.DEFAULT_IMPL ("tc"); "ffma" = strict-fp32 kernels
+        self.generator = None                     # optional torch.Generator (cuda) for sample="sample"
 
     # -- packed weights are a cache over the parameters; rebuilt when any of them changes
     def _packed_weights(self):
@@ -183,8 +184,6 @@ class PointerNet(nn.Module):
         """inputs [B, L, F] -> (prev_probs, prev_idxs, prev_logits), K-long each (modelPN.py:241)."""
         B, L, _ = inputs.shape
         assert L == self.seq_len
-        if sample != "greedy":
-            raise NotImplementedError("sampled decoding is provided by gnnpn_sc_b200.trainPN (REINFORCE replay)")
         if self.embedding_size != 0 or self.n_glimpses != 0 or self.pointer.name != "Dot":
             raise NotImplementedError("CUDA path covers embedding_size=0, n_glimpses=0, attention='Dot' "
                                       "(every PN section of environment.ini)")
@@ -199,11 +198,14 @@ class PointerNet(nn.Module):
             lat = _window_of(latent, K, N) if latent else None
             forced = None if forced_idxs is None else torch.stack([t.to(torch.int32) for t in forced_idxs])
             use_tanh, C = bool(self.pointer.use_tanh), float(self.pointer.C)
+            # sample != "greedy": multinomial draw per step (modelPN.py:227-228) as an inverse-CDF pick in the kernel
+            uniform = None if sample == "greedy" else torch.rand(K, B, device=x.device, generator=self.generator)
             dec_h, idx, win_logits, win_probs = ops.pn_decode_greedy(
                 x, enc_out, c, dec_w, K, N, latent_win=lat, alpha=float(self.alpha), attention="Dot",
-                use_tanh=use_tanh, C=C, forced_idx=forced, workspace=ws)
+                use_tanh=use_tanh, C=C, forced_idx=forced, workspace=ws, sample_uniform=uniform)
         idx64 = idx.long()
-        self.last = {"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "enc_out": enc_out, "dec_h": dec_h}
+        self.last = {"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "enc_out": enc_out, "dec_h": dec_h,
+                     "latent_win": lat}
 
         fed = idx if forced is None else forced.contiguous()     # the picks the visited mask follows
 
@@ -219,6 +221,34 @@ class PointerNet(nn.Module):
         prev_probs.window = win_probs
         prev_logits = WindowLogits(K, win_logits, dense_logits)
         return prev_probs, list(idx64.unbind(0)), prev_logits
+
+
+    def replay_action_probs(self, inputs, idx, latent_win=None):
+        """Differentiable probabilities of the picks ``idx`` [K,B] (REINFORCE needs d log p / d theta).
+
+        The decode itself runs in the CUDA kernels without autograd; this replays it with torch ops restricted to
+        the windows -- outside window k the reference's probabilities are exactly 0 and carry no gradient
+        (modelPN.py:220-224) -- so the gradient equals the reference's.  Encoder via nn.LSTM (cuDNN), K cell steps."""
+        B, L, _ = inputs.shape
+        K, N = self.serCategory, self.serNumber
+        rows = torch.arange(B, device=inputs.device)
+        emb = self.embedding2(inputs.float())
+        enc_out, (h, c) = self.encoder(emb)
+        dec_in = self.decoder_start_input.unsqueeze(0).expand(B, -1)
+        out = []
+        C = float(self.pointer.C)
+        for k in range(K):
+            _, (h, c) = self.decoder(dec_in.unsqueeze(1), (h, c))
+            win = enc_out[:, k * N:(k + 1) * N, :]
+            logits = torch.bmm(win, h[0].unsqueeze(2)).squeeze(2)
+            if self.pointer.use_tanh:
+                logits = C * torch.tanh(logits)
+            if latent_win is not None:
+                logits = logits + float(self.alpha) * latent_win[:, k * N:(k + 1) * N]
+            p = torch.softmax(logits, dim=1)
+            out.append(p.gather(1, (idx[k] - k * N).unsqueeze(1)).squeeze(1))
+            dec_in = emb[rows, idx[k]]
+        return out
 
 
 # --------------------------------------------------------------------------- CombinatorialRL
@@ -245,7 +275,10 @@ class CombinatorialRL(nn.Module):
         B = inputs.shape[0]
         rows = torch.arange(B, device=inputs.device)
         actions = list(inputs[rows.unsqueeze(0), idx].unbind(0))                    # K x [B, F]
-        action_probs = list(probs.window.gather(1, idx.t()).t().unbind(0))          # K x [B]
+        if self.training and torch.is_grad_enabled():                               # REINFORCE: differentiable replay
+            action_probs = self.actor.replay_action_probs(inputs, idx, self.actor.last["latent_win"])
+        else:
+            action_probs = list(probs.window.gather(1, idx.t()).t().unbind(0))      # K x [B]
         if training == "RL":
             R = self.reward(actions, labs, self.serCategory, USE_CUDA=self.use_cuda, level=self.level,
                             embedding_size=self.embedding_size)

@@ -80,7 +80,8 @@ def lstm_encode(inputs: torch.Tensor, packed: torch.Tensor, hidden: int = 256,
 
 def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, latent_win=None, alpha: float = 1.0,
                      attention: str = "Dot", att_params=None, use_tanh: bool = True, C: float = 10.0,
-                     forced_idx=None, out=None, workspace: Optional[torch.Tensor] = None):
+                     forced_idx=None, out=None, workspace: Optional[torch.Tensor] = None,
+                     sample_uniform: Optional[torch.Tensor] = None):
     """Returns (dec_h [n,K,H], idx int32 [K,n], win_logits [n,L], win_probs [n,L]).  ``c_state`` is updated in place."""
     x = _f32(inputs, "inputs")
     n, L, F = x.shape
@@ -99,11 +100,14 @@ def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, laten
     if forced_idx is not None:
         forced_idx = forced_idx.to(torch.int32).contiguous()
         assert forced_idx.shape == (K, n)
+    if sample_uniform is not None:
+        sample_uniform = _f32(sample_uniform, "sample_uniform")
+        assert sample_uniform.shape == (K, n)
     check(lib().gnnpn_pn_decode_greedy_f32(
         x.data_ptr(), enc_out.data_ptr(), c_state.data_ptr(), _ptr(latent_win), float(alpha),
         packed_dec.data_ptr(), ATT[attention], _ptr(att_params), int(bool(use_tanh)), float(C),
         n, L, F, H, K, N, dec_h.data_ptr(), idx.data_ptr(), wl.data_ptr(), wp.data_ptr(),
-        _ptr(forced_idx), *_ws(workspace), _stream()), "pn_decode_greedy")
+        _ptr(forced_idx), _ptr(sample_uniform), *_ws(workspace), _stream()), "pn_decode_greedy")
     return dec_h, idx, wl, wp
 
 

@@ -1,0 +1,2 @@
+"""Reference import path shim: ``src/models/trainPNHigh.py`` -> gnnpn_sc_b200.trainPN."""
+from .trainPN import SCDataset, TrainModel, PNLow, PNHigh  # noqa: F401

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNNPN_ABI_VERSION 2
+#define GNNPN_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define GNNPN_API __attribute__((visibility("default")))
@@ -105,14 +105,18 @@ GNNPN_API size_t gnnpn_pn_workspace_bytes(int64_t n, int hidden);
  *   win_probs    fp32 [n, L]        out: softmax probability at position l at step l/N
  *   forced_idx   int32 [K, n] or NULL: teacher forcing -- feed these picks to the next step
  *                                   while idx_out still records the free choice
+ *   sample_uniform fp32 [K, n] or NULL: sample="sample" (modelPN.py:227-228) -- with uniforms in [0,1)
+ *                                   the pick is an inverse-CDF draw from the window distribution instead
+ *                                   of the first maximum (same distribution as torch.multinomial, not the
+ *                                   same random stream)
  */
 GNNPN_API int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float* c_state,
                                const float* latent_win, float alpha, const float* packed_decoder,
                                int attention, const float* att_params, int use_tanh, float C,
                                int64_t n, int L, int in_features, int hidden, int K, int N,
                                float* dec_h, int32_t* idx_out, float* win_logits, float* win_probs,
-                               const int32_t* forced_idx, void* workspace, size_t workspace_bytes,
-                               void* stream);
+                               const int32_t* forced_idx, const float* sample_uniform,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* Interface-faithful materialisation of PointerNet.forward's prev_logits (modelPN.py:213-214,239):
  *   logits_full fp32 [K, n, L] = C*tanh(<enc_out[b,l,:], dec_h[b,k,:]>) with -inf at the positions

@@ -1,0 +1,120 @@
+"""GPU tests of the callers either side of the hot path: sampled decode, REINFORCE replay gradients,
+PNLow/PNHigh trainers, ML2PN scoring."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pn_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(K, N, level="Low", seed=1):
+    from gnnpn_sc_b200 import modelPN as M
+    cfg = po.PNConfig(seq_len=K * N, s_number=N, s_category=K)
+    m = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level=level)
+    sd = po.make_state_dict(cfg, seed)
+    m.load_state_dict(sd)
+    return cfg, sd, m.cuda()
+
+
+def test_sampled_decode_follows_the_window_distribution():
+    from gnnpn_sc_b200.synth import pn_instances
+    K, N = 4, 5
+    cfg, sd, m = _model(K, N)
+    x = pn_instances(1, K, N, seed=3).repeat(20000, 1, 1).cuda()         # same instance 20k times
+    m.eval()
+    with torch.no_grad():
+        probs, idx, _ = m.actor(x, None, sample="sample")
+    idx = torch.stack(idx)
+    assert bool(((idx >= torch.arange(K, device="cuda").view(K, 1) * N) & (idx < torch.arange(1, K + 1, device="cuda").view(K, 1) * N)).all())
+    # step 0 is identical across the copies: empirical pick frequencies ~ its softmax
+    p0 = probs.window[0, :N].cpu().numpy()
+    freq = np.bincount(idx[0].cpu().numpy(), minlength=N)[:N] / idx.shape[1]
+    assert np.abs(freq - p0).max() < 0.015, (freq, p0)
+    assert len(set(idx[0].tolist())) > 1                                   # actually stochastic
+
+
+def test_replay_gradient_equals_oracle_autograd():
+    """d/dtheta of sum_k log p_k(action_k) through replay_action_probs == autograd through the oracle's graph."""
+    from gnnpn_sc_b200.synth import pn_instances
+    K, N, B = 6, 4, 16
+    cfg, sd, m = _model(K, N, seed=5)
+    x = pn_instances(B, K, N, seed=2)
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    probs, idx, _ = po.pointer_forward(sd_g, cfg, x, None, "greedy")
+    logp = sum(torch.log(p[torch.arange(B), a]) for p, a in zip(probs, idx)).sum()
+    logp.backward()
+    m.train()
+    idx_c = torch.stack(idx).cuda()
+    ap = m.actor.replay_action_probs(x.cuda(), idx_c, None)
+    sum(torch.log(p) for p in ap).sum().backward()
+    worst = 0.0
+    for name, p in m.named_parameters():
+        g_ref = sd_g[name].grad
+        d = (p.grad.cpu() - g_ref).abs().max() / g_ref.abs().max().clamp(min=1e-3)
+        worst = max(worst, float(d))
+    print(f"replay gradient max relative deviation vs oracle autograd: {worst:.2e}")
+    assert worst < 1e-4
+
+
+def _toy_pn_data(n, K, N, seed=0):
+    from gnnpn_sc_b200.synth import pn_instances
+    x = pn_instances(n, K, N, seed=seed)
+    cat = torch.arange(K).repeat_interleave(N).float().view(1, -1, 1).expand(n, -1, 1)
+    feats = torch.cat([cat, x], dim=2).tolist()                            # loadDataPN rows: [cat, 8 values]
+    return feats, [0.5] * n
+
+
+def test_pnlow_then_pnhigh_trainers_and_ml2pn(tmp_path):
+    from gnnpn_sc_b200 import trainPN
+    K, N = 6, 4
+    data = _toy_pn_data(64, K, N)
+    root = str(tmp_path)
+    low = trainPN.PNLow("toy", 0, 1, K, 1, N, 256, 0, 10, 1, 0.9, 2.0, 1e-4, -1, root=root)
+    tr = low.start(data=data, n_epochs=2)
+    assert len(tr.train_tour) == 2 and len(tr.val_tour) == 2
+    ck = torch.load(os.path.join(root, "solutions", "PNLow", "toy", "epoch1.model"))
+    assert set(ck) == {"epoch", "model", "optimizer"}
+    with open(os.path.join(root, "solutions", "PNLow", "toy", "allActions1.txt")) as f:
+        acts = json.load(f)
+    assert len(acts) == K + 2 and len(acts[0]) == 16 and len(acts[0][0]) == 8      # K+2 slots (trainPNLow.py:122)
+    before = {k: v.clone() for k, v in ck["model"].items()}
+    high = trainPN.PNHigh("toy", 0, 1, K, 1, N, 256, 0, 10, 1, 0.9, 2.0, 5e-5, -1, -1, root=root)
+    th = high.start(data=data, n_epochs=1, low_state=ck["model"])
+    assert os.path.exists(os.path.join(root, "solutions", "PNHigh", "toy", "epoch0_low.model"))
+    with open(os.path.join(root, "solutions", "PNHigh", "toy", "allActions0.txt")) as f:
+        acts_h = json.load(f)
+    assert len(acts_h) == K
+    # PNLow's weights are not stepped by PNHigh training (only model.actor is in the optimiser, trainPNHigh.py:62)
+    after = th.low_model.state_dict()
+    assert all(torch.equal(before[k].cpu(), after[k].cpu()) for k in before)
+    # ML2PN scoring of the saved picks == oracle objective (+ violations)
+    from gnnpn_sc_b200 import ML2PN
+    x = torch.tensor(data[0])[48:, :, 1:]                                  # validation quarter
+    cons = x[:, 0, 4:8].numpy()
+    got = ML2PN.composition_scores(acts_h, K, cons)
+    a = np.asarray(acts_h, dtype=np.float32)                                # [K, n, 8]
+    for i in range(a.shape[1]):
+        rows = a[:, i, :]
+        real = rows[rows[:, :4].sum(axis=1) != 3]
+        obj = 0.5 * (np.average(real[:, 0]) + 1 - np.min(real[:, 1]))
+        for j, (lo, hi) in enumerate(((cons[i, 0], cons[i, 1]), (cons[i, 2], cons[i, 3]))):
+            pr = np.cumprod(real[:, 2 + j])[-1]
+            obj += float(pr < lo or pr > hi)
+        assert abs(got[i] - obj) < 1e-6
+
+
+def test_reinforce_step_reduces_loss_surrogate():
+    """A few REINFORCE updates on one batch move the sampled reward mean down (sanity of sign and plumbing)."""
+    from gnnpn_sc_b200 import trainPN
+    K, N = 5, 4
+    data = _toy_pn_data(256, K, N, seed=4)
+    low = trainPN.PNLow("toy", 0, 1, K, 1, N, 256, 0, 10, 1, 0.9, 2.0, 3e-3, -1, root="/tmp/gnnpn_toy")
+    tr = low.start(data=data, n_epochs=6)
+    first, last = np.mean(tr.train_tour[:2]), np.mean(tr.train_tour[-2:])
+    print(f"mean sampled reward (violations): first epochs {first:.3f} -> last epochs {last:.3f}")
+    assert last <= first + 0.05
