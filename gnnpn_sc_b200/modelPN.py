@@ -229,6 +229,8 @@ class PointerNet(nn.Module):
         The decode itself runs in the CUDA kernels without autograd; this replays it with torch ops restricted to
         the windows -- outside window k the reference's probabilities are exactly 0 and carry no gradient
         (modelPN.py:220-224) -- so the gradient equals the reference's.  Encoder via nn.LSTM (cuDNN), K cell steps."""
+        # strict fp32 (set process-wide in gnnpn_sc_b200/__init__.py: cuDNN's TF32 default would put ~5e-4 relative
+        # error into forward AND backward of the nn.LSTM calls below)
         B, L, _ = inputs.shape
         K, N = self.serCategory, self.serNumber
         rows = torch.arange(B, device=inputs.device)
