@@ -1,6 +1,7 @@
 // Pointer-network entry points: weight packing, encoder scan, fused greedy decode,
 // interface-faithful logits materialisation, composition objective / reward.
 #include <math.h>
+#include <cuda_fp16.h>
 #include "lstm_step.cuh"
 #include "tc_lstm.cuh"
 
@@ -30,8 +31,20 @@ __global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __
   const int rows = H + Fpad + 2;  // + bias row + start row
   const int64_t ffma_total = (int64_t)rows * G;
   const int64_t tc_total = (int64_t)G * Kp;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ffma_total + tc_total;
+  const int64_t tc16_total = (int64_t)G * kKp16;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ffma_total + tc_total + tc16_total;
        e += (int64_t)gridDim.x * blockDim.x) {
+    if (e >= ffma_total + tc_total) {              // fp16-split tcgen05 operand: [4H][kKp16] halfs, weights x 2^4
+      const int64_t t = e - ffma_total - tc_total;
+      const int nn = (int)(t / kKp16), k = (int)(t % kKp16);
+      const int r = (nn & 3) * H + (nn >> 2);
+      const float w = kW16Scale * folded_weight(w_ih, w_hh, w_e, H, F, r, k);
+      const __half hi = __float2half_rn(w);
+      __half* base = reinterpret_cast<__half*>(packed + ffma_total + 2 * tc_total);
+      base[t] = hi;
+      base[tc16_total + t] = __float2half_rn(w - __half2float(hi));
+      continue;
+    }
     if (e >= ffma_total) {                         // tcgen05 operand: [4H gate columns][Kp], K contiguous
       const int64_t t = e - ffma_total;
       const int nn = (int)(t / Kp), k = (int)(t % Kp);
@@ -90,7 +103,7 @@ __global__ void __launch_bounds__(256) pointer_step_dot_kernel(
     const float* __restrict__ latent_win, float alpha, int use_tanh, float C, int64_t n, int L, int k,
     int N, int32_t* __restrict__ idx_out, float* __restrict__ win_logits, float* __restrict__ win_probs,
     const int32_t* __restrict__ forced, const float* __restrict__ uniform, const float* __restrict__ inputs, int F,
-    float* __restrict__ a_hi_next, float* __restrict__ a_lo_next, int64_t a_ld) {
+    void* __restrict__ a_hi_next, void* __restrict__ a_lo_next, int64_t a_ld, int a_f16) {
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= n) return;
@@ -162,10 +175,16 @@ __global__ void __launch_bounds__(256) pointer_step_dot_kernel(
     // tensor-core path: the chosen candidate's raw row becomes columns [H, H+F) of the next step's A operand
     const int fed = forced ? forced[b] : k * N + best_j;   // the xor butterfly left best_j in every lane
     const float v = __ldg(inputs + (b * L + fed) * (int64_t)F + lane);
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-    a_hi_next[b * a_ld + kH + lane] = __uint_as_float(hb);
-    a_lo_next[b * a_ld + kH + lane] = v - __uint_as_float(hb);
+    if (a_f16) {
+      const __half hi = __float2half_rn(v);
+      reinterpret_cast<__half*>(a_hi_next)[b * a_ld + kH + lane] = hi;
+      reinterpret_cast<__half*>(a_lo_next)[b * a_ld + kH + lane] = __float2half_rn(v - __half2float(hi));
+    } else {
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      reinterpret_cast<float*>(a_hi_next)[b * a_ld + kH + lane] = __uint_as_float(hb);
+      reinterpret_cast<float*>(a_lo_next)[b * a_ld + kH + lane] = v - __uint_as_float(hb);
+    }
   }
 }
 
@@ -404,7 +423,8 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
         k, N, idx_out + (int64_t)k * n, win_logits, win_probs,
         forced_idx ? forced_idx + (int64_t)k * n : nullptr,
         sample_uniform ? sample_uniform + (int64_t)k * n : nullptr, inputs, in_features,
-        use_tc ? plan.hi[nxt] : nullptr, use_tc ? plan.lo[nxt] : nullptr, (int64_t)kKp);
+        use_tc ? plan.hi[nxt] : nullptr, use_tc ? plan.lo[nxt] : nullptr, use_tc ? (int64_t)plan.ld : 0,
+        use_tc ? plan.f16 : 0);
     if ((rc = after_launch())) return rc;
   }
   return GNNPN_OK;

@@ -64,8 +64,21 @@ struct MainloopParams {
   int dbg;                  // profiling experiments only (GNNPN_TC_DBG): 1 = hi.hi MMA only, 2 = epilogue skips math
 };
 
+// Operand flavour of the mainloop: every smem tile row is 128 bytes either way.
+template <bool F16> struct Kind;
+template <> struct Kind<false> {                    // tf32-in-fp32: 32 elements / row, K = 8 per MMA
+  static constexpr int BKE = 32;
+  __device__ static uint32_t idesc(int n) { return idesc_tf32(BM, n); }
+  __device__ static void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) { mma_tf32_ss(d, a, b, i, acc); }
+};
+template <> struct Kind<true> {                     // fp16: 64 elements / row, K = 16 per MMA
+  static constexpr int BKE = 64;
+  __device__ static uint32_t idesc(int n) { return idesc_f16(BM, n); }
+  __device__ static void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) { mma_f16_ss(d, a, b, i, acc); }
+};
+
 // ------------------------------------------------------------------------------------------------
-template <class Epilogue, class EpiParams>
+template <class Epilogue, class EpiParams, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -100,7 +113,8 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const uint32_t stage_tx = 2u * A_TILE_BYTES + 2u * (uint32_t)mp.bn * BK * 4u;
+  constexpr int BKE = Kind<F16>::BKE;                 // elements per 128-byte k-block row
+  const uint32_t stage_tx = 2u * A_TILE_BYTES + 2u * (uint32_t)mp.bn * 128u;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -111,10 +125,10 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_arrive_expect_tx(full_bar(s), stage_tx);
           const uint32_t st = smem_base + s * STAGE_BYTES;
-          tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
-          tma_load_2d(st + A_TILE_BYTES, &map_a_lo, full_bar(s), kb * BK, m0);
-          tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, full_bar(s), kb * BK, nt * mp.bn);
-          tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, full_bar(s), kb * BK, nt * mp.bn);
+          tma_load_2d(st, &map_a_hi, full_bar(s), kb * BKE, m0);
+          tma_load_2d(st + A_TILE_BYTES, &map_a_lo, full_bar(s), kb * BKE, m0);
+          tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, full_bar(s), kb * BKE, nt * mp.bn);
+          tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, full_bar(s), kb * BKE, nt * mp.bn);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -122,7 +136,7 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   } else if (warp == 1) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(BM, mp.bn);
+      const uint32_t idesc = Kind<F16>::idesc(mp.bn);
       int s = 0; uint32_t ph = 0;
       for (int nt = 0; nt < mp.n_tiles; ++nt) {
         const int buf = nt & 1;
@@ -137,16 +151,16 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           const uint64_t a_hi = smem_desc_k_sw128(st), a_lo = smem_desc_k_sw128(st + A_TILE_BYTES);
           const uint64_t b_hi = smem_desc_k_sw128(st + 2 * A_TILE_BYTES);
           const uint64_t b_lo = smem_desc_k_sw128(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
-          const int ksteps = (kb == mp.k_blocks - 1) ? mp.last_block_ksteps : BK / 8;
+          const int ksteps = (kb == mp.k_blocks - 1) ? mp.last_block_ksteps : 4;
           for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 8 * 4 >> 4);   // +32 B per k-step inside the swizzle row
+            const uint64_t adv = (uint64_t)(ks * 2);            // +32 B per k-step inside the 128-byte swizzle row
             const uint32_t acc0 = (kb | ks) != 0;
             if (mp.dbg != 1) {
-              mma_tf32_ss(d, a_lo + adv, b_hi + adv, idesc, acc0);
-              mma_tf32_ss(d, a_hi + adv, b_lo + adv, idesc, 1u);
-              mma_tf32_ss(d, a_hi + adv, b_hi + adv, idesc, 1u);
+              Kind<F16>::mma(d, a_lo + adv, b_hi + adv, idesc, acc0);
+              Kind<F16>::mma(d, a_hi + adv, b_lo + adv, idesc, 1u);
+              Kind<F16>::mma(d, a_hi + adv, b_hi + adv, idesc, 1u);
             } else {
-              mma_tf32_ss(d, a_hi + adv, b_hi + adv, idesc, acc0);
+              Kind<F16>::mma(d, a_hi + adv, b_hi + adv, idesc, acc0);
             }
           }
           mma_commit(empty_bar(s));                 // smem slot reusable once these MMAs retire
@@ -222,59 +236,90 @@ struct GemmEpilogue {
   }
 };
 
-struct LstmEpilogue {
+// 256-bit global accesses (sm_100): one full 32-byte sector per thread per instruction
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
+template <bool F16>
+struct LstmEpilogueT {
   const LstmEpilogueParams& p; int64_t row; bool ok;
   const float* sbias;            // the 1024 gate biases, staged once per CTA
-  float4 c_pre[2 * (BN_MAX / (32 * EPI_GROUPS))];   // prefetched cell state: 8 hidden units per owned chunk
+  float c_pre[BN_MAX / (32 * EPI_GROUPS)][8];   // prefetched cell state: 8 hidden units per owned chunk
   __device__ static void stage_smem(const LstmEpilogueParams& p, float* smem, int tid, int nthreads) {
     for (int i = tid; i < kG; i += nthreads) smem[i] = __ldg(p.bias + i);
   }
-  __device__ LstmEpilogue(const LstmEpilogueParams& p_, const float* smem, int row_, bool ok_, bool primary)
+  __device__ LstmEpilogueT(const LstmEpilogueParams& p_, const float* smem, int row_, bool ok_, bool primary)
       : p(p_), row(row_), ok(ok_), sbias(smem) {
     if (ok && primary && p.x_next && p.x_row_next >= 0) {   // stage the next step's raw input as A columns 256..
       const float* x = p.x_next + row * p.x_inst_ld + (int64_t)p.x_row_next * p.F;
       for (int f = 0; f < p.F; ++f) {
-        float hi, lo;
-        split_tf32(__ldg(x + f), hi, lo);
-        p.a_hi_next[row * p.a_ld + kH + f] = hi;
-        p.a_lo_next[row * p.a_ld + kH + f] = lo;
+        const float xv = __ldg(x + f);
+        if (F16) {
+          __half hi, lo;
+          split_f16(xv, hi, lo);
+          reinterpret_cast<__half*>(p.a_hi_next)[row * p.a_ld + kH + f] = hi;
+          reinterpret_cast<__half*>(p.a_lo_next)[row * p.a_ld + kH + f] = lo;
+        } else {
+          float hi, lo;
+          split_tf32(xv, hi, lo);
+          p.a_hi_next[row * p.a_ld + kH + f] = hi;
+          p.a_lo_next[row * p.a_ld + kH + f] = lo;
+        }
       }
     }
   }
   __device__ void prefetch(int slot, int col0) {
     if (ok && !p.first) {
-      const float4* cp = reinterpret_cast<const float4*>(p.c + row * kH + (col0 >> 2));
-      c_pre[2 * slot] = cp[0];
-      c_pre[2 * slot + 1] = cp[1];
+      ldg256(p.c + row * kH + (col0 >> 2), c_pre[slot]);
     } else {
-      c_pre[2 * slot] = c_pre[2 * slot + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) c_pre[slot][u] = 0.f;
     }
   }
   // 32 gate columns = 8 hidden units x (i,f,g,o)
   __device__ void chunk(int slot, int col0, int /*ncols*/, const float* v) {
     if (!ok) return;
     const int j0 = col0 >> 2;
-    float hv[8], hh[8], hl[8];
-    const float4 c_lo = c_pre[2 * slot], c_hi = c_pre[2 * slot + 1];
-    float cv[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
+    float hv[8], cv[8];
     const float4* bias4 = reinterpret_cast<const float4*>(sbias + col0);
+    constexpr float kAccScale = F16 ? 1.0f / kW16Scale : 1.0f;      // fp16 weights are stored pre-scaled
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const float4 b = bias4[u];
-      const float gi = v[4 * u + 0] + b.x, gf = v[4 * u + 1] + b.y, gg = v[4 * u + 2] + b.z, go = v[4 * u + 3] + b.w;
-      const float cn = fmaf(sigmoid_mufu(gf), cv[u], sigmoid_mufu(gi) * tanh_mufu(gg));
+      const float gi = fmaf(v[4 * u + 0], kAccScale, b.x), gf = fmaf(v[4 * u + 1], kAccScale, b.y);
+      const float gg = fmaf(v[4 * u + 2], kAccScale, b.z), go = fmaf(v[4 * u + 3], kAccScale, b.w);
+      const float cn = fmaf(sigmoid_mufu(gf), c_pre[slot][u], sigmoid_mufu(gi) * tanh_mufu(gg));
       cv[u] = cn;
       hv[u] = sigmoid_mufu(go) * tanh_mufu(cn);
-      split_tf32(hv[u], hh[u], hl[u]);
     }
-    auto st8 = [](float* dst, const float* s) {
-      *reinterpret_cast<float4*>(dst) = make_float4(s[0], s[1], s[2], s[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(s[4], s[5], s[6], s[7]);
-    };
-    st8(p.c + row * kH + j0, cv);
-    st8(p.h_out + row * p.h_out_ld + j0, hv);
-    st8(p.a_hi_next + row * p.a_ld + j0, hh);
-    st8(p.a_lo_next + row * p.a_ld + j0, hl);
+    stg256(p.c + row * kH + j0, cv);
+    stg256(p.h_out + row * p.h_out_ld + j0, hv);
+    if (F16) {
+      __half2 hh[4], hl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        __half a0, l0, a1, l1;
+        split_f16(hv[2 * u], a0, l0);
+        split_f16(hv[2 * u + 1], a1, l1);
+        hh[u] = __halves2half2(a0, a1);
+        hl[u] = __halves2half2(l0, l1);
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.a_hi_next) + row * p.a_ld + j0) = *reinterpret_cast<uint4*>(hh);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.a_lo_next) + row * p.a_ld + j0) = *reinterpret_cast<uint4*>(hl);
+    } else {
+      float hh[8], hl[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) split_tf32(hv[u], hh[u], hl[u]);
+      stg256(p.a_hi_next + row * p.a_ld + j0, hh);
+      stg256(p.a_lo_next + row * p.a_ld + j0, hl);
+    }
   }
 };
 
@@ -312,23 +357,27 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// row-major fp32 [rows, cols] with leading dimension ld (floats); box = {32 cols, box_rows}; 128B swizzle
-int make_map_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// row-major [rows, cols] fp32 (or fp16) with leading dimension ld (elements); box = {128 bytes of columns,
+// box_rows}; 128B swizzle
+int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                bool f16 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return GNNPN_EUNSUPPORTED;
+  const int esz = f16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
+                  strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? GNNPN_OK : GNNPN_ESHAPE;
 }
 
-template <class Epi, class EpiParams>
+template <class Epi, class EpiParams, bool F16>
 int launch_mainloop(const CUtensorMap maps[4], const MainloopParams& mp, const EpiParams& ep, cudaStream_t st) {
-  auto kern = tc_mainloop_kernel<Epi, EpiParams>;
+  auto kern = tc_mainloop_kernel<Epi, EpiParams, F16>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -376,48 +425,87 @@ int launch_gemm_tc(const float* A, int64_t lda, const float* W, int64_t ldw, con
   if ((rc = make_map_2d(&maps[3], w_lo, N, Kp, Kp, bn))) return rc;
   MainloopParams mp{(int)M, n_tiles, bn, Kp / BK, BK / 8, 0};
   GemmEpilogueParams ep{bias, scale, shift, act, C, ldc, N};
-  return launch_mainloop<GemmEpilogue, GemmEpilogueParams>(maps, mp, ep, st);
+  return launch_mainloop<GemmEpilogue, GemmEpilogueParams, false>(maps, mp, ep, st);
 }
 
 // ------------------------------------------------------------------------------------------------
 // LSTM recurrence on tcgen05
 namespace {
 
+template <bool F16>
 __global__ void stage_x_kernel(const float* __restrict__ inputs, int64_t x_inst_ld, int row, int F, int64_t n,
-                               float* __restrict__ hi, float* __restrict__ lo) {
+                               void* __restrict__ hi, void* __restrict__ lo, int ld) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= n * F) return;
   const int64_t m = e / F;
   const int f = (int)(e % F);
-  float h, l;
-  tc::split_tf32(inputs[m * x_inst_ld + (int64_t)row * F + f], h, l);
-  hi[m * kKp + kH + f] = h;
-  lo[m * kKp + kH + f] = l;
+  const float v = inputs[m * x_inst_ld + (int64_t)row * F + f];
+  if (F16) {
+    __half h, l;
+    tc::split_f16(v, h, l);
+    reinterpret_cast<__half*>(hi)[m * ld + kH + f] = h;
+    reinterpret_cast<__half*>(lo)[m * ld + kH + f] = l;
+  } else {
+    float h, l;
+    tc::split_tf32(v, h, l);
+    reinterpret_cast<float*>(hi)[m * ld + kH + f] = h;
+    reinterpret_cast<float*>(lo)[m * ld + kH + f] = l;
+  }
+}
+
+// rows of fp32 h (ld apart) -> fp16 hi/lo rows of kKp16 columns, padding zeroed
+__global__ void split_f16_rows_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int K, int Kpad,
+                                      __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int64_t total = rows * Kpad;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / Kpad;
+    const int k = (int)(e % Kpad);
+    __half h = __float2half_rn(0.f), l = h;
+    if (k < K) tc::split_f16(src[r * ld + k], h, l);
+    hi[e] = h;
+    lo[e] = l;
+  }
 }
 
 }  // namespace
 
+int tc_lstm_default_f16() {
+  static const int f16 = [] {
+    const char* e = getenv("GNNPN_TC_KIND");
+    return (e && (e[0] == 't' || e[0] == 'T')) ? 0 : 1;
+  }();
+  return f16;
+}
+
+// sized for the larger (tf32) layout so one query serves both operand kinds
 size_t tc_lstm_workspace_bytes(int64_t n) { return (size_t)4 * n * kKp * sizeof(float) + 1024; }
 
 int tc_lstm_plan(TcLstmPlan* plan, void* workspace, size_t workspace_bytes, int64_t n, const float* packed) {
   if (workspace_bytes < tc_lstm_workspace_bytes(n)) return GNNPN_EWORKSPACE;
-  float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
-  const size_t one = (size_t)n * kKp;
+  char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  const int f16 = tc_lstm_default_f16();
   plan->n = n;
+  plan->f16 = f16;
+  plan->ld = f16 ? kKp16 : kKp;
+  const size_t one = (size_t)n * plan->ld * (f16 ? 2 : 4);       // multiple of 64 bytes
   plan->hi[0] = ws; plan->lo[0] = ws + one; plan->hi[1] = ws + 2 * one; plan->lo[1] = ws + 3 * one;
   int rc;
   for (int b = 0; b < 2; ++b) {
-    if ((rc = tc::make_map_2d(&plan->a_hi[b], plan->hi[b], n, kKp, kKp, tc::BM))) return rc;
-    if ((rc = tc::make_map_2d(&plan->a_lo[b], plan->lo[b], n, kKp, kKp, tc::BM))) return rc;
+    if ((rc = tc::make_map_2d(&plan->a_hi[b], plan->hi[b], n, plan->ld, plan->ld, tc::BM, f16))) return rc;
+    if ((rc = tc::make_map_2d(&plan->a_lo[b], plan->lo[b], n, plan->ld, plan->ld, tc::BM, f16))) return rc;
   }
-  if ((rc = tc::make_map_2d(&plan->b_hi, packed + kOffTcHi, kG, kKp, kKp, tc::BN_MAX))) return rc;
-  if ((rc = tc::make_map_2d(&plan->b_lo, packed + kOffTcLo, kG, kKp, kKp, tc::BN_MAX))) return rc;
+  const float* w_hi = packed + (f16 ? kOffTc16Hi : kOffTcHi);
+  const float* w_lo = packed + (f16 ? kOffTc16Lo : kOffTcLo);
+  if ((rc = tc::make_map_2d(&plan->b_hi, w_hi, kG, plan->ld, plan->ld, tc::BN_MAX, f16))) return rc;
+  if ((rc = tc::make_map_2d(&plan->b_lo, w_lo, kG, plan->ld, plan->ld, tc::BN_MAX, f16))) return rc;
   return GNNPN_OK;
 }
 
 int tc_lstm_zero(const TcLstmPlan& plan, int which, cudaStream_t st) {
   // hi[which] and lo[which] are adjacent in the workspace
-  cudaError_t e = cudaMemsetAsync(plan.hi[which], 0, (size_t)2 * plan.n * kKp * sizeof(float), st);
+  const size_t bytes = (size_t)2 * plan.n * plan.ld * (plan.f16 ? 2 : 4);
+  cudaError_t e = cudaMemsetAsync(plan.hi[which], 0, bytes, st);
   return e == cudaSuccess ? GNNPN_OK : (int)e;
 }
 
@@ -426,31 +514,41 @@ int tc_lstm_reset(const TcLstmPlan& plan, const float* inputs, int64_t x_inst_ld
   int rc;
   if ((rc = tc_lstm_zero(plan, 0, st))) return rc;
   if ((rc = tc_lstm_zero(plan, 1, st))) return rc;
-  stage_x_kernel<<<(unsigned)ceil_div(plan.n * F, 256), 256, 0, st>>>(inputs, x_inst_ld, row0, F, plan.n,
-                                                                     plan.hi[0], plan.lo[0]);
+  const unsigned grid = (unsigned)ceil_div(plan.n * F, 256);
+  if (plan.f16)
+    stage_x_kernel<true><<<grid, 256, 0, st>>>(inputs, x_inst_ld, row0, F, plan.n, plan.hi[0], plan.lo[0], plan.ld);
+  else
+    stage_x_kernel<false><<<grid, 256, 0, st>>>(inputs, x_inst_ld, row0, F, plan.n, plan.hi[0], plan.lo[0], plan.ld);
   return after_launch();
 }
 
 int tc_lstm_load_h(const TcLstmPlan& plan, int dst, const float* h, int64_t ld, cudaStream_t st) {
-  tc::split_tf32_kernel<<<kNumSMs * 4, 256, 0, st>>>(h, ld, plan.n, kH, kKp, plan.hi[dst], plan.lo[dst]);
+  if (plan.f16)
+    split_f16_rows_kernel<<<kNumSMs * 4, 256, 0, st>>>(h, ld, plan.n, kH, kKp16, (__half*)plan.hi[dst],
+                                                       (__half*)plan.lo[dst]);
+  else
+    tc::split_tf32_kernel<<<kNumSMs * 4, 256, 0, st>>>(h, ld, plan.n, kH, kKp, (float*)plan.hi[dst],
+                                                       (float*)plan.lo[dst]);
   return after_launch();
 }
 
 int tc_lstm_step(const TcLstmPlan& plan, const TcLstmStep& s, cudaStream_t st) {
   using namespace tc;
   const CUtensorMap maps[4] = {plan.a_hi[s.cur], plan.a_lo[s.cur], plan.b_hi, plan.b_lo};
+  const int bke = plan.f16 ? 64 : 32;
   MainloopParams mp;
   mp.M = (int)plan.n;
   mp.n_tiles = kG / BN_MAX;
   mp.bn = BN_MAX;
-  mp.k_blocks = kH / BK + (s.use_x ? 1 : 0);
-  mp.last_block_ksteps = s.use_x ? (s.F + 7) / 8 : BK / 8;
+  mp.k_blocks = kH / bke + (s.use_x ? 1 : 0);
+  mp.last_block_ksteps = s.use_x ? (s.F + (bke / 4) - 1) / (bke / 4) : 4;
   mp.dbg = 0;
   LstmEpilogueParams ep;
   ep.bias = s.bias; ep.c = s.c; ep.h_out = s.h_out; ep.h_out_ld = s.h_out_ld;
-  ep.a_hi_next = plan.hi[s.cur ^ 1]; ep.a_lo_next = plan.lo[s.cur ^ 1]; ep.a_ld = kKp;
+  ep.a_hi_next = (float*)plan.hi[s.cur ^ 1]; ep.a_lo_next = (float*)plan.lo[s.cur ^ 1]; ep.a_ld = plan.ld;
   ep.x_next = s.x_next; ep.x_inst_ld = s.x_inst_ld; ep.x_row_next = s.x_row_next; ep.F = s.F; ep.first = s.first;
-  return launch_mainloop<LstmEpilogue, LstmEpilogueParams>(maps, mp, ep, st);
+  if (plan.f16) return launch_mainloop<LstmEpilogueT<true>, LstmEpilogueParams, true>(maps, mp, ep, st);
+  return launch_mainloop<LstmEpilogueT<false>, LstmEpilogueParams, false>(maps, mp, ep, st);
 }
 
 }  // namespace gnnpn

@@ -12,14 +12,22 @@ constexpr size_t kOffBias = (size_t)(kH + kXPad) * kG;
 constexpr size_t kOffStart = kOffBias + kG;
 constexpr size_t kOffTcHi = kOffStart + kG;
 constexpr size_t kOffTcLo = kOffTcHi + (size_t)kG * kKp;
-constexpr size_t kPackedFloats = kOffTcLo + (size_t)kG * kKp;
+// fp16-split operand blocks (default recurrence path): [4H][kKp16] halfs, weights pre-scaled by kW16Scale
+constexpr int kKp16 = kH + 64;   // [h | x | zero pad] as 5 k-blocks of 64 halfs (128-byte swizzle rows)
+constexpr float kW16Scale = 16.0f;   // |w| <~ 0.06 would push the fp16 "lo" parts into subnormals; 2^4 is exact to undo
+constexpr size_t kOffTc16Hi = kOffTcLo + (size_t)kG * kKp;
+constexpr size_t kOffTc16Lo = kOffTc16Hi + (size_t)kG * kKp16 / 2;
+constexpr size_t kPackedFloats = kOffTc16Lo + (size_t)kG * kKp16 / 2;
 
 struct TcLstmPlan {
   CUtensorMap a_hi[2], a_lo[2], b_hi, b_lo;
-  float* hi[2];
-  float* lo[2];
+  void* hi[2];          // [n, ld] tf32-in-fp32 or fp16
+  void* lo[2];
   int64_t n;
+  int f16;              // 1: fp16 split (kKp16 columns), 0: tf32 split (kKp columns)
+  int ld;               // elements per row
 };
+int tc_lstm_default_f16();     // GNNPN_TC_KIND=tf32 selects the tf32 split, anything else fp16
 
 size_t tc_lstm_workspace_bytes(int64_t n);
 // carve the workspace into the two ping-pong [n, kKp] hi/lo pairs and build the TMA descriptors
