@@ -60,9 +60,12 @@ def import_reference():
     if not os.path.isdir(REFERENCE):
         raise SystemExit("reference tree not present; fixtures can only be generated in the build container")
     torch.Tensor.cuda = lambda self, *a, **k: self      # modelPN.py:151 workaround, CPU run
-    sys.path.insert(0, REFERENCE)
-    from src.models import modelPN as ref               # type: ignore
-    sys.path.pop(0)
+    # loaded by file path under a private name: this repo ships its own ``src.models.modelPN`` shim
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_reference_modelPN",
+                                                  os.path.join(REFERENCE, "src", "models", "modelPN.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
     return ref
 
 
