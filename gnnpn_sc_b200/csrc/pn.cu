@@ -1,9 +1,12 @@
 // Pointer-network entry points: weight packing, encoder scan, fused greedy decode,
 // interface-faithful logits materialisation, composition objective / reward.
 #include <math.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include "lstm_step.cuh"
 #include "tc_lstm.cuh"
+#include "tc_seq.cuh"
+#include "pointer.cuh"
 
 namespace gnnpn {
 namespace {
@@ -87,94 +90,18 @@ __global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __
 //   pick  = first j with maximal p                  -> idx_out[b] = kN + j
 // Positions outside the window carry -inf after modelPN.py:220-222 and contribute exp(-inf)=0.
 // ---------------------------------------------------------------------------
-constexpr int kMaxWindow = 32;
-
-// <row, q> over the 8 elements a lane owns, explicit fma chain so every kernel that forms a
-// pointer logit rounds identically (window logits == the same entries of the full logits).
-__device__ __forceinline__ float dot8(const float4 r0, const float4 r1, const float4 q0, const float4 q1) {
-  float s = r0.x * q0.x;
-  s = fmaf(r0.y, q0.y, s); s = fmaf(r0.z, q0.z, s); s = fmaf(r0.w, q0.w, s);
-  s = fmaf(r1.x, q1.x, s); s = fmaf(r1.y, q1.y, s); s = fmaf(r1.z, q1.z, s); s = fmaf(r1.w, q1.w, s);
-  return s;
-}
-
 __global__ void __launch_bounds__(256) pointer_step_dot_kernel(
-    const float* __restrict__ enc_out, int64_t enc_inst_ld, const float* __restrict__ q, int64_t q_ld,
-    const float* __restrict__ latent_win, float alpha, int use_tanh, float C, int64_t n, int L, int k,
-    int N, int32_t* __restrict__ idx_out, float* __restrict__ win_logits, float* __restrict__ win_probs,
-    const int32_t* __restrict__ forced, const float* __restrict__ uniform, const float* __restrict__ inputs, int F,
+    const PointerStepArgs pa, const float* __restrict__ q, int64_t q_ld, const float* __restrict__ inputs, int F,
     void* __restrict__ a_hi_next, void* __restrict__ a_lo_next, int64_t a_ld, int a_f16) {
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= n) return;
+  if (b >= pa.n) return;
   const float4* qp = reinterpret_cast<const float4*>(q + b * q_ld);
   const float4 q0 = __ldg(qp + lane), q1 = __ldg(qp + 32 + lane);
-  const float* base = enc_out + b * enc_inst_ld + (int64_t)k * N * kH;
-
-  float my_w = -INFINITY, my_l = 0.f;          // lane j holds candidate j
-  for (int j0 = 0; j0 < N; j0 += 4) {          // 4 rows in flight per iteration
-    float part[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      part[u] = 0.f;
-      if (j0 + u < N) {
-        const float4* rp = reinterpret_cast<const float4*>(base + (int64_t)(j0 + u) * kH);
-        const float4 r0 = ldg_stream(rp + lane), r1 = ldg_stream(rp + 32 + lane);
-        part[u] = dot8(r0, r1, q0, q1);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float d = warp_sum(part[u]);
-      if (j0 + u < N && lane == j0 + u) {
-        my_l = use_tanh ? C * tanhf(d) : d;
-        my_w = my_l;
-      }
-    }
-  }
-  const int64_t wpos = b * L + (int64_t)k * N + lane;
-  if (lane < N) {
-    if (latent_win) my_w = my_l + alpha * __ldg(latent_win + wpos);
-    win_logits[wpos] = my_l;
-  }
-  float mx = my_w;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const float e = lane < N ? expf(my_w - mx) : 0.f;
-  // sequential sum in candidate order (deterministic, independent of warp shuffles' tree)
-  float s = 0.f;
-  for (int j = 0; j < N; ++j) s += __shfl_sync(0xffffffffu, e, j);
-  const float p = e / s;
-  if (lane < N) win_probs[wpos] = p;
-  // first maximal probability (torch.max tie rule, modelPN.py:225-226)
-  float best = p;
-  int best_j = lane < N ? lane : 0x7fffffff;
-  if (lane >= N) best = -1.f;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
-    if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
-  }
-  if (uniform) {
-    // sample="sample" (modelPN.py:227-228): inverse-CDF draw from the window distribution with a caller-supplied
-    // uniform in [0,1); falls back to the last candidate with non-zero probability on round-off
-    const float u = __ldg(uniform + b);
-    float cum = 0.f;
-    int pick = -1, last_pos = 0;
-    for (int j = 0; j < N; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, p, j);
-      cum += pj;
-      if (pj > 0.f) last_pos = j;
-      if (pick < 0 && u < cum) pick = j;
-    }
-    best_j = pick < 0 ? last_pos : pick;
-  }
-  if (lane == 0) idx_out[b] = k * N + best_j;
+  const int fed = pointer_step_warp(pa, b, q0, q1, lane);
   if (a_hi_next && lane < F) {
     // tensor-core path: the chosen candidate's raw row becomes columns [H, H+F) of the next step's A operand
-    const int fed = forced ? forced[b] : k * N + best_j;   // the xor butterfly left best_j in every lane
-    const float v = __ldg(inputs + (b * L + fed) * (int64_t)F + lane);
+    const float v = __ldg(inputs + (b * pa.L + fed) * (int64_t)F + lane);
     if (a_f16) {
       const __half hi = __float2half_rn(v);
       reinterpret_cast<__half*>(a_hi_next)[b * a_ld + kH + lane] = hi;
@@ -294,6 +221,16 @@ __global__ void reward_kernel(const float* __restrict__ inputs, const int32_t* _
   }
 }
 
+// GNNPN_SEQ: bit 0 = persistent encoder scan, bit 1 = persistent fused decode (default 3); 0 selects the
+// one-launch-per-step kernels (kept as the A/B reference for the persistent ones)
+int seq_mode() {
+  static const int m = [] {
+    const char* e = getenv("GNNPN_SEQ");
+    return e ? atoi(e) : 3;
+  }();
+  return m;
+}
+
 }  // namespace
 }  // namespace gnnpn
 
@@ -330,8 +267,15 @@ int gnnpn_lstm_encode_f32(const float* inputs, int64_t n, int L, int in_features
   GNNPN_REQUIRE(aligned16(enc_out) && aligned16(c_state) && aligned16(packed), GNNPN_EALIGN);
   if (n == 0) return GNNPN_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (workspace && (seq_mode() & 1) && in_features <= 8) {
+    // ---- persistent tcgen05 scan: one launch for all L steps, h resident in shared memory
+    GNNPN_REQUIRE((reinterpret_cast<uintptr_t>(enc_out) & 31u) == 0 && (reinterpret_cast<uintptr_t>(c_state) & 31u) == 0,
+                  GNNPN_EALIGN);
+    SeqEncodeArgs sa{inputs, n, L, in_features, packed, enc_out, c_state};
+    return tc_seq_encode(sa, st);
+  }
   if (workspace) {
-    // ---- tcgen05 recurrence: [h|x] kept as tf32 hi/lo pairs in two ping-pong buffers
+    // ---- tcgen05 recurrence, one launch per step: [h|x] kept as hi/lo pairs in two ping-pong buffers
     TcLstmPlan plan;
     int rc = tc_lstm_plan(&plan, workspace, workspace_bytes, n, packed);
     if (rc) return rc;
@@ -384,6 +328,13 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
   const float* start = packed + kOffStart;
   const unsigned att_blocks = (unsigned)ceil_div(n, 8);
   const bool use_tc = workspace != nullptr;
+  if (use_tc && (seq_mode() & 2) && in_features <= 8) {
+    GNNPN_REQUIRE((reinterpret_cast<uintptr_t>(enc_out) & 31u) == 0 && (reinterpret_cast<uintptr_t>(c_state) & 31u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(dec_h) & 31u) == 0, GNNPN_EALIGN);
+    SeqDecodeArgs sa{inputs, enc_out, c_state, latent_win, alpha, packed, use_tanh, C, n, L, in_features, K, N,
+                     dec_h, idx_out, win_logits, win_probs, forced_idx, sample_uniform};
+    return tc_seq_decode(sa, st);
+  }
   TcLstmPlan plan;
   TcLstmStep ts{};
   LstmStepArgs a{};
@@ -418,11 +369,14 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
       if ((rc = launch_lstm_step(a, st))) return rc;
     }
     const int nxt = (k + 1) & 1;
+    PointerStepArgs pa;
+    pa.enc_out = enc_out; pa.enc_inst_ld = (int64_t)L * kH; pa.latent_win = latent_win; pa.alpha = alpha;
+    pa.use_tanh = use_tanh; pa.C = C; pa.n = n; pa.L = L; pa.k = k; pa.N = N;
+    pa.idx_out = idx_out + (int64_t)k * n; pa.win_logits = win_logits; pa.win_probs = win_probs;
+    pa.forced = forced_idx ? forced_idx + (int64_t)k * n : nullptr;
+    pa.uniform = sample_uniform ? sample_uniform + (int64_t)k * n : nullptr;
     pointer_step_dot_kernel<<<att_blocks, 256, 0, st>>>(
-        enc_out, (int64_t)L * kH, dec_h + (int64_t)k * kH, (int64_t)K * kH, latent_win, alpha, use_tanh, C, n, L,
-        k, N, idx_out + (int64_t)k * n, win_logits, win_probs,
-        forced_idx ? forced_idx + (int64_t)k * n : nullptr,
-        sample_uniform ? sample_uniform + (int64_t)k * n : nullptr, inputs, in_features,
+        pa, dec_h + (int64_t)k * kH, (int64_t)K * kH, inputs, in_features,
         use_tc ? plan.hi[nxt] : nullptr, use_tc ? plan.lo[nxt] : nullptr, use_tc ? (int64_t)plan.ld : 0,
         use_tc ? plan.f16 : 0);
     if ((rc = after_launch())) return rc;

@@ -1,0 +1,115 @@
+// Pointer step for one composition instance, executed by one warp (Dot attention, modelPN.py:111-120,
+// 213-228).  Shared by the stand-alone pointer kernel (pn.cu) and the persistent decode kernel (tc_seq.cu)
+// so both round identically.
+//   u_j   = <enc_out[b, kN+j, :], q[b,:]>            j in [0,N)
+//   l_j   = use_tanh ? C*tanh(u_j) : u_j            -> win_logits[b, kN+j]
+//   w_j   = l_j + alpha*latent[b, kN+j]
+//   p     = softmax_j(w)  (exp(w-max)/sum, fp32)    -> win_probs[b, kN+j]
+//   pick  = first j with maximal p                  -> idx_out[b] = kN + j
+// Positions outside the window carry -inf after modelPN.py:220-222 and contribute exp(-inf)=0.
+#pragma once
+#include <math.h>
+#include "common.cuh"
+#include "lstm_step.cuh"
+
+namespace gnnpn {
+
+constexpr int kMaxWindow = 32;
+
+struct PointerStepArgs {
+  const float* enc_out;      // [n, L, kH]
+  int64_t enc_inst_ld;
+  const float* latent_win;   // [n, L] or nullptr
+  float alpha;
+  int use_tanh;
+  float C;
+  int64_t n;
+  int L, k, N;
+  int32_t* idx_out;          // [n]   (already offset to step k)
+  float* win_logits;         // [n, L]
+  float* win_probs;          // [n, L]
+  const int32_t* forced;     // [n] step-k teacher-forced picks or nullptr
+  const float* uniform;      // [n] step-k uniforms (sample="sample") or nullptr
+};
+
+// <row, q> over the 8 elements a lane owns, explicit fma chain so every kernel that forms a
+// pointer logit rounds identically (window logits == the same entries of the full logits).
+__device__ __forceinline__ float dot8(const float4 r0, const float4 r1, const float4 q0, const float4 q1) {
+  float s = r0.x * q0.x;
+  s = fmaf(r0.y, q0.y, s); s = fmaf(r0.z, q0.z, s); s = fmaf(r0.w, q0.w, s);
+  s = fmaf(r1.x, q1.x, s); s = fmaf(r1.y, q1.y, s); s = fmaf(r1.z, q1.z, s); s = fmaf(r1.w, q1.w, s);
+  return s;
+}
+
+// q0/q1: the lane's 8 query elements (float4 index lane and 32+lane of the 256-float query).
+// Returns, in every lane, the position fed to the next decoder step (the pick, or forced[b]).
+__device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int64_t b, const float4 q0,
+                                                 const float4 q1, int lane) {
+  const int N = a.N, k = a.k;
+  const float* base = a.enc_out + b * a.enc_inst_ld + (int64_t)k * N * kH;
+
+  float my_w = -INFINITY, my_l = 0.f;          // lane j holds candidate j
+  for (int j0 = 0; j0 < N; j0 += 4) {          // 4 rows in flight per iteration
+    float part[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      part[u] = 0.f;
+      if (j0 + u < N) {
+        const float4* rp = reinterpret_cast<const float4*>(base + (int64_t)(j0 + u) * kH);
+        const float4 r0 = ldg_stream(rp + lane), r1 = ldg_stream(rp + 32 + lane);
+        part[u] = dot8(r0, r1, q0, q1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float d = warp_sum(part[u]);
+      if (j0 + u < N && lane == j0 + u) {
+        my_l = a.use_tanh ? a.C * tanhf(d) : d;
+        my_w = my_l;
+      }
+    }
+  }
+  const int64_t wpos = b * a.L + (int64_t)k * N + lane;
+  if (lane < N) {
+    if (a.latent_win) my_w = my_l + a.alpha * __ldg(a.latent_win + wpos);
+    a.win_logits[wpos] = my_l;
+  }
+  float mx = my_w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float e = lane < N ? expf(my_w - mx) : 0.f;
+  // sequential sum in candidate order (deterministic, independent of warp shuffles' tree)
+  float s = 0.f;
+  for (int j = 0; j < N; ++j) s += __shfl_sync(0xffffffffu, e, j);
+  const float p = e / s;
+  if (lane < N) a.win_probs[wpos] = p;
+  // first maximal probability (torch.max tie rule, modelPN.py:225-226)
+  float best = p;
+  int best_j = lane < N ? lane : 0x7fffffff;
+  if (lane >= N) best = -1.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+    if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+  }
+  if (a.uniform) {
+    // sample="sample" (modelPN.py:227-228): inverse-CDF draw from the window distribution with a caller-supplied
+    // uniform in [0,1); falls back to the last candidate with non-zero probability on round-off
+    const float u = __ldg(a.uniform + b);
+    float cum = 0.f;
+    int pick = -1, last_pos = 0;
+    for (int j = 0; j < N; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      cum += pj;
+      if (pj > 0.f) last_pos = j;
+      if (pick < 0 && u < cum) pick = j;
+    }
+    best_j = pick < 0 ? last_pos : pick;
+  }
+  if (lane == 0) a.idx_out[b] = k * N + best_j;
+  // the xor butterfly left best_j in every lane
+  return a.forced ? a.forced[b] : k * N + best_j;
+}
+
+}  // namespace gnnpn

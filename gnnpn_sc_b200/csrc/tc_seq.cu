@@ -1,0 +1,533 @@
+// Persistent tcgen05 LSTM scan: one launch = one whole recurrence (encoder: L steps; decoder: K steps with
+// the pointer step fused in between).  Reference semantics: nn.LSTM cell, gate order i,f,g,o
+// (modelPN.py:157-158,191,205) and the decode loop modelPN.py:204-239.
+//
+// A CTA owns 128 composition instances for the whole scan, so the step-to-step dependency is CTA-local:
+//   * A operand  [h | x]  lives in SHARED MEMORY as fp16 hi/lo pairs (error-compensated 3xFP16, fp32 accumulate:
+//     a.w ~= a_lo.w_hi + a_hi.w_hi + a_hi.w_lo) in the 128B-swizzled K-major UMMA layout; the epilogue of step t
+//     writes h'(t) there directly -- h never goes through global memory between steps;
+//   * B operand (the 4H x (H+F) folded weights, fp16 hi/lo, 1.1 MB, L2-resident) is streamed by TMA through a
+//     ring of 16 KB slots, one (N tile, k block, hi|lo) box per slot;
+//   * accumulators: two 128-column TMEM buffers (N tile = 128 gate columns = 32 hidden units), so the
+//     epilogue of tile j overlaps the MMAs of tile j+1;
+//   * h'(t) of tiles 0..6 cannot be written over A while the MMAs of step t still read it: it is staged in the
+//     other 256 TMEM columns (tcgen05.st) and copied to shared memory once the last MMA of the step has retired.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = x producer (encoder inputs),
+// 4..19 = epilogue (TMEM lane quarter = warp & 3, column group = (warp - 4) / 4) and, in the decoder, the
+// pointer step (one warp per instance, 8 instances per warp).
+#include <stdlib.h>
+#include <cuda_fp16.h>
+#include "tc_common.cuh"
+#include "common.cuh"
+#include "lstm_step.cuh"
+#include "tc_lstm.cuh"
+#include "tc_seq.cuh"
+#include "pointer.cuh"
+
+namespace gnnpn {
+namespace tc {
+int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f16);
+}
+namespace seq {
+
+using namespace tc;
+
+constexpr int BM = 128;                    // instances per CTA = UMMA M = TMEM lanes
+constexpr int TILE_N = 128;                // gate columns per accumulator tile
+constexpr int N_TILES = kG / TILE_N;       // 8
+constexpr int KB_H = kH / 64;              // 4 k-blocks of 64 halfs (128-byte swizzle rows)
+constexpr int BLK_BYTES = 128 * 128;       // one [128 rows x 64 halfs] block
+constexpr int RING = 5;
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = 128 + 32 * EPI_WARPS;
+constexpr int TMEM_COLS = 512;             // [0,256): 2 accumulator buffers; [256,512): h' staging
+constexpr int STAGE_COL0 = 256;
+constexpr int XROW_BYTES = 32;             // x block: 16 halfs per row, 32-byte swizzle layout
+
+constexpr uint32_t OFF_A_HI = 0;
+constexpr uint32_t OFF_A_LO = OFF_A_HI + KB_H * BLK_BYTES;
+constexpr uint32_t OFF_AX_HI = OFF_A_LO + KB_H * BLK_BYTES;
+constexpr uint32_t OFF_AX_LO = OFF_AX_HI + BM * XROW_BYTES;
+constexpr uint32_t OFF_RING = OFF_AX_LO + BM * XROW_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_RING + RING * BLK_BYTES;      // two transformed bias sets
+constexpr uint32_t OFF_BAR = OFF_BIAS + 2 * kG * 4;
+constexpr uint32_t SMEM_USED = OFF_BAR + 256;
+constexpr int SMEM_BYTES = SMEM_USED + 1024;                     // + alignment slack
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kClampT = 30.0f;           // exponentials are clamped to 2^30 so products of three stay finite
+
+struct SeqParams {
+  int64_t n;
+  int steps;
+  int L, F;
+  const float* inputs; int64_t x_inst_ld;
+  const float* bias0;      // [kG] gate-interleaved bias of step 0 (decoder: start-token bias)
+  const float* bias;       // [kG] bias of steps >= 1
+  float* c;                // [n, kH]
+  int c_zero_init;
+  const float* h0; int64_t h0_ld;          // initial hidden rows or nullptr (zeros)
+  float* h_out; int64_t h_out_inst_ld;     // step t of instance m at h_out + m*ld + t*kH
+  PointerStepArgs pa;      // decoder only (k, idx_out, forced, uniform are per-step: see *_base below)
+  int32_t* idx_base; const int32_t* forced_base; const float* uniform_base;
+};
+
+// K-major operand block with 32-byte rows (16 halfs), 32B swizzle, 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t smem_desc_k_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                         // SWIZZLE_32B
+  return d;
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x32_x8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :: "memory");
+}
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {       // {lo16 = a, hi16 = b}
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+
+// byte offset of the 16-byte chunk holding halfs [8*c16, 8*c16+8) of row r inside a 128B-swizzled block
+__device__ __forceinline__ uint32_t sw128_off(int r, int c16) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
+}
+
+// LSTM cell for 8 hidden units from their 32 gate accumulators (columns 4u+{i,f,g,o}).
+// bias4[u] = (-log2e*b_i, -log2e*b_f, -2log2e*b_g, -log2e*b_o); acc = 16 * (pre-activation without bias).
+// One reciprocal serves sigm(f), sigm(i) and tanh(g); a second one sigm(o) and tanh(c'):
+//   c' = [c(1+Ei)(1+Eg) + (1-Eg)(1+Ef)] / [(1+Ei)(1+Ef)(1+Eg)],   h' = (1-Ec) / [(1+Eo)(1+Ec)]
+// with Ex = 2^min(t_x, 30) = e^-x (e^-2x for the tanh arguments).  MUFU.EX2 / MUFU.RCP + one Newton step.
+__device__ __forceinline__ void lstm_cell8(const float* v, const float4* bias4, const float* c_old, float* c_new,
+                                           float* h_new) {
+  constexpr float S1 = -kLog2e / kW16Scale, S2 = -2.0f * kLog2e / kW16Scale;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float4 b = bias4[u];
+    const float Ei = ex2_approx(fminf(fmaf(v[4 * u + 0], S1, b.x), kClampT));
+    const float Ef = ex2_approx(fminf(fmaf(v[4 * u + 1], S1, b.y), kClampT));
+    const float Eg = ex2_approx(fminf(fmaf(v[4 * u + 2], S2, b.z), kClampT));
+    const float Eo = ex2_approx(fminf(fmaf(v[4 * u + 3], S1, b.w), kClampT));
+    const float a = 1.0f + Ei, d = 1.0f + Ef, g = 1.0f + Eg;
+    const float ag = a * g;
+    const float r = rcp_refined(ag * d);
+    const float cn = fmaf(1.0f - Eg, d, c_old[u] * ag) * r;
+    const float Ec = ex2_approx(fminf(cn * (-2.0f * kLog2e), kClampT));
+    const float r2 = rcp_refined((1.0f + Eo) * (1.0f + Ec));
+    c_new[u] = cn;
+    h_new[u] = (1.0f - Ec) * r2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool DEC>
+__global__ void __launch_bounds__(THREADS, 1)
+lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_constant__ CUtensorMap map_wh_lo,
+                const __grid_constant__ CUtensorMap map_wx_hi, const __grid_constant__ CUtensorMap map_wx_lo,
+                const SeqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));          // generic pointer to the aligned base
+  const uint32_t bar0 = sbase + OFF_BAR;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (RING + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * RING + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * RING + 2 + b); };
+  const uint32_t a_ready_bar = bar0 + 8u * (2 * RING + 4);
+  const uint32_t mma_done_bar = bar0 + 8u * (2 * RING + 5);
+  const uint32_t tmem_slot = bar0 + 8u * (2 * RING + 6);
+  float* sbias = reinterpret_cast<float*>(sgen + OFF_BIAS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_wh_hi); tma_prefetch_desc(&map_wh_lo);
+    tma_prefetch_desc(&map_wx_hi); tma_prefetch_desc(&map_wx_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < RING; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), EPI_WARPS); }
+    mbar_init(a_ready_bar, EPI_WARPS + (DEC ? 0 : 1));
+    mbar_init(mma_done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+
+  // ---- initial A operand: h(-1) split to fp16 hi/lo (zeros for the encoder), x block of step 0
+  {
+    for (int it = threadIdx.x; it < BM * 32; it += THREADS) {       // (row, 8-unit chunk)
+      const int r = it >> 5, ch = it & 31;
+      uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+      if (p.h0 && m0 + r < p.n) {
+        float hv[8];
+        ldg256(p.h0 + (m0 + r) * p.h0_ld + ch * 8, hv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          hi[j] = pack_h2(hv[2 * j], hv[2 * j + 1]);
+          const float2 bk = unpack_h2(hi[j]);
+          lo[j] = pack_h2(hv[2 * j] - bk.x, hv[2 * j + 1] - bk.y);
+        }
+      }
+      const uint32_t off = (uint32_t)(ch >> 3) * BLK_BYTES + sw128_off(r, ch & 7);
+      st_shared_v4(sbase + OFF_A_HI + off, hi[0], hi[1], hi[2], hi[3]);
+      st_shared_v4(sbase + OFF_A_LO + off, lo[0], lo[1], lo[2], lo[3]);
+    }
+    // transformed biases: (i,f,o) * -log2e, g * -2log2e
+    for (int i = threadIdx.x; i < 2 * kG; i += THREADS) {
+      const int col = i & (kG - 1);
+      const float b = __ldg((i < kG ? p.bias0 : p.bias) + col);
+      sbias[i] = b * ((col & 3) == 2 ? -2.0f * kLog2e : -kLog2e);
+    }
+  }
+
+  // x block writer (warp 3): row r -> 16 halfs = [x hi (8) | same again]; the weight block has zeros in
+  // halfs 8..15, so the duplicate makes the 32B swizzle pattern irrelevant on the A side.
+  auto write_x_rows = [&](const float (*xv)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = lane + 32 * i;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hi[j] = pack_h2(xv[i][2 * j], xv[i][2 * j + 1]);
+        const float2 bk = unpack_h2(hi[j]);
+        lo[j] = pack_h2(xv[i][2 * j] - bk.x, xv[i][2 * j + 1] - bk.y);
+      }
+      const uint32_t o = (uint32_t)r * XROW_BYTES;
+      st_shared_v4(sbase + OFF_AX_HI + o, hi[0], hi[1], hi[2], hi[3]);
+      st_shared_v4(sbase + OFF_AX_HI + o + 16, hi[0], hi[1], hi[2], hi[3]);
+      st_shared_v4(sbase + OFF_AX_LO + o, lo[0], lo[1], lo[2], lo[3]);
+      st_shared_v4(sbase + OFF_AX_LO + o + 16, lo[0], lo[1], lo[2], lo[3]);
+    }
+  };
+  auto load_x_rows = [&](int t, float (*xv)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = m0 + lane + 32 * i;
+#pragma unroll
+      for (int f = 0; f < 8; ++f)
+        xv[i][f] = (m < p.n && f < p.F) ? __ldg(p.inputs + m * p.x_inst_ld + (int64_t)t * p.F + f) : 0.f;
+    }
+  };
+  if (warp == 3) {
+    float xv[4][8];
+    if (DEC) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int f = 0; f < 8; ++f) xv[i][f] = 0.f;
+    } else {
+      load_x_rows(0, xv);
+    }
+    write_x_rows(xv);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================= TMA producer: weights, the same 72 boxes every step =================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = 0; t < p.steps; ++t) {
+        for (int nt = 0; nt < N_TILES; ++nt) {
+          for (int kb = 0; kb < KB_H; ++kb) {
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+              mbar_wait(empty_bar(s), ph ^ 1u);
+              mbar_arrive_expect_tx(full_bar(s), BLK_BYTES);
+              tma_load_2d(sbase + OFF_RING + s * BLK_BYTES, part ? &map_wh_lo : &map_wh_hi, full_bar(s), kb * 64,
+                          nt * TILE_N);
+              if (++s == RING) { s = 0; ph ^= 1u; }
+            }
+          }
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), 2 * TILE_N * XROW_BYTES);
+          tma_load_2d(sbase + OFF_RING + s * BLK_BYTES, &map_wx_hi, full_bar(s), kH, nt * TILE_N);
+          tma_load_2d(sbase + OFF_RING + s * BLK_BYTES + TILE_N * XROW_BYTES, &map_wx_lo, full_bar(s), kH,
+                      nt * TILE_N);
+          if (++s == RING) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_f16(BM, TILE_N);
+      const uint64_t ax_hi = smem_desc_k_sw32(sbase + OFF_AX_HI), ax_lo = smem_desc_k_sw32(sbase + OFF_AX_LO);
+      int s = 0; uint32_t ph = 0;
+      uint32_t uses = 0;                                   // per-buffer use count = uses >> 1 (tiles alternate)
+      for (int t = 0; t < p.steps; ++t) {
+        if (t > 0) {
+          mbar_wait(a_ready_bar, (uint32_t)(t - 1) & 1u);  // h'(t-1) and x(t) are in shared memory
+          tc_fence_after();
+        }
+        for (int nt = 0; nt < N_TILES; ++nt, ++uses) {
+          const int buf = nt & 1;
+          mbar_wait(tempty_bar(buf), ((uses >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(buf * TILE_N);
+          for (int kb = 0; kb < KB_H; ++kb) {
+            const uint64_t a_hi = smem_desc_k_sw128(sbase + OFF_A_HI + kb * BLK_BYTES);
+            const uint64_t a_lo = smem_desc_k_sw128(sbase + OFF_A_LO + kb * BLK_BYTES);
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint64_t b_hi = smem_desc_k_sw128(sbase + OFF_RING + s * BLK_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_f16_ss(d, a_lo + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), idesc, (uint32_t)((kb | ks) != 0));
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma_f16_ss(d, a_hi + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), idesc, 1u);
+            mma_commit(empty_bar(s));
+            if (++s == RING) { s = 0; ph ^= 1u; }
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint64_t b_lo = smem_desc_k_sw128(sbase + OFF_RING + s * BLK_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma_f16_ss(d, a_hi + (uint64_t)(ks * 2), b_lo + (uint64_t)(ks * 2), idesc, 1u);
+            mma_commit(empty_bar(s));
+            if (++s == RING) { s = 0; ph ^= 1u; }
+          }
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint64_t bx_hi = smem_desc_k_sw32(sbase + OFF_RING + s * BLK_BYTES);
+          const uint64_t bx_lo = smem_desc_k_sw32(sbase + OFF_RING + s * BLK_BYTES + TILE_N * XROW_BYTES);
+          mma_f16_ss(d, ax_lo, bx_hi, idesc, 1u);
+          mma_f16_ss(d, ax_hi, bx_hi, idesc, 1u);
+          mma_f16_ss(d, ax_hi, bx_lo, idesc, 1u);
+          mma_commit(empty_bar(s));
+          if (++s == RING) { s = 0; ph ^= 1u; }
+          mma_commit(tfull_bar(buf));
+        }
+        mma_commit(mma_done_bar);
+      }
+    }
+  } else if (warp == 3) {
+    // ================= x producer (encoder): raw input row of step t+1 -> fp16 hi/lo x block =================
+    if (!DEC) {
+      for (int t = 0; t + 1 < p.steps; ++t) {
+        float xv[4][8];
+        load_x_rows(t + 1, xv);
+        mbar_wait(mma_done_bar, (uint32_t)t & 1u);        // the MMAs of step t no longer read the x block
+        write_x_rows(xv);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready_bar);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: thread = one instance (TMEM lane), 32 gate columns = 8 hidden units per tile ====
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int r = q * 32 + lane;                       // row inside the CTA
+    const int64_t m = m0 + r;
+    const bool ok = m < p.n;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* const c_row = p.c + (ok ? m : 0) * kH;
+    float* const h_row = p.h_out + (ok ? m : 0) * p.h_out_inst_ld;
+    uint32_t uses = 0;
+    for (int t = 0; t < p.steps; ++t) {
+      const float4* bias4 = reinterpret_cast<const float4*>(sbias + (t == 0 ? 0 : kG));
+      const bool have_c = ok && !(p.c_zero_init && t == 0);
+      for (int nt = 0; nt < N_TILES; ++nt, ++uses) {
+        const int buf = nt & 1;
+        const int u0 = nt * 32 + grp * 8;              // first hidden unit of this thread's chunk
+        float c_old[8];
+        if (have_c) {
+          ldg256(c_row + u0, c_old);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) c_old[u] = 0.f;
+        }
+        mbar_wait(tfull_bar(buf), (uses >> 1) & 1u);
+        tc_fence_after();
+        float v[32];
+        tmem_ld_32x32_issue(t_lane + (uint32_t)(buf * TILE_N + grp * 32), v);
+        tmem_ld_wait(v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));    // accumulators are in registers: MMA may reuse the buffer
+        float cn[8], hn[8];
+        lstm_cell8(v, bias4 + u0, c_old, cn, hn);
+        if (ok) {
+          stg256(c_row + u0, cn);
+          stg256(h_row + (int64_t)t * kH + u0, hn);
+        }
+        uint32_t pk[8];                                  // {hi01, hi23, hi45, hi67, lo01, lo23, lo45, lo67}
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pk[j] = pack_h2(hn[2 * j], hn[2 * j + 1]);
+          const float2 bk = unpack_h2(pk[j]);
+          pk[4 + j] = pack_h2(hn[2 * j] - bk.x, hn[2 * j + 1] - bk.y);
+        }
+        if (nt < N_TILES - 1) {
+          tmem_st_32x32_x8(t_lane + (uint32_t)(STAGE_COL0 + nt * 32 + grp * 8), pk);
+        } else {
+          // tile 7's accumulators were committed after the last MMA of the step: nothing reads A any more.
+          const uint32_t off7 = (uint32_t)(nt >> 1) * BLK_BYTES + sw128_off(r, (nt & 1) * 4 + grp);
+          st_shared_v4(sbase + OFF_A_HI + off7, pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(sbase + OFF_A_LO + off7, pk[4], pk[5], pk[6], pk[7]);
+          tmem_st_wait();
+#pragma unroll
+          for (int j = 0; j < N_TILES - 1; ++j) {
+            uint32_t sg[8];
+            tmem_ld_32x32_x8(t_lane + (uint32_t)(STAGE_COL0 + j * 32 + grp * 8), sg);
+            tmem_ld_wait8(sg);
+            const uint32_t off = (uint32_t)(j >> 1) * BLK_BYTES + sw128_off(r, (j & 1) * 4 + grp);
+            st_shared_v4(sbase + OFF_A_HI + off, sg[0], sg[1], sg[2], sg[3]);
+            st_shared_v4(sbase + OFF_A_LO + off, sg[4], sg[5], sg[6], sg[7]);
+          }
+        }
+      }
+      if (DEC) {
+        // ---- pointer step k = t: query = h'(t) (just written to dec_h by this CTA), window rows of enc_out
+        __threadfence_block();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        PointerStepArgs pa = p.pa;
+        pa.k = t;
+        pa.idx_out = p.idx_base + (int64_t)t * p.n;
+        pa.forced = p.forced_base ? p.forced_base + (int64_t)t * p.n : nullptr;
+        pa.uniform = p.uniform_base ? p.uniform_base + (int64_t)t * p.n : nullptr;
+        const int e = warp - 4;
+        for (int i = 0; i < BM / EPI_WARPS; ++i) {
+          const int rr = e * (BM / EPI_WARPS) + i;
+          const int64_t b = m0 + rr;
+          if (b >= p.n) break;
+          const float4* qp = reinterpret_cast<const float4*>(p.h_out + b * p.h_out_inst_ld + (int64_t)t * kH);
+          const float4 q0 = qp[lane], q1 = qp[32 + lane];           // coherent loads: written by this CTA
+          const int fed = pointer_step_warp(pa, b, q0, q1, lane);
+          if (t + 1 < p.steps && lane < 8) {
+            const float xv = lane < p.F ? __ldg(p.inputs + (b * p.L + fed) * (int64_t)p.F + lane) : 0.f;
+            const __half hi = __float2half_rn(xv);
+            const __half lo = __float2half_rn(xv - __half2float(hi));
+            __half* ax_hi = reinterpret_cast<__half*>(sgen + OFF_AX_HI + rr * XROW_BYTES);
+            __half* ax_lo = reinterpret_cast<__half*>(sgen + OFF_AX_LO + rr * XROW_BYTES);
+            ax_hi[lane] = hi; ax_hi[8 + lane] = hi;
+            ax_lo[lane] = lo; ax_lo[8 + lane] = lo;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <bool DEC>
+int launch_seq(const float* packed, const SeqParams& p, cudaStream_t st) {
+  CUtensorMap maps[4];
+  const float* w_hi = packed + kOffTc16Hi;
+  const float* w_lo = packed + kOffTc16Lo;
+  int rc;
+  if ((rc = make_map_2d(&maps[0], w_hi, kG, kKp16, kKp16, TILE_N, true))) return rc;
+  if ((rc = make_map_2d(&maps[1], w_lo, kG, kKp16, kKp16, TILE_N, true))) return rc;
+  // x block: 16 halfs (32 bytes) per gate column, 32B swizzle
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      return GNNPN_EUNSUPPORTED;
+    fn = (EncodeTiledFn)ptr;
+  }
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[2] = {(cuuint64_t)kKp16, (cuuint64_t)kG};
+    cuuint64_t strides[1] = {(cuuint64_t)kKp16 * 2};
+    cuuint32_t box[2] = {16, (cuuint32_t)TILE_N};
+    cuuint32_t estr[2] = {1, 1};
+    if (fn(&maps[2 + i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)(i ? w_lo : w_hi), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return GNNPN_ESHAPE;
+  }
+  auto kern = lstm_seq_kernel<DEC>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const unsigned grid = (unsigned)ceil_div(p.n, BM);
+  kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  return after_launch();
+}
+
+}  // namespace seq
+
+int tc_seq_encode(const SeqEncodeArgs& a, cudaStream_t st) {
+  if (a.F < 1 || a.F > 8 || a.L < 1) return GNNPN_EUNSUPPORTED;
+  seq::SeqParams p{};
+  p.n = a.n; p.steps = a.L; p.L = a.L; p.F = a.F;
+  p.inputs = a.inputs; p.x_inst_ld = (int64_t)a.L * a.F;
+  p.bias0 = p.bias = a.packed + kOffBias;
+  p.c = a.c_state; p.c_zero_init = 1;
+  p.h0 = nullptr; p.h0_ld = 0;
+  p.h_out = a.enc_out; p.h_out_inst_ld = (int64_t)a.L * kH;
+  return seq::launch_seq<false>(a.packed, p, st);
+}
+
+int tc_seq_decode(const SeqDecodeArgs& a, cudaStream_t st) {
+  if (a.F < 1 || a.F > 8 || a.K < 1 || a.N < 1 || a.N > kMaxWindow) return GNNPN_EUNSUPPORTED;
+  seq::SeqParams p{};
+  p.n = a.n; p.steps = a.K; p.L = a.L; p.F = a.F;
+  p.inputs = a.inputs; p.x_inst_ld = (int64_t)a.L * a.F;
+  p.bias0 = a.packed + kOffStart; p.bias = a.packed + kOffBias;
+  p.c = a.c_state; p.c_zero_init = 0;
+  p.h0 = a.enc_out + (int64_t)(a.L - 1) * kH; p.h0_ld = (int64_t)a.L * kH;
+  p.h_out = a.dec_h; p.h_out_inst_ld = (int64_t)a.K * kH;
+  p.pa.enc_out = a.enc_out; p.pa.enc_inst_ld = (int64_t)a.L * kH; p.pa.latent_win = a.latent_win;
+  p.pa.alpha = a.alpha; p.pa.use_tanh = a.use_tanh; p.pa.C = a.C; p.pa.n = a.n; p.pa.L = a.L; p.pa.k = 0;
+  p.pa.N = a.N; p.pa.idx_out = nullptr; p.pa.win_logits = a.win_logits; p.pa.win_probs = a.win_probs;
+  p.pa.forced = nullptr; p.pa.uniform = nullptr;
+  p.idx_base = a.idx_out; p.forced_base = a.forced_idx; p.uniform_base = a.sample_uniform;
+  return seq::launch_seq<true>(a.packed, p, st);
+}
+
+}  // namespace gnnpn

@@ -1,0 +1,45 @@
+// Host-side interface of the persistent tcgen05 LSTM sequence kernels (implemented in tc_seq.cu).
+//
+// One launch runs a whole LSTM scan (encoder: L steps; decoder: K steps with the pointer step fused
+// between them).  A CTA owns 128 composition instances for the whole scan; the recurrence is CTA-local
+// (h never leaves the SM between steps), so there is no grid-wide synchronisation.
+#pragma once
+#include <cuda.h>
+#include "lstm_step.cuh"
+#include "tc_lstm.cuh"
+
+namespace gnnpn {
+
+struct SeqEncodeArgs {
+  const float* inputs;     // [n, L, F]
+  int64_t n;
+  int L;
+  int F;                   // <= 8
+  const float* packed;     // packed LSTM block (uses the bias and the fp16 hi/lo operand blocks)
+  float* enc_out;          // [n, L, kH]
+  float* c_state;          // [n, kH] out
+};
+// returns GNNPN_EUNSUPPORTED when the shape is outside what the persistent kernel covers
+int tc_seq_encode(const SeqEncodeArgs& a, cudaStream_t st);
+
+struct SeqDecodeArgs {
+  const float* inputs;     // [n, L, F]
+  const float* enc_out;    // [n, L, kH]
+  float* c_state;          // [n, kH] in/out
+  const float* latent_win; // [n, L] or nullptr
+  float alpha;
+  const float* packed;     // decoder block
+  int use_tanh;
+  float C;
+  int64_t n;
+  int L, F, K, N;
+  float* dec_h;            // [n, K, kH]
+  int32_t* idx_out;        // [K, n]
+  float* win_logits;       // [n, L]
+  float* win_probs;        // [n, L]
+  const int32_t* forced_idx;     // [K, n] or nullptr
+  const float* sample_uniform;   // [K, n] or nullptr
+};
+int tc_seq_decode(const SeqDecodeArgs& a, cudaStream_t st);
+
+}  // namespace gnnpn
