@@ -271,7 +271,9 @@ int gnnpn_lstm_encode_f32(const float* inputs, int64_t n, int L, int in_features
     // ---- persistent tcgen05 scan: one launch for all L steps, h resident in shared memory
     GNNPN_REQUIRE((reinterpret_cast<uintptr_t>(enc_out) & 31u) == 0 && (reinterpret_cast<uintptr_t>(c_state) & 31u) == 0,
                   GNNPN_EALIGN);
-    SeqEncodeArgs sa{inputs, n, L, in_features, packed, enc_out, c_state};
+    GNNPN_REQUIRE(workspace_bytes >= tc_lstm_workspace_bytes(n), GNNPN_EWORKSPACE);
+    float* scr = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+    SeqEncodeArgs sa{inputs, n, L, in_features, packed, enc_out, c_state, scr};
     return tc_seq_encode(sa, st);
   }
   if (workspace) {
@@ -332,7 +334,9 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
     GNNPN_REQUIRE((reinterpret_cast<uintptr_t>(enc_out) & 31u) == 0 && (reinterpret_cast<uintptr_t>(c_state) & 31u) == 0 &&
                       (reinterpret_cast<uintptr_t>(dec_h) & 31u) == 0, GNNPN_EALIGN);
     SeqDecodeArgs sa{inputs, enc_out, c_state, latent_win, alpha, packed, use_tanh, C, n, L, in_features, K, N,
-                     dec_h, idx_out, win_logits, win_probs, forced_idx, sample_uniform};
+                     dec_h, idx_out, win_logits, win_probs, forced_idx, sample_uniform,
+                     reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023))};
+    GNNPN_REQUIRE(workspace_bytes >= tc_lstm_workspace_bytes(n), GNNPN_EWORKSPACE);
     return tc_seq_decode(sa, st);
   }
   TcLstmPlan plan;

@@ -479,7 +479,12 @@ int tc_lstm_default_f16() {
 }
 
 // sized for the larger (tf32) layout so one query serves both operand kinds
-size_t tc_lstm_workspace_bytes(int64_t n) { return (size_t)4 * n * kKp * sizeof(float) + 1024; }
+// (also covers the persistent kernels' blocked cell-state scratch, tc_seq_scratch_floats(n))
+size_t tc_lstm_workspace_bytes(int64_t n) {
+  const size_t step = (size_t)4 * n * kKp * sizeof(float) + 1024;
+  const size_t seq = (size_t)((n + 127) / 128) * 128 * kH * sizeof(float) + 1024;
+  return step > seq ? step : seq;
+}
 
 int tc_lstm_plan(TcLstmPlan* plan, void* workspace, size_t workspace_bytes, int64_t n, const float* packed) {
   if (workspace_bytes < tc_lstm_workspace_bytes(n)) return GNNPN_EWORKSPACE;

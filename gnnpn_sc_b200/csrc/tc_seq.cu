@@ -15,6 +15,7 @@
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = x producer (encoder inputs),
 // 4..19 = epilogue (TMEM lane quarter = warp & 3, column group = (warp - 4) / 4) and, in the decoder, the
 // pointer step (one warp per instance, 8 instances per warp).
+#include <stdio.h>
 #include <stdlib.h>
 #include <cuda_fp16.h>
 #include "tc_common.cuh"
@@ -37,7 +38,7 @@ constexpr int TILE_N = 128;                // gate columns per accumulator tile
 constexpr int N_TILES = kG / TILE_N;       // 8
 constexpr int KB_H = kH / 64;              // 4 k-blocks of 64 halfs (128-byte swizzle rows)
 constexpr int BLK_BYTES = 128 * 128;       // one [128 rows x 64 halfs] block
-constexpr int RING = 5;
+constexpr int RING = 4;
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;             // [0,256): 2 accumulator buffers; [256,512): h' staging
@@ -49,7 +50,8 @@ constexpr uint32_t OFF_A_LO = OFF_A_HI + KB_H * BLK_BYTES;
 constexpr uint32_t OFF_AX_HI = OFF_A_LO + KB_H * BLK_BYTES;
 constexpr uint32_t OFF_AX_LO = OFF_AX_HI + BM * XROW_BYTES;
 constexpr uint32_t OFF_RING = OFF_AX_LO + BM * XROW_BYTES;
-constexpr uint32_t OFF_BIAS = OFF_RING + RING * BLK_BYTES;      // two transformed bias sets
+constexpr uint32_t OFF_HBUF = OFF_RING + RING * BLK_BYTES;      // [128 rows x 32 fp32] h' tile for the TMA store
+constexpr uint32_t OFF_BIAS = OFF_HBUF + BLK_BYTES;              // two transformed bias sets
 constexpr uint32_t OFF_BAR = OFF_BIAS + 2 * kG * 4;
 constexpr uint32_t SMEM_USED = OFF_BAR + 256;
 constexpr int SMEM_BYTES = SMEM_USED + 1024;                     // + alignment slack
@@ -71,6 +73,9 @@ struct SeqParams {
   float* h_out; int64_t h_out_inst_ld;     // step t of instance m at h_out + m*ld + t*kH
   PointerStepArgs pa;      // decoder only (k, idx_out, forced, uniform are per-step: see *_base below)
   int32_t* idx_base; const int32_t* forced_base; const float* uniform_base;
+  int rotate;
+  unsigned long long* prof; // debug (GNNPN_SEQ_PROF): per-CTA wait-cycle counters, 16 per CTA, or nullptr
+  float* c_scr;            // blocked cell-state scratch, 128*kH floats per CTA (coalesced 128-bit accesses)
 };
 
 // K-major operand block with 32-byte rows (16 halfs), 32B swizzle, 8-row groups 256 B apart
@@ -84,6 +89,12 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw32(uint32_t smem_addr) {
   return d;
 }
 
+// 1 in exactly one lane of a fully active warp
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -113,6 +124,21 @@ __device__ __forceinline__ void ldg256(const float* p, float* v) {
 __device__ __forceinline__ void stg256(float* p, const float* v) {
   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float4 ldg128(const float* p) {
+  float4 r;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg128(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {       // {lo16 = a, hi16 = b}
   const __half2 h = __floats2half2_rn(a, b);
@@ -153,12 +179,23 @@ __device__ __forceinline__ void lstm_cell8(const float* v, const float4* bias4, 
   }
 }
 
+// mbar_wait that adds the cycles spent waiting to *acc (debug counters; acc lives in a register)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool prof, long long& acc) {
+  if (prof) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 template <bool DEC>
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_constant__ CUtensorMap map_wh_lo,
                 const __grid_constant__ CUtensorMap map_wx_hi, const __grid_constant__ CUtensorMap map_wx_lo,
-                const SeqParams p) {
+                const __grid_constant__ CUtensorMap map_h, const SeqParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));          // generic pointer to the aligned base
@@ -169,21 +206,29 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * RING + 2 + b); };
   const uint32_t a_ready_bar = bar0 + 8u * (2 * RING + 4);
   const uint32_t mma_done_bar = bar0 + 8u * (2 * RING + 5);
-  const uint32_t tmem_slot = bar0 + 8u * (2 * RING + 6);
+  const uint32_t hfull_bar = bar0 + 8u * (2 * RING + 6);
+  const uint32_t hempty_bar = bar0 + 8u * (2 * RING + 7);
+  const uint32_t tmem_slot = bar0 + 8u * (2 * RING + 8);
   float* sbias = reinterpret_cast<float*>(sgen + OFF_BIAS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
+  // every CTA walks the 8 N tiles in a rotated order so the CTAs do not all pull the same weight lines from
+  // the same L2 slices at the same time
+  const int rot = p.rotate ? (int)(blockIdx.x & (N_TILES - 1)) : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_wh_hi); tma_prefetch_desc(&map_wh_lo);
     tma_prefetch_desc(&map_wx_hi); tma_prefetch_desc(&map_wx_lo);
+    if (!DEC) tma_prefetch_desc(&map_h);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < RING; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), EPI_WARPS); }
     mbar_init(a_ready_bar, EPI_WARPS + (DEC ? 0 : 1));
     mbar_init(mma_done_bar, 1);
+    mbar_init(hfull_bar, EPI_WARPS);
+    mbar_init(hempty_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -268,7 +313,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int t = 0; t < p.steps; ++t) {
-        for (int nt = 0; nt < N_TILES; ++nt) {
+        for (int it = 0; it < N_TILES; ++it) {
+          const int nt = (it + rot) & (N_TILES - 1);
           for (int kb = 0; kb < KB_H; ++kb) {
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
@@ -289,56 +335,92 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
+    // ================= MMA issuer: the whole warp walks the pipeline (uniform control flow keeps the descriptors
+    // in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit =================
+    {
+      const uint32_t leader = elect_one();
       const uint32_t idesc = idesc_f16(BM, TILE_N);
       const uint64_t ax_hi = smem_desc_k_sw32(sbase + OFF_AX_HI), ax_lo = smem_desc_k_sw32(sbase + OFF_AX_LO);
       int s = 0; uint32_t ph = 0;
       uint32_t uses = 0;                                   // per-buffer use count = uses >> 1 (tiles alternate)
+      const bool prof = p.prof != nullptr;
+      long long w_aready = 0, w_tempty = 0, w_full = 0;
+      const long long t_begin = clock64();
       for (int t = 0; t < p.steps; ++t) {
         if (t > 0) {
-          mbar_wait(a_ready_bar, (uint32_t)(t - 1) & 1u);  // h'(t-1) and x(t) are in shared memory
+          mbar_wait_t(a_ready_bar, (uint32_t)(t - 1) & 1u, prof, w_aready);  // h'(t-1) and x(t) are in shared memory
           tc_fence_after();
         }
         for (int nt = 0; nt < N_TILES; ++nt, ++uses) {
           const int buf = nt & 1;
-          mbar_wait(tempty_bar(buf), ((uses >> 1) & 1u) ^ 1u);
+          mbar_wait_t(tempty_bar(buf), ((uses >> 1) & 1u) ^ 1u, prof, w_tempty);
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(buf * TILE_N);
           for (int kb = 0; kb < KB_H; ++kb) {
             const uint64_t a_hi = smem_desc_k_sw128(sbase + OFF_A_HI + kb * BLK_BYTES);
             const uint64_t a_lo = smem_desc_k_sw128(sbase + OFF_A_LO + kb * BLK_BYTES);
-            mbar_wait(full_bar(s), ph);
+            mbar_wait_t(full_bar(s), ph, prof, w_full);
             tc_fence_after();
             const uint64_t b_hi = smem_desc_k_sw128(sbase + OFF_RING + s * BLK_BYTES);
+            if (leader) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              mma_f16_ss(d, a_lo + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), idesc, (uint32_t)((kb | ks) != 0));
+              for (int ks = 0; ks < 4; ++ks)
+                mma_f16_ss(d, a_lo + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), idesc, (uint32_t)((kb | ks) != 0));
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma_f16_ss(d, a_hi + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), idesc, 1u);
-            mma_commit(empty_bar(s));
+              for (int ks = 0; ks < 4; ++ks)
+                mma_f16_ss(d, a_hi + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), idesc, 1u);
+              mma_commit(empty_bar(s));
+            }
+            __syncwarp();
             if (++s == RING) { s = 0; ph ^= 1u; }
-            mbar_wait(full_bar(s), ph);
+            mbar_wait_t(full_bar(s), ph, prof, w_full);
             tc_fence_after();
             const uint64_t b_lo = smem_desc_k_sw128(sbase + OFF_RING + s * BLK_BYTES);
+            if (leader) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma_f16_ss(d, a_hi + (uint64_t)(ks * 2), b_lo + (uint64_t)(ks * 2), idesc, 1u);
-            mma_commit(empty_bar(s));
+              for (int ks = 0; ks < 4; ++ks)
+                mma_f16_ss(d, a_hi + (uint64_t)(ks * 2), b_lo + (uint64_t)(ks * 2), idesc, 1u);
+              mma_commit(empty_bar(s));
+            }
+            __syncwarp();
             if (++s == RING) { s = 0; ph ^= 1u; }
           }
-          mbar_wait(full_bar(s), ph);
+          mbar_wait_t(full_bar(s), ph, prof, w_full);
           tc_fence_after();
           const uint64_t bx_hi = smem_desc_k_sw32(sbase + OFF_RING + s * BLK_BYTES);
           const uint64_t bx_lo = smem_desc_k_sw32(sbase + OFF_RING + s * BLK_BYTES + TILE_N * XROW_BYTES);
-          mma_f16_ss(d, ax_lo, bx_hi, idesc, 1u);
-          mma_f16_ss(d, ax_hi, bx_hi, idesc, 1u);
-          mma_f16_ss(d, ax_hi, bx_lo, idesc, 1u);
-          mma_commit(empty_bar(s));
+          if (leader) {
+            mma_f16_ss(d, ax_lo, bx_hi, idesc, 1u);
+            mma_f16_ss(d, ax_hi, bx_hi, idesc, 1u);
+            mma_f16_ss(d, ax_hi, bx_lo, idesc, 1u);
+            mma_commit(empty_bar(s));
+            mma_commit(tfull_bar(buf));
+            if (nt == N_TILES - 1) mma_commit(mma_done_bar);
+          }
+          __syncwarp();
           if (++s == RING) { s = 0; ph ^= 1u; }
-          mma_commit(tfull_bar(buf));
         }
-        mma_commit(mma_done_bar);
       }
+      if (prof && leader) {
+        unsigned long long* o = p.prof + (size_t)blockIdx.x * 16;
+        o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_aready; o[2] = w_tempty; o[3] = w_full;
+      }
+    }
+  } else if (warp == 2) {
+    // ================= h' store issuer (encoder): one TMA store per tile, [128 instances x 32 units] -> enc_out ====
+    if (!DEC && lane == 0) {
+      uint32_t g = 0;
+      for (int t = 0; t < p.steps; ++t) {
+        for (int it = 0; it < N_TILES; ++it, ++g) {
+          const int nt = (it + rot) & (N_TILES - 1);
+          mbar_wait(hfull_bar, g & 1u);
+          tma_store_3d(&map_h, sbase + OFF_HBUF, nt * 32, t, (int)m0);
+          bulk_commit();
+          bulk_wait_read0();                             // the tile has been read out of shared memory
+          mbar_arrive(hempty_bar);
+        }
+      }
+      bulk_wait0();
     }
   } else if (warp == 3) {
     // ================= x producer (encoder): raw input row of step t+1 -> fp16 hi/lo x block =================
@@ -363,21 +445,32 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     float* const c_row = p.c + (ok ? m : 0) * kH;
     float* const h_row = p.h_out + (ok ? m : 0) * p.h_out_inst_ld;
+    // blocked scratch: float4 index (((cta*8 + nt)*4 + grp)*2 + half)*128 + row  -> a warp touches 512 contiguous bytes
+    float* const c_blk = p.c_scr + ((int64_t)blockIdx.x * (BM * kH) + (int64_t)grp * (2 * BM * 4) + r * 4);
     uint32_t uses = 0;
+    const bool prof = p.prof != nullptr;
+    long long w_tfull = 0, w_hempty = 0, w_ptr = 0;
+    const long long t_begin = clock64();
     for (int t = 0; t < p.steps; ++t) {
       const float4* bias4 = reinterpret_cast<const float4*>(sbias + (t == 0 ? 0 : kG));
-      const bool have_c = ok && !(p.c_zero_init && t == 0);
-      for (int nt = 0; nt < N_TILES; ++nt, ++uses) {
-        const int buf = nt & 1;
+      const bool last = t == p.steps - 1;
+      for (int it = 0; it < N_TILES; ++it, ++uses) {
+        const int buf = it & 1;
+        const int nt = (it + rot) & (N_TILES - 1);      // which 128 gate columns this tile holds
         const int u0 = nt * 32 + grp * 8;              // first hidden unit of this thread's chunk
+        float* const c_t = c_blk + nt * (4 * 2 * BM * 4);
         float c_old[8];
-        if (have_c) {
+        if (t > 0) {
+          const float4 a = ldg128(c_t), b = ldg128(c_t + BM * 4);
+          c_old[0] = a.x; c_old[1] = a.y; c_old[2] = a.z; c_old[3] = a.w;
+          c_old[4] = b.x; c_old[5] = b.y; c_old[6] = b.z; c_old[7] = b.w;
+        } else if (ok && !p.c_zero_init) {
           ldg256(c_row + u0, c_old);
         } else {
 #pragma unroll
           for (int u = 0; u < 8; ++u) c_old[u] = 0.f;
         }
-        mbar_wait(tfull_bar(buf), (uses >> 1) & 1u);
+        mbar_wait_t(tfull_bar(buf), (uses >> 1) & 1u, prof, w_tfull);
         tc_fence_after();
         float v[32];
         tmem_ld_32x32_issue(t_lane + (uint32_t)(buf * TILE_N + grp * 32), v);
@@ -387,9 +480,25 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         if (lane == 0) mbar_arrive(tempty_bar(buf));    // accumulators are in registers: MMA may reuse the buffer
         float cn[8], hn[8];
         lstm_cell8(v, bias4 + u0, c_old, cn, hn);
-        if (ok) {
+        if (!last) {
+          stg128(c_t, cn[0], cn[1], cn[2], cn[3]);
+          stg128(c_t + BM * 4, cn[4], cn[5], cn[6], cn[7]);
+        } else if (ok) {
           stg256(c_row + u0, cn);
-          stg256(h_row + (int64_t)t * kH + u0, hn);
+        }
+        if (DEC) {
+          if (ok) stg256(h_row + (int64_t)t * kH + u0, hn);
+        } else {
+          // fp32 h' -> 128B-swizzled [128 x 32] tile; the store issuer (warp 2) sends it to enc_out by TMA
+          mbar_wait_t(hempty_bar, (uses & 1u) ^ 1u, prof, w_hempty);   // the previous tile's store has left shared memory
+          const uint32_t hb = sbase + OFF_HBUF + (uint32_t)r * 128;
+          st_shared_v4(hb + (uint32_t)(((2 * grp) ^ (r & 7)) << 4), __float_as_uint(hn[0]), __float_as_uint(hn[1]),
+                       __float_as_uint(hn[2]), __float_as_uint(hn[3]));
+          st_shared_v4(hb + (uint32_t)(((2 * grp + 1) ^ (r & 7)) << 4), __float_as_uint(hn[4]), __float_as_uint(hn[5]),
+                       __float_as_uint(hn[6]), __float_as_uint(hn[7]));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(hfull_bar);
         }
         uint32_t pk[8];                                  // {hi01, hi23, hi45, hi67, lo01, lo23, lo45, lo67}
 #pragma unroll
@@ -398,7 +507,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
           const float2 bk = unpack_h2(pk[j]);
           pk[4 + j] = pack_h2(hn[2 * j] - bk.x, hn[2 * j + 1] - bk.y);
         }
-        if (nt < N_TILES - 1) {
+        if (it < N_TILES - 1) {
           tmem_st_32x32_x8(t_lane + (uint32_t)(STAGE_COL0 + nt * 32 + grp * 8), pk);
         } else {
           // tile 7's accumulators were committed after the last MMA of the step: nothing reads A any more.
@@ -407,7 +516,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
           st_shared_v4(sbase + OFF_A_LO + off7, pk[4], pk[5], pk[6], pk[7]);
           tmem_st_wait();
 #pragma unroll
-          for (int j = 0; j < N_TILES - 1; ++j) {
+          for (int jj = 1; jj < N_TILES; ++jj) {
+            const int j = (nt + jj) & (N_TILES - 1);        // the seven tiles staged earlier in this step
             uint32_t sg[8];
             tmem_ld_32x32_x8(t_lane + (uint32_t)(STAGE_COL0 + j * 32 + grp * 8), sg);
             tmem_ld_wait8(sg);
@@ -419,6 +529,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
       }
       if (DEC) {
         // ---- pointer step k = t: query = h'(t) (just written to dec_h by this CTA), window rows of enc_out
+        const long long tp0 = prof ? clock64() : 0;
         __threadfence_block();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
         PointerStepArgs pa = p.pa;
@@ -444,11 +555,16 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
             ax_lo[lane] = lo; ax_lo[8 + lane] = lo;
           }
         }
+        if (prof) w_ptr += clock64() - tp0;
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready_bar);
+    }
+    if (prof && warp == 4 && lane == 0) {
+      unsigned long long* o = p.prof + (size_t)blockIdx.x * 16;
+      o[4] = (unsigned long long)(clock64() - t_begin); o[5] = w_tfull; o[6] = w_hempty; o[7] = w_ptr;
     }
   }
   tc_fence_before();
@@ -487,6 +603,22 @@ int launch_seq(const float* packed, const SeqParams& p, cudaStream_t st) {
            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return GNNPN_ESHAPE;
   }
+  CUtensorMap map_h;
+  {
+    // h_out as a 3-D tensor {unit, step, instance}; box = 32 units x 1 step x 128 instances, 128B swizzle
+    const int64_t T = p.h_out_inst_ld / kH;
+    cuuint64_t dims[3] = {(cuuint64_t)kH, (cuuint64_t)T, (cuuint64_t)p.n};
+    cuuint64_t strides[2] = {(cuuint64_t)kH * 4, (cuuint64_t)p.h_out_inst_ld * 4};
+    cuuint32_t box[3] = {32, 1, (cuuint32_t)BM};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (fn(&map_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.h_out, dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return GNNPN_ESHAPE;
+  }
+  SeqParams pp = p;
+  static const int rotate = getenv("GNNPN_SEQ_ROT") ? atoi(getenv("GNNPN_SEQ_ROT")) : 0;
+  pp.rotate = rotate;
   auto kern = lstm_seq_kernel<DEC>;
   static bool configured = false;
   if (!configured) {
@@ -495,8 +627,29 @@ int launch_seq(const float* packed, const SeqParams& p, cudaStream_t st) {
     configured = true;
   }
   const unsigned grid = (unsigned)ceil_div(p.n, BM);
-  kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], p);
-  return after_launch();
+  static const int do_prof = getenv("GNNPN_SEQ_PROF") ? atoi(getenv("GNNPN_SEQ_PROF")) : 0;
+  unsigned long long* prof = nullptr;
+  if (do_prof) {                                       // debug only: synchronous, allocates
+    if (cudaMalloc(&prof, (size_t)grid * 16 * 8) != cudaSuccess) return GNNPN_EUNSUPPORTED;
+    cudaMemsetAsync(prof, 0, (size_t)grid * 16 * 8, st);
+  }
+  pp.prof = prof;
+  kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], map_h, pp);
+  const int rc_launch = after_launch();
+  if (do_prof) {
+    unsigned long long* hbuf = (unsigned long long*)malloc((size_t)grid * 16 * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf, prof, (size_t)grid * 16 * 8, cudaMemcpyDeviceToHost);
+    double acc[8] = {0};
+    for (unsigned c = 0; c < grid; ++c) for (int i = 0; i < 8; ++i) acc[i] += (double)hbuf[c * 16 + i];
+    fprintf(stderr, "[seq prof %s steps=%d grid=%u] per-step cycles: mma total %.0f (wait a_ready %.0f, tmem_empty %.0f, "
+            "B full %.0f) | epi total %.0f (wait tmem_full %.0f, h buf %.0f, pointer %.0f)\n", DEC ? "dec" : "enc", p.steps,
+            grid, acc[0] / grid / p.steps, acc[1] / grid / p.steps, acc[2] / grid / p.steps, acc[3] / grid / p.steps,
+            acc[4] / grid / p.steps, acc[5] / grid / p.steps, acc[6] / grid / p.steps, acc[7] / grid / p.steps);
+    free(hbuf);
+    cudaFree(prof);
+  }
+  return rc_launch;
 }
 
 }  // namespace seq
@@ -510,6 +663,7 @@ int tc_seq_encode(const SeqEncodeArgs& a, cudaStream_t st) {
   p.c = a.c_state; p.c_zero_init = 1;
   p.h0 = nullptr; p.h0_ld = 0;
   p.h_out = a.enc_out; p.h_out_inst_ld = (int64_t)a.L * kH;
+  p.c_scr = a.c_scratch;
   return seq::launch_seq<false>(a.packed, p, st);
 }
 
@@ -527,6 +681,7 @@ int tc_seq_decode(const SeqDecodeArgs& a, cudaStream_t st) {
   p.pa.N = a.N; p.pa.idx_out = nullptr; p.pa.win_logits = a.win_logits; p.pa.win_probs = a.win_probs;
   p.pa.forced = nullptr; p.pa.uniform = nullptr;
   p.idx_base = a.idx_out; p.forced_base = a.forced_idx; p.uniform_base = a.sample_uniform;
+  p.c_scr = a.c_scratch;
   return seq::launch_seq<true>(a.packed, p, st);
 }
 

@@ -10,6 +10,9 @@
 
 namespace gnnpn {
 
+// cell-state scratch of the persistent kernels: 128 x kH floats per CTA (blocked layout)
+inline size_t tc_seq_scratch_floats(int64_t n) { return (size_t)((n + 127) / 128) * 128 * kH; }
+
 struct SeqEncodeArgs {
   const float* inputs;     // [n, L, F]
   int64_t n;
@@ -18,6 +21,7 @@ struct SeqEncodeArgs {
   const float* packed;     // packed LSTM block (uses the bias and the fp16 hi/lo operand blocks)
   float* enc_out;          // [n, L, kH]
   float* c_state;          // [n, kH] out
+  float* c_scratch;        // tc_seq_scratch_floats(n) floats
 };
 // returns GNNPN_EUNSUPPORTED when the shape is outside what the persistent kernel covers
 int tc_seq_encode(const SeqEncodeArgs& a, cudaStream_t st);
@@ -39,6 +43,7 @@ struct SeqDecodeArgs {
   float* win_probs;        // [n, L]
   const int32_t* forced_idx;     // [K, n] or nullptr
   const float* sample_uniform;   // [K, n] or nullptr
+  float* c_scratch;              // tc_seq_scratch_floats(n) floats
 };
 int tc_seq_decode(const SeqDecodeArgs& a, cudaStream_t st);
 
