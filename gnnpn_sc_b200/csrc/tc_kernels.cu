@@ -482,7 +482,7 @@ int tc_lstm_default_f16() {
 // (also covers the persistent kernels' blocked cell-state scratch, tc_seq_scratch_floats(n))
 size_t tc_lstm_workspace_bytes(int64_t n) {
   const size_t step = (size_t)4 * n * kKp * sizeof(float) + 1024;
-  const size_t seq = (size_t)((n + 127) / 128) * 128 * kH * sizeof(float) + 1024;
+  const size_t seq = (size_t)((n + 255) / 256) * 256 * kH * sizeof(float) + 1024;
   return step > seq ? step : seq;
 }
 

@@ -38,7 +38,8 @@ constexpr int TILE_N = 128;                // gate columns per accumulator tile
 constexpr int N_TILES = kG / TILE_N;       // 8
 constexpr int KB_H = kH / 64;              // 4 k-blocks of 64 halfs (128-byte swizzle rows)
 constexpr int BLK_BYTES = 128 * 128;       // one [128 rows x 64 halfs] block
-constexpr int RING = 4;
+constexpr int RING_BYTES = 4 * BLK_BYTES;  // weight ring: 4 slots of 16 KB (1 CTA) / 8 slots of 8 KB (CTA pair)
+constexpr int MAX_RING = 8;
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;             // [0,256): 2 accumulator buffers; [256,512): h' staging
@@ -50,7 +51,7 @@ constexpr uint32_t OFF_A_LO = OFF_A_HI + KB_H * BLK_BYTES;
 constexpr uint32_t OFF_AX_HI = OFF_A_LO + KB_H * BLK_BYTES;
 constexpr uint32_t OFF_AX_LO = OFF_AX_HI + BM * XROW_BYTES;
 constexpr uint32_t OFF_RING = OFF_AX_LO + BM * XROW_BYTES;
-constexpr uint32_t OFF_HBUF = OFF_RING + RING * BLK_BYTES;      // [128 rows x 32 fp32] h' tile for the TMA store
+constexpr uint32_t OFF_HBUF = OFF_RING + RING_BYTES;      // [128 rows x 32 fp32] h' tile for the TMA store
 constexpr uint32_t OFF_BIAS = OFF_HBUF + BLK_BYTES;              // two transformed bias sets
 constexpr uint32_t OFF_BAR = OFF_BIAS + 2 * kG * 4;
 constexpr uint32_t SMEM_USED = OFF_BAR + 256;
@@ -87,6 +88,65 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw32(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)6 << 61;                         // SWIZZLE_32B
   return d;
+}
+
+// ---- thread-block-cluster helpers (CTA pair, cta_group::2)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITC_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAITC_DONE;\n\t"
+      "bra WAITC_LOOP;\n\t"
+      "WAITC_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA load whose completion is signalled on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once all previously issued MMAs retire) on the barrier at this CTA-relative offset in BOTH CTAs of the pair
+__device__ __forceinline__ void mma_commit_cg2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
 // 1 in exactly one lane of a fully active warp
@@ -180,18 +240,20 @@ __device__ __forceinline__ void lstm_cell8(const float* v, const float4* bias4, 
 }
 
 // mbar_wait that adds the cycles spent waiting to *acc (debug counters; acc lives in a register)
+template <bool CLUSTER = false>
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool prof, long long& acc) {
-  if (prof) {
-    const long long t0 = clock64();
-    mbar_wait(bar, parity);
-    acc += clock64() - t0;
-  } else {
-    mbar_wait(bar, parity);
-  }
+  const long long t0 = prof ? clock64() : 0;
+  if (CLUSTER) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+  if (prof) acc += clock64() - t0;
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool DEC>
+// CG = 1: one CTA per 128 instances, cta_group::1 MMAs (M=128, N=128).
+// CG = 2: CTA pair (cluster of 2 = one TPC), cta_group::2 MMAs (M=256: 128 instances per CTA, N=128): each CTA
+//         streams only HALF of every weight tile (64 of the 128 gate columns) and the tensor cores read the
+//         other half from the peer -- half the L2->SM weight traffic, half the B-operand shared-memory reads,
+//         twice the ring depth.  CTA rank 0 issues the MMAs for the pair; both CTAs run producer / epilogue.
+template <bool DEC, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_constant__ CUtensorMap map_wh_lo,
                 const __grid_constant__ CUtensorMap map_wx_hi, const __grid_constant__ CUtensorMap map_wx_lo,
@@ -199,16 +261,25 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));          // generic pointer to the aligned base
+  constexpr int RING = 4 * CG;                          // slots
+  constexpr int SLOT_BYTES = BLK_BYTES / CG;            // [128/CG gate columns x 64 halfs]
+  constexpr int SLOT_ROWS = TILE_N / CG;
   const uint32_t bar0 = sbase + OFF_BAR;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (RING + s); };
-  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * RING + b); };
-  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * RING + 2 + b); };
-  const uint32_t a_ready_bar = bar0 + 8u * (2 * RING + 4);
-  const uint32_t mma_done_bar = bar0 + 8u * (2 * RING + 5);
-  const uint32_t hfull_bar = bar0 + 8u * (2 * RING + 6);
-  const uint32_t hempty_bar = bar0 + 8u * (2 * RING + 7);
-  const uint32_t tmem_slot = bar0 + 8u * (2 * RING + 8);
+  auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_RING + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * MAX_RING + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * MAX_RING + 2 + b); };
+  const uint32_t a_ready_bar = bar0 + 8u * (2 * MAX_RING + 4);
+  const uint32_t mma_done_bar = bar0 + 8u * (2 * MAX_RING + 5);
+  const uint32_t hfull_bar = bar0 + 8u * (2 * MAX_RING + 6);
+  const uint32_t hempty_bar = bar0 + 8u * (2 * MAX_RING + 7);
+  const uint32_t tmem_slot = bar0 + 8u * (2 * MAX_RING + 8);
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  // barriers the MMA issuer (rank 0) waits on collect arrivals from both CTAs of the pair
+  const uint32_t a_ready_remote = CG == 2 ? mapa_rank(a_ready_bar, 0) : a_ready_bar;
+  auto arrive_leader = [&](uint32_t local_bar) {
+    if (CG == 2) mbar_arrive_cluster(mapa_rank(local_bar, 0)); else mbar_arrive(local_bar);
+  };
   float* sbias = reinterpret_cast<float*>(sgen + OFF_BIAS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -224,14 +295,14 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < RING; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), EPI_WARPS); }
-    mbar_init(a_ready_bar, EPI_WARPS + (DEC ? 0 : 1));
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), CG * EPI_WARPS); }
+    mbar_init(a_ready_bar, CG * (EPI_WARPS + (DEC ? 0 : 1)));
     mbar_init(mma_done_bar, 1);
     mbar_init(hfull_bar, EPI_WARPS);
     mbar_init(hempty_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) { if (CG == 2) tmem_alloc_cg2(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
 
   // ---- initial A operand: h(-1) split to fp16 hi/lo (zeros for the encoder), x block of step 0
   {
@@ -303,15 +374,17 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
   }
   fence_proxy_async_smem();
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();     // barrier inits / TMEM / A operand visible pair-wide
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ================= TMA producer: weights, the same 72 boxes every step =================
+    // ================= TMA producer: weights, the same 72 boxes every step (each CTA of a pair loads its
+    // half of the gate columns of every box and signals the leader's barrier) =================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
+      const int row_off = (int)rank * SLOT_ROWS;
       for (int t = 0; t < p.steps; ++t) {
         for (int it = 0; it < N_TILES; ++it) {
           const int nt = (it + rot) & (N_TILES - 1);
@@ -319,17 +392,30 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
               mbar_wait(empty_bar(s), ph ^ 1u);
-              mbar_arrive_expect_tx(full_bar(s), BLK_BYTES);
-              tma_load_2d(sbase + OFF_RING + s * BLK_BYTES, part ? &map_wh_lo : &map_wh_hi, full_bar(s), kb * 64,
-                          nt * TILE_N);
+              const uint32_t dst = sbase + OFF_RING + s * SLOT_BYTES;
+              if (CG == 2) {
+                if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * SLOT_BYTES);
+                tma_load_2d_cg2(dst, part ? &map_wh_lo : &map_wh_hi, mapa_rank(full_bar(s), 0), kb * 64,
+                                nt * TILE_N + row_off);
+              } else {
+                mbar_arrive_expect_tx(full_bar(s), SLOT_BYTES);
+                tma_load_2d(dst, part ? &map_wh_lo : &map_wh_hi, full_bar(s), kb * 64, nt * TILE_N);
+              }
               if (++s == RING) { s = 0; ph ^= 1u; }
             }
           }
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_arrive_expect_tx(full_bar(s), 2 * TILE_N * XROW_BYTES);
-          tma_load_2d(sbase + OFF_RING + s * BLK_BYTES, &map_wx_hi, full_bar(s), kH, nt * TILE_N);
-          tma_load_2d(sbase + OFF_RING + s * BLK_BYTES + TILE_N * XROW_BYTES, &map_wx_lo, full_bar(s), kH,
-                      nt * TILE_N);
+          const uint32_t dst = sbase + OFF_RING + s * SLOT_BYTES;
+          if (CG == 2) {
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * 2 * SLOT_ROWS * XROW_BYTES);
+            const uint32_t fb = mapa_rank(full_bar(s), 0);
+            tma_load_2d_cg2(dst, &map_wx_hi, fb, kH, nt * TILE_N + row_off);
+            tma_load_2d_cg2(dst + SLOT_ROWS * XROW_BYTES, &map_wx_lo, fb, kH, nt * TILE_N + row_off);
+          } else {
+            mbar_arrive_expect_tx(full_bar(s), 2 * TILE_N * XROW_BYTES);
+            tma_load_2d(dst, &map_wx_hi, full_bar(s), kH, nt * TILE_N);
+            tma_load_2d(dst + TILE_N * XROW_BYTES, &map_wx_lo, full_bar(s), kH, nt * TILE_N);
+          }
           if (++s == RING) { s = 0; ph ^= 1u; }
         }
       }
@@ -337,9 +423,13 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
   } else if (warp == 1) {
     // ================= MMA issuer: the whole warp walks the pipeline (uniform control flow keeps the descriptors
     // in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit =================
-    {
+    if (rank == 0) {
       const uint32_t leader = elect_one();
-      const uint32_t idesc = idesc_f16(BM, TILE_N);
+      const uint32_t idesc = idesc_f16(CG * BM, TILE_N);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+        if (CG == 2) mma_f16_ss_cg2(d, a, b, idesc, acc); else mma_f16_ss(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) { if (CG == 2) mma_commit_cg2(bar); else mma_commit(bar); };
       const uint64_t ax_hi = smem_desc_k_sw32(sbase + OFF_AX_HI), ax_lo = smem_desc_k_sw32(sbase + OFF_AX_LO);
       int s = 0; uint32_t ph = 0;
       uint32_t uses = 0;                                   // per-buffer use count = uses >> 1 (tiles alternate)
@@ -348,12 +438,12 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
       const long long t_begin = clock64();
       for (int t = 0; t < p.steps; ++t) {
         if (t > 0) {
-          mbar_wait_t(a_ready_bar, (uint32_t)(t - 1) & 1u, prof, w_aready);  // h'(t-1) and x(t) are in shared memory
+          mbar_wait_t<CG == 2>(a_ready_bar, (uint32_t)(t - 1) & 1u, prof, w_aready);  // h'(t-1), x(t) are in smem
           tc_fence_after();
         }
         for (int nt = 0; nt < N_TILES; ++nt, ++uses) {
           const int buf = nt & 1;
-          mbar_wait_t(tempty_bar(buf), ((uses >> 1) & 1u) ^ 1u, prof, w_tempty);
+          mbar_wait_t<CG == 2>(tempty_bar(buf), ((uses >> 1) & 1u) ^ 1u, prof, w_tempty);
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(buf * TILE_N);
           for (int kb = 0; kb < KB_H; ++kb) {
@@ -361,41 +451,41 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
             const uint64_t a_lo = smem_desc_k_sw128(sbase + OFF_A_LO + kb * BLK_BYTES);
             mbar_wait_t(full_bar(s), ph, prof, w_full);
             tc_fence_after();
-            const uint64_t b_hi = smem_desc_k_sw128(sbase + OFF_RING + s * BLK_BYTES);
+            const uint64_t b_hi = smem_desc_k_sw128(sbase + OFF_RING + s * SLOT_BYTES);
             if (leader) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                mma_f16_ss(d, a_lo + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), idesc, (uint32_t)((kb | ks) != 0));
+                mma(d, a_lo + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), (uint32_t)((kb | ks) != 0));
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                mma_f16_ss(d, a_hi + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), idesc, 1u);
-              mma_commit(empty_bar(s));
+                mma(d, a_hi + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), 1u);
+              commit(empty_bar(s));
             }
             __syncwarp();
             if (++s == RING) { s = 0; ph ^= 1u; }
             mbar_wait_t(full_bar(s), ph, prof, w_full);
             tc_fence_after();
-            const uint64_t b_lo = smem_desc_k_sw128(sbase + OFF_RING + s * BLK_BYTES);
+            const uint64_t b_lo = smem_desc_k_sw128(sbase + OFF_RING + s * SLOT_BYTES);
             if (leader) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                mma_f16_ss(d, a_hi + (uint64_t)(ks * 2), b_lo + (uint64_t)(ks * 2), idesc, 1u);
-              mma_commit(empty_bar(s));
+                mma(d, a_hi + (uint64_t)(ks * 2), b_lo + (uint64_t)(ks * 2), 1u);
+              commit(empty_bar(s));
             }
             __syncwarp();
             if (++s == RING) { s = 0; ph ^= 1u; }
           }
           mbar_wait_t(full_bar(s), ph, prof, w_full);
           tc_fence_after();
-          const uint64_t bx_hi = smem_desc_k_sw32(sbase + OFF_RING + s * BLK_BYTES);
-          const uint64_t bx_lo = smem_desc_k_sw32(sbase + OFF_RING + s * BLK_BYTES + TILE_N * XROW_BYTES);
+          const uint64_t bx_hi = smem_desc_k_sw32(sbase + OFF_RING + s * SLOT_BYTES);
+          const uint64_t bx_lo = smem_desc_k_sw32(sbase + OFF_RING + s * SLOT_BYTES + SLOT_ROWS * XROW_BYTES);
           if (leader) {
-            mma_f16_ss(d, ax_lo, bx_hi, idesc, 1u);
-            mma_f16_ss(d, ax_hi, bx_hi, idesc, 1u);
-            mma_f16_ss(d, ax_hi, bx_lo, idesc, 1u);
-            mma_commit(empty_bar(s));
-            mma_commit(tfull_bar(buf));
-            if (nt == N_TILES - 1) mma_commit(mma_done_bar);
+            mma(d, ax_lo, bx_hi, 1u);
+            mma(d, ax_hi, bx_hi, 1u);
+            mma(d, ax_hi, bx_lo, 1u);
+            commit(empty_bar(s));
+            commit(tfull_bar(buf));
+            if (nt == N_TILES - 1) commit(mma_done_bar);
           }
           __syncwarp();
           if (++s == RING) { s = 0; ph ^= 1u; }
@@ -432,7 +522,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         write_x_rows(xv);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready_bar);
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(a_ready_remote); else mbar_arrive(a_ready_bar); }
       }
     }
   } else if (warp >= 4) {
@@ -477,7 +567,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         tmem_ld_wait(v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(buf));    // accumulators are in registers: MMA may reuse the buffer
+        if (lane == 0) arrive_leader(tempty_bar(buf));  // accumulators are in registers: MMA may reuse the buffer
         float cn[8], hn[8];
         lstm_cell8(v, bias4 + u0, c_old, cn, hn);
         if (!last) {
@@ -560,7 +650,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready_bar);
+      if (lane == 0) { if (CG == 2) mbar_arrive_cluster(a_ready_remote); else mbar_arrive(a_ready_bar); }
     }
     if (prof && warp == 4 && lane == 0) {
       unsigned long long* o = p.prof + (size_t)blockIdx.x * 16;
@@ -568,39 +658,51 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) { if (CG == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
-template <bool DEC>
-int launch_seq(const float* packed, const SeqParams& p, cudaStream_t st) {
-  CUtensorMap maps[4];
-  const float* w_hi = packed + kOffTc16Hi;
-  const float* w_lo = packed + kOffTc16Lo;
-  int rc;
-  if ((rc = make_map_2d(&maps[0], w_hi, kG, kKp16, kKp16, TILE_N, true))) return rc;
-  if ((rc = make_map_2d(&maps[1], w_lo, kG, kKp16, kKp16, TILE_N, true))) return rc;
-  // x block: 16 halfs (32 bytes) per gate column, 32B swizzle
-  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* ptr = nullptr;
     cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) != cudaSuccess ||
-        qr != cudaDriverEntryPointSuccess)
-      return GNNPN_EUNSUPPORTED;
-    fn = (EncodeTiledFn)ptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
   }
-  for (int i = 0; i < 2; ++i) {
+  return fn;
+}
+
+// GNNPN_SEQ_CG=1 selects the single-CTA variant (cta_group::1); default is the CTA pair
+static int seq_cta_group() {
+  static const int cg = [] {
+    const char* e = getenv("GNNPN_SEQ_CG");
+    return (e && atoi(e) == 1) ? 1 : 2;
+  }();
+  return cg;
+}
+
+template <bool DEC, int CG>
+int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return GNNPN_EUNSUPPORTED;
+  CUtensorMap maps[4];
+  const float* w_hi = packed + kOffTc16Hi;
+  const float* w_lo = packed + kOffTc16Lo;
+  const cuuint32_t box_rows = TILE_N / CG;
+  for (int i = 0; i < 4; ++i) {
+    // i<2: h part, 64 halfs (128 bytes) per gate column, 128B swizzle; i>=2: x part, 16 halfs, 32B swizzle
     cuuint64_t dims[2] = {(cuuint64_t)kKp16, (cuuint64_t)kG};
     cuuint64_t strides[1] = {(cuuint64_t)kKp16 * 2};
-    cuuint32_t box[2] = {16, (cuuint32_t)TILE_N};
+    cuuint32_t box[2] = {i < 2 ? 64u : 16u, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    if (fn(&maps[2 + i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)(i ? w_lo : w_hi), dims, strides, box, estr,
-           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    if (fn(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)((i & 1) ? w_lo : w_hi), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, i < 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return GNNPN_ESHAPE;
   }
   CUtensorMap map_h;
@@ -619,14 +721,14 @@ int launch_seq(const float* packed, const SeqParams& p, cudaStream_t st) {
   SeqParams pp = p;
   static const int rotate = getenv("GNNPN_SEQ_ROT") ? atoi(getenv("GNNPN_SEQ_ROT")) : 0;
   pp.rotate = rotate;
-  auto kern = lstm_seq_kernel<DEC>;
+  auto kern = lstm_seq_kernel<DEC, CG>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const unsigned grid = (unsigned)ceil_div(p.n, BM);
+  const unsigned grid = (unsigned)(ceil_div(p.n, BM * CG) * CG);
   static const int do_prof = getenv("GNNPN_SEQ_PROF") ? atoi(getenv("GNNPN_SEQ_PROF")) : 0;
   unsigned long long* prof = nullptr;
   if (do_prof) {                                       // debug only: synchronous, allocates
@@ -634,22 +736,40 @@ int launch_seq(const float* packed, const SeqParams& p, cudaStream_t st) {
     cudaMemsetAsync(prof, 0, (size_t)grid * 16 * 8, st);
   }
   pp.prof = prof;
-  kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], map_h, pp);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], map_h, pp);
+  if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
   const int rc_launch = after_launch();
   if (do_prof) {
     unsigned long long* hbuf = (unsigned long long*)malloc((size_t)grid * 16 * 8);
     cudaStreamSynchronize(st);
     cudaMemcpy(hbuf, prof, (size_t)grid * 16 * 8, cudaMemcpyDeviceToHost);
     double acc[8] = {0};
-    for (unsigned c = 0; c < grid; ++c) for (int i = 0; i < 8; ++i) acc[i] += (double)hbuf[c * 16 + i];
-    fprintf(stderr, "[seq prof %s steps=%d grid=%u] per-step cycles: mma total %.0f (wait a_ready %.0f, tmem_empty %.0f, "
-            "B full %.0f) | epi total %.0f (wait tmem_full %.0f, h buf %.0f, pointer %.0f)\n", DEC ? "dec" : "enc", p.steps,
-            grid, acc[0] / grid / p.steps, acc[1] / grid / p.steps, acc[2] / grid / p.steps, acc[3] / grid / p.steps,
-            acc[4] / grid / p.steps, acc[5] / grid / p.steps, acc[6] / grid / p.steps, acc[7] / grid / p.steps);
+    unsigned leaders = 0;
+    for (unsigned c = 0; c < grid; ++c) {
+      if (hbuf[c * 16]) ++leaders;
+      for (int i = 0; i < 8; ++i) acc[i] += (double)hbuf[c * 16 + i];
+    }
+    if (!leaders) leaders = 1;
+    fprintf(stderr, "[seq prof %s cg=%d steps=%d grid=%u] per-step cycles: mma total %.0f (wait a_ready %.0f, tmem_empty %.0f, "
+            "B full %.0f) | epi total %.0f (wait tmem_full %.0f, h buf %.0f, pointer %.0f)\n", DEC ? "dec" : "enc", CG,
+            p.steps, grid, acc[0] / leaders / p.steps, acc[1] / leaders / p.steps, acc[2] / leaders / p.steps,
+            acc[3] / leaders / p.steps, acc[4] / grid / p.steps, acc[5] / grid / p.steps, acc[6] / grid / p.steps,
+            acc[7] / grid / p.steps);
     free(hbuf);
     cudaFree(prof);
   }
   return rc_launch;
+}
+
+template <bool DEC>
+int launch_seq(const float* packed, const SeqParams& p, cudaStream_t st) {
+  return seq_cta_group() == 2 ? launch_seq_cg<DEC, 2>(packed, p, st) : launch_seq_cg<DEC, 1>(packed, p, st);
 }
 
 }  // namespace seq

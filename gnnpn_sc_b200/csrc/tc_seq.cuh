@@ -10,8 +10,8 @@
 
 namespace gnnpn {
 
-// cell-state scratch of the persistent kernels: 128 x kH floats per CTA (blocked layout)
-inline size_t tc_seq_scratch_floats(int64_t n) { return (size_t)((n + 127) / 128) * 128 * kH; }
+// cell-state scratch of the persistent kernels: 128 x kH floats per CTA (blocked layout), CTAs launched in pairs
+inline size_t tc_seq_scratch_floats(int64_t n) { return (size_t)((n + 255) / 256) * 256 * kH; }
 
 struct SeqEncodeArgs {
   const float* inputs;     // [n, L, F]
