@@ -30,6 +30,19 @@ K_TASKS, N_CAND, HID, FEAT = 47, 5, 256, 8          # environment.ini [QWS-PNLow
 L_SEQ = K_TASKS * N_CAND
 WORKLOAD = "qws_greedy_pnlow_pnhigh_decode"
 FLOPS_PER_INSTANCE_STEP = 2 * HID * 4 * HID + 2 * FEAT * 4 * HID   # h.W_hh^T + folded x projection
+ISSUED_OVER_ALGORITHMIC = 3 * (HID + 16) / (HID + FEAT)            # a_lo.w_hi + a_hi.w_hi + a_hi.w_lo, x padded to 16
+
+
+def ncu_traffic(n: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/*_seq_traffic.json), per launch; only reported when it was captured at this n."""
+    p = os.path.join(ROOT, "profiles", "r01_seq_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return d["encoder_dram_bytes"] if int(d["instances"]) == int(n) else None
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def peaks():
@@ -53,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -202,12 +215,14 @@ def run_ours(args):
     launches0 = _lib.launch_count()
     ms_total = timed(lambda: device_step(True), args.steps)
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    enc_ms = sum(a.elapsed_time(b) for a, b in enc_ev) / (len(enc_ev) * L_SEQ)     # avg lstm_step launch, ms
+    enc_launch_ms = sum(a.elapsed_time(b) for a, b in enc_ev) / len(enc_ev)        # avg encoder-scan launch, ms
+    seq_on = args.kernel == "tc" and (int(os.environ.get("GNNPN_SEQ", "3")) & 1)
+    enc_ms = enc_launch_ms / L_SEQ                                                 # per recurrence step
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
     e2e_ms = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
 
     lt = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
@@ -219,6 +234,14 @@ def run_ours(args):
         e2e_value = world * n / (e2e_ms / args.steps * 1e-3)
         achieved = n * FLOPS_PER_INSTANCE_STEP / (enc_ms * 1e-3) / 1e12
         peak = pk["bf16_sustained"] / 2
+        issued = achieved * ISSUED_OVER_ALGORITHMIC if args.kernel == "tc" else achieved
+        if seq_on:
+            kname = ("lstm_seq_kernel<false,2> (persistent tcgen05 encoder scan: all L steps in one launch, "
+                     "3xFP16-split MMAs with fp32 accumulate in TMEM + fused LSTM cell)")
+        elif args.kernel == "tc":
+            kname = "tc_mainloop_kernel<LstmEpilogue> (tcgen05 recurrence GEMM + fused cell, one launch per step)"
+        else:
+            kname = "lstm_step_ffma_kernel (fp32 FFMA recurrence GEMM + fused cell)"
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             rate, times = cpu_reference_rate(args.cpu_batches)
@@ -233,11 +256,15 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "instances_per_gpu_per_step": n, "K": K_TASKS, "N": N_CAND,
                        "L": L_SEQ, "hidden": HID, "kernel": args.kernel, "parallelism": f"instance-sharded x{world}, no collective",
                        "l2": f"working set {(enc_out.numel() * 4) >> 20} MiB of encodings per step >> 126 MB L2"},
-            "roofline": {"kernel": ("tc_mainloop_kernel<LstmEpilogue> (tcgen05 3xTF32 recurrence GEMM + fused cell)"
-                                    if args.kernel == "tc" else "lstm_step_ffma_kernel (fp32 FFMA recurrence GEMM + fused cell)"), "bound": "tensor",
+            "roofline": {"kernel": kname, "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "avg_launch_ms": enc_ms,
-                         "peak_source": f"{pk['src']}: TF32 proxy = 1/2 bf16 sustained (SURVEY 8d)"},
+                         "traffic": ncu_traffic(n), "avg_launch_ms": enc_launch_ms if seq_on else enc_ms,
+                         "steps_per_launch": L_SEQ if seq_on else 1,
+                         "algorithmic_flops_per_launch": n * FLOPS_PER_INSTANCE_STEP * (L_SEQ if seq_on else 1),
+                         "issued_tflops": issued, "issued_frac_of_bf16_sustained": issued / pk["bf16_sustained"],
+                         "peak_source": f"{pk['src']}: fp32-accuracy GEMM -> TF32 dense proxy = 1/2 bf16 sustained "
+                                        f"({pk['bf16_sustained']:.0f} TFLOP/s, SURVEY 8d); the 3 fp16 passes the split "
+                                        "issues are not counted in `achieved`"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": K_TASKS * n * 4 + n * 4, "ms_per_step": e2e_ms / args.steps},
@@ -254,7 +281,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--instances", type=int, default=16384, help="composition instances per GPU per step")
+    ap.add_argument("--instances", type=int, default=18944,
+                    help="composition instances per GPU per step (default: one full wave, 148 SMs x 128)")
     ap.add_argument("--cpu-batches", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", default="tc", choices=["tc", "ffma"],
