@@ -41,42 +41,23 @@ __device__ __forceinline__ float dot8(const float4 r0, const float4 r1, const fl
   return s;
 }
 
-// q0/q1: the lane's 8 query elements (float4 index lane and 32+lane of the 256-float query).
-// Returns, in every lane, the position fed to the next decoder step (the pick, or forced[b]).
-__device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int64_t b, const float4 q0,
-                                                 const float4 q1, int lane) {
+// Second half of the pointer step, from the window logit pre-activations: lane j (< N) holds d_j = <row_j, q> in
+// `d` and (when a.latent_win != nullptr) latent[b, kN+j] in `lat`.  Writes win_logits / win_probs / idx_out and
+// returns, in every lane, the position fed to the next decoder step (the pick, or forced[b]).
+__device__ __forceinline__ int pointer_finish_warp(const PointerStepArgs& a, int64_t b, float d, float lat, int lane) {
   const int N = a.N, k = a.k;
-  const float* base = a.enc_out + b * a.enc_inst_ld + (int64_t)k * N * kH;
-
-  float my_w = -INFINITY, my_l = 0.f;          // lane j holds candidate j
-  for (int j0 = 0; j0 < N; j0 += 4) {          // 4 rows in flight per iteration
-    float part[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      part[u] = 0.f;
-      if (j0 + u < N) {
-        const float4* rp = reinterpret_cast<const float4*>(base + (int64_t)(j0 + u) * kH);
-        const float4 r0 = ldg_stream(rp + lane), r1 = ldg_stream(rp + 32 + lane);
-        part[u] = dot8(r0, r1, q0, q1);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float d = warp_sum(part[u]);
-      if (j0 + u < N && lane == j0 + u) {
-        my_l = a.use_tanh ? a.C * tanhf(d) : d;
-        my_w = my_l;
-      }
-    }
-  }
+  const float my_l = a.use_tanh ? a.C * tanhf(d) : d;
+  float my_w = -INFINITY;
   const int64_t wpos = b * a.L + (int64_t)k * N + lane;
   if (lane < N) {
-    if (a.latent_win) my_w = my_l + a.alpha * __ldg(a.latent_win + wpos);
+    my_w = a.latent_win ? my_l + a.alpha * lat : my_l;
     a.win_logits[wpos] = my_l;
   }
+  // windows of <= 8 candidates live in lanes 0..7: 3 butterfly levels instead of 5 (max / argmax are exact, so the
+  // result does not depend on the tree)
+  const int top = N <= 8 ? 4 : 16;
   float mx = my_w;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  for (int o = top; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   const float e = lane < N ? expf(my_w - mx) : 0.f;
   // sequential sum in candidate order (deterministic, independent of warp shuffles' tree)
   float s = 0.f;
@@ -87,12 +68,12 @@ __device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int64
   float best = p;
   int best_j = lane < N ? lane : 0x7fffffff;
   if (lane >= N) best = -1.f;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = top; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
     const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
     if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
   }
+  best_j = __shfl_sync(0xffffffffu, best_j, 0);
   if (a.uniform) {
     // sample="sample" (modelPN.py:227-228): inverse-CDF draw from the window distribution with a caller-supplied
     // uniform in [0,1); falls back to the last candidate with non-zero probability on round-off
@@ -108,8 +89,86 @@ __device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int64
     best_j = pick < 0 ? last_pos : pick;
   }
   if (lane == 0) a.idx_out[b] = k * N + best_j;
-  // the xor butterfly left best_j in every lane
   return a.forced ? a.forced[b] : k * N + best_j;
+}
+
+// q0/q1: the lane's 8 query elements (float4 index lane and 32+lane of the 256-float query).
+// Returns, in every lane, the position fed to the next decoder step (the pick, or forced[b]).
+__device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int64_t b, const float4 q0,
+                                                 const float4 q1, int lane) {
+  const int N = a.N, k = a.k;
+  const float* base = a.enc_out + b * a.enc_inst_ld + (int64_t)k * N * kH;
+  float my_d = 0.f;                            // lane j holds candidate j
+  for (int j0 = 0; j0 < N; j0 += 4) {          // 4 rows in flight per iteration
+    float part[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      part[u] = 0.f;
+      if (j0 + u < N) {
+        const float4* rp = reinterpret_cast<const float4*>(base + (int64_t)(j0 + u) * kH);
+        const float4 r0 = ldg_stream(rp + lane), r1 = ldg_stream(rp + 32 + lane);
+        part[u] = dot8(r0, r1, q0, q1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float d = warp_sum(part[u]);
+      if (lane == j0 + u) my_d = d;
+    }
+  }
+  float lat = 0.f;
+  if (a.latent_win && lane < N) lat = __ldg(a.latent_win + b * a.L + (int64_t)k * N + lane);
+  return pointer_finish_warp(a, b, my_d, lat, lane);
+}
+
+// ---- form used by the fused decode kernel: one warp walks `count` consecutive instances.  Per instance only ONE
+// memory round trip is exposed (the window rows, all CH rows of a chunk in flight at once): the query and the
+// latent of the next instance are fetched during the reductions / softmax / pick of the current one.
+// Same dot8 + warp_sum arithmetic as pointer_step_warp -> same bits.
+// `feed(i, b, fed)` is called once per instance with the position fed to the next step.
+template <int CH, class Feed>
+__device__ __forceinline__ void pointer_steps_hoisted(const PointerStepArgs& a, int64_t b0, int count,
+                                                      const float* q_base, int64_t q_ld, int lane, Feed feed) {
+  if (count <= 0) return;
+  const int N = a.N, k = a.k;
+  const float* rows = a.enc_out + b0 * a.enc_inst_ld + (int64_t)k * N * kH;
+  const float* qrow = q_base + b0 * q_ld;
+  const float* latp = a.latent_win ? a.latent_win + b0 * a.L + (int64_t)k * N + lane : nullptr;
+  float4 q0 = reinterpret_cast<const float4*>(qrow)[lane];        // coherent loads: written earlier in this
+  float4 q1 = reinterpret_cast<const float4*>(qrow)[32 + lane];   // launch by this CTA
+  float lat = (latp && lane < N) ? __ldg(latp) : 0.f;
+#pragma unroll 1
+  for (int i = 0; i < count; ++i) {
+    float my_d = 0.f;
+    for (int j0 = 0; j0 < N; j0 += CH) {
+      float4 r0[CH], r1[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int j = j0 + u < N ? j0 + u : N - 1;                // clamp: every register is always written
+        const float4* rp = reinterpret_cast<const float4*>(rows + (int64_t)j * kH);
+        r0[u] = ldg_stream(rp + lane);
+        r1[u] = ldg_stream(rp + 32 + lane);
+      }
+      float part[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) part[u] = dot8(r0[u], r1[u], q0, q1);
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const float d = warp_sum(part[u]);
+        if (lane == j0 + u) my_d = d;
+      }
+    }
+    const float lat_cur = lat;
+    rows += a.enc_inst_ld;
+    qrow += q_ld;
+    if (i + 1 < count) {                                          // next instance's query / latent go in flight now
+      q0 = reinterpret_cast<const float4*>(qrow)[lane];
+      q1 = reinterpret_cast<const float4*>(qrow)[32 + lane];
+      if (latp) { latp += a.L; if (lane < N) lat = __ldg(latp); }
+    }
+    const int fed = pointer_finish_warp(a, b0 + i, my_d, lat_cur, lane);
+    feed(i, b0 + i, fed);
+  }
 }
 
 }  // namespace gnnpn

@@ -75,6 +75,7 @@ struct SeqParams {
   PointerStepArgs pa;      // decoder only (k, idx_out, forced, uniform are per-step: see *_base below)
   int32_t* idx_base; const int32_t* forced_base; const float* uniform_base;
   int rotate;
+  int dec_flags;          // bit 0: L2 prefetch of the next window; bit 1: software-pipelined pointer phase
   unsigned long long* prof; // debug (GNNPN_SEQ_PROF): per-CTA wait-cycle counters, 16 per CTA, or nullptr
   float* c_scr;            // blocked cell-state scratch, 128*kH floats per CTA (coalesced 128-bit accesses)
 };
@@ -106,7 +107,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release.cta): a .release.cluster arrive compiles to MEMBAR.ALL.GPU, which also waits for
+  // every global store this thread has in flight (c scratch / h rows) -- ~10% of the epilogue warps' time.  What
+  // the leader's MMAs consume is ordered by tcgen05.fence::before_thread_sync (TMEM reads) and
+  // fence.proxy.async (shared-memory operand writes) issued before the arrive.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -247,6 +252,52 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool 
   if (prof) acc += clock64() - t0;
 }
 
+
+// Pointer phase of decode step t for the 8 instances of one epilogue warp (rows rr0..rr0+7 of the CTA): a separate
+// (non-inlined) function so that it gets its own register allocation -- the window rows of the NEXT instance
+// (5 KB per warp) stay in flight in registers during the reductions / softmax / pick of the current one, and the raw
+// row of the pick (next decoder input) is fetched one instance ahead of its shared-memory store.
+__device__ __forceinline__ void pointer_phase(const SeqParams& p, int t, int rr0, int64_t m0, int lane, uint8_t* sgen) {
+  PointerStepArgs pa = p.pa;
+  pa.k = t;
+  pa.idx_out = p.idx_base + (int64_t)t * p.n;
+  pa.forced = p.forced_base ? p.forced_base + (int64_t)t * p.n : nullptr;
+  pa.uniform = p.uniform_base ? p.uniform_base + (int64_t)t * p.n : nullptr;
+  const int64_t b0 = m0 + rr0;
+  const int64_t left = p.n - b0;
+  const int count = left <= 0 ? 0 : (left < BM / EPI_WARPS ? (int)left : BM / EPI_WARPS);
+  const bool feed_next = t + 1 < p.steps;
+  float pend_x = 0.f;
+  int pend_rr = -1;
+  auto store_x = [&](int rr, float xv) {
+    if (lane < 8) {
+      const __half hi = __float2half_rn(xv);
+      const __half lo = __float2half_rn(xv - __half2float(hi));
+      __half* ax_hi = reinterpret_cast<__half*>(sgen + OFF_AX_HI + rr * XROW_BYTES);
+      __half* ax_lo = reinterpret_cast<__half*>(sgen + OFF_AX_LO + rr * XROW_BYTES);
+      ax_hi[lane] = hi; ax_hi[8 + lane] = hi;
+      ax_lo[lane] = lo; ax_lo[8 + lane] = lo;
+    }
+  };
+  auto feed = [&](int i, int64_t b, int fed) {
+    if (!feed_next) return;
+    // store the previous instance's row first: its load and the one issued below would share a scoreboard
+    if (pend_rr >= 0) store_x(pend_rr, pend_x);
+    pend_x = lane < p.F ? __ldg(p.inputs + (b * p.L + fed) * (int64_t)p.F + lane) : 0.f;
+    pend_rr = rr0 + i;
+  };
+  const float* q_base = p.h_out + (int64_t)t * kH;
+  if (!(p.dec_flags & 2)) {
+    for (int i = 0; i < count; ++i) {
+      const float4* qp = reinterpret_cast<const float4*>(q_base + (b0 + i) * p.h_out_inst_ld);
+      const float4 q0 = qp[lane], q1 = qp[32 + lane];
+      feed(i, b0 + i, pointer_step_warp(pa, b0 + i, q0, q1, lane));
+    }
+  } else if (pa.N % 5 == 0) pointer_steps_hoisted<5>(pa, b0, count, q_base, p.h_out_inst_ld, lane, feed);
+  else                      pointer_steps_hoisted<4>(pa, b0, count, q_base, p.h_out_inst_ld, lane, feed);
+  if (pend_rr >= 0) store_x(pend_rr, pend_x);
+}
+
 // ------------------------------------------------------------------------------------------------
 // CG = 1: one CTA per 128 instances, cta_group::1 MMAs (M=128, N=128).
 // CG = 2: CTA pair (cluster of 2 = one TPC), cta_group::2 MMAs (M=256: 128 instances per CTA, N=128): each CTA
@@ -257,7 +308,7 @@ template <bool DEC, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_constant__ CUtensorMap map_wh_lo,
                 const __grid_constant__ CUtensorMap map_wx_hi, const __grid_constant__ CUtensorMap map_wx_lo,
-                const __grid_constant__ CUtensorMap map_h, const SeqParams p) {
+                const __grid_constant__ CUtensorMap map_h, const __grid_constant__ SeqParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));          // generic pointer to the aligned base
@@ -514,6 +565,26 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     }
   } else if (warp == 3) {
     // ================= x producer (encoder): raw input row of step t+1 -> fp16 hi/lo x block =================
+    if (DEC) {
+      // L2 prefetcher: the window rows of enc_out that step t+1's pointer phase will read (N*kH contiguous floats
+      // per instance) are requested as soon as step t's MMAs retire, one whole MMA phase ahead of their use
+      auto prefetch_window = [&](int k) {
+        const uint32_t bytes = (uint32_t)(p.pa.N * kH * 4);
+        for (int r = lane; r < BM; r += 32) {
+          const int64_t m = m0 + r;
+          if (m < p.n)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pa.enc_out + m * p.pa.enc_inst_ld +
+                                                                            (int64_t)k * p.pa.N * kH), "r"(bytes) : "memory");
+        }
+      };
+      if (p.dec_flags & 1) {
+        prefetch_window(0);
+        for (int t = 0; t + 1 < p.steps; ++t) {
+          mbar_wait(mma_done_bar, (uint32_t)t & 1u);
+          prefetch_window(t + 1);
+        }
+      }
+    }
     if (!DEC) {
       for (int t = 0; t + 1 < p.steps; ++t) {
         float xv[4][8];
@@ -622,29 +693,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         const long long tp0 = prof ? clock64() : 0;
         __threadfence_block();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-        PointerStepArgs pa = p.pa;
-        pa.k = t;
-        pa.idx_out = p.idx_base + (int64_t)t * p.n;
-        pa.forced = p.forced_base ? p.forced_base + (int64_t)t * p.n : nullptr;
-        pa.uniform = p.uniform_base ? p.uniform_base + (int64_t)t * p.n : nullptr;
-        const int e = warp - 4;
-        for (int i = 0; i < BM / EPI_WARPS; ++i) {
-          const int rr = e * (BM / EPI_WARPS) + i;
-          const int64_t b = m0 + rr;
-          if (b >= p.n) break;
-          const float4* qp = reinterpret_cast<const float4*>(p.h_out + b * p.h_out_inst_ld + (int64_t)t * kH);
-          const float4 q0 = qp[lane], q1 = qp[32 + lane];           // coherent loads: written by this CTA
-          const int fed = pointer_step_warp(pa, b, q0, q1, lane);
-          if (t + 1 < p.steps && lane < 8) {
-            const float xv = lane < p.F ? __ldg(p.inputs + (b * p.L + fed) * (int64_t)p.F + lane) : 0.f;
-            const __half hi = __float2half_rn(xv);
-            const __half lo = __float2half_rn(xv - __half2float(hi));
-            __half* ax_hi = reinterpret_cast<__half*>(sgen + OFF_AX_HI + rr * XROW_BYTES);
-            __half* ax_lo = reinterpret_cast<__half*>(sgen + OFF_AX_LO + rr * XROW_BYTES);
-            ax_hi[lane] = hi; ax_hi[8 + lane] = hi;
-            ax_lo[lane] = lo; ax_lo[8 + lane] = lo;
-          }
-        }
+        pointer_phase(p, t, (warp - 4) * (BM / EPI_WARPS), m0, lane, sgen);
         if (prof) w_ptr += clock64() - tp0;
       }
       fence_proxy_async_smem();
@@ -721,6 +770,8 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
   SeqParams pp = p;
   static const int rotate = getenv("GNNPN_SEQ_ROT") ? atoi(getenv("GNNPN_SEQ_ROT")) : 0;
   pp.rotate = rotate;
+  static const int dec_flags = getenv("GNNPN_SEQ_DEC") ? atoi(getenv("GNNPN_SEQ_DEC")) : 2;
+  pp.dec_flags = dec_flags;
   auto kern = lstm_seq_kernel<DEC, CG>;
   static bool configured = false;
   if (!configured) {

@@ -3,7 +3,9 @@ usage: ncu -i rep --page source --csv --launch-skip K --launch-count 1 > src.csv
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr = rows[hdr_i]; data = rows[hdr_i + 1:]
+hdr = rows[hdr_i]
+end = next((i for i in range(hdr_i + 1, len(rows)) if rows[i] and rows[i][0] == 'Kernel Name'), len(rows))
+data = [r for r in rows[hdr_i + 1:end] if len(r) >= len(hdr)]
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 si = hdr.index("# Samples"); src = hdr.index("Source"); ie = hdr.index("Instructions Executed")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
