@@ -91,14 +91,14 @@ __global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __
 // Positions outside the window carry -inf after modelPN.py:220-222 and contribute exp(-inf)=0.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pointer_step_dot_kernel(
-    const PointerStepArgs pa, const float* __restrict__ q, int64_t q_ld, const float* __restrict__ inputs, int F,
+    const PointerStepArgs pa, int k, const float* __restrict__ q, int64_t q_ld, const float* __restrict__ inputs, int F,
     void* __restrict__ a_hi_next, void* __restrict__ a_lo_next, int64_t a_ld, int a_f16) {
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= pa.n) return;
   const float4* qp = reinterpret_cast<const float4*>(q + b * q_ld);
   const float4 q0 = __ldg(qp + lane), q1 = __ldg(qp + 32 + lane);
-  const int fed = pointer_step_warp(pa, b, q0, q1, lane);
+  const int fed = pointer_step_warp(pa, k, b, q0, q1, lane);
   if (a_hi_next && lane < F) {
     // tensor-core path: the chosen candidate's raw row becomes columns [H, H+F) of the next step's A operand
     const float v = __ldg(inputs + (b * pa.L + fed) * (int64_t)F + lane);
@@ -375,12 +375,11 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
     const int nxt = (k + 1) & 1;
     PointerStepArgs pa;
     pa.enc_out = enc_out; pa.enc_inst_ld = (int64_t)L * kH; pa.latent_win = latent_win; pa.alpha = alpha;
-    pa.use_tanh = use_tanh; pa.C = C; pa.n = n; pa.L = L; pa.k = k; pa.N = N;
-    pa.idx_out = idx_out + (int64_t)k * n; pa.win_logits = win_logits; pa.win_probs = win_probs;
-    pa.forced = forced_idx ? forced_idx + (int64_t)k * n : nullptr;
-    pa.uniform = sample_uniform ? sample_uniform + (int64_t)k * n : nullptr;
+    pa.use_tanh = use_tanh; pa.C = C; pa.n = n; pa.L = L; pa.N = N;
+    pa.idx_out = idx_out; pa.win_logits = win_logits; pa.win_probs = win_probs;
+    pa.forced = forced_idx; pa.uniform = sample_uniform;
     pointer_step_dot_kernel<<<att_blocks, 256, 0, st>>>(
-        pa, dec_h + (int64_t)k * kH, (int64_t)K * kH, inputs, in_features,
+        pa, k, dec_h + (int64_t)k * kH, (int64_t)K * kH, inputs, in_features,
         use_tc ? plan.hi[nxt] : nullptr, use_tc ? plan.lo[nxt] : nullptr, use_tc ? (int64_t)plan.ld : 0,
         use_tc ? plan.f16 : 0);
     if ((rc = after_launch())) return rc;

@@ -24,13 +24,14 @@ struct PointerStepArgs {
   int use_tanh;
   float C;
   int64_t n;
-  int L, k, N;
-  int32_t* idx_out;          // [n]   (already offset to step k)
+  int L, N;
+  int32_t* idx_out;          // [K, n]
   float* win_logits;         // [n, L]
   float* win_probs;          // [n, L]
-  const int32_t* forced;     // [n] step-k teacher-forced picks or nullptr
-  const float* uniform;      // [n] step-k uniforms (sample="sample") or nullptr
+  const int32_t* forced;     // [K, n] teacher-forced picks or nullptr
+  const float* uniform;      // [K, n] uniforms (sample="sample") or nullptr
 };
+// The decode step k is passed separately so that the argument block itself can stay in constant memory.
 
 // <row, q> over the 8 elements a lane owns, explicit fma chain so every kernel that forms a
 // pointer logit rounds identically (window logits == the same entries of the full logits).
@@ -44,13 +45,13 @@ __device__ __forceinline__ float dot8(const float4 r0, const float4 r1, const fl
 // Second half of the pointer step, from the window logit pre-activations: lane j (< N) holds d_j = <row_j, q> in
 // `d` and (when a.latent_win != nullptr) latent[b, kN+j] in `lat`.  Writes win_logits / win_probs / idx_out and
 // returns, in every lane, the position fed to the next decoder step (the pick, or forced[b]).
-__device__ __forceinline__ int pointer_finish_warp(const PointerStepArgs& a, int64_t b, float d, float lat, int lane) {
-  const int N = a.N, k = a.k;
+__device__ __forceinline__ int pointer_finish_warp(const PointerStepArgs& a, int k, int64_t b, float d, float lat, int lane) {
+  const int N = a.N;
   const float my_l = a.use_tanh ? a.C * tanhf(d) : d;
   float my_w = -INFINITY;
   const int64_t wpos = b * a.L + (int64_t)k * N + lane;
   if (lane < N) {
-    my_w = a.latent_win ? my_l + a.alpha * lat : my_l;
+    my_w = a.latent_win ? fmaf(a.alpha, lat, my_l) : my_l;
     a.win_logits[wpos] = my_l;
   }
   // windows of <= 8 candidates live in lanes 0..7: 3 butterfly levels instead of 5 (max / argmax are exact, so the
@@ -77,7 +78,7 @@ __device__ __forceinline__ int pointer_finish_warp(const PointerStepArgs& a, int
   if (a.uniform) {
     // sample="sample" (modelPN.py:227-228): inverse-CDF draw from the window distribution with a caller-supplied
     // uniform in [0,1); falls back to the last candidate with non-zero probability on round-off
-    const float u = __ldg(a.uniform + b);
+    const float u = __ldg(a.uniform + (int64_t)k * a.n + b);
     float cum = 0.f;
     int pick = -1, last_pos = 0;
     for (int j = 0; j < N; ++j) {
@@ -88,15 +89,15 @@ __device__ __forceinline__ int pointer_finish_warp(const PointerStepArgs& a, int
     }
     best_j = pick < 0 ? last_pos : pick;
   }
-  if (lane == 0) a.idx_out[b] = k * N + best_j;
-  return a.forced ? a.forced[b] : k * N + best_j;
+  if (lane == 0) a.idx_out[(int64_t)k * a.n + b] = k * N + best_j;
+  return a.forced ? a.forced[(int64_t)k * a.n + b] : k * N + best_j;
 }
 
 // q0/q1: the lane's 8 query elements (float4 index lane and 32+lane of the 256-float query).
 // Returns, in every lane, the position fed to the next decoder step (the pick, or forced[b]).
-__device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int64_t b, const float4 q0,
+__device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int k, int64_t b, const float4 q0,
                                                  const float4 q1, int lane) {
-  const int N = a.N, k = a.k;
+  const int N = a.N;
   const float* base = a.enc_out + b * a.enc_inst_ld + (int64_t)k * N * kH;
   float my_d = 0.f;                            // lane j holds candidate j
   for (int j0 = 0; j0 < N; j0 += 4) {          // 4 rows in flight per iteration
@@ -118,33 +119,54 @@ __device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int64
   }
   float lat = 0.f;
   if (a.latent_win && lane < N) lat = __ldg(a.latent_win + b * a.L + (int64_t)k * N + lane);
-  return pointer_finish_warp(a, b, my_d, lat, lane);
+  return pointer_finish_warp(a, k, b, my_d, lat, lane);
 }
 
-// ---- form used by the fused decode kernel: one warp walks `count` consecutive instances.  Per instance only ONE
-// memory round trip is exposed (the window rows, all CH rows of a chunk in flight at once): the query and the
-// latent of the next instance are fetched during the reductions / softmax / pick of the current one.
-// Same dot8 + warp_sum arithmetic as pointer_step_warp -> same bits.
-// `feed(i, b, fed)` is called once per instance with the position fed to the next step.
-template <int CH, class Feed>
-__device__ __forceinline__ void pointer_steps_hoisted(const PointerStepArgs& a, int64_t b0, int count,
-                                                      const float* q_base, int64_t q_ld, int lane, Feed feed) {
+// ---- form used by the fused decode kernel: one warp owns WI = 8 consecutive instances.
+// Phase 1 streams the window rows: per instance one chunk of CH rows is in flight in registers and the next chunk is
+// requested as soon as the dot products have consumed the current one, so the DRAM round trips of consecutive
+// instances overlap the butterfly reductions.  The logit pre-activations are parked lane-wise: instance i,
+// candidate j -> register i / IPP, lane (i % IPP) * SEG + j  (SEG = 8, 16 or 32 lanes per instance, IPP = 32 / SEG).
+// Phase 2 then runs tanh / latent / softmax / pick for IPP instances at once with SEG-wide segmented shuffles.
+// Per candidate the arithmetic is exactly that of pointer_step_warp (dot8 + warp_sum, fmaf latent, sequential
+// softmax sum in candidate order) -> same bits.
+// `feed(i, b, fed, j)` is called by every lane of a pass with the position fed to the next step for ITS instance
+// (i = instance slot 0..7, j = lane index inside the segment); slots >= count must be ignored by the callee.
+constexpr int kWarpInstances = 8;
+#ifdef GNNPN_PTR_PROF
+#define g_ptr_tick ptr_tick_local                  // diagnostics build only: timestamps of the phase boundaries
+#endif
+
+template <int SEG, int CH, class Feed>
+__device__ __forceinline__ void pointer_steps_batched(const PointerStepArgs& a, int k, int64_t b0, int count,
+                                                      const float* q_base, int64_t q_ld, int lane, Feed feed
+#ifdef GNNPN_PTR_PROF
+                                                      , long long* ptr_tick_local
+#endif
+                                                      ) {
+  constexpr int IPP = 32 / SEG;                    // instances per phase-2 pass
+  constexpr int PASSES = kWarpInstances / IPP;
   if (count <= 0) return;
-  const int N = a.N, k = a.k;
+  const int N = a.N;
+  const int seg_i = lane / SEG, seg_j = lane % SEG;
+
+  // ---- phase 1: one exposed memory round trip per chunk (all CH rows + the query in flight together)
+  float dv[PASSES];
+#pragma unroll
+  for (int r = 0; r < PASSES; ++r) dv[r] = 0.f;
   const float* rows = a.enc_out + b0 * a.enc_inst_ld + (int64_t)k * N * kH;
   const float* qrow = q_base + b0 * q_ld;
-  const float* latp = a.latent_win ? a.latent_win + b0 * a.L + (int64_t)k * N + lane : nullptr;
-  float4 q0 = reinterpret_cast<const float4*>(qrow)[lane];        // coherent loads: written earlier in this
-  float4 q1 = reinterpret_cast<const float4*>(qrow)[32 + lane];   // launch by this CTA
-  float lat = (latp && lane < N) ? __ldg(latp) : 0.f;
 #pragma unroll 1
   for (int i = 0; i < count; ++i) {
-    float my_d = 0.f;
+    const float4 q0 = reinterpret_cast<const float4*>(qrow)[lane];        // coherent loads: written earlier in this
+    const float4 q1 = reinterpret_cast<const float4*>(qrow)[32 + lane];   // launch by this CTA
+    const int slot = i / IPP, base = (i % IPP) * SEG;
+#pragma unroll 1
     for (int j0 = 0; j0 < N; j0 += CH) {
       float4 r0[CH], r1[CH];
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
-        const int j = j0 + u < N ? j0 + u : N - 1;                // clamp: every register is always written
+        const int j = j0 + u < N ? j0 + u : N - 1;                        // clamp: every register is always written
         const float4* rp = reinterpret_cast<const float4*>(rows + (int64_t)j * kH);
         r0[u] = ldg_stream(rp + lane);
         r1[u] = ldg_stream(rp + 32 + lane);
@@ -155,19 +177,71 @@ __device__ __forceinline__ void pointer_steps_hoisted(const PointerStepArgs& a, 
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
         const float d = warp_sum(part[u]);
-        if (lane == j0 + u) my_d = d;
+        const bool mine = j0 + u < N && lane == base + j0 + u;
+#pragma unroll
+        for (int r = 0; r < PASSES; ++r) dv[r] = (mine && slot == r) ? d : dv[r];   // selects: dv stays in registers
       }
     }
-    const float lat_cur = lat;
     rows += a.enc_inst_ld;
     qrow += q_ld;
-    if (i + 1 < count) {                                          // next instance's query / latent go in flight now
-      q0 = reinterpret_cast<const float4*>(qrow)[lane];
-      q1 = reinterpret_cast<const float4*>(qrow)[32 + lane];
-      if (latp) { latp += a.L; if (lane < N) lat = __ldg(latp); }
+  }
+
+  float lat[PASSES];
+#pragma unroll
+  for (int r = 0; r < PASSES; ++r) {
+    const int i = r * IPP + seg_i;
+    lat[r] = (a.latent_win && i < count && seg_j < N)
+                 ? __ldg(a.latent_win + (b0 + i) * a.L + (int64_t)k * N + seg_j) : 0.f;
+  }
+#ifdef GNNPN_PTR_PROF
+  g_ptr_tick[1] = clock64();
+#endif
+  // ---- phase 2
+#pragma unroll
+  for (int r = 0; r < PASSES; ++r) {
+    const int si = r * IPP + seg_i;                // this lane's instance slot
+    if (r * IPP >= count) break;                   // warp-uniform
+    const bool inst_ok = si < count;
+    const bool valid = inst_ok && seg_j < N;
+    const int64_t b = b0 + (inst_ok ? si : 0);
+    const float my_l = a.use_tanh ? a.C * tanhf(dv[r]) : dv[r];
+    const int64_t wpos = b * a.L + (int64_t)k * N + seg_j;
+    float my_w = -INFINITY;
+    if (valid) {
+      my_w = a.latent_win ? fmaf(a.alpha, lat[r], my_l) : my_l;
+      a.win_logits[wpos] = my_l;
     }
-    const int fed = pointer_finish_warp(a, b0 + i, my_d, lat_cur, lane);
-    feed(i, b0 + i, fed);
+    float mx = my_w;
+#pragma unroll
+    for (int o = SEG / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = valid ? expf(my_w - mx) : 0.f;
+    float s = 0.f;
+    for (int j = 0; j < N; ++j) s += __shfl_sync(0xffffffffu, e, j, SEG);   // candidate order, per segment
+    const float p = e / s;
+    if (valid) a.win_probs[wpos] = p;
+    float best = valid ? p : -1.f;
+    int best_j = valid ? seg_j : 0x7fffffff;
+#pragma unroll
+    for (int o = SEG / 2; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+      if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+    }
+    if (a.uniform) {                               // sample="sample": inverse-CDF draw, see pointer_finish_warp
+      const float uu = __ldg(a.uniform + (int64_t)k * a.n + b);
+      float cum = 0.f;
+      int pick = -1, last_pos = 0;
+      for (int j = 0; j < N; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, p, j, SEG);
+        cum += pj;
+        if (pj > 0.f) last_pos = j;
+        if (pick < 0 && uu < cum) pick = j;
+      }
+      best_j = pick < 0 ? last_pos : pick;
+    }
+    if (inst_ok && seg_j == 0) a.idx_out[(int64_t)k * a.n + b] = k * N + best_j;
+    const int fed = a.forced ? a.forced[(int64_t)k * a.n + b] : k * N + best_j;
+    feed(si, b, fed, seg_j);
   }
 }
 

@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "tc_common.cuh"
 #include "common.cuh"
 #include "lstm_step.cuh"
@@ -72,10 +73,11 @@ struct SeqParams {
   int c_zero_init;
   const float* h0; int64_t h0_ld;          // initial hidden rows or nullptr (zeros)
   float* h_out; int64_t h_out_inst_ld;     // step t of instance m at h_out + m*ld + t*kH
-  PointerStepArgs pa;      // decoder only (k, idx_out, forced, uniform are per-step: see *_base below)
-  int32_t* idx_base; const int32_t* forced_base; const float* uniform_base;
+  PointerStepArgs pa;      // decoder only
   int rotate;
-  int dec_flags;          // bit 0: L2 prefetch of the next window; bit 1: software-pipelined pointer phase
+  int dec_flags;          // bit 0: L2 prefetch of the next window; bit 1: batched pointer phase; bit 2: stagger
+  int stagger;            // cycles by which every other CTA pair starts late (decoder), so that the DRAM-bound pointer
+                          // phases of one half of the GPU fall into the MMA phases of the other half
   unsigned long long* prof; // debug (GNNPN_SEQ_PROF): per-CTA wait-cycle counters, 16 per CTA, or nullptr
   float* c_scr;            // blocked cell-state scratch, 128*kH floats per CTA (coalesced 128-bit accesses)
 };
@@ -253,50 +255,83 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool 
 }
 
 
-// Pointer phase of decode step t for the 8 instances of one epilogue warp (rows rr0..rr0+7 of the CTA): a separate
-// (non-inlined) function so that it gets its own register allocation -- the window rows of the NEXT instance
-// (5 KB per warp) stay in flight in registers during the reductions / softmax / pick of the current one, and the raw
-// row of the pick (next decoder input) is fetched one instance ahead of its shared-memory store.
-__device__ __forceinline__ void pointer_phase(const SeqParams& p, int t, int rr0, int64_t m0, int lane, uint8_t* sgen) {
-  PointerStepArgs pa = p.pa;
-  pa.k = t;
-  pa.idx_out = p.idx_base + (int64_t)t * p.n;
-  pa.forced = p.forced_base ? p.forced_base + (int64_t)t * p.n : nullptr;
-  pa.uniform = p.uniform_base ? p.uniform_base + (int64_t)t * p.n : nullptr;
+// x block of the next decoder step: row rr, feature f -> halfs f and 8+f of the hi and lo 32-byte rows
+__device__ __forceinline__ void store_ax(uint8_t* sgen, int rr, int f, float xv) {
+  const __half hi = __float2half_rn(xv);
+  const __half lo = __float2half_rn(xv - __half2float(hi));
+  __half* ax_hi = reinterpret_cast<__half*>(sgen + OFF_AX_HI + rr * XROW_BYTES);
+  __half* ax_lo = reinterpret_cast<__half*>(sgen + OFF_AX_LO + rr * XROW_BYTES);
+  ax_hi[f] = hi; ax_hi[8 + f] = hi;
+  ax_lo[f] = lo; ax_lo[8 + f] = lo;
+}
+
+// Pointer phase of decode step t for the 8 instances of one epilogue warp (rows rr0..rr0+7 of the CTA); see
+// pointer_steps_batched in pointer.cuh.
+__device__ __forceinline__ void pointer_phase(const SeqParams& p, int t, int rr0, int64_t m0, int lane, uint8_t* sgen
+#ifdef GNNPN_PTR_PROF
+                                              , long long* tick
+#endif
+                                              ) {
+  const PointerStepArgs& pa = p.pa;                 // stays in constant memory (p is a __grid_constant__ parameter)
   const int64_t b0 = m0 + rr0;
   const int64_t left = p.n - b0;
   const int count = left <= 0 ? 0 : (left < BM / EPI_WARPS ? (int)left : BM / EPI_WARPS);
   const bool feed_next = t + 1 < p.steps;
-  float pend_x = 0.f;
-  int pend_rr = -1;
-  auto store_x = [&](int rr, float xv) {
-    if (lane < 8) {
-      const __half hi = __float2half_rn(xv);
-      const __half lo = __float2half_rn(xv - __half2float(hi));
-      __half* ax_hi = reinterpret_cast<__half*>(sgen + OFF_AX_HI + rr * XROW_BYTES);
-      __half* ax_lo = reinterpret_cast<__half*>(sgen + OFF_AX_LO + rr * XROW_BYTES);
-      ax_hi[lane] = hi; ax_hi[8 + lane] = hi;
-      ax_lo[lane] = lo; ax_lo[8 + lane] = lo;
-    }
-  };
-  auto feed = [&](int i, int64_t b, int fed) {
-    if (!feed_next) return;
-    // store the previous instance's row first: its load and the one issued below would share a scoreboard
-    if (pend_rr >= 0) store_x(pend_rr, pend_x);
-    pend_x = lane < p.F ? __ldg(p.inputs + (b * p.L + fed) * (int64_t)p.F + lane) : 0.f;
-    pend_rr = rr0 + i;
-  };
   const float* q_base = p.h_out + (int64_t)t * kH;
   if (!(p.dec_flags & 2)) {
+    // reference form: one instance at a time (kept for A/B runs, GNNPN_SEQ_DEC=0)
     for (int i = 0; i < count; ++i) {
       const float4* qp = reinterpret_cast<const float4*>(q_base + (b0 + i) * p.h_out_inst_ld);
       const float4 q0 = qp[lane], q1 = qp[32 + lane];
-      feed(i, b0 + i, pointer_step_warp(pa, b0 + i, q0, q1, lane));
+      const int fed = pointer_step_warp(pa, t, b0 + i, q0, q1, lane);
+      if (feed_next && lane < 8) {
+        const float xv = lane < p.F ? __ldg(p.inputs + ((b0 + i) * p.L + fed) * (int64_t)p.F + lane) : 0.f;
+        store_ax(sgen, rr0 + i, lane, xv);
+      }
     }
-  } else if (pa.N % 5 == 0) pointer_steps_hoisted<5>(pa, b0, count, q_base, p.h_out_inst_ld, lane, feed);
-  else                      pointer_steps_hoisted<4>(pa, b0, count, q_base, p.h_out_inst_ld, lane, feed);
-  if (pend_rr >= 0) store_x(pend_rr, pend_x);
+    return;
+  }
+  // batched form: the raw rows of the picks (next decoder inputs) of a whole pass are fetched together and written
+  // to the x block after the last pass, so their latency is paid once
+  float pend_x[kWarpInstances];
+#pragma unroll
+  for (int r = 0; r < kWarpInstances; ++r) pend_x[r] = 0.f;
+  auto run = [&](auto seg_tag, auto ch_tag) {
+    constexpr int SEG = decltype(seg_tag)::value, CH = decltype(ch_tag)::value;
+    constexpr int IPP = 32 / SEG;
+    auto feed = [&](int si, int64_t b, int fed, int j) {
+      if (!feed_next) return;
+      const float xv = (si < count && j < p.F) ? __ldg(p.inputs + (b * p.L + fed) * (int64_t)p.F + j) : 0.f;
+#pragma unroll
+      for (int r = 0; r < kWarpInstances / IPP; ++r)
+        if (si / IPP == r) pend_x[r] = xv;
+    };
+    pointer_steps_batched<SEG, CH>(pa, t, b0, count, q_base, p.h_out_inst_ld, lane, feed
+#ifdef GNNPN_PTR_PROF
+                                   , tick
+#endif
+                                   );
+#ifdef GNNPN_PTR_PROF
+    tick[2] = clock64();
+#endif
+    if (feed_next) {
+      const int seg_i = lane / SEG, seg_j = lane % SEG;
+#pragma unroll
+      for (int r = 0; r < kWarpInstances / IPP; ++r) {
+        const int si = r * IPP + seg_i;
+        if (si < count && seg_j < 8) store_ax(sgen, rr0 + si, seg_j, pend_x[r]);
+      }
+    }
+  };
+  using std::integral_constant;
+  const bool five = pa.N % 5 == 0;
+  if (pa.N <= 8)       { if (five) run(integral_constant<int, 8>{}, integral_constant<int, 5>{});
+                         else      run(integral_constant<int, 8>{}, integral_constant<int, 4>{}); }
+  else if (pa.N <= 16) { if (five) run(integral_constant<int, 16>{}, integral_constant<int, 5>{});
+                         else      run(integral_constant<int, 16>{}, integral_constant<int, 4>{}); }
+  else                 run(integral_constant<int, 32>{}, integral_constant<int, 4>{});
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // CG = 1: one CTA per 128 instances, cta_group::1 MMAs (M=128, N=128).
@@ -335,6 +370,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
+  if (DEC && (p.dec_flags & 4) && ((blockIdx.x / CG) & 1)) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < p.stagger) __nanosleep(200);
+  }
   // every CTA walks the 8 N tiles in a rotated order so the CTAs do not all pull the same weight lines from
   // the same L2 slices at the same time
   const int rot = p.rotate ? (int)(blockIdx.x & (N_TILES - 1)) : 0;
@@ -611,6 +650,9 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     uint32_t uses = 0;
     const bool prof = p.prof != nullptr;
     long long w_tfull = 0, w_hempty = 0, w_ptr = 0;
+#ifdef GNNPN_PTR_PROF
+    long long w_pp[4] = {0, 0, 0, 0};
+#endif
     const long long t_begin = clock64();
     for (int t = 0; t < p.steps; ++t) {
       const float4* bias4 = reinterpret_cast<const float4*>(sbias + (t == 0 ? 0 : kG));
@@ -648,7 +690,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
           stg256(c_row + u0, cn);
         }
         if (DEC) {
-          if (ok) stg256(h_row + (int64_t)t * kH + u0, hn);
+          if (ok && !(p.dec_flags & 8)) stg256(h_row + (int64_t)t * kH + u0, hn);   // bit 3: timing experiment only
         } else {
           // fp32 h' -> 128B-swizzled [128 x 32] tile; the store issuer (warp 2) sends it to enc_out by TMA
           mbar_wait_t(hempty_bar, (uses & 1u) ^ 1u, prof, w_hempty);   // the previous tile's store has left shared memory
@@ -693,7 +735,15 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         const long long tp0 = prof ? clock64() : 0;
         __threadfence_block();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+#ifdef GNNPN_PTR_PROF
+        long long tick[3];
+        tick[0] = clock64(); tick[1] = tick[2] = tick[0];
+        pointer_phase(p, t, (warp - 4) * (BM / EPI_WARPS), m0, lane, sgen, tick);
+        const long long tend = clock64();
+        w_pp[0] += tick[0] - tp0; w_pp[1] += tick[1] - tick[0]; w_pp[2] += tick[2] - tick[1]; w_pp[3] += tend - tick[2];
+#else
         pointer_phase(p, t, (warp - 4) * (BM / EPI_WARPS), m0, lane, sgen);
+#endif
         if (prof) w_ptr += clock64() - tp0;
       }
       fence_proxy_async_smem();
@@ -704,6 +754,9 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     if (prof && warp == 4 && lane == 0) {
       unsigned long long* o = p.prof + (size_t)blockIdx.x * 16;
       o[4] = (unsigned long long)(clock64() - t_begin); o[5] = w_tfull; o[6] = w_hempty; o[7] = w_ptr;
+#ifdef GNNPN_PTR_PROF
+      for (int i = 0; i < 4; ++i) o[8 + i] = w_pp[i];
+#endif
     }
   }
   tc_fence_before();
@@ -772,6 +825,8 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
   pp.rotate = rotate;
   static const int dec_flags = getenv("GNNPN_SEQ_DEC") ? atoi(getenv("GNNPN_SEQ_DEC")) : 2;
   pp.dec_flags = dec_flags;
+  static const int stagger = getenv("GNNPN_SEQ_STAGGER") ? atoi(getenv("GNNPN_SEQ_STAGGER")) : 40000;
+  pp.stagger = stagger;
   auto kern = lstm_seq_kernel<DEC, CG>;
   static bool configured = false;
   if (!configured) {
@@ -800,11 +855,11 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
     unsigned long long* hbuf = (unsigned long long*)malloc((size_t)grid * 16 * 8);
     cudaStreamSynchronize(st);
     cudaMemcpy(hbuf, prof, (size_t)grid * 16 * 8, cudaMemcpyDeviceToHost);
-    double acc[8] = {0};
+    double acc[12] = {0};
     unsigned leaders = 0;
     for (unsigned c = 0; c < grid; ++c) {
       if (hbuf[c * 16]) ++leaders;
-      for (int i = 0; i < 8; ++i) acc[i] += (double)hbuf[c * 16 + i];
+      for (int i = 0; i < 12; ++i) acc[i] += (double)hbuf[c * 16 + i];
     }
     if (!leaders) leaders = 1;
     fprintf(stderr, "[seq prof %s cg=%d steps=%d grid=%u] per-step cycles: mma total %.0f (wait a_ready %.0f, tmem_empty %.0f, "
@@ -812,6 +867,10 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
             p.steps, grid, acc[0] / leaders / p.steps, acc[1] / leaders / p.steps, acc[2] / leaders / p.steps,
             acc[3] / leaders / p.steps, acc[4] / grid / p.steps, acc[5] / grid / p.steps, acc[6] / grid / p.steps,
             acc[7] / grid / p.steps);
+#ifdef GNNPN_PTR_PROF
+    fprintf(stderr, "   pointer phase split: fence+barrier %.0f, rows/dots %.0f, softmax/pick %.0f, x stores %.0f\n",
+            acc[8] / grid / p.steps, acc[9] / grid / p.steps, acc[10] / grid / p.steps, acc[11] / grid / p.steps);
+#endif
     free(hbuf);
     cudaFree(prof);
   }
@@ -848,10 +907,9 @@ int tc_seq_decode(const SeqDecodeArgs& a, cudaStream_t st) {
   p.h0 = a.enc_out + (int64_t)(a.L - 1) * kH; p.h0_ld = (int64_t)a.L * kH;
   p.h_out = a.dec_h; p.h_out_inst_ld = (int64_t)a.K * kH;
   p.pa.enc_out = a.enc_out; p.pa.enc_inst_ld = (int64_t)a.L * kH; p.pa.latent_win = a.latent_win;
-  p.pa.alpha = a.alpha; p.pa.use_tanh = a.use_tanh; p.pa.C = a.C; p.pa.n = a.n; p.pa.L = a.L; p.pa.k = 0;
-  p.pa.N = a.N; p.pa.idx_out = nullptr; p.pa.win_logits = a.win_logits; p.pa.win_probs = a.win_probs;
-  p.pa.forced = nullptr; p.pa.uniform = nullptr;
-  p.idx_base = a.idx_out; p.forced_base = a.forced_idx; p.uniform_base = a.sample_uniform;
+  p.pa.alpha = a.alpha; p.pa.use_tanh = a.use_tanh; p.pa.C = a.C; p.pa.n = a.n; p.pa.L = a.L;
+  p.pa.N = a.N; p.pa.idx_out = a.idx_out; p.pa.win_logits = a.win_logits; p.pa.win_probs = a.win_probs;
+  p.pa.forced = a.forced_idx; p.pa.uniform = a.sample_uniform;
   p.c_scr = a.c_scratch;
   return seq::launch_seq<true>(a.packed, p, st);
 }
