@@ -32,6 +32,13 @@ SIGNATURES = {
     "gnnpn_pn_workspace_bytes": (C.c_size_t, [_i64, _i]),
     "gnnpn_pn_decode_greedy_f32": (_i, [_p, _p, _p, _p, _f, _p, _i, _p, _i, _f, _i64, _i, _i, _i, _i, _i,
                                         _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "gnnpn_pn_att_block_floats": (C.c_size_t, [_i]),
+    "gnnpn_pn_decode_general_workspace_bytes": (C.c_size_t, [_i64, _i, _i, _i, _i, _i, _i]),
+    "gnnpn_pn_decode_general_f32": (_i, [_p, _p, _p, _p, _f, _p, _i, _p, _i, _i, _f, _i64, _i, _i, _i, _i, _i,
+                                         _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, C.c_size_t, _p]),
+    "gnnpn_pn_ref_transform_f32": (_i, [_p, _p, _i64, _i, _p, _p]),
+    "gnnpn_pn_query_transform_f32": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p]),
+    "gnnpn_pn_full_logits_bahdanau_f32": (_i, [_p, _p, _p, _p, _i, _f, _i64, _i, _i, _i, _p, _p]),
     "gnnpn_pn_full_logits_f32": (_i, [_p, _p, _p, _i, _p, _i, _f, _i64, _i, _i, _i, _p, _p]),
     "gnnpn_pn_reward_f32": (_i, [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p]),
     "gnnpn_pn_greedy_low_high_host": (_i, [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _i, _f, _f, _p, _p, _p]),
@@ -64,7 +71,7 @@ def lib():
                 fn = getattr(h, name)          # AttributeError if the ABI lost a symbol
                 fn.restype = res
                 fn.argtypes = args
-            if h.gnnpn_abi_version() != 3:
+            if h.gnnpn_abi_version() != 4:
                 raise GnnpnError("libgnnpn_b200.so ABI version mismatch")
             _lib = h
     return _lib

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(TPB, 2) lstm_step_ffma_kernel(const LstmStepAr
   }
 
   const int kt_begin = a.first ? kH / BK : 0;
-  const int kt_end = kH / BK + (a.use_x ? 1 : 0);
+  const int kt_end = kH / BK + (a.use_x ? (a.F + BK - 1) / BK : 0);   // one or two k-tiles of raw input columns
 
   float4 ra[2], rb[2];
   auto load_regs = [&](int kt) {
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(TPB, 2) lstm_step_ffma_kernel(const LstmStepAr
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int f = a_half * 8 + i;
+        const int f = (kt - kH / BK) * BK + a_half * 8 + i;
         v[i] = (x_row && f < a.F) ? __ldg(x_row + f) : 0.f;
       }
       ra[0] = make_float4(v[0], v[1], v[2], v[3]);

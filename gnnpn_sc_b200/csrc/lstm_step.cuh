@@ -12,7 +12,7 @@ namespace gnnpn {
 
 constexpr int kH = 256;        // hidden_size of every PN ini section (environment.ini:24,39,54,70)
 constexpr int kG = 4 * kH;     // gate columns
-constexpr int kXPad = 16;      // raw input columns padded to one k-tile
+constexpr int kXPad = 32;      // raw input columns padded to two k-tiles of 16 (embedding_size 20 + 8 QoS/constraint columns = 28)
 
 struct LstmStepArgs {
   const float* h_in;      // [M, kH] rows h_in_ld apart; ignored when first != 0

@@ -76,6 +76,7 @@ struct SeqParams {
   PointerStepArgs pa;      // decoder only
   int rotate;
   int dec_flags;          // bit 0: L2 prefetch of the next window; bit 1: batched pointer phase; bit 2: stagger
+  int pf_slots;           // L2 prefetch covers the first pf_slots of every warp's 8 instances (L2 cannot hold a whole window)
   int stagger;            // cycles by which every other CTA pair starts late (decoder), so that the DRAM-bound pointer
                           // phases of one half of the GPU fall into the MMA phases of the other half
   unsigned long long* prof; // debug (GNNPN_SEQ_PROF): per-CTA wait-cycle counters, 16 per CTA, or nullptr
@@ -611,7 +612,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         const uint32_t bytes = (uint32_t)(p.pa.N * kH * 4);
         for (int r = lane; r < BM; r += 32) {
           const int64_t m = m0 + r;
-          if (m < p.n)
+          if (m < p.n && (r & 7) < p.pf_slots)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pa.enc_out + m * p.pa.enc_inst_ld +
                                                                             (int64_t)k * p.pa.N * kH), "r"(bytes) : "memory");
         }
@@ -827,6 +828,8 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
   pp.dec_flags = dec_flags;
   static const int stagger = getenv("GNNPN_SEQ_STAGGER") ? atoi(getenv("GNNPN_SEQ_STAGGER")) : 40000;
   pp.stagger = stagger;
+  static const int pf_slots = getenv("GNNPN_SEQ_PF") ? atoi(getenv("GNNPN_SEQ_PF")) : 8;
+  pp.pf_slots = pf_slots;
   auto kern = lstm_seq_kernel<DEC, CG>;
   static bool configured = false;
   if (!configured) {

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNNPN_ABI_VERSION 3
+#define GNNPN_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define GNNPN_API __attribute__((visibility("default")))
@@ -117,6 +117,42 @@ GNNPN_API int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_o
                                float* dec_h, int32_t* idx_out, float* win_logits, float* win_probs,
                                const int32_t* forced_idx, const float* sample_uniform,
                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- general decode: every PointerNet variant outside the fused fast path above --------------------------
+ * Attention parameter block (gnnpn_pn_att_block_floats(H) floats per Attention module, modelPN.py:83-91):
+ *   [ W_query.weight H x H (out, in) | W_query.bias H | W_ref.weight H x H (Conv1d kernel 1 -> out, in) | W_ref.bias H | V H ]
+ * `att_params` = the pointer's block, followed by the glimpse's block when n_glimpses > 0 (Bahdanau only; NULL for Dot). */
+GNNPN_API size_t gnnpn_pn_att_block_floats(int hidden);
+
+/* Decode loop modelPN.py:204-239 with attention Dot or Bahdanau, n_glimpses >= 0, any window width N, up to 32 raw
+ * input columns.  Same outputs as gnnpn_pn_decode_greedy_f32 plus
+ *   dec_q       fp32 [n, K, H]   the pointer's query of every step (= dec_h when n_glimpses == 0; must be a distinct
+ *                                buffer when n_glimpses > 0)
+ *   qw_pointer  fp32 [n, K, H]   Bahdanau: W_query.q + b of every step (input of gnnpn_pn_full_logits_bahdanau_f32); NULL for Dot
+ * use_tc != 0 runs the LSTM cell on tcgen05 (3xFP16 split), 0 on the strict-fp32 FFMA kernel.
+ * Workspace: gnnpn_pn_decode_general_workspace_bytes(); for Bahdanau it holds E = W_ref.enc_out + b_ref for every
+ * position, computed once per call (the reference re-runs the 1x1 convolution at every step, modelPN.py:105). */
+GNNPN_API size_t gnnpn_pn_decode_general_workspace_bytes(int64_t n, int L, int K, int hidden, int attention,
+                                                         int n_glimpses, int use_tc);
+GNNPN_API int gnnpn_pn_decode_general_f32(const float* inputs, const float* enc_out, float* c_state,
+                                const float* latent_win, float alpha, const float* packed_decoder, int attention,
+                                const float* att_params, int n_glimpses, int use_tanh, float C,
+                                int64_t n, int L, int in_features, int hidden, int K, int N,
+                                float* dec_h, float* dec_q, float* qw_pointer, int32_t* idx_out, float* win_logits,
+                                float* win_probs, const int32_t* forced_idx, const float* sample_uniform, int use_tc,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Building blocks of Attention.forward for name == 'Bahdanau' (modelPN.py:103-109):
+ *   E  [rows, H] = W_ref . enc_out[rows, H] + b_ref          (the Conv1d(H, H, 1))
+ *   qw [rows, H] = W_query . q + b_query
+ *   logits_full [K, n, L] = C*tanh( V . tanh(qw[b,k,:] + E[b,l,:]) ), -inf at the picks of steps < k */
+GNNPN_API int gnnpn_pn_ref_transform_f32(const float* enc_out, const float* att_block, int64_t rows, int hidden,
+                               float* E, void* stream);
+GNNPN_API int gnnpn_pn_query_transform_f32(const float* q, int64_t q_ld, const float* att_block, int64_t rows,
+                                 int hidden, float* qw, int64_t qw_ld, void* stream);
+GNNPN_API int gnnpn_pn_full_logits_bahdanau_f32(const float* E, const float* qw, const float* att_block,
+                                      const int32_t* idx, int use_tanh, float C, int64_t n, int L, int hidden,
+                                      int K, float* logits_full, void* stream);
 
 /* Interface-faithful materialisation of PointerNet.forward's prev_logits (modelPN.py:213-214,239):
  *   logits_full fp32 [K, n, L] = C*tanh(<enc_out[b,l,:], dec_h[b,k,:]>) with -inf at the positions

@@ -239,3 +239,21 @@ def test_argument_errors_are_reported_not_thrown():
     with pytest.raises(RuntimeError):
         m = M.CombinatorialRL(0, 256, 6, 0, 10, 1, M.reward, "Dot", 2, 3).cuda()
         m(torch.zeros(2, 6, 8), None, sample="greedy", training="SL")                       # CPU tensor -> loud error
+
+
+def test_host_batch_pipeline_matches_direct_calls():
+    """gnnpn_sc_b200.pipeline.GreedyLowHigh (double-buffered uploads) == calling the modules batch by batch."""
+    from gnnpn_sc_b200.pipeline import GreedyLowHigh
+    from gnnpn_sc_b200.synth import pn_instances
+    cfg, _, low, high = _models("qws_b4")
+    K, N = cfg.s_category, cfg.s_number
+    batches = [pn_instances(n, K, N, seed=90 + i) for i, n in enumerate((130, 64, 200))]     # ragged sizes
+    outs = list(GreedyLowHigh(low, high, "cuda").run(batches))
+    assert len(outs) == len(batches)
+    for x, (idx_host, r_host) in zip(batches, outs):
+        with torch.no_grad():
+            _, _, _, _, latent = low(x.cuda(), None, sample="greedy", training="SL")
+            R, _, _, idx, _ = high(x.cuda(), None, latent, sample="greedy", training="RL")
+        assert not idx_host.is_cuda and idx_host.dtype == torch.int32
+        assert torch.equal(idx_host.long(), torch.stack(idx).cpu())
+        assert torch.equal(r_host, R.cpu())
