@@ -54,7 +54,9 @@ __global__ void __launch_bounds__(kAttThreads) glimpse_step_kernel(const General
   extern __shared__ uint32_t smem_u[];
   uint32_t* visited = smem_u;                              // bitmap of L bits
   const int words = (a.L + 31) / 32;
-  float* red = reinterpret_cast<float*>(smem_u + words);   // [8 warps][2 + kH]
+  const int words4 = (words + 3) & ~3;                     // keep the float4 accesses below 16-byte aligned
+  float* red_ms = reinterpret_cast<float*>(smem_u + words4);           // [8 warps][2] running max, sum
+  float* red_acc = red_ms + 4 * kAttWarps;                               // [8 warps][kH] weighted row sums
   const int64_t b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < words; i += kAttThreads) visited[i] = 0u;
@@ -85,24 +87,23 @@ __global__ void __launch_bounds__(kAttThreads) glimpse_step_kernel(const General
     acc[6] = fmaf(acc[6], sc, p * r1.z); acc[7] = fmaf(acc[7], sc, p * r1.w);
     m = nm;
   }
-  float* mine = red + warp * (2 + kH);
-  if (lane == 0) { mine[0] = m; mine[1] = s; }
+  if (lane == 0) { red_ms[2 * warp] = m; red_ms[2 * warp + 1] = s; }
   // lane owns hidden elements 4*lane..+3 and 128+4*lane..+3 (float4 index lane and 32+lane)
-  reinterpret_cast<float4*>(mine + 2)[lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  reinterpret_cast<float4*>(mine + 2)[32 + lane] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  reinterpret_cast<float4*>(red_acc + warp * kH)[lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  reinterpret_cast<float4*>(red_acc + warp * kH)[32 + lane] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   __syncthreads();
   float M = -INFINITY;
-  for (int w = 0; w < kAttWarps; ++w) M = fmaxf(M, red[w * (2 + kH)]);
+  for (int w = 0; w < kAttWarps; ++w) M = fmaxf(M, red_ms[2 * w]);
   float S = 0.f;
   for (int w = 0; w < kAttWarps; ++w) {
-    const float mw = red[w * (2 + kH)];
-    if (mw > -INFINITY) S += red[w * (2 + kH) + 1] * expf(mw - M);
+    const float mw = red_ms[2 * w];
+    if (mw > -INFINITY) S += red_ms[2 * w + 1] * expf(mw - M);
   }
   for (int h = threadIdx.x; h < kH; h += kAttThreads) {
     float o = 0.f;
     for (int w = 0; w < kAttWarps; ++w) {
-      const float mw = red[w * (2 + kH)];
-      if (mw > -INFINITY) o = fmaf(red[w * (2 + kH) + 2 + h], expf(mw - M), o);
+      const float mw = red_ms[2 * w];
+      if (mw > -INFINITY) o = fmaf(red_acc[w * kH + h], expf(mw - M), o);
     }
     q_out[b * q_out_ld + h] = o / S;
   }
@@ -356,7 +357,7 @@ int gnnpn_pn_decode_general_f32(const float* inputs, const float* enc_out, float
     a.h_out_ld = (int64_t)K * kH;
   }
   const int32_t* fed_all = forced_idx ? forced_idx : idx_out;
-  const size_t glimpse_smem = (size_t)((L + 31) / 32) * 4 + (size_t)kAttWarps * (2 + kH) * 4;
+  const size_t glimpse_smem = (size_t)((((L + 31) / 32) + 3) & ~3) * 4 + (size_t)kAttWarps * (4 + kH) * 4;
   const size_t ptr_smem = (size_t)N * 2 * sizeof(float);
   if (glimpse_smem > 48 * 1024) {
     cudaFuncSetAttribute(glimpse_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)glimpse_smem);

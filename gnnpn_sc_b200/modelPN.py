@@ -120,16 +120,39 @@ class Attention(nn.Module):
             bound = 1.0 / math.sqrt(hidden_size)
             self.V = nn.Parameter(torch.empty(hidden_size).uniform_(-bound, bound))
 
+    def block(self) -> torch.Tensor:
+        """Bahdanau parameters packed for the kernels (``gnnpn_pn_att_block_floats`` layout)."""
+        return ops.att_block(self.W_query.weight, self.W_query.bias, self.W_ref.weight, self.W_ref.bias, self.V)
+
     def forward(self, query, ref):
-        """query [B,H], ref [B,L,H] -> (ref as [B,H,L], logits [B,L])."""
-        if self.name != 'Dot':
-            raise NotImplementedError(f"attention {self.name!r}: only 'Dot' has a CUDA kernel so far")
+        """query [B,H], ref [B,L,H] -> (ref as [B,H,L] (Bahdanau: W_ref(ref)), logits [B,L])  (modelPN.py:93-123)."""
         B, L, H = ref.shape
-        refc = ref.contiguous()
+        refc = ref.detach().float().contiguous()
+        q = query.detach().float().contiguous()
         none_picked = torch.zeros(1, B, device=ref.device, dtype=torch.int32)
-        logits = ops.pn_full_logits(refc, query.contiguous().view(B, 1, H), none_picked, "Dot", None,
-                                    bool(self.use_tanh), float(self.C))[0]
-        return ref.permute(0, 2, 1), logits
+        if self.name == 'Dot':
+            logits = ops.pn_full_logits(refc, q.view(B, 1, H), none_picked, "Dot", None, bool(self.use_tanh),
+                                        float(self.C))[0]
+            return ref.permute(0, 2, 1), logits
+        if self.name != 'Bahdanau':
+            raise NotImplementedError(self.name)
+        blk = self.block()
+        E = ops.pn_ref_transform(refc, blk)
+        qw = ops.pn_query_transform(q, blk)
+        logits = ops.pn_full_logits_bahdanau(E, qw.view(B, 1, H), blk, none_picked, bool(self.use_tanh), float(self.C))[0]
+        return E.permute(0, 2, 1), logits
+
+    def torch_rows(self, query, rows):
+        """Differentiable torch evaluation on a subset of positions: rows [B,l,H] -> (ref' [B,l,H], logits [B,l])."""
+        if self.name == 'Dot':
+            logits = torch.bmm(rows, query.unsqueeze(2)).squeeze(2)
+            refp = rows
+        else:
+            refp = torch.nn.functional.linear(rows, self.W_ref.weight.squeeze(2), self.W_ref.bias)
+            logits = torch.tanh(self.W_query(query).unsqueeze(1) + refp) @ self.V
+        if self.use_tanh:
+            logits = self.C * torch.tanh(logits)
+        return refp, logits
 
 
 # --------------------------------------------------------------------------- PointerNet
@@ -163,6 +186,7 @@ class PointerNet(nn.Module):
         self.last = None                          # device-side results of the most recent forward
         self.impl = None                          # None -> ops.DEFAULT_IMPL ("tc"); "ffma" = strict-fp32 kernels
         self.generator = None                     # optional torch.Generator (cuda) for sample="sample"
+        self.force_general = False                # route a fast-path configuration through the general kernels (tests)
 
     # -- packed weights are a cache over the parameters; rebuilt when any of them changes
     def _packed_weights(self):
@@ -180,37 +204,65 @@ class PointerNet(nn.Module):
             self._packed, self._pack_key = (enc, dec), key
         return self._packed
 
+    def _kernel_inputs(self, inputs):
+        """Raw rows the LSTM kernels consume: with a category embedding (modelPN.py:183-188) column 0 is replaced by
+        its ``embedding1`` row (``gnnpn_embed_concat_f32``), giving 20 + 8 = 28 columns."""
+        x = inputs.detach().float().contiguous()
+        if self.embedding_size == 0:
+            return x
+        B, L, C = x.shape
+        return ops.embed_concat(x.view(B * L, C), self.embedding1.weight.detach()).view(B, L, -1)
+
+    def _fast_path(self, F: int) -> bool:
+        return (not self.force_general and self.embedding_size == 0 and self.n_glimpses == 0
+                and self.pointer.name == "Dot" and self.serNumber <= 32 and F <= 8)
+
     def forward(self, inputs, latent, sample="sample", forced_idxs=None):
         """inputs [B, L, F] -> (prev_probs, prev_idxs, prev_logits), K-long each (modelPN.py:241)."""
         B, L, _ = inputs.shape
         assert L == self.seq_len
-        if self.embedding_size != 0 or self.n_glimpses != 0 or self.pointer.name != "Dot":
-            raise NotImplementedError("CUDA path covers embedding_size=0, n_glimpses=0, attention='Dot' "
-                                      "(every PN section of environment.ini)")
+        if self.pointer.name not in ("Dot", "Bahdanau"):
+            raise NotImplementedError(self.pointer.name)
         if not inputs.is_cuda:
             raise RuntimeError("PointerNet.forward needs CUDA tensors: the B200 path has no CPU fallback")
         K, N = self.serCategory, self.serNumber
-        x = inputs.detach().float().contiguous()
+        x = self._kernel_inputs(inputs)
+        fast = self._fast_path(x.shape[2])
         enc_w, dec_w = self._packed_weights()
+        use_tanh, C = bool(self.pointer.use_tanh), float(self.pointer.C)
+        att = self.pointer.name
         with torch.no_grad():
             ws = ops.pn_workspace(B, self.hidden_size, x.device, self.impl)
             enc_out, c = ops.lstm_encode(x, enc_w, self.hidden_size, workspace=ws)
             lat = _window_of(latent, K, N) if latent else None
             forced = None if forced_idxs is None else torch.stack([t.to(torch.int32) for t in forced_idxs])
-            use_tanh, C = bool(self.pointer.use_tanh), float(self.pointer.C)
             # sample != "greedy": multinomial draw per step (modelPN.py:227-228) as an inverse-CDF pick in the kernel
             uniform = None if sample == "greedy" else torch.rand(K, B, device=x.device, generator=self.generator)
-            dec_h, idx, win_logits, win_probs = ops.pn_decode_greedy(
-                x, enc_out, c, dec_w, K, N, latent_win=lat, alpha=float(self.alpha), attention="Dot",
-                use_tanh=use_tanh, C=C, forced_idx=forced, workspace=ws, sample_uniform=uniform)
+            ptr_blk = qw = None
+            if fast:
+                dec_h, idx, win_logits, win_probs = ops.pn_decode_greedy(
+                    x, enc_out, c, dec_w, K, N, latent_win=lat, alpha=float(self.alpha), attention="Dot",
+                    use_tanh=use_tanh, C=C, forced_idx=forced, workspace=ws, sample_uniform=uniform)
+                dec_q = dec_h
+            else:
+                blocks = None
+                if att == "Bahdanau":
+                    ptr_blk = self.pointer.block()
+                    blocks = torch.cat([ptr_blk, self.glimpse.block()]) if self.n_glimpses else ptr_blk
+                dec_h, dec_q, qw, idx, win_logits, win_probs = ops.pn_decode_general(
+                    x, enc_out, c, dec_w, K, N, latent_win=lat, alpha=float(self.alpha), attention=att,
+                    att_params=blocks, n_glimpses=self.n_glimpses, use_tanh=use_tanh, C=C, forced_idx=forced,
+                    sample_uniform=uniform, use_tc=ws is not None)
         idx64 = idx.long()
         self.last = {"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "enc_out": enc_out, "dec_h": dec_h,
-                     "latent_win": lat}
+                     "dec_q": dec_q, "latent_win": lat}
 
         fed = idx if forced is None else forced.contiguous()     # the picks the visited mask follows
 
         def dense_logits():
-            return ops.pn_full_logits(enc_out, dec_h, fed, "Dot", None, use_tanh, C)
+            if att == "Dot":
+                return ops.pn_full_logits(enc_out, dec_q, fed, "Dot", None, use_tanh, C)
+            return ops.pn_full_logits_bahdanau(ops.pn_ref_transform(enc_out, ptr_blk), qw, ptr_blk, fed, use_tanh, C)
 
         def dense_probs():      # exactly zero outside window k (SURVEY 3.4)
             out = torch.zeros(K, B, L, device=x.device, dtype=torch.float32)
@@ -228,28 +280,36 @@ class PointerNet(nn.Module):
 
         The decode itself runs in the CUDA kernels without autograd; this replays it with torch ops restricted to
         the windows -- outside window k the reference's probabilities are exactly 0 and carry no gradient
-        (modelPN.py:220-224) -- so the gradient equals the reference's.  Encoder via nn.LSTM (cuDNN), K cell steps."""
+        (modelPN.py:220-224) -- so the gradient equals the reference's.  Encoder via nn.LSTM (cuDNN), K cell steps;
+        glimpses (when configured) attend over all positions with the cumulative visited mask as in modelPN.py:208-211."""
         # strict fp32 (set process-wide in gnnpn_sc_b200/__init__.py: cuDNN's TF32 default would put ~5e-4 relative
         # error into forward AND backward of the nn.LSTM calls below)
         B, L, _ = inputs.shape
         K, N = self.serCategory, self.serNumber
         rows = torch.arange(B, device=inputs.device)
-        emb = self.embedding2(inputs.float())
+        x = inputs.float()
+        if self.embedding_size != 0:
+            x = torch.cat((self.embedding1(x[:, :, 0].long()), x[:, :, 1:]), 2)
+        emb = self.embedding2(x)
         enc_out, (h, c) = self.encoder(emb)
         dec_in = self.decoder_start_input.unsqueeze(0).expand(B, -1)
+        visited = torch.zeros(B, L, dtype=torch.bool, device=inputs.device)
         out = []
-        C = float(self.pointer.C)
         for k in range(K):
             _, (h, c) = self.decoder(dec_in.unsqueeze(1), (h, c))
-            win = enc_out[:, k * N:(k + 1) * N, :]
-            logits = torch.bmm(win, h[0].unsqueeze(2)).squeeze(2)
-            if self.pointer.use_tanh:
-                logits = C * torch.tanh(logits)
+            query = h[0]
+            for _ in range(self.n_glimpses):
+                refp, gl = self.glimpse.torch_rows(query, enc_out)
+                gl = gl.masked_fill(visited, float("-inf"))
+                query = torch.bmm(refp.transpose(1, 2), torch.softmax(gl, dim=1).unsqueeze(2)).squeeze(2)
+            _, logits = self.pointer.torch_rows(query, enc_out[:, k * N:(k + 1) * N, :])
             if latent_win is not None:
                 logits = logits + float(self.alpha) * latent_win[:, k * N:(k + 1) * N]
             p = torch.softmax(logits, dim=1)
             out.append(p.gather(1, (idx[k] - k * N).unsqueeze(1)).squeeze(1))
             dec_in = emb[rows, idx[k]]
+            visited = visited.clone()
+            visited[rows, idx[k]] = True
         return out
 
 

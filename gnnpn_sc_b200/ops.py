@@ -111,6 +111,79 @@ def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, laten
     return dec_h, idx, wl, wp
 
 
+def att_block(W_query_w, W_query_b, W_ref_w, W_ref_b, V) -> torch.Tensor:
+    """One Attention module's Bahdanau parameters in the layout of ``gnnpn_pn_att_block_floats``."""
+    H = V.numel()
+    parts = [W_query_w.reshape(H * H), W_query_b.reshape(H), W_ref_w.reshape(H * H), W_ref_b.reshape(H), V.reshape(H)]
+    out = torch.cat([_f32(t.detach(), "attention parameter") for t in parts])
+    assert out.numel() == int(lib().gnnpn_pn_att_block_floats(H))
+    return out
+
+
+def pn_decode_general(inputs, enc_out, c_state, packed_dec, K: int, N: int, latent_win=None, alpha: float = 1.0,
+                      attention: str = "Dot", att_params=None, n_glimpses: int = 0, use_tanh: bool = True,
+                      C: float = 10.0, forced_idx=None, sample_uniform=None, use_tc: bool = True):
+    """Every PointerNet variant (Bahdanau, glimpses, any window width, <= 32 raw columns).
+    Returns (dec_h, dec_q, qw_pointer | None, idx int32 [K,n], win_logits [n,L], win_probs [n,L])."""
+    x = _f32(inputs, "inputs")
+    n, L, F = x.shape
+    H = enc_out.shape[2]
+    dev = x.device
+    dec_h = torch.empty(n, K, H, device=dev, dtype=torch.float32)
+    dec_q = torch.empty(n, K, H, device=dev, dtype=torch.float32) if n_glimpses > 0 else dec_h
+    qw = torch.empty(n, K, H, device=dev, dtype=torch.float32) if attention == "Bahdanau" else None
+    idx = torch.empty(K, n, device=dev, dtype=torch.int32)
+    wl = torch.empty(n, L, device=dev, dtype=torch.float32)
+    wp = torch.empty(n, L, device=dev, dtype=torch.float32)
+    if latent_win is not None:
+        latent_win = _f32(latent_win, "latent_win")
+        assert latent_win.shape == (n, L)
+    if forced_idx is not None:
+        forced_idx = forced_idx.to(torch.int32).contiguous()
+        assert forced_idx.shape == (K, n)
+    if sample_uniform is not None:
+        sample_uniform = _f32(sample_uniform, "sample_uniform")
+        assert sample_uniform.shape == (K, n)
+    nbytes = int(lib().gnnpn_pn_decode_general_workspace_bytes(n, L, K, H, ATT[attention], n_glimpses, int(use_tc)))
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    check(lib().gnnpn_pn_decode_general_f32(
+        x.data_ptr(), enc_out.data_ptr(), c_state.data_ptr(), _ptr(latent_win), float(alpha), packed_dec.data_ptr(),
+        ATT[attention], _ptr(att_params), int(n_glimpses), int(bool(use_tanh)), float(C), n, L, F, H, K, N,
+        dec_h.data_ptr(), dec_q.data_ptr(), _ptr(qw), idx.data_ptr(), wl.data_ptr(), wp.data_ptr(),
+        _ptr(forced_idx), _ptr(sample_uniform), int(use_tc), ws.data_ptr(), ws.numel(), _stream()), "pn_decode_general")
+    return dec_h, dec_q, qw, idx, wl, wp
+
+
+def pn_ref_transform(enc_out, block) -> torch.Tensor:
+    """Bahdanau ``W_ref`` (Conv1d(H,H,1), modelPN.py:87,105) on every position: [.., H] -> [.., H]."""
+    x = _f32(enc_out, "enc_out")
+    H = x.shape[-1]
+    out = torch.empty_like(x)
+    check(lib().gnnpn_pn_ref_transform_f32(x.data_ptr(), block.data_ptr(), x.numel() // H, H, out.data_ptr(), _stream()),
+          "pn_ref_transform")
+    return out
+
+
+def pn_query_transform(q, block) -> torch.Tensor:
+    """Bahdanau ``W_query`` (modelPN.py:85,104): [rows, H] -> [rows, H]."""
+    x = _f32(q, "query")
+    rows, H = x.shape
+    out = torch.empty_like(x)
+    check(lib().gnnpn_pn_query_transform_f32(x.data_ptr(), H, block.data_ptr(), rows, H, out.data_ptr(), H, _stream()),
+          "pn_query_transform")
+    return out
+
+
+def pn_full_logits_bahdanau(E, qw, block, idx, use_tanh: bool = True, C: float = 10.0) -> torch.Tensor:
+    n, L, H = E.shape
+    K = qw.shape[1]
+    out = torch.empty(K, n, L, device=E.device, dtype=torch.float32)
+    check(lib().gnnpn_pn_full_logits_bahdanau_f32(E.data_ptr(), qw.data_ptr(), block.data_ptr(), idx.data_ptr(),
+                                                  int(bool(use_tanh)), float(C), n, L, H, K, out.data_ptr(), _stream()),
+          "pn_full_logits_bahdanau")
+    return out
+
+
 def pn_full_logits(enc_out, dec_h, idx, attention: str = "Dot", att_params=None, use_tanh: bool = True,
                    C: float = 10.0) -> torch.Tensor:
     n, L, H = enc_out.shape

@@ -60,7 +60,7 @@ GNNPN_API uint64_t gnnpn_launch_count(void);
 
 /* Size in floats of one packed LSTM ("[h | x] -> 4H gates") weight block for hidden size H and
  * `in_features` raw input columns.  Layout (Kp = H + 32):
- *   [ (H + 16) x 4H   k-major block for the strict-fp32 FFMA step kernel ]
+ *   [ (H + 32) x 4H   k-major block for the strict-fp32 FFMA step kernel ]
  *   [ 4H bias ] [ 4H start ]
  *   [ 4H x Kp  tf32 "hi" part, gate-column-major (K contiguous) for the tcgen05 step kernel ]
  *   [ 4H x Kp  tf32 "lo" part ( = w - hi ) ] */

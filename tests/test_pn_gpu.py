@@ -15,7 +15,7 @@ from oracle import pn_oracle as po
 
 pytestmark = pytest.mark.gpu
 LOGIT_TOL = 1e-5
-CUDA_CASES = ["qws_b4", "normal_b2", "small_b16", "sharp_b4", "notanh_b3"]
+CUDA_CASES = ["qws_b4", "normal_b2", "small_b16", "sharp_b4", "notanh_b3", "bahdanau_b3", "glimpse_b3", "embed20_b3"]
 
 
 IMPLS = ["tc", "ffma"]        # tcgen05 3xTF32 recurrence (default) and the strict-fp32 FFMA kernels
@@ -102,9 +102,9 @@ def test_greedy_low_high_matches_reference_fixture(name, impl, golden_dir):
     assert np.array_equal(torch.stack(act_hi).cpu().numpy(), g["actions_high"])
     assert np.array_equal(R_hi.cpu().numpy(), g["reward_high"])          # bit-exact objective evaluator
     from gnnpn_sc_b200 import ops
-    _, obj, _ = ops.pn_reward(xc, torch.stack(idx_hi_t).to(torch.int32))
+    _, obj, _ = ops.pn_reward(xc, torch.stack(idx_hi_t).to(torch.int32), tag=0 if cfg.embedding_size == 0 else 1)
     assert np.array_equal(obj.cpu().numpy(), g["objfunc_high"])          # unrounded objFunc, exact
-    r_low = high.reward(act_hi, None, cfg.s_category, USE_CUDA=True, level="Low", embedding_size=0)
+    r_low = high.reward(act_hi, None, cfg.s_category, USE_CUDA=True, level="Low", embedding_size=cfg.embedding_size)
     assert np.array_equal(r_low.cpu().numpy(), g["viol_high"])
 
 
@@ -257,3 +257,74 @@ def test_host_batch_pipeline_matches_direct_calls():
         assert not idx_host.is_cuda and idx_host.dtype == torch.int32
         assert torch.equal(idx_host.long(), torch.stack(idx).cpu())
         assert torch.equal(r_host, R.cpu())
+
+
+@pytest.mark.parametrize("impl", ["ffma"])
+def test_general_kernels_equal_fused_path_bitwise(impl):
+    """Dot / no glimpse / N <= 32 through the general (one-CTA-per-instance) kernels == the fused path, bit for bit
+    (same LSTM kernel on both sides: with impl="tc" the fused path runs the persistent scan, whose cell epilogue rounds
+    differently from the per-step tcgen05 kernel the general path uses)."""
+    from gnnpn_sc_b200.synth import pn_instances
+    cfg, _, low, high = _models("qws_b4", impl=impl)
+    x = pn_instances(200, cfg.s_category, cfg.s_number, seed=31).cuda()
+    outs = []
+    for general in (False, True):
+        low.actor.force_general = high.actor.force_general = general
+        with torch.no_grad():
+            _, _, _, idx_lo, latent = low(x, None, sample="greedy", training="SL")
+            R, ap, _, idx_hi, lg = high(x, None, latent, sample="greedy", training="RL")
+        outs.append((torch.stack(idx_lo), torch.stack(idx_hi), latent.window.clone(), lg.window.clone(),
+                     high.actor.last["win_probs"].clone(), R))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("kw,n", [
+    (dict(s_category=5, s_number=40), 37),                                        # window wider than a warp
+    (dict(s_category=6, s_number=4, attention="Bahdanau", n_glimpses=1), 33),     # additive attention + glimpse
+    (dict(s_category=4, s_number=6, n_glimpses=2), 20),                           # two Dot glimpses
+    (dict(s_category=7, s_number=3, embedding_size=20, attention="Bahdanau"), 19),
+    (dict(s_category=3, s_number=1000), 6),                                       # scale-up window width (BASELINE config 4)
+])
+def test_general_variants_teacher_forced_against_oracle(kw, n):
+    from gnnpn_sc_b200 import modelPN as M
+    K, N = kw["s_category"], kw["s_number"]
+    cfg = po.PNConfig(seq_len=K * N, **kw)
+    sd = po.make_state_dict(cfg, 123)
+    x = mg.build_inputs(cfg, n, 17, "qws")
+    with torch.no_grad():
+        pr_ref, idx_ref, lg_ref = po.pointer_forward(sd, cfg, x, None, "greedy")
+    m = M.CombinatorialRL(cfg.embedding_size, 256, K * N, cfg.n_glimpses, 10, 1, M.reward, cfg.attention, N, K, level="Low")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    for impl in IMPLS:
+        m.actor.impl = impl
+        with torch.no_grad():
+            probs, idx, lg = m.actor(x.cuda(), None, sample="greedy", forced_idxs=[t.cuda() for t in idx_ref])
+        ref_lg = torch.stack(lg_ref).numpy()
+        flips = _explain_flips(torch.stack(idx).cpu().numpy(), torch.stack(idx_ref).numpy(), ref_lg, N)
+        dense = torch.stack([lg[k] for k in range(K)]).cpu().numpy()
+        assert np.array_equal(np.isneginf(dense), np.isneginf(ref_lg))
+        fin = np.isfinite(ref_lg)
+        err = np.abs(dense[fin] - ref_lg[fin]).max()
+        print(f"general {kw} [{impl}]: {flips} tolerance-limited picks, max |dlogit| {err:.2e}")
+        assert _close(dense[fin], ref_lg[fin]).all(), err
+        pd = torch.stack([probs[k] for k in range(K)]).cpu().numpy()
+        assert _close(pd, torch.stack(pr_ref).numpy()).all()
+
+
+def test_bahdanau_attention_module_against_oracle():
+    """Attention.forward(query, ref) for name='Bahdanau' (modelPN.py:93-123): W_ref(ref) and C*tanh(V.tanh(..))."""
+    from gnnpn_sc_b200 import modelPN as M
+    cfg = po.PNConfig(seq_len=12, s_number=3, s_category=4, attention="Bahdanau")
+    sd = po.make_state_dict(cfg, 5)
+    att = M.Attention(256, use_tanh=True, C=10, name="Bahdanau")
+    att.load_state_dict({k[len("actor.pointer."):]: v for k, v in sd.items() if k.startswith("actor.pointer.")})
+    att = att.cuda()
+    g = torch.Generator().manual_seed(3)
+    q, ref = torch.randn(5, 256, generator=g) * 0.5, torch.randn(5, 12, 256, generator=g) * 0.5
+    refp_o, lg_o = po.attention(sd, "pointer", cfg, q, ref, True, 10.0)
+    refp, lg = att(q.cuda(), ref.cuda())
+    assert refp.shape == refp_o.shape
+    assert _close(refp.cpu().numpy(), refp_o.numpy()).all()
+    assert _close(lg.cpu().numpy(), lg_o.numpy()).all()
