@@ -1,0 +1,125 @@
+// Candidate selection between the two accelerated stages: the ML ranking -> per-category top-N
+// feasible services -> pointer-network input rows, on the device.
+//
+// Reference semantics (src/loadData.py:99-150, the body of loadDataPN), per instance b and category c:
+//   walk the services in ranking order (descending ML score); take the first N of category c that satisfy the
+//   task's local bounds  lo2 <= q2 <= hi2  and  lo3 <= q3 <= hi3  (loadData.py:120-124);
+//   if the request uses category c and at least one service is feasible: pad the list by self-duplication to N
+//   (loadData.py:137-138) and emit rows [c, q0, q1, q2, q3, tail]; otherwise N neutral rows [c, 0, 1, 1, 1, tail]
+//   (loadData.py:148); tail = the four global bounds on category 0, zeros elsewhere (loadData.py:130-133).
+// The reference then shuffles each candidate list with the unseeded global numpy RNG (loadData.py:135); this kernel
+// keeps ranking order (the deterministic realisation SURVEY 8d config 3 prescribes).  Ties in the score are broken
+// towards the lower service id (= a stable descending sort).
+//
+// One CTA per (instance, category): bitonic sort of (score, id) over the category's services in shared memory.
+#include <math.h>
+#include "common.cuh"
+
+namespace gnnpn {
+namespace {
+
+constexpr int kSelThreads = 128;
+
+// a sorts before b: higher score first, lower id on ties; infeasible entries carry -inf and id = INT_MAX
+__device__ __forceinline__ bool sel_before(float sa, int ia, float sb, int ib) {
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(
+    const float* __restrict__ scores, int64_t scores_ld, const float* __restrict__ svc_qos,
+    const int32_t* __restrict__ cat_ptr, const float* __restrict__ local_bounds, const uint8_t* __restrict__ used,
+    const float* __restrict__ global_bounds, int K, int N, int P, int with_category,
+    float* __restrict__ rows, int32_t* __restrict__ picked) {
+  extern __shared__ float sel_smem[];
+  float* key = sel_smem;                                  // [P]
+  int* ids = reinterpret_cast<int*>(sel_smem + P);        // [P]
+  __shared__ int s_count;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int64_t b = blockIdx.y;
+  const int s0 = cat_ptr[c], s1 = cat_ptr[c + 1];
+  const float* lb = local_bounds + (b * K + c) * 4;
+  const float lo2 = lb[0], hi2 = lb[1], lo3 = lb[2], hi3 = lb[3];
+  const bool use = used[b * K + c] != 0;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i = tid; i < P; i += kSelThreads) {
+    const int s = s0 + i;
+    float k = -INFINITY;
+    int id = 0x7fffffff;
+    if (use && s < s1) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(svc_qos) + s);
+      if (lo2 <= q.z && q.z <= hi2 && lo3 <= q.w && q.w <= hi3) {
+        k = __ldg(scores + b * scores_ld + s);
+        id = s;
+        ++mine;
+      }
+    }
+    key[i] = k; ids[i] = id;
+  }
+  if (mine) atomicAdd(&s_count, mine);
+  __syncthreads();
+  const int count = s_count;
+  // bitonic sort, "before" order ascending in position
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < P / 2; i += kSelThreads) {
+        const int lo = 2 * i - (i & (stride - 1));        // index with the `stride` bit clear
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;                 // this sub-sequence sorts "best first"
+        const float ka = key[lo], kb = key[hi];
+        const int ia = ids[lo], ib = ids[hi];
+        const bool swap = up ? sel_before(kb, ib, ka, ia) : sel_before(ka, ia, kb, ib);
+        if (swap) { key[lo] = kb; key[hi] = ka; ids[lo] = ib; ids[hi] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+  const int F = 8 + (with_category ? 1 : 0);
+  float tail[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tail[i] = global_bounds[b * 4 + i];
+  }
+  for (int j = tid; j < N; j += kSelThreads) {
+    float* r = rows + ((b * K + c) * (int64_t)N + j) * F;
+    int sid = -1;
+    float4 q = make_float4(0.f, 1.f, 1.f, 1.f);           // neutral row (loadData.py:148)
+    if (count > 0) {
+      sid = ids[j % count];                               // self-duplication padding = cyclic repetition
+      q = __ldg(reinterpret_cast<const float4*>(svc_qos) + sid);
+    }
+    if (with_category) *r++ = (float)c;
+    r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w;
+    r[4] = tail[0]; r[5] = tail[1]; r[6] = tail[2]; r[7] = tail[3];
+    if (picked) picked[(b * K + c) * (int64_t)N + j] = sid;
+  }
+}
+
+}  // namespace
+}  // namespace gnnpn
+
+using namespace gnnpn;
+
+extern "C" int gnnpn_select_candidates_f32(const float* scores, int64_t scores_ld, const float* svc_qos,
+                                           const int32_t* cat_ptr, int max_category_size,
+                                           const float* local_bounds, const uint8_t* used,
+                                           const float* global_bounds, int64_t n, int K, int N, int with_category,
+                                           float* rows, int32_t* picked, void* stream) {
+  GNNPN_REQUIRE(scores && svc_qos && cat_ptr && local_bounds && used && global_bounds && rows, GNNPN_ENULL);
+  GNNPN_REQUIRE(K >= 1 && N >= 1 && max_category_size >= 1 && max_category_size <= 16384, GNNPN_ESHAPE);
+  GNNPN_REQUIRE(n >= 0 && n < 65536, GNNPN_ERANGE);
+  GNNPN_REQUIRE(aligned16(svc_qos), GNNPN_EALIGN);
+  if (n == 0) return GNNPN_OK;
+  int P = 32;
+  while (P < max_category_size) P <<= 1;
+  const size_t smem = (size_t)P * 8;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 grid((unsigned)K, (unsigned)n);
+  select_candidates_kernel<<<grid, kSelThreads, smem, (cudaStream_t)stream>>>(
+      scores, scores_ld, svc_qos, cat_ptr, local_bounds, used, global_bounds, K, N, P, with_category, rows, picked);
+  return after_launch();
+}

@@ -203,7 +203,8 @@ class Net(nn.Module):
         with torch.no_grad():
             return self._forward_infer(data)
 
-    def _forward_infer(self, data):
+    def _encode_requests(self, data):
+        """Request side (modelML.py:133-143,165-166): GIN layers -> nodeLin -> mean over each request graph -> [B, H]."""
         x_raw = data.x.squeeze().float()
         n_req = x_raw.shape[0]
         x = ops.embed_concat(x_raw, self.nodeEncoder.embeddings[0].weight)                 # [n, 28] (26 + pad)
@@ -215,7 +216,13 @@ class Net(nn.Module):
             h = ops.gemm_bias_act(agg, _pad_w(lin0.weight, agg.shape[1]), bias=lin0.bias, scale=s0, shift=t0, act="relu")
             s1, t1 = self._fold(bn)
             x = ops.gemm_bias_act(h, lin1.weight, bias=lin1.bias, scale=s1, shift=t1, act="relu")
+        x = ops.gemm_bias_act(x, self.nodeLin.weight, bias=self.nodeLin.bias)
+        B = int(data.batch.max().item()) + 1 if n_req else 0
+        memb = self._membership_csr(data.batch, B)
+        return ops.spmm_csr(memb.rowptr, memb.col, None, x, n_rows=B, mean=True), B        # [B, H]
 
+    def _encode_service_nodes(self, data):
+        """Service side (modelML.py:145-164): GCN layers (or the Linear stand-ins) -> serviceLin -> [n_svc, H]."""
         xs_raw = data.x_service.squeeze().float()
         n_svc = xs_raw.shape[0]
         xs = ops.embed_concat(xs_raw, self.serviceEncoder.embeddings[0].weight)            # [B*S, 24]
@@ -231,17 +238,34 @@ class Net(nn.Module):
             else:
                 lin = self.noServicesLins[i]
                 xs = ops.gemm_bias_act(xs, _pad_w(lin.weight, xs.shape[1]), bias=lin.bias, scale=s, shift=t, act="relu")
+        return ops.gemm_bias_act(xs, self.serviceLin.weight, bias=self.serviceLin.bias), n_svc
 
-        xs = ops.gemm_bias_act(xs, self.serviceLin.weight, bias=self.serviceLin.bias)
-        x = ops.gemm_bias_act(x, self.nodeLin.weight, bias=self.nodeLin.bias)
-        B = int(data.batch.max().item()) + 1 if n_req else 0
-        memb = self._membership_csr(data.batch, B)
-        x = ops.spmm_csr(memb.rowptr, memb.col, None, x, n_rows=B, mean=True)              # [B, H]
+    def _forward_infer(self, data):
+        x, B = self._encode_requests(data)
+        xs, n_svc = self._encode_service_nodes(data)
         S = self.outChannels
         svc_batch = torch.arange(S, device=xs.device).repeat(B)[:n_svc]                    # modelML.py:167-171
         memb_s = self._membership_csr(svc_batch, S)
         xs = ops.spmm_csr(memb_s.rowptr, memb_s.col, None, xs, n_rows=S, mean=True)        # [S, H]
         return ops.gemm_bias_act(x, xs, act="sigmoid")                                     # sigmoid(x @ xs^T)
+
+    # ---- batched inference with the (static) service side computed once ------------------------------------
+    @torch.no_grad()
+    def service_encodings(self, sample):
+        """[S, H] service encodings from ONE copy of the service graph (``sample.x_service [S,5]``,
+        ``edge_index_service``, ``edge_attr_service``).  The reference embeds the whole service graph in every
+        sample and re-encodes B copies per batch (trainML.py:91-114); with an S-offset collation all copies are
+        identical, so encoding one copy and reusing it for every request gives the same scores."""
+        xs, n_svc = self._encode_service_nodes(sample)
+        assert n_svc == self.outChannels
+        return xs
+
+    @torch.no_grad()
+    def score_requests(self, data, service_enc):
+        """sigmoid(x_req . service_enc^T) ``[B, S]`` for a collated batch of request graphs (``data.x``,
+        ``data.edge_index``, ``data.batch``) against cached ``service_encodings``."""
+        x, _ = self._encode_requests(data)
+        return ops.gemm_bias_act(x, service_enc, act="sigmoid")
 
     def _fold(self, bn: BatchNorm1d):
         if self.training:

@@ -209,6 +209,28 @@ def pn_reward(inputs, idx, tag: int = 0):
     return viol, obj, rew
 
 
+# ------------------------------------------------------------------ candidate selection (loadDataPN on the device)
+def select_candidates(scores, svc_qos, cat_ptr, local_bounds, used, global_bounds, N: int, with_category: bool = False,
+                      return_picked: bool = False):
+    """ML scores ``[n, S]`` -> PN input rows ``[n, K*N, 8(+1)]`` (see ``gnnpn_select_candidates_f32``)."""
+    scores = _f32(scores, "scores")
+    n, S = scores.shape
+    K = cat_ptr.numel() - 1
+    svc_qos = _f32(svc_qos, "svc_qos")
+    assert svc_qos.shape == (S, 4) and local_bounds.shape == (n, K, 4) and used.shape == (n, K)
+    cat_ptr = cat_ptr.to(torch.int32).contiguous()
+    sizes = cat_ptr[1:] - cat_ptr[:-1]
+    max_size = int(sizes.max().item())
+    rows = torch.empty(n, K * N, 9 if with_category else 8, device=scores.device, dtype=torch.float32)
+    picked = torch.empty(n, K * N, device=scores.device, dtype=torch.int32) if return_picked else None
+    check(lib().gnnpn_select_candidates_f32(
+        scores.data_ptr(), scores.stride(0), svc_qos.data_ptr(), cat_ptr.data_ptr(), max_size,
+        _f32(local_bounds, "local_bounds").data_ptr(), used.to(torch.uint8).contiguous().data_ptr(),
+        _f32(global_bounds, "global_bounds").data_ptr(), n, K, N, int(with_category), rows.data_ptr(), _ptr(picked),
+        _stream()), "select_candidates")
+    return (rows, picked) if return_picked else rows
+
+
 # ------------------------------------------------------------------ graph ops
 def csr_build(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], n_nodes: int, mode: int = CSR_PLAIN):
     """Destination-major CSR, stable in edge order.  Returns (rowptr int64 [n+1], col int32 [nnz], val fp32 [nnz] | None)."""

@@ -60,3 +60,71 @@ class GreedyLowHigh:
             self._consumed[cur_slot] = ev
             yield idx32.cpu(), R.cpu()                    # device->host reads synchronise this batch
             slot = cur_slot ^ 1
+
+
+# ----------------------------------------------------------------------------- ML -> candidates -> 2PN on the device
+def constraint_arrays(nodefeatures, K: int):
+    """Per-instance constraint tensors from the raw ``nodefeatures.data`` rows (one-hot(K+1) + 6 floats), as
+    ``loadDataPN`` reads them (loadData.py:107-114): local bounds ``[n,K,4]`` = (lo2,hi2,lo3,hi3) of the task node
+    of each category, ``used [n,K]``, global bounds ``[n,4]`` of the global-constraint node."""
+    import numpy as np
+    n = len(nodefeatures)
+    local = np.zeros((n, K, 4), dtype=np.float32)
+    used = np.zeros((n, K), dtype=np.uint8)
+    glob = np.zeros((n, 4), dtype=np.float32)
+    for b, inst in enumerate(nodefeatures):
+        a = np.asarray(inst, dtype=np.float64)
+        kind = np.argmax(a[:, :-6] == 1, axis=1)
+        bounds = np.concatenate([a[:, -5:-3], a[:, -2:]], axis=1)
+        for t, row in zip(kind, bounds):
+            if t == 0:
+                glob[b] = row
+            else:
+                local[b, t - 1] = row
+                used[b, t - 1] = 1
+    return local, used, glob
+
+
+def service_arrays(serviceFeature):
+    """``svc_qos [S,4]`` (last four attributes, loadData.py:40) and ``cat_ptr [K+1]`` in category-key order."""
+    import numpy as np
+    keys = sorted(int(k) for k in serviceFeature.keys())
+    qos, ptr = [], [0]
+    for k in keys:
+        rows = np.asarray(serviceFeature[str(k)], dtype=np.float64)[:, -4:]
+        qos.append(rows)
+        ptr.append(ptr[-1] + len(rows))
+    return np.concatenate(qos).astype(np.float32), np.asarray(ptr, dtype=np.int32)
+
+
+class ML2PN:
+    """The whole inference pipeline of ``main.py <ds> ML+2PN`` on one device, batched over request instances:
+    ``Net`` scores (modelML.py:131-176) -> per-category top-N feasible candidates (loadDataPN, loadData.py:99-150,
+    ranking order) -> PNLow greedy -> PNHigh greedy (trainPNHigh.py:131-144) -> objective (ML2PN.py:6-12).
+    Nothing leaves the GPU between the stages."""
+
+    def __init__(self, net, low, high, service_sample, serviceFeature, device=None):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.net, self.low, self.high = net.eval(), low.eval(), high.eval()
+        qos, ptr = service_arrays(serviceFeature)
+        self.svc_qos = torch.from_numpy(qos).to(self.device)
+        self.cat_ptr = torch.from_numpy(ptr).to(self.device)
+        self.K = len(ptr) - 1
+        self.N = low.sNumber
+        self.service_enc = net.service_encodings(service_sample)          # static: encoded once
+
+    @torch.no_grad()
+    def compose(self, request_batch, local_bounds, used, global_bounds):
+        """``request_batch``: collated request graphs (x, edge_index, batch) on the device; constraint tensors from
+        ``constraint_arrays``.  Returns scores, PN rows, picked service ids per row, PNHigh picks and objective."""
+        from . import ops
+        scores = self.net.score_requests(request_batch, self.service_enc)                     # [B, S]
+        rows, picked = ops.select_candidates(scores, self.svc_qos, self.cat_ptr, local_bounds, used, global_bounds,
+                                             self.N, with_category=False, return_picked=True)  # [B, K*N, 8]
+        _, _, _, _, latent = self.low(rows, None, sample="greedy", training="SL")
+        R, _, actions, idx, _ = self.high(rows, None, latent, sample="greedy", training="RL")
+        idx = torch.stack(idx)                                                                # [K, B]
+        services = picked.gather(1, idx.t())                                                  # chosen service per task (-1: unused)
+        viol, obj, _ = ops.pn_reward(rows, idx.to(torch.int32))
+        return {"scores": scores, "rows": rows, "picked": picked, "idx_high": idx, "services": services,
+                "reward": R, "violations": viol, "objective": obj}

@@ -179,6 +179,28 @@ GNNPN_API int gnnpn_pn_greedy_low_high_host(const float* inputs_host, int64_t n,
                                   int32_t* idx_low_host, int32_t* idx_high_host, float* reward_high_host);
 
 /* ---------------------------------------------------------------------------
+ * Between the stages: ML ranking -> pointer-network input rows  (reference: src/loadData.py:99-150, loadDataPN)
+ * ------------------------------------------------------------------------- */
+
+/* Per instance b and category c: the first N services of category c in descending-score order that satisfy the
+ * task's local bounds (lo2 <= q2 <= hi2 and lo3 <= q3 <= hi3, loadData.py:120-124), padded to N by cyclic
+ * self-duplication (loadData.py:137-138); categories the request does not use, or with no feasible service, become
+ * N neutral rows [0,1,1,1] (loadData.py:148).  Ranking order is kept (the reference's unseeded shuffle,
+ * loadData.py:135, is not reproduced); score ties go to the lower service id.
+ *   scores        fp32 [n, >=S] rows scores_ld apart   Net.forward output (modelML.py:176)
+ *   svc_qos       fp32 [S, 4]    q0..q3 of every service, service-id (= category-major) order, 16-byte aligned
+ *   cat_ptr       int32 [K+1]    service-id range of every category
+ *   local_bounds  fp32 [n, K, 4] lo2, hi2, lo3, hi3 of the task node of category c (loadData.py:112-113)
+ *   used          uint8 [n, K]   1 when the request has a task of category c
+ *   global_bounds fp32 [n, 4]    bounds of the global-constraint node (loadData.py:109-110): tail of category 0's rows
+ *   rows          fp32 [n, K*N, 8 (+1 leading category column when with_category)]   the PN input
+ *   picked        int32 [n, K*N] service id per row, -1 for neutral rows (may be NULL) */
+GNNPN_API int gnnpn_select_candidates_f32(const float* scores, int64_t scores_ld, const float* svc_qos,
+                                const int32_t* cat_ptr, int max_category_size, const float* local_bounds,
+                                const uint8_t* used, const float* global_bounds, int64_t n, int K, int N,
+                                int with_category, float* rows, int32_t* picked, void* stream);
+
+/* ---------------------------------------------------------------------------
  * ML stage: graph message passing  (reference: src/models/modelML.py + PyG 1.7.0 ops)
  * ------------------------------------------------------------------------- */
 

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-grep -v "^$" gpurun_out/pytest_gpu.log | tail -40
+timeout 1500 python -m pytest tests -m gpu -x -q -s ${GNNPN_TEST_ARGS} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+grep -v "^$" gpurun_out/pytest_gpu.log | tail -${GNNPN_TAIL:-40}
