@@ -133,16 +133,10 @@ __device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int k
 // `feed(i, b, fed, j)` is called by every lane of a pass with the position fed to the next step for ITS instance
 // (i = instance slot 0..7, j = lane index inside the segment); slots >= count must be ignored by the callee.
 constexpr int kWarpInstances = 8;
-#ifdef GNNPN_PTR_PROF
-#define g_ptr_tick ptr_tick_local                  // diagnostics build only: timestamps of the phase boundaries
-#endif
 
 template <int SEG, int CH, class Feed>
 __device__ __forceinline__ void pointer_steps_batched(const PointerStepArgs& a, int k, int64_t b0, int count,
                                                       const float* q_base, int64_t q_ld, int lane, Feed feed
-#ifdef GNNPN_PTR_PROF
-                                                      , long long* ptr_tick_local
-#endif
                                                       ) {
   constexpr int IPP = 32 / SEG;                    // instances per phase-2 pass
   constexpr int PASSES = kWarpInstances / IPP;
@@ -193,9 +187,6 @@ __device__ __forceinline__ void pointer_steps_batched(const PointerStepArgs& a, 
     lat[r] = (a.latent_win && i < count && seg_j < N)
                  ? __ldg(a.latent_win + (b0 + i) * a.L + (int64_t)k * N + seg_j) : 0.f;
   }
-#ifdef GNNPN_PTR_PROF
-  g_ptr_tick[1] = clock64();
-#endif
   // ---- phase 2
 #pragma unroll
   for (int r = 0; r < PASSES; ++r) {

@@ -32,7 +32,6 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256
 constexpr int EPI_GROUPS = 4;
 constexpr int EPI_WARPS = 4 * EPI_GROUPS;
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
-constexpr int EPI_SMEM_BYTES = 4096;       // epilogue-owned scratch (LSTM: the 1024 gate biases)
 constexpr int TMEM_COLS = 512;
 
 struct GemmEpilogueParams {

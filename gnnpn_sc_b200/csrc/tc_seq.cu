@@ -14,7 +14,9 @@
 //     other 256 TMEM columns (tcgen05.st) and copied to shared memory once the last MMA of the step has retired.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = x producer (encoder inputs),
 // 4..19 = epilogue (TMEM lane quarter = warp & 3, column group = (warp - 4) / 4) and, in the decoder, the
-// pointer step (one warp per instance, 8 instances per warp).
+// pointer phase (each warp owns 8 instances: rows streamed per instance, softmax / pick for 4 instances at once,
+// pointer.cuh::pointer_steps_batched).
+// Cross-CTA mbarrier arrives use .release.cta semantics on purpose (see mbar_arrive_cluster).
 #include <stdio.h>
 #include <stdlib.h>
 #include <cuda_fp16.h>
@@ -75,10 +77,7 @@ struct SeqParams {
   float* h_out; int64_t h_out_inst_ld;     // step t of instance m at h_out + m*ld + t*kH
   PointerStepArgs pa;      // decoder only
   int rotate;
-  int dec_flags;          // bit 0: L2 prefetch of the next window; bit 1: batched pointer phase; bit 2: stagger
-  int pf_slots;           // L2 prefetch covers the first pf_slots of every warp's 8 instances (L2 cannot hold a whole window)
-  int stagger;            // cycles by which every other CTA pair starts late (decoder), so that the DRAM-bound pointer
-                          // phases of one half of the GPU fall into the MMA phases of the other half
+  int dec_flags;          // bit 1: batched two-phase pointer step (default); 0: one instance at a time (A/B reference)
   unsigned long long* prof; // debug (GNNPN_SEQ_PROF): per-CTA wait-cycle counters, 16 per CTA, or nullptr
   float* c_scr;            // blocked cell-state scratch, 128*kH floats per CTA (coalesced 128-bit accesses)
 };
@@ -269,9 +268,6 @@ __device__ __forceinline__ void store_ax(uint8_t* sgen, int rr, int f, float xv)
 // Pointer phase of decode step t for the 8 instances of one epilogue warp (rows rr0..rr0+7 of the CTA); see
 // pointer_steps_batched in pointer.cuh.
 __device__ __forceinline__ void pointer_phase(const SeqParams& p, int t, int rr0, int64_t m0, int lane, uint8_t* sgen
-#ifdef GNNPN_PTR_PROF
-                                              , long long* tick
-#endif
                                               ) {
   const PointerStepArgs& pa = p.pa;                 // stays in constant memory (p is a __grid_constant__ parameter)
   const int64_t b0 = m0 + rr0;
@@ -308,13 +304,7 @@ __device__ __forceinline__ void pointer_phase(const SeqParams& p, int t, int rr0
         if (si / IPP == r) pend_x[r] = xv;
     };
     pointer_steps_batched<SEG, CH>(pa, t, b0, count, q_base, p.h_out_inst_ld, lane, feed
-#ifdef GNNPN_PTR_PROF
-                                   , tick
-#endif
                                    );
-#ifdef GNNPN_PTR_PROF
-    tick[2] = clock64();
-#endif
     if (feed_next) {
       const int seg_i = lane / SEG, seg_j = lane % SEG;
 #pragma unroll
@@ -371,10 +361,6 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
-  if (DEC && (p.dec_flags & 4) && ((blockIdx.x / CG) & 1)) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < p.stagger) __nanosleep(200);
-  }
   // every CTA walks the 8 N tiles in a rotated order so the CTAs do not all pull the same weight lines from
   // the same L2 slices at the same time
   const int rot = p.rotate ? (int)(blockIdx.x & (N_TILES - 1)) : 0;
@@ -605,26 +591,6 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     }
   } else if (warp == 3) {
     // ================= x producer (encoder): raw input row of step t+1 -> fp16 hi/lo x block =================
-    if (DEC) {
-      // L2 prefetcher: the window rows of enc_out that step t+1's pointer phase will read (N*kH contiguous floats
-      // per instance) are requested as soon as step t's MMAs retire, one whole MMA phase ahead of their use
-      auto prefetch_window = [&](int k) {
-        const uint32_t bytes = (uint32_t)(p.pa.N * kH * 4);
-        for (int r = lane; r < BM; r += 32) {
-          const int64_t m = m0 + r;
-          if (m < p.n && (r & 7) < p.pf_slots)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pa.enc_out + m * p.pa.enc_inst_ld +
-                                                                            (int64_t)k * p.pa.N * kH), "r"(bytes) : "memory");
-        }
-      };
-      if (p.dec_flags & 1) {
-        prefetch_window(0);
-        for (int t = 0; t + 1 < p.steps; ++t) {
-          mbar_wait(mma_done_bar, (uint32_t)t & 1u);
-          prefetch_window(t + 1);
-        }
-      }
-    }
     if (!DEC) {
       for (int t = 0; t + 1 < p.steps; ++t) {
         float xv[4][8];
@@ -651,9 +617,6 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     uint32_t uses = 0;
     const bool prof = p.prof != nullptr;
     long long w_tfull = 0, w_hempty = 0, w_ptr = 0;
-#ifdef GNNPN_PTR_PROF
-    long long w_pp[4] = {0, 0, 0, 0};
-#endif
     const long long t_begin = clock64();
     for (int t = 0; t < p.steps; ++t) {
       const float4* bias4 = reinterpret_cast<const float4*>(sbias + (t == 0 ? 0 : kG));
@@ -691,7 +654,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
           stg256(c_row + u0, cn);
         }
         if (DEC) {
-          if (ok && !(p.dec_flags & 8)) stg256(h_row + (int64_t)t * kH + u0, hn);   // bit 3: timing experiment only
+          if (ok) stg256(h_row + (int64_t)t * kH + u0, hn);
         } else {
           // fp32 h' -> 128B-swizzled [128 x 32] tile; the store issuer (warp 2) sends it to enc_out by TMA
           mbar_wait_t(hempty_bar, (uses & 1u) ^ 1u, prof, w_hempty);   // the previous tile's store has left shared memory
@@ -736,15 +699,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         const long long tp0 = prof ? clock64() : 0;
         __threadfence_block();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-#ifdef GNNPN_PTR_PROF
-        long long tick[3];
-        tick[0] = clock64(); tick[1] = tick[2] = tick[0];
-        pointer_phase(p, t, (warp - 4) * (BM / EPI_WARPS), m0, lane, sgen, tick);
-        const long long tend = clock64();
-        w_pp[0] += tick[0] - tp0; w_pp[1] += tick[1] - tick[0]; w_pp[2] += tick[2] - tick[1]; w_pp[3] += tend - tick[2];
-#else
         pointer_phase(p, t, (warp - 4) * (BM / EPI_WARPS), m0, lane, sgen);
-#endif
         if (prof) w_ptr += clock64() - tp0;
       }
       fence_proxy_async_smem();
@@ -755,9 +710,6 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     if (prof && warp == 4 && lane == 0) {
       unsigned long long* o = p.prof + (size_t)blockIdx.x * 16;
       o[4] = (unsigned long long)(clock64() - t_begin); o[5] = w_tfull; o[6] = w_hempty; o[7] = w_ptr;
-#ifdef GNNPN_PTR_PROF
-      for (int i = 0; i < 4; ++i) o[8 + i] = w_pp[i];
-#endif
     }
   }
   tc_fence_before();
@@ -826,10 +778,6 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
   pp.rotate = rotate;
   static const int dec_flags = getenv("GNNPN_SEQ_DEC") ? atoi(getenv("GNNPN_SEQ_DEC")) : 2;
   pp.dec_flags = dec_flags;
-  static const int stagger = getenv("GNNPN_SEQ_STAGGER") ? atoi(getenv("GNNPN_SEQ_STAGGER")) : 40000;
-  pp.stagger = stagger;
-  static const int pf_slots = getenv("GNNPN_SEQ_PF") ? atoi(getenv("GNNPN_SEQ_PF")) : 8;
-  pp.pf_slots = pf_slots;
   auto kern = lstm_seq_kernel<DEC, CG>;
   static bool configured = false;
   if (!configured) {
@@ -858,11 +806,11 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
     unsigned long long* hbuf = (unsigned long long*)malloc((size_t)grid * 16 * 8);
     cudaStreamSynchronize(st);
     cudaMemcpy(hbuf, prof, (size_t)grid * 16 * 8, cudaMemcpyDeviceToHost);
-    double acc[12] = {0};
+    double acc[8] = {0};
     unsigned leaders = 0;
     for (unsigned c = 0; c < grid; ++c) {
       if (hbuf[c * 16]) ++leaders;
-      for (int i = 0; i < 12; ++i) acc[i] += (double)hbuf[c * 16 + i];
+      for (int i = 0; i < 8; ++i) acc[i] += (double)hbuf[c * 16 + i];
     }
     if (!leaders) leaders = 1;
     fprintf(stderr, "[seq prof %s cg=%d steps=%d grid=%u] per-step cycles: mma total %.0f (wait a_ready %.0f, tmem_empty %.0f, "
@@ -870,10 +818,6 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
             p.steps, grid, acc[0] / leaders / p.steps, acc[1] / leaders / p.steps, acc[2] / leaders / p.steps,
             acc[3] / leaders / p.steps, acc[4] / grid / p.steps, acc[5] / grid / p.steps, acc[6] / grid / p.steps,
             acc[7] / grid / p.steps);
-#ifdef GNNPN_PTR_PROF
-    fprintf(stderr, "   pointer phase split: fence+barrier %.0f, rows/dots %.0f, softmax/pick %.0f, x stores %.0f\n",
-            acc[8] / grid / p.steps, acc[9] / grid / p.steps, acc[10] / grid / p.steps, acc[11] / grid / p.steps);
-#endif
     free(hbuf);
     cudaFree(prof);
   }
