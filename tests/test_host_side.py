@@ -70,3 +70,31 @@ def test_window_compaction_of_dense_latent():
     w = _window_of(dense, K, N)
     for k in range(K):
         assert torch.equal(w[:, k * N:(k + 1) * N], dense[k][:, k * N:(k + 1) * N])
+
+
+def test_constraint_and_service_arrays_follow_loaddatapn():
+    """pipeline.constraint_arrays / service_arrays (inputs of the device candidate selection) against the rows the
+    numpy restatement of loadDataPN builds from the same JSON objects."""
+    import numpy as np
+    from gnnpn_sc_b200 import synth, loadData
+    from gnnpn_sc_b200.pipeline import constraint_arrays, service_arrays
+    K, S, N = 7, 90, 3
+    ds = synth.ml_dataset(n_instances=5, K=K, S=S, seed=1, min_tasks=3)
+    local, used, glob = constraint_arrays(ds["nodefeatures"], K)
+    qos, ptr = service_arrays(ds["serviceFeature"])
+    assert qos.shape == (S, 4) and ptr[0] == 0 and ptr[-1] == S and len(ptr) == K + 1
+    sf = ds["serviceFeature"]
+    ser2cat = np.concatenate([[int(k) - 1] * len(sf[k]) for k in sf.keys()])
+    ser2pos = np.concatenate([np.arange(len(sf[k])) for k in sf.keys()])
+    for b, nf in enumerate(ds["nodefeatures"]):
+        rows = np.asarray(loadData.pn_rows_from_ranking(nf, list(range(S)), sf, ser2cat, ser2pos, N, rng=False))
+        rows = rows.reshape(K, N, 9)
+        assert np.allclose(rows[0, :, 5:], glob[b])                          # category 0 carries the global bounds
+        assert (rows[1:, :, 5:] == 0).all()
+        neutral = (rows[:, 0, 1:5] == [0, 1, 1, 1]).all(axis=1)
+        assert (~neutral <= used[b].astype(bool)).all()                       # a non-neutral category is a used one
+        for c in range(K):
+            if not neutral[c]:
+                lo2, hi2, lo3, hi3 = local[b, c]
+                assert (lo2 <= rows[c, :, 3]).all() and (rows[c, :, 3] <= hi2).all()
+                assert (lo3 <= rows[c, :, 4]).all() and (rows[c, :, 4] <= hi3).all()
