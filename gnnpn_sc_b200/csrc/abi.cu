@@ -12,6 +12,12 @@ size_t tc_gemm_workspace_bytes(int64_t M, int N, int K);
 int launch_gemm_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* scale,
                    const float* shift, int act, float* C, int64_t ldc, int64_t M, int N, int K, void* workspace,
                    cudaStream_t st);
+// persistent fp16-split node transform (node_transform.cu): K <= 256, N <= 256, N % 16 == 0, K % 4 == 0
+bool node_transform_supported(int64_t M, int N, int K);
+size_t node_transform_workspace_bytes(int N, int K);
+int launch_node_transform(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                          const float* scale, const float* shift, int act, float* C, int64_t ldc, int64_t M, int N,
+                          int K, void* workspace, cudaStream_t st);
 }  // namespace gnnpn
 
 using namespace gnnpn;
@@ -38,7 +44,8 @@ const char* gnnpn_error_string(int code) {
 }
 
 size_t gnnpn_gemm_workspace_bytes(int64_t M, int N, int K) {
-  return (M < 0 || N < 1 || K < 1) ? 0 : tc_gemm_workspace_bytes(M, N, K);
+  if (M < 0 || N < 1 || K < 1) return 0;
+  return node_transform_supported(M, N, K) ? node_transform_workspace_bytes(N, K) : tc_gemm_workspace_bytes(M, N, K);
 }
 
 int gnnpn_gemm_f32_bias_act(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
@@ -49,6 +56,11 @@ int gnnpn_gemm_f32_bias_act(const float* A, int64_t lda, const float* W, int64_t
   GNNPN_REQUIRE((scale == nullptr) == (shift == nullptr), GNNPN_ENULL);
   GNNPN_REQUIRE(M < (1ll << 31) * 64, GNNPN_ERANGE);
   if (M == 0) return GNNPN_OK;
+  if (workspace && node_transform_supported(M, N, K) && (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0) {
+    GNNPN_REQUIRE(workspace_bytes >= node_transform_workspace_bytes(N, K), GNNPN_EWORKSPACE);
+    return launch_node_transform(A, lda, W, ldw, bias, scale, shift, act, C, ldc, M, N, K, workspace,
+                                 (cudaStream_t)stream);
+  }
   if (workspace) {
     GNNPN_REQUIRE(workspace_bytes >= tc_gemm_workspace_bytes(M, N, K), GNNPN_EWORKSPACE);
     GNNPN_REQUIRE(M < (1ll << 31), GNNPN_ERANGE);

@@ -1,0 +1,337 @@
+// Node transform  C = act((A . W^T + bias) * scale + shift)  for the service-side shapes of the ML stage
+// (nn.Linear / GCNConv's X.W, modelML.py:77-93,98-106,164-165: K <= 256 input channels, N <= 256 output channels,
+// M = B.S service rows), as ONE persistent tcgen05 kernel that reads fp32 A once and writes fp32 C once.
+//
+// The shape is HBM-bound (2KN/(4K+4N) = 64 flop/B at K = N = 256), so the design goal is "A and C cross HBM
+// exactly once, everything else stays on chip":
+//   * CTA pair (cluster of 2, cta_group::2, UMMA M = 256): each CTA owns 128 rows of a 256-row tile and HALF of
+//     the weight rows.  The weights are split once into fp16 hi/lo (pre-scaled by 2^4, error-compensated 3xFP16:
+//     a.w ~= a_lo.w_hi + a_hi.w_hi + a_hi.w_lo, fp32 accumulate in TMEM) and stay RESIDENT in shared memory for
+//     the whole kernel (<= 128 KB per CTA) -- no per-tile weight traffic at all;
+//   * A is never materialised in split form: 8 converter warps stream the fp32 rows from global memory (256-bit
+//     coalesced loads, next k-block prefetched in registers), split them to fp16 hi/lo (x 2^4) and write the
+//     128B-swizzled K-major UMMA tiles of a 2-stage ring directly;
+//   * two 256-column TMEM accumulators: 8 epilogue warps drain tile i (bias / eval-BatchNorm scale+shift / ReLU or
+//     sigmoid, 256-bit row stores) while the MMAs of tile i+1 run;
+//   * persistent grid: one CTA pair per TPC (74 pairs), tiles strided over the pairs.
+// Input range: |a| < 4095 (fp16 after the 2^4 pre-scale); the ML stage feeds O(1) features / BatchNorm outputs.
+// Shapes outside (K > 256, N > 256, N % 16 != 0, K % 4 != 0) use the 3xTF32 mainloop in tc_kernels.cu.
+#include <stdlib.h>
+#include <cuda_fp16.h>
+#include "tc_common.cuh"
+#include "common.cuh"
+#include "tc_seq_dev.cuh"
+
+namespace gnnpn {
+namespace tc {
+int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f16);
+}
+namespace nt {
+
+using namespace tc;
+using namespace seq;       // cluster / cta_group::2 helpers
+
+constexpr int BM = 128;                      // rows per CTA (pair tile = 256 rows)
+constexpr int KB = 64;                       // halfs per k-block = one 128-byte swizzle row
+constexpr int MAX_KB = 4;                    // K <= 256
+constexpr int MAX_N = 256;
+constexpr int BLK_BYTES = 128 * 128;         // [128 rows x 64 halfs]
+constexpr int A_STAGES = 2;
+constexpr int CONV_WARPS = 8, EPI_WARPS = 8;
+constexpr int THREADS = 128 + 32 * (CONV_WARPS + EPI_WARPS);
+constexpr float kScale = 16.0f;              // both operands are pre-scaled by 2^4 (keeps the fp16 "lo" parts normal)
+
+constexpr uint32_t OFF_W_HI = 0;
+constexpr uint32_t OFF_W_LO = OFF_W_HI + MAX_KB * BLK_BYTES;
+constexpr uint32_t OFF_A = OFF_W_LO + MAX_KB * BLK_BYTES;               // A_STAGES x {hi, lo}
+constexpr uint32_t OFF_EPI = OFF_A + A_STAGES * 2 * BLK_BYTES;          // bias | scale | shift, MAX_N floats each
+constexpr uint32_t OFF_BAR = OFF_EPI + 3 * MAX_N * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+
+struct Params {
+  const float* A; int64_t lda;
+  float* C; int64_t ldc;
+  const float* bias; const float* scale; const float* shift; int act;
+  int64_t M; int N; int K;
+  int nkb;                 // k-blocks of 64
+  int64_t n_tiles;         // 256-row pair tiles
+  int c_vec;               // 8: 256-bit row stores allowed, 4: 128-bit, 1: scalar
+};
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                      const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar0 = sbase + OFF_BAR;
+  const uint32_t w_full = bar0;
+  auto a_full = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto a_empty = [&](int s) { return bar0 + 8u * (1 + A_STAGES + s); };
+  auto tfull = [&](int b) { return bar0 + 8u * (1 + 2 * A_STAGES + b); };
+  auto tempty = [&](int b) { return bar0 + 8u * (3 + 2 * A_STAGES + b); };
+  const uint32_t tmem_slot = bar0 + 8u * (5 + 2 * A_STAGES);
+  const uint32_t rank = cluster_ctarank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int half_n = p.N >> 1;                       // weight rows held by this CTA
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(w_full, 1);
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(a_full(s), 2 * CONV_WARPS); mbar_init(a_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull(b), 1); mbar_init(tempty(b), 2 * EPI_WARPS); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_cg2(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================= weights: loaded once, resident for the whole kernel =================
+    if (lane == 0) {
+      const uint32_t blk = (uint32_t)half_n * 128u;               // bytes of one [N/2 x 64 halfs] box
+      if (rank == 0) mbar_arrive_expect_tx(w_full, 2u * 2u * (uint32_t)p.nkb * blk);
+      const uint32_t fb = mapa_rank(w_full, 0);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        tma_load_2d_cg2(sbase + OFF_W_HI + kb * BLK_BYTES, &map_w_hi, fb, kb * KB, (int)rank * half_n);
+        tma_load_2d_cg2(sbase + OFF_W_LO + kb * BLK_BYTES, &map_w_lo, fb, kb * KB, (int)rank * half_n);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA): 12 MMAs per k-block, M = 256 over the pair =================
+    if (rank == 0) {
+      const uint32_t leader = elect_one();
+      const uint32_t idesc = idesc_f16(2 * BM, p.N);
+      mbar_wait_cluster(w_full, 0);
+      tc_fence_after();
+      int s = 0; uint32_t ph = 0;
+      int64_t it = 0;
+      for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs, ++it) {
+        const int buf = (int)(it & 1);
+        mbar_wait_cluster(tempty(buf), (uint32_t)((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * MAX_N);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait_cluster(a_full(s), ph);
+          tc_fence_after();
+          const uint32_t st = sbase + OFF_A + (uint32_t)s * 2 * BLK_BYTES;
+          const uint64_t a_hi = smem_desc_k_sw128(st), a_lo = smem_desc_k_sw128(st + BLK_BYTES);
+          const uint64_t b_hi = smem_desc_k_sw128(sbase + OFF_W_HI + kb * BLK_BYTES);
+          const uint64_t b_lo = smem_desc_k_sw128(sbase + OFF_W_LO + kb * BLK_BYTES);
+          const int rem = p.K - kb * KB;
+          const int ksteps = rem >= KB ? 4 : (rem + 15) >> 4;
+          if (leader) {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t adv = (uint64_t)(ks * 2);
+              mma_f16_ss_cg2(d, a_lo + adv, b_hi + adv, idesc, (uint32_t)((kb | ks) != 0));
+              mma_f16_ss_cg2(d, a_hi + adv, b_hi + adv, idesc, 1u);
+              mma_f16_ss_cg2(d, a_hi + adv, b_lo + adv, idesc, 1u);
+            }
+            mma_commit_cg2(a_empty(s));
+            if (kb == p.nkb - 1) mma_commit_cg2(tfull(buf));
+          }
+          __syncwarp();
+          if (++s == A_STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + CONV_WARPS) {
+    // ================= converters: fp32 rows -> fp16 hi/lo UMMA tiles =================
+    // thread -> 16-byte smem chunk c16 (8 halfs = 8 floats = 32 contiguous global bytes) of rows r0 + 32 i
+    const int t = threadIdx.x - 128;
+    const int c16 = t & 7, r0 = t >> 3;
+    const bool vec8 = ((p.lda & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 31u) == 0);
+    auto load_block = [&](int64_t tile, int kb, float (*v)[8]) {
+      const int col = kb * KB + c16 * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t m = tile * (2 * BM) + (int64_t)rank * BM + r0 + 32 * i;
+        const float* src = p.A + m * p.lda + col;
+        if (m < p.M && col + 8 <= p.K) {
+          if (vec8) {
+            ldg256(src, v[i]);
+          } else {
+            const float4 a = ldg_f4(src), b = ldg_f4(src + 4);
+            v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+            v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] = (m < p.M && col + j < p.K) ? __ldg(src + j) : 0.f;
+        }
+      }
+    };
+    int s = 0; uint32_t ph = 0;
+    float cur[4][8], nxt[4][8];
+    int64_t tile = pair;
+    int kb = 0;
+    if (tile < p.n_tiles) load_block(tile, 0, cur);
+    while (tile < p.n_tiles) {
+      // prefetch the following k-block (possibly of the next tile) before blocking on the ring slot
+      int64_t ntile = tile; int nkb_i = kb + 1;
+      if (nkb_i == p.nkb) { nkb_i = 0; ntile += n_pairs; }
+      if (ntile < p.n_tiles) load_block(ntile, nkb_i, nxt);
+      mbar_wait(a_empty(s), ph ^ 1u);
+      const uint32_t st = sbase + OFF_A + (uint32_t)s * 2 * BLK_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * i;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = cur[i][2 * j] * kScale, b = cur[i][2 * j + 1] * kScale;
+          hi[j] = pack_h2(a, b);
+          const float2 bk = unpack_h2(hi[j]);
+          lo[j] = pack_h2(a - bk.x, b - bk.y);
+        }
+        const uint32_t off = sw128_off(r, c16);
+        st_shared_v4(st + off, hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(st + BLK_BYTES + off, lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(a_full(s), 0));
+      if (++s == A_STAGES) { s = 0; ph ^= 1u; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[i][j] = nxt[i][j];
+      tile = ntile; kb = nkb_i;
+    }
+  } else if (warp >= 4 + CONV_WARPS) {
+    // ================= epilogue: thread = one row, 32-column chunks grp, grp+2, ... =================
+    const int e = warp - (4 + CONV_WARPS);
+    const int q = warp & 3, grp = e >> 2;
+    float* sE = reinterpret_cast<float*>(sgen + OFF_EPI);
+    for (int i = threadIdx.x - 32 * (4 + CONV_WARPS); i < MAX_N; i += 32 * EPI_WARPS) {
+      const bool in = i < p.N;
+      sE[i] = (in && p.bias) ? __ldg(p.bias + i) : 0.f;
+      sE[MAX_N + i] = ((in && p.scale) ? __ldg(p.scale + i) : 1.f) ;
+      sE[2 * MAX_N + i] = (in && p.scale && p.shift) ? __ldg(p.shift + i) : 0.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    constexpr float kInv = 1.0f / (kScale * kScale);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    int64_t it = 0;
+    for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs, ++it) {
+      const int buf = (int)(it & 1);
+      const int64_t m = tile * (2 * BM) + (int64_t)rank * BM + q * 32 + lane;
+      const bool ok = m < p.M;
+      float* out = p.C + (ok ? m : 0) * p.ldc;
+      mbar_wait(tfull(buf), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      for (int c0 = grp * 32; c0 < p.N; c0 += 64) {
+        float v[32];
+        tmem_ld_32x32_issue(t_lane + (uint32_t)(buf * MAX_N + c0), v);
+        tmem_ld_wait(v);
+        const int ncols = min(32, p.N - c0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = c0 + j;                         // sE is padded to MAX_N: reads beyond N are harmless
+          float r = fmaf(v[j], kInv, sE[n & (MAX_N - 1)]);
+          r = fmaf(r, sE[MAX_N + (n & (MAX_N - 1))], sE[2 * MAX_N + (n & (MAX_N - 1))]);
+          if (p.act == GNNPN_ACT_RELU) r = fmaxf(r, 0.f);
+          else if (p.act == GNNPN_ACT_SIGMOID) r = sigmoid_accurate(r);
+          v[j] = r;
+        }
+        if (ok) {
+          if (p.c_vec == 8) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (g * 8 < ncols) stg256(out + c0 + g * 8, v + g * 8);
+          } else if (p.c_vec == 4) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              if (g * 4 < ncols) stg128(out + c0 + g * 4, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) out[c0 + j] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty(buf), 0));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_cg2(tmem_base, 512);
+}
+
+// W [N, K] fp32 -> fp16 hi/lo [N, Kp] (x 2^4), K zero-padded to Kp
+__global__ void split_w_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, int Kp, __half* __restrict__ hi,
+                               __half* __restrict__ lo) {
+  const int total = N * Kp;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int r = e / Kp, k = e - r * Kp;
+    __half h = __float2half_rn(0.f), l = h;
+    if (k < K) split_f16(W[(int64_t)r * ldw + k] * kScale, h, l);
+    hi[e] = h;
+    lo[e] = l;
+  }
+}
+
+}  // namespace nt
+
+bool node_transform_supported(int64_t M, int N, int K) {
+  static const int off = getenv("GNNPN_GEMM_V1") ? atoi(getenv("GNNPN_GEMM_V1")) : 0;   // A/B: force the 3xTF32 mainloop
+  return !off && M >= 1 && N >= 16 && N <= nt::MAX_N && (N % 16) == 0 && K >= 4 && K <= nt::MAX_KB * nt::KB && (K % 4) == 0;
+}
+
+size_t node_transform_workspace_bytes(int N, int K) {
+  const int Kp = round_up(K, nt::KB);
+  return (size_t)2 * N * Kp * sizeof(__half) + 1024;
+}
+
+int launch_node_transform(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                          const float* scale, const float* shift, int act, float* C, int64_t ldc, int64_t M, int N,
+                          int K, void* workspace, cudaStream_t st) {
+  using namespace nt;
+  if ((lda & 3) || (reinterpret_cast<uintptr_t>(A) & 15u)) return GNNPN_EALIGN;
+  const int Kp = round_up(K, KB);
+  __half* w_hi = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  __half* w_lo = w_hi + (size_t)N * Kp;
+  split_w_kernel<<<(N * Kp + 255) / 256, 256, 0, st>>>(W, ldw, N, K, Kp, w_hi, w_lo);
+  int rc = after_launch();
+  if (rc) return rc;
+  CUtensorMap maps[2];
+  if ((rc = tc::make_map_2d(&maps[0], w_hi, N, Kp, Kp, N / 2, true))) return rc;
+  if ((rc = tc::make_map_2d(&maps[1], w_lo, N, Kp, Kp, N / 2, true))) return rc;
+  Params p{};
+  p.A = A; p.lda = lda; p.C = C; p.ldc = ldc; p.bias = bias; p.scale = scale; p.shift = shift; p.act = act;
+  p.M = M; p.N = N; p.K = K; p.nkb = Kp / KB; p.n_tiles = ceil_div(M, 2 * BM);
+  const uintptr_t ca = reinterpret_cast<uintptr_t>(C);
+  p.c_vec = ((ldc & 7) == 0 && (ca & 31u) == 0) ? 8 : ((ldc & 3) == 0 && (ca & 15u) == 0) ? 4 : 1;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(node_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int64_t pairs = p.n_tiles < kNumSMs / 2 ? p.n_tiles : kNumSMs / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, node_transform_kernel, maps[0], maps[1], p);
+  if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
+  return after_launch();
+}
+
+}  // namespace gnnpn

@@ -118,9 +118,11 @@ def test_gcn_layer_epilogue():
 
 @pytest.mark.parametrize("impl", ["tc", "ffma"])
 @pytest.mark.parametrize("M,N,K", [(1, 128, 128), (97, 256, 28), (5014, 256, 24), (1000, 128, 256), (130, 2507, 128),
-                                   (5014, 256, 256), (200000, 256, 256)])
+                                   (5014, 256, 256), (200000, 256, 256), (257, 48, 4), (300, 16, 60),
+                                   (70000, 128, 136), (40000, 240, 252)])
 def test_node_transform_gemm(M, N, K, impl):
-    """tcgen05 3xTF32 and FFMA node transforms against torch fp32 on the CPU, 1e-5 relative."""
+    """tcgen05 (persistent 3xFP16-split kernel for K, N <= 256; 3xTF32 mainloop otherwise) and FFMA node
+    transforms against torch fp32 on the CPU, 1e-5 relative."""
     from gnnpn_sc_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
     a, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
@@ -131,3 +133,36 @@ def test_node_transform_gemm(M, N, K, impl):
     err = (y.cpu() - ref).abs() / ref.abs().max().clamp(min=1)
     print(f"gemm[{impl}] M={M} N={N} K={K}: max err / max|ref| {err.max():.2e}")
     assert err.max() <= 1e-5, err.max()
+
+
+@pytest.mark.parametrize("mag", [1e-3, 1.0, 300.0])
+def test_node_transform_input_range(mag):
+    """The fp16-split node transform keeps fp32-level accuracy over the input magnitudes the ML stage produces
+    (raw QoS features ~1e-3..1, post-aggregation sums up to a few hundred); checked against fp64."""
+    from gnnpn_sc_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 4096, 256, 256
+    a = torch.randn(M, K, generator=g) * mag
+    a[:, ::7] *= 1e-3                                        # mixed magnitudes inside a row
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    ref = (a.double() @ w.double().T)
+    y = ops.gemm_bias_act(a.cuda(), w.cuda(), impl="tc").cpu().double()
+    err = (y - ref).abs().max() / ref.abs().max()
+    ref32 = (torch.nn.functional.linear(a, w).double() - ref).abs().max() / ref.abs().max()
+    print(f"gemm range mag={mag}: max err / max|ref| {err:.2e} (torch fp32 CPU: {ref32:.2e})")
+    assert err <= 2e-6, err
+
+
+def test_node_transform_strided_output():
+    """C with a leading dimension that is not a multiple of 8 floats takes the narrower store paths."""
+    from gnnpn_sc_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    M, N, K = 1500, 64, 128
+    a, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    ref = torch.nn.functional.linear(a, w)
+    for ld in (N + 4, N + 1):
+        buf = torch.full((M, ld), 7.0, device="cuda")
+        out = buf[:, :N]
+        ops.gemm_bias_act(a.cuda(), w.cuda(), out=out, impl="tc")
+        assert (out.cpu() - ref).abs().max() <= 1e-5 * ref.abs().max()
+        assert torch.all(buf[:, N:] == 7.0)
