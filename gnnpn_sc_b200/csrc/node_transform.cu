@@ -9,10 +9,13 @@
 //     a.w ~= a_lo.w_hi + a_hi.w_hi + a_hi.w_lo, fp32 accumulate in TMEM) and stay RESIDENT in shared memory for
 //     the whole kernel (<= 128 KB per CTA) -- no per-tile weight traffic at all;
 //   * A is never materialised in split form: 8 converter warps stream the fp32 rows from global memory (256-bit
-//     coalesced loads, next k-block prefetched in registers), split them to fp16 hi/lo (x 2^4) and write the
-//     128B-swizzled K-major UMMA tiles of a 2-stage ring directly;
+//     coalesced loads, next k-block in flight in registers), split them to fp16 hi/lo (x 2^4) and write the
+//     128B-swizzled K-major UMMA tiles of a 2-stage ring directly.  (Measured and rejected: a cp.async.bulk.prefetch.L2
+//     warp running two tiles ahead -- +30% DRAM reads, no gain; 16 converter warps with two blocks in flight -- the
+//     72-register cap spills);
 //   * two 256-column TMEM accumulators: 8 epilogue warps drain tile i (bias / eval-BatchNorm scale+shift / ReLU or
-//     sigmoid, 256-bit row stores) while the MMAs of tile i+1 run;
+//     sigmoid; each warp's [32 x 32] result tile leaves through shared memory and a TMA store) while the MMAs of
+//     tile i+1 run;
 //   * persistent grid: one CTA pair per TPC (74 pairs), tiles strided over the pairs.
 // Input range: |a| < 4095 (fp16 after the 2^4 pre-scale); the ML stage feeds O(1) features / BatchNorm outputs.
 // Shapes outside (K > 256, N > 256, N % 16 != 0, K % 4 != 0) use the 3xTF32 mainloop in tc_kernels.cu.
@@ -27,6 +30,21 @@ namespace tc {
 int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f16);
 }
 namespace nt {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
 
 using namespace tc;
 using namespace seq;       // cluster / cta_group::2 helpers
@@ -44,8 +62,8 @@ constexpr float kScale = 16.0f;              // both operands are pre-scaled by 
 constexpr uint32_t OFF_W_HI = 0;
 constexpr uint32_t OFF_W_LO = OFF_W_HI + MAX_KB * BLK_BYTES;
 constexpr uint32_t OFF_A = OFF_W_LO + MAX_KB * BLK_BYTES;               // A_STAGES x {hi, lo}
-constexpr uint32_t OFF_EPI = OFF_A + A_STAGES * 2 * BLK_BYTES;          // bias | scale | shift, MAX_N floats each
-constexpr uint32_t OFF_BAR = OFF_EPI + 3 * MAX_N * 4;
+constexpr uint32_t OFF_STAGE = OFF_A + A_STAGES * 2 * BLK_BYTES;        // per epilogue warp: [32 rows x 32 fp32] TMA-store tile
+constexpr uint32_t OFF_BAR = OFF_STAGE + EPI_WARPS * 4096;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
@@ -56,7 +74,8 @@ struct Params {
   int64_t M; int N; int K;
   int nkb;                 // k-blocks of 64
   int64_t n_tiles;         // 256-row pair tiles
-  int c_vec;               // 8: 256-bit row stores allowed, 4: 128-bit, 1: scalar
+  int c_vec;               // 0: TMA stores through shared memory; 8 / 4 / 1: direct 256-bit / 128-bit / scalar row stores
+  const float2* st_tab;    // [MAX_N] per column {s', t'}: out = act(acc * s' + t')
 };
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
@@ -68,7 +87,7 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) {
 
 __global__ void __launch_bounds__(THREADS, 1)
 node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                      const __grid_constant__ Params p) {
+                      const __grid_constant__ CUtensorMap map_c, const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -84,7 +103,7 @@ node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid
   const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int half_n = p.N >> 1;                       // weight rows held by this CTA
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo); tma_prefetch_desc(&map_c); }
   if (warp == 1 && lane == 0) {
     mbar_init(w_full, 1);
     for (int s = 0; s < A_STAGES; ++s) { mbar_init(a_full(s), 2 * CONV_WARPS); mbar_init(a_empty(s), 1); }
@@ -149,15 +168,24 @@ node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid
     }
   } else if (warp >= 4 && warp < 4 + CONV_WARPS) {
     // ================= converters: fp32 rows -> fp16 hi/lo UMMA tiles =================
-    // thread -> 16-byte smem chunk c16 (8 halfs = 8 floats = 32 contiguous global bytes) of rows r0 + 32 i
+    // thread -> 16-byte smem chunk c16 (8 halfs = 8 floats = 32 contiguous global bytes) of rows r0 + RSTEP i.
+    // Two register buffers: the next k-block is in flight while the current one is converted.
+    constexpr int RPT = (BM * 8) / (32 * CONV_WARPS);      // rows per thread per k-block
+    constexpr int RSTEP = BM / RPT;
     const int t = threadIdx.x - 128;
     const int c16 = t & 7, r0 = t >> 3;
     const bool vec8 = ((p.lda & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 31u) == 0);
-    auto load_block = [&](int64_t tile, int kb, float (*v)[8]) {
+    const int64_t n_mine = p.n_tiles > pair ? (p.n_tiles - pair + n_pairs - 1) / n_pairs : 0;
+    const int64_t n_blocks = n_mine * p.nkb;              // k-blocks this CTA converts, in order
+    auto load_block = [&](int64_t g, float (*v)[8]) {
+      if (g >= n_blocks) return;
+      const int64_t it = g / p.nkb;
+      const int kb = (int)(g - it * p.nkb);
+      const int64_t tile = pair + it * n_pairs;
       const int col = kb * KB + c16 * 8;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int64_t m = tile * (2 * BM) + (int64_t)rank * BM + r0 + 32 * i;
+      for (int i = 0; i < RPT; ++i) {
+        const int64_t m = tile * (2 * BM) + (int64_t)rank * BM + r0 + RSTEP * i;
         const float* src = p.A + m * p.lda + col;
         if (m < p.M && col + 8 <= p.K) {
           if (vec8) {
@@ -174,24 +202,16 @@ node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid
       }
     };
     int s = 0; uint32_t ph = 0;
-    float cur[4][8], nxt[4][8];
-    int64_t tile = pair;
-    int kb = 0;
-    if (tile < p.n_tiles) load_block(tile, 0, cur);
-    while (tile < p.n_tiles) {
-      // prefetch the following k-block (possibly of the next tile) before blocking on the ring slot
-      int64_t ntile = tile; int nkb_i = kb + 1;
-      if (nkb_i == p.nkb) { nkb_i = 0; ntile += n_pairs; }
-      if (ntile < p.n_tiles) load_block(ntile, nkb_i, nxt);
+    auto convert_block = [&](const float (*v)[8]) {
       mbar_wait(a_empty(s), ph ^ 1u);
       const uint32_t st = sbase + OFF_A + (uint32_t)s * 2 * BLK_BYTES;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = r0 + 32 * i;
+      for (int i = 0; i < RPT; ++i) {
+        const int r = r0 + RSTEP * i;
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float a = cur[i][2 * j] * kScale, b = cur[i][2 * j + 1] * kScale;
+          const float a = v[i][2 * j] * kScale, b = v[i][2 * j + 1] * kScale;
           hi[j] = pack_h2(a, b);
           const float2 bk = unpack_h2(hi[j]);
           lo[j] = pack_h2(a - bk.x, b - bk.y);
@@ -204,25 +224,24 @@ node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(a_full(s), 0));
       if (++s == A_STAGES) { s = 0; ph ^= 1u; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cur[i][j] = nxt[i][j];
-      tile = ntile; kb = nkb_i;
+    };
+    float b0[RPT][8], b1[RPT][8];
+    load_block(0, b0);
+    for (int64_t g = 0; g < n_blocks; g += 2) {
+      load_block(g + 1, b1);
+      convert_block(b0);
+      if (g + 1 >= n_blocks) break;
+      load_block(g + 2, b0);
+      convert_block(b1);
     }
   } else if (warp >= 4 + CONV_WARPS) {
     // ================= epilogue: thread = one row, 32-column chunks grp, grp+2, ... =================
     const int e = warp - (4 + CONV_WARPS);
     const int q = warp & 3, grp = e >> 2;
-    float* sE = reinterpret_cast<float*>(sgen + OFF_EPI);
-    for (int i = threadIdx.x - 32 * (4 + CONV_WARPS); i < MAX_N; i += 32 * EPI_WARPS) {
-      const bool in = i < p.N;
-      sE[i] = (in && p.bias) ? __ldg(p.bias + i) : 0.f;
-      sE[MAX_N + i] = ((in && p.scale) ? __ldg(p.scale + i) : 1.f) ;
-      sE[2 * MAX_N + i] = (in && p.scale && p.shift) ? __ldg(p.shift + i) : 0.f;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-    constexpr float kInv = 1.0f / (kScale * kScale);
+    // out = act((acc / 256 + bias) * scale + shift) = act(acc * s' + t'), {s', t'} per column from p.st_tab (L1-resident).
+    // Results leave through a per-warp [32 rows x 32 columns] shared-memory tile and a TMA store: a direct row store
+    // scatters every warp instruction over 32 rows (32 L1 tag cycles each), which made the L1/LSU the busiest unit.
+    const uint32_t stage = sbase + OFF_STAGE + (uint32_t)e * 4096u + (uint32_t)lane * 128u;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     int64_t it = 0;
     for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs, ++it) {
@@ -237,16 +256,39 @@ node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid
         tmem_ld_32x32_issue(t_lane + (uint32_t)(buf * MAX_N + c0), v);
         tmem_ld_wait(v);
         const int ncols = min(32, p.N - c0);
+        const float4* st4 = reinterpret_cast<const float4*>(p.st_tab + c0);   // c0 + 32 <= MAX_N: padded entries are harmless
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = c0 + j;                         // sE is padded to MAX_N: reads beyond N are harmless
-          float r = fmaf(v[j], kInv, sE[n & (MAX_N - 1)]);
-          r = fmaf(r, sE[MAX_N + (n & (MAX_N - 1))], sE[2 * MAX_N + (n & (MAX_N - 1))]);
-          if (p.act == GNNPN_ACT_RELU) r = fmaxf(r, 0.f);
-          else if (p.act == GNNPN_ACT_SIGMOID) r = sigmoid_accurate(r);
-          v[j] = r;
+        for (int j = 0; j < 32; j += 2) {
+          const float4 st = __ldg(st4 + (j >> 1));
+          v[j] = fmaf(v[j], st.x, st.y);
+          v[j + 1] = fmaf(v[j + 1], st.z, st.w);
         }
-        if (ok) {
+        if (p.act == GNNPN_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act == GNNPN_ACT_SIGMOID) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = sigmoid_accurate(v[j]);
+        }
+        if (p.c_vec == 0) {
+          if (lane == 0) bulk_wait_read0();                 // the previous chunk's tile has left shared memory
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            st_shared_v4(stage + (uint32_t)((g ^ (lane & 7)) << 4), __float_as_uint(v[4 * g]), __float_as_uint(v[4 * g + 1]),
+                         __float_as_uint(v[4 * g + 2]), __float_as_uint(v[4 * g + 3]));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int64_t row0 = tile * (2 * BM) + (int64_t)rank * BM + q * 32;
+            if (row0 < p.M) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_c),
+                           "r"(stage), "r"(c0), "r"((int)row0) : "memory");
+              bulk_commit();
+            }
+          }
+          __syncwarp();
+        } else if (ok) {
           if (p.c_vec == 8) {
 #pragma unroll
             for (int g = 0; g < 4; ++g)
@@ -266,6 +308,8 @@ node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty(buf), 0));
     }
+    if (lane == 0) bulk_wait0();
+    __syncwarp();
   }
   tc_fence_before();
   cluster_sync_all();
@@ -274,8 +318,16 @@ node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid
 
 // W [N, K] fp32 -> fp16 hi/lo [N, Kp] (x 2^4), K zero-padded to Kp
 __global__ void split_w_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, int Kp, __half* __restrict__ hi,
-                               __half* __restrict__ lo) {
+                               __half* __restrict__ lo, const float* __restrict__ bias, const float* __restrict__ scale,
+                               const float* __restrict__ shift, float2* __restrict__ st_tab) {
   const int total = N * Kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < MAX_N; i += gridDim.x * blockDim.x) {
+    const bool in = i < N;
+    const float b = (in && bias) ? bias[i] : 0.f;
+    const float sc = (in && scale) ? scale[i] : 1.f;
+    const float sh = (in && scale && shift) ? shift[i] : 0.f;
+    st_tab[i] = make_float2(sc * (1.0f / (kScale * kScale)), fmaf(b, sc, sh));
+  }
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int r = e / Kp, k = e - r * Kp;
     __half h = __float2half_rn(0.f), l = h;
@@ -294,7 +346,7 @@ bool node_transform_supported(int64_t M, int N, int K) {
 
 size_t node_transform_workspace_bytes(int N, int K) {
   const int Kp = round_up(K, nt::KB);
-  return (size_t)2 * N * Kp * sizeof(__half) + 1024;
+  return (size_t)2 * N * Kp * sizeof(__half) + nt::MAX_N * sizeof(float2) + 1024;
 }
 
 int launch_node_transform(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
@@ -305,7 +357,8 @@ int launch_node_transform(const float* A, int64_t lda, const float* W, int64_t l
   const int Kp = round_up(K, KB);
   __half* w_hi = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   __half* w_lo = w_hi + (size_t)N * Kp;
-  split_w_kernel<<<(N * Kp + 255) / 256, 256, 0, st>>>(W, ldw, N, K, Kp, w_hi, w_lo);
+  float2* st_tab = reinterpret_cast<float2*>(w_lo + (size_t)N * Kp);            // 16-byte aligned: N * Kp * 2 is a multiple of 2 KB
+  split_w_kernel<<<(N * Kp + 255) / 256, 256, 0, st>>>(W, ldw, N, K, Kp, w_hi, w_lo, bias, scale, shift, st_tab);
   int rc = after_launch();
   if (rc) return rc;
   CUtensorMap maps[2];
@@ -316,6 +369,24 @@ int launch_node_transform(const float* A, int64_t lda, const float* W, int64_t l
   p.M = M; p.N = N; p.K = K; p.nkb = Kp / KB; p.n_tiles = ceil_div(M, 2 * BM);
   const uintptr_t ca = reinterpret_cast<uintptr_t>(C);
   p.c_vec = ((ldc & 7) == 0 && (ca & 31u) == 0) ? 8 : ((ldc & 3) == 0 && (ca & 15u) == 0) ? 4 : 1;
+  p.st_tab = st_tab;
+  CUtensorMap map_c;
+  static const int direct = getenv("GNNPN_GEMM_DIRECT_STORE") ? atoi(getenv("GNNPN_GEMM_DIRECT_STORE")) : 0;   // A/B knob
+  if (p.c_vec >= 4 && !direct) {
+    // C as a 2-D fp32 tensor {N, M}; box = 32 columns x 32 rows, 128B swizzle (one epilogue warp's tile)
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return GNNPN_EUNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)ldc * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    if (fn(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return GNNPN_ESHAPE;
+    p.c_vec = 0;
+  } else {
+    map_c = maps[0];                                       // unused by the direct-store path
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(node_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -329,7 +400,7 @@ int launch_node_transform(const float* A, int64_t lda, const float* W, int64_t l
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, node_transform_kernel, maps[0], maps[1], p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, node_transform_kernel, maps[0], maps[1], map_c, p);
   if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
   return after_launch();
 }
