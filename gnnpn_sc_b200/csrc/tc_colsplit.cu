@@ -1,0 +1,465 @@
+// Column-split persistent tcgen05 LSTM scan for SMALL batches (latency mode).
+//
+// tc_seq.cu gives every CTA (pair) 128 instances and all 4H = 1024 gate columns: a time step costs ~31k cycles no
+// matter how few instances there are, so a batch of n <= ~4k instances (the reference's own batch is 128; the
+// scale-up configuration fits ~1.5k instances of L = 100,000 in HBM) leaves most of the 148 SMs idle while the L
+// dependent steps run.  Here a CLUSTER of 8 CTAs shares one group of 128 instances and splits the gate columns:
+// CTA r owns hidden units [32r, 32r+32) = gate columns [128r, 128r+128) for the whole scan.
+//   * its slice of the folded weights (fp16 hi/lo, 136 KB) is loaded ONCE and stays resident in shared memory;
+//   * its cell state lives in REGISTERS (thread = instance row x 8 units) for the whole scan;
+//   * per step it issues 51 MMAs (M=128, N=128, K=16; 3xFP16 split, fp32 accumulate in TMEM) instead of 408;
+//   * h'(t) is exchanged through an L2-resident scratch: every CTA writes its [128 x 32] slice as fp16 hi/lo rows,
+//     publishes it with remote mbarrier arrives to the 8 CTAs of the cluster (one barrier per 64-unit k-block and
+//     step parity), and every CTA pulls the full [128 x 256] operand back with TMA (128B swizzle = UMMA layout)
+//     through a 5-slot ring, k-block by k-block, as soon as the two CTAs that produce that k-block have arrived.
+//     (DSMEM stores were not used for the exchange: ~21 B/cycle per SM would cost ~6k cycles per step.)
+// Reference semantics: nn.LSTM cell, gate order i,f,g,o (modelPN.py:157,191); same packed weights, same cell
+// epilogue (lstm_cell8) as tc_seq.cu.
+#include <stdio.h>
+#include <stdlib.h>
+#include <cuda_fp16.h>
+#include "tc_common.cuh"
+#include "common.cuh"
+#include "lstm_step.cuh"
+#include "tc_lstm.cuh"
+#include "tc_seq.cuh"
+#include "tc_seq_dev.cuh"
+
+namespace gnnpn {
+namespace cs {
+
+using namespace tc;
+using namespace seq;
+
+constexpr int CL = 8;                      // CTAs per cluster = column slices
+constexpr int BM = 128;                    // instances per cluster = UMMA M
+constexpr int TILE_N = kG / CL;            // 128 gate columns per CTA
+constexpr int UNITS = kH / CL;             // 32 hidden units per CTA
+constexpr int KB_H = kH / 64;              // 4 k-blocks of 64 halfs
+constexpr int BLK_BYTES = 128 * 128;       // [128 rows x 64 halfs]
+constexpr int NSLOT = 5;                   // A ring slots (one per k-block half: lo or hi)
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = 128 + 32 * EPI_WARPS;
+
+constexpr uint32_t OFF_W_HI = 0;
+constexpr uint32_t OFF_W_LO = OFF_W_HI + KB_H * BLK_BYTES;
+constexpr uint32_t OFF_WX_HI = OFF_W_LO + KB_H * BLK_BYTES;
+constexpr uint32_t OFF_WX_LO = OFF_WX_HI + TILE_N * XROW_BYTES;
+constexpr uint32_t OFF_AX_HI = OFF_WX_LO + TILE_N * XROW_BYTES;
+constexpr uint32_t OFF_AX_LO = OFF_AX_HI + BM * XROW_BYTES;
+constexpr uint32_t OFF_RING = OFF_AX_LO + BM * XROW_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_RING + NSLOT * BLK_BYTES;
+constexpr uint32_t OFF_BAR = OFF_BIAS + TILE_N * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+constexpr uint32_t W_BYTES = 2 * KB_H * BLK_BYTES + 2 * TILE_N * XROW_BYTES;
+
+struct Params {
+  int64_t n;
+  int steps, F;
+  const float* inputs; int64_t x_inst_ld;
+  const float* bias;       // [kG] gate-interleaved
+  float* c_out;            // [n, kH]
+  float* h_out; int64_t h_out_inst_ld;
+  __half* scratch;         // [groups][parity 2][hi|lo][128][kH] halfs
+  unsigned long long* prof;
+};
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// remote arrive that releases this thread's prior global writes at cluster scope (compiles to a GPU-scope membar +
+// arrive; issued by 8 lanes once per step, after the warp's own __threadfence, so it is cheap here)
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void stg128_u(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_constant__ CUtensorMap map_wh_lo,
+                     const __grid_constant__ CUtensorMap map_wx_hi, const __grid_constant__ CUtensorMap map_wx_lo,
+                     const __grid_constant__ CUtensorMap map_scr, const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar0 = sbase + OFF_BAR;
+  const uint32_t w_full = bar0;
+  auto full_bar = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (1 + NSLOT + s); };
+  const uint32_t tfull = bar0 + 8u * (1 + 2 * NSLOT);
+  const uint32_t tempty = tfull + 8u;
+  const uint32_t x_rdy = tfull + 16u;
+  auto a_rdy = [&](int par, int kb) { return tfull + 24u + 8u * (par * KB_H + kb); };
+  const uint32_t tmem_slot = tfull + 24u + 8u * (2 * KB_H);
+  const uint32_t rank = cluster_ctarank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t group = blockIdx.x / CL;
+  const int64_t m0 = group * BM;
+  float* sbias = reinterpret_cast<float*>(sgen + OFF_BIAS);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_wh_hi); tma_prefetch_desc(&map_wh_lo);
+    tma_prefetch_desc(&map_wx_hi); tma_prefetch_desc(&map_wx_lo); tma_prefetch_desc(&map_scr);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(w_full, 1);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, EPI_WARPS);
+    mbar_init(x_rdy, 1);
+    for (int par = 0; par < 2; ++par)
+      for (int kb = 0; kb < KB_H; ++kb) mbar_init(a_rdy(par, kb), 2 * EPI_WARPS);   // the two CTAs producing this k-block
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TILE_N);
+  // transformed biases of this CTA's 128 gate columns: (i,f,o) * -log2e, g * -2log2e
+  for (int i = threadIdx.x; i < TILE_N; i += THREADS) {
+    const float b = __ldg(p.bias + rank * TILE_N + i);
+    sbias[i] = b * ((i & 3) == 2 ? -2.0f * kLog2e : -kLog2e);
+  }
+
+  auto write_x_rows = [&](const float (*xv)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = lane + 32 * i;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hi[j] = pack_h2(xv[i][2 * j], xv[i][2 * j + 1]);
+        const float2 bk = unpack_h2(hi[j]);
+        lo[j] = pack_h2(xv[i][2 * j] - bk.x, xv[i][2 * j + 1] - bk.y);
+      }
+      const uint32_t o = (uint32_t)r * XROW_BYTES;
+      st_shared_v4(sbase + OFF_AX_HI + o, hi[0], hi[1], hi[2], hi[3]);
+      st_shared_v4(sbase + OFF_AX_HI + o + 16, hi[0], hi[1], hi[2], hi[3]);
+      st_shared_v4(sbase + OFF_AX_LO + o, lo[0], lo[1], lo[2], lo[3]);
+      st_shared_v4(sbase + OFF_AX_LO + o + 16, lo[0], lo[1], lo[2], lo[3]);
+    }
+  };
+  auto load_x_rows = [&](int t, float (*xv)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = m0 + lane + 32 * i;
+#pragma unroll
+      for (int f = 0; f < 8; ++f)
+        xv[i][f] = (m < p.n && f < p.F) ? __ldg(p.inputs + m * p.x_inst_ld + (int64_t)t * p.F + f) : 0.f;
+    }
+  };
+  if (warp == 3) {
+    float xv[4][8];
+    load_x_rows(0, xv);
+    write_x_rows(xv);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();                       // barrier inits visible cluster-wide before any remote arrive
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const bool prof = p.prof != nullptr;
+
+  if (warp == 0) {
+    // ================= TMA: resident weight slice once; then the A operand of every step from the exchange scratch ===
+    if (lane == 0) {
+      const int col0 = (int)rank * TILE_N;
+      mbar_arrive_expect_tx(w_full, W_BYTES);
+      for (int kb = 0; kb < KB_H; ++kb) {
+        tma_load_2d(sbase + OFF_W_HI + kb * BLK_BYTES, &map_wh_hi, w_full, kb * 64, col0);
+        tma_load_2d(sbase + OFF_W_LO + kb * BLK_BYTES, &map_wh_lo, w_full, kb * 64, col0);
+      }
+      tma_load_2d(sbase + OFF_WX_HI, &map_wx_hi, w_full, kH, col0);
+      tma_load_2d(sbase + OFF_WX_LO, &map_wx_lo, w_full, kH, col0);
+      int s = 0; uint32_t ph = 0;
+      long long w_rdy = 0;
+      for (int t = 1; t < p.steps; ++t) {
+        const int par = (t - 1) & 1;
+        const uint32_t rph = (uint32_t)((t - 1) >> 1) & 1u;
+        const int row_base = (int)((group * 2 + par) * 2) * BM;       // hi rows; lo rows follow BM later
+        for (int kb = 0; kb < KB_H; ++kb) {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_wait_cluster(a_rdy(par, kb), rph);                      // both producers of units [64kb, 64kb+64) published h'(t-1)
+          if (prof) w_rdy += clock64() - t0;
+          fence_proxy_async_all();
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {                       // lo first: its 4 MMAs free the slot early
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            mbar_arrive_expect_tx(full_bar(s), BLK_BYTES);
+            tma_load_2d(sbase + OFF_RING + s * BLK_BYTES, &map_scr, full_bar(s), kb * 64, row_base + (part ? 0 : BM));
+            if (++s == NSLOT) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+      if (prof) p.prof[(size_t)blockIdx.x * 8 + 0] = (unsigned long long)w_rdy;
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t leader = elect_one();
+    const uint32_t idesc = idesc_f16(BM, TILE_N);
+    const uint64_t ax_hi = smem_desc_k_sw32(sbase + OFF_AX_HI), ax_lo = smem_desc_k_sw32(sbase + OFF_AX_LO);
+    const uint64_t wx_hi = smem_desc_k_sw32(sbase + OFF_WX_HI), wx_lo = smem_desc_k_sw32(sbase + OFF_WX_LO);
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    int s = 0; uint32_t ph = 0;
+    long long w_full_c = 0;
+    const long long t_begin = clock64();
+    for (int t = 0; t < p.steps; ++t) {
+      if (t > 0) mbar_wait(x_rdy, (uint32_t)(t - 1) & 1u);
+      mbar_wait(tempty, ((uint32_t)t & 1u) ^ 1u);
+      tc_fence_after();
+      if (leader) {
+        mma_f16_ss(tmem_base, ax_lo, wx_hi, idesc, 0u);      // x part first: it does not depend on the exchange
+        mma_f16_ss(tmem_base, ax_hi, wx_hi, idesc, 1u);
+        mma_f16_ss(tmem_base, ax_hi, wx_lo, idesc, 1u);
+      }
+      __syncwarp();
+      if (t > 0) {
+        for (int kb = 0; kb < KB_H; ++kb) {
+          const uint64_t w_hi = smem_desc_k_sw128(sbase + OFF_W_HI + kb * BLK_BYTES);
+          const uint64_t w_lo = smem_desc_k_sw128(sbase + OFF_W_LO + kb * BLK_BYTES);
+          long long t0 = prof ? clock64() : 0;
+          mbar_wait(full_bar(s), ph);
+          if (prof) w_full_c += clock64() - t0;
+          tc_fence_after();
+          const uint64_t a_lo = smem_desc_k_sw128(sbase + OFF_RING + s * BLK_BYTES);
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma_f16_ss(tmem_base, a_lo + (uint64_t)(ks * 2), w_hi + (uint64_t)(ks * 2), idesc, 1u);
+            mma_commit(empty_bar(s));
+          }
+          __syncwarp();
+          if (++s == NSLOT) { s = 0; ph ^= 1u; }
+          t0 = prof ? clock64() : 0;
+          mbar_wait(full_bar(s), ph);
+          if (prof) w_full_c += clock64() - t0;
+          tc_fence_after();
+          const uint64_t a_hi = smem_desc_k_sw128(sbase + OFF_RING + s * BLK_BYTES);
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma_f16_ss(tmem_base, a_hi + (uint64_t)(ks * 2), w_hi + (uint64_t)(ks * 2), idesc, 1u);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma_f16_ss(tmem_base, a_hi + (uint64_t)(ks * 2), w_lo + (uint64_t)(ks * 2), idesc, 1u);
+            mma_commit(empty_bar(s));
+          }
+          __syncwarp();
+          if (++s == NSLOT) { s = 0; ph ^= 1u; }
+        }
+      }
+      if (leader) mma_commit(tfull);
+      __syncwarp();
+    }
+    if (prof && leader) {
+      p.prof[(size_t)blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_begin);
+      p.prof[(size_t)blockIdx.x * 8 + 2] = (unsigned long long)w_full_c;
+    }
+  } else if (warp == 3) {
+    // ================= x producer: raw input row of step t+1 -> fp16 hi/lo x block =================
+    for (int t = 0; t + 1 < p.steps; ++t) {
+      float xv[4][8];
+      load_x_rows(t + 1, xv);
+      mbar_wait(tfull, (uint32_t)t & 1u);             // the MMAs of step t no longer read the x block
+      write_x_rows(xv);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_rdy);
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: thread = one instance row x 8 hidden units, cell state in registers ===========
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    const int64_t m = m0 + r;
+    const bool ok = m < p.n;
+    const int u0 = (int)rank * UNITS + grp * 8;                       // first hidden unit of this thread
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 32);
+    const float4* bias4 = reinterpret_cast<const float4*>(sbias) + grp * 8;
+    float* const h_row = p.h_out + (ok ? m : 0) * p.h_out_inst_ld + u0;
+    __half* const scr = p.scratch + (size_t)group * (2 * 2 * BM * kH) + (size_t)r * kH + u0;
+    const uint32_t kb_mine = rank >> 1;
+    float c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c[u] = 0.f;
+    long long w_tfull = 0, d_ld = 0, d_cell = 0, d_pub = 0, d_out = 0;
+    for (int t = 0; t < p.steps; ++t) {
+      const long long t0 = prof ? clock64() : 0;
+      mbar_wait(tfull, (uint32_t)t & 1u);
+      const long long t1 = prof ? clock64() : 0;
+      if (prof) w_tfull += t1 - t0;
+      tc_fence_after();
+      float v[32];
+      tmem_ld_32x32_issue(t_addr, v);
+      tmem_ld_wait(v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+      const long long t2 = prof ? clock64() : 0;
+      float cn[8], hn[8];
+      lstm_cell8(v, bias4, c, cn, hn);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) c[u] = cn[u];
+      if (t + 1 < p.steps) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pk[j] = pack_h2(hn[2 * j], hn[2 * j + 1]);
+          const float2 bk = unpack_h2(pk[j]);
+          pk[4 + j] = pack_h2(hn[2 * j] - bk.x, hn[2 * j + 1] - bk.y);
+        }
+        const long long t3 = prof ? clock64() : 0;
+        if (prof) { d_ld += t2 - t1; d_cell += t3 - t2; }
+        __half* dst = scr + (size_t)(t & 1) * (2 * BM * kH);
+        stg128_u(dst, pk[0], pk[1], pk[2], pk[3]);                    // hi rows
+        stg128_u(dst + BM * kH, pk[4], pk[5], pk[6], pk[7]);          // lo rows
+        // publish: the warp's stores happen-before the release below through __syncwarp; ONE cumulative
+        // release.cluster arrive per destination CTA (8 lanes in parallel) instead of a GPU-scope fence in every lane
+        __syncwarp();
+        if (lane < CL) {
+          fence_proxy_async_all();
+          mbar_arrive_release_cluster(mapa_rank(a_rdy(t & 1, (int)kb_mine), (uint32_t)lane));
+        }
+        __syncwarp();
+        if (prof) d_pub += clock64() - t3;
+      }
+      const long long t4 = prof ? clock64() : 0;
+      if (ok) stg256(h_row + (int64_t)t * kH, hn);
+      if (prof) d_out += clock64() - t4;
+    }
+    if (ok) stg256(p.c_out + m * kH + u0, c);
+    if (prof && warp == 4 && lane == 0) {
+      unsigned long long* o = p.prof + (size_t)blockIdx.x * 8;
+      o[3] = (unsigned long long)w_tfull; o[4] = (unsigned long long)d_ld; o[5] = (unsigned long long)d_cell;
+      o[6] = (unsigned long long)d_pub; o[7] = (unsigned long long)d_out;
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc(tmem_base, TILE_N);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+}  // namespace cs
+
+size_t tc_colsplit_scratch_bytes(int64_t n) { return (size_t)ceil_div(n, cs::BM) * 2 * 2 * cs::BM * kH * sizeof(__half); }
+
+// how many 8-CTA clusters of this kernel the device can hold at once (GPC packing decides; measured, not assumed)
+static int max_active_clusters() {
+  static const int v = [] {
+    using namespace cs;
+    if (cudaFuncSetAttribute(lstm_colsplit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, lstm_colsplit_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nc;
+  }();
+  return v;
+}
+int tc_colsplit_max_active_clusters() { return max_active_clusters(); }
+
+// GNNPN_COLSPLIT: -1 (default) = automatic, 0 = never, 1 = always.  Automatic: a step of the column-split scan costs
+// ~6.8 us per wave of clusters against ~16.7 us for the CTA-pair scan at any batch up to 18,944, so it is used while
+// the batch fits two waves (measured 2.45x / 1.2x faster at one / two waves, profiles/r01_colsplit_timing.jsonl).
+bool tc_colsplit_wanted(int64_t n) {
+  const char* e = getenv("GNNPN_COLSPLIT");              // read per call: tests and benches flip it between launches
+  const int mode = e ? atoi(e) : -1;
+  if (mode == 0) return false;
+  if (mode == 1) return true;
+  return ceil_div(n, cs::BM) <= 2 * (int64_t)max_active_clusters();
+}
+
+int tc_colsplit_encode(const SeqEncodeArgs& a, void* scratch, cudaStream_t st) {
+  using namespace cs;
+  if (a.F < 1 || a.F > 8 || a.L < 1) return GNNPN_EUNSUPPORTED;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return GNNPN_EUNSUPPORTED;
+  const int64_t groups = ceil_div(a.n, BM);
+  CUtensorMap maps[5];
+  const float* w_hi = a.packed + kOffTc16Hi;
+  const float* w_lo = a.packed + kOffTc16Lo;
+  for (int i = 0; i < 4; ++i) {
+    cuuint64_t dims[2] = {(cuuint64_t)kKp16, (cuuint64_t)kG};
+    cuuint64_t strides[1] = {(cuuint64_t)kKp16 * 2};
+    cuuint32_t box[2] = {i < 2 ? 64u : 16u, (cuuint32_t)TILE_N};
+    cuuint32_t estr[2] = {1, 1};
+    if (fn(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)((i & 1) ? w_lo : w_hi), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, i < 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return GNNPN_ESHAPE;
+  }
+  {
+    // exchange scratch as one 2-D fp16 tensor {kH, groups * 2 parities * (hi|lo) * 128 rows}; box = one k-block
+    cuuint64_t dims[2] = {(cuuint64_t)kH, (cuuint64_t)(groups * 4 * BM)};
+    cuuint64_t strides[1] = {(cuuint64_t)kH * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    if (fn(&maps[4], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, scratch, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return GNNPN_ESHAPE;
+  }
+  Params p{};
+  p.n = a.n; p.steps = a.L; p.F = a.F;
+  p.inputs = a.inputs; p.x_inst_ld = (int64_t)a.L * a.F;
+  p.bias = a.packed + kOffBias;
+  p.c_out = a.c_state;
+  p.h_out = a.enc_out; p.h_out_inst_ld = (int64_t)a.L * kH;
+  p.scratch = reinterpret_cast<__half*>(scratch);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_colsplit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  static const int do_prof = getenv("GNNPN_SEQ_PROF") ? atoi(getenv("GNNPN_SEQ_PROF")) : 0;
+  const unsigned grid = (unsigned)(groups * CL);
+  unsigned long long* prof = nullptr;
+  if (do_prof) {
+    if (cudaMalloc(&prof, (size_t)grid * 8 * 8) != cudaSuccess) return GNNPN_EUNSUPPORTED;
+    cudaMemsetAsync(prof, 0, (size_t)grid * 8 * 8, st);
+  }
+  p.prof = prof;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, lstm_colsplit_kernel, maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
+  const int rc = after_launch();
+  if (do_prof) {
+    unsigned long long* h = (unsigned long long*)malloc((size_t)grid * 8 * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, prof, (size_t)grid * 8 * 8, cudaMemcpyDeviceToHost);
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (unsigned c = 0; c < grid; ++c)
+      for (int i = 0; i < 8; ++i) acc[i] += (double)h[c * 8 + i];
+    fprintf(stderr, "[colsplit prof steps=%d grid=%u max_active_clusters=%d] per-step cycles: mma total %.0f (wait A full %.0f) | tma wait a_rdy %.0f | "
+            "epi wait tmem_full %.0f, tmem ld %.0f, cell %.0f, publish %.0f, h store %.0f\n", a.L, grid, max_active_clusters(),
+            acc[1] / grid / a.L, acc[2] / grid / a.L, acc[0] / grid / a.L, acc[3] / grid / a.L, acc[4] / grid / a.L,
+            acc[5] / grid / a.L, acc[6] / grid / a.L, acc[7] / grid / a.L);
+    free(h);
+    cudaFree(prof);
+  }
+  return rc;
+}
+
+}  // namespace gnnpn

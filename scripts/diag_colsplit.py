@@ -1,0 +1,61 @@
+"""GPU bring-up diagnostic for the column-split cluster scan (tc_colsplit.cu): encoder outputs against the
+CTA-pair persistent scan (GNNPN_COLSPLIT=0) and the strict-fp32 FFMA path, then timing of both over batch sizes."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gnnpn_sc_b200 import ops, modelPN as M
+from gnnpn_sc_b200.synth import pn_instances
+from gnnpn_sc_b200.weights import reference_shaped_state_dict
+
+dev = torch.device("cuda")
+m = M.CombinatorialRL(0, 256, 235, 0, 10, 1, M.reward, "Dot", 5, 47, level="Low")
+m.load_state_dict(reference_shaped_state_dict(256, 8, 77)); m = m.cuda().eval()
+enc_w, dec_w = m.actor._packed_weights()
+
+
+def encode(x, mode, ws):
+    os.environ["GNNPN_COLSPLIT"] = str(mode)
+    out = ops.lstm_encode(x, enc_w, 256, workspace=ws)
+    torch.cuda.synchronize()
+    return out
+
+
+if "--time-only" not in sys.argv:
+    for n, K, N in [(1, 3, 2), (128, 6, 4), (300, 47, 5), (1000, 20, 5)]:
+        x = pn_instances(n, K, N, seed=5).to(dev)
+        ws = ops.pn_workspace(n, 256, dev, "tc")
+        e_cs, c_cs = encode(x, 1, ws)
+        e_cs, c_cs = e_cs.clone(), c_cs.clone()
+        e_sq, c_sq = encode(x, 0, ws)
+        e_ff, c_ff = ops.lstm_encode(x, enc_w, 256, workspace=None)
+        torch.cuda.synchronize()
+        d1 = (e_cs - e_sq).abs(); d2 = (e_cs - e_ff).abs(); d3 = (e_sq - e_ff).abs()
+        print(f"n={n} L={K*N}: colsplit-vs-pair enc {d1.max():.2e} c {(c_cs-c_sq).abs().max():.2e} | colsplit-vs-ffma {d2.max():.2e} "
+              f"(t=0 {d2[:,0].max():.1e}, t=1 {d2[:,1].max():.1e}, last {d2[:,-1].max():.1e}) | pair-vs-ffma {d3.max():.2e}", flush=True)
+        if d2.max() > 1e-3:
+            bad = d2 > 1e-3
+            print("   first bad t:", bad.any(2).any(0).nonzero().flatten()[:5].tolist(), "rows:", bad.any(2).any(1).nonzero().flatten()[:8].tolist(),
+                  "units:", bad.any(1).any(0).nonzero().flatten()[:16].tolist())
+
+rows = []
+for n in [128, 512, 1024, 2048, 4096, 6144, 8192]:
+    x = pn_instances(n, 47, 5, seed=5).to(dev)
+    ws = ops.pn_workspace(n, 256, dev, "tc")
+    enc_out = torch.empty(n, 235, 256, device=dev); c = torch.empty(n, 256, device=dev)
+    r = {"n": n, "L": 235}
+    for mode, name in ((1, "colsplit_ms"), (0, "pair_ms")):
+        os.environ["GNNPN_COLSPLIT"] = str(mode)
+        ts = []
+        for i in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); ops.lstm_encode(x, enc_w, 256, enc_out, c, workspace=ws); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        r[name] = sorted(ts[1:])[len(ts[1:]) // 2]
+    r["us_per_step_colsplit"] = r["colsplit_ms"] * 1e3 / 235
+    r["us_per_step_pair"] = r["pair_ms"] * 1e3 / 235
+    rows.append(r)
+    print(json.dumps(r), flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+with open("gpurun_out/colsplit_timing.jsonl", "w") as f:
+    for r in rows:
+        f.write(json.dumps(r) + "\n")
