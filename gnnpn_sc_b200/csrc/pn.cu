@@ -338,6 +338,7 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
                      dec_h, idx_out, win_logits, win_probs, forced_idx, sample_uniform,
                      reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023))};
     GNNPN_REQUIRE(workspace_bytes >= tc_lstm_workspace_bytes(n), GNNPN_EWORKSPACE);
+    if (tc_colsplit_wanted(n)) return tc_colsplit_decode(sa, sa.c_scratch, st);    // small batch: column-split cluster scan
     return tc_seq_decode(sa, st);
   }
   TcLstmPlan plan;

@@ -24,6 +24,7 @@
 #include "tc_lstm.cuh"
 #include "tc_seq.cuh"
 #include "tc_seq_dev.cuh"
+#include "pointer.cuh"
 
 namespace gnnpn {
 namespace cs {
@@ -49,32 +50,41 @@ constexpr uint32_t OFF_AX_HI = OFF_WX_LO + TILE_N * XROW_BYTES;
 constexpr uint32_t OFF_AX_LO = OFF_AX_HI + BM * XROW_BYTES;
 constexpr uint32_t OFF_RING = OFF_AX_LO + BM * XROW_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_RING + NSLOT * BLK_BYTES;
-constexpr uint32_t OFF_BAR = OFF_BIAS + TILE_N * 4;
+constexpr uint32_t OFF_BAR = OFF_BIAS + 2 * TILE_N * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 constexpr uint32_t W_BYTES = 2 * KB_H * BLK_BYTES + 2 * TILE_N * XROW_BYTES;
 
 struct Params {
   int64_t n;
-  int steps, F;
+  int steps, F, L;
   const float* inputs; int64_t x_inst_ld;
-  const float* bias;       // [kG] gate-interleaved
-  float* c_out;            // [n, kH]
-  float* h_out; int64_t h_out_inst_ld;
+  const float* bias0;      // [kG] gate-interleaved bias of step 0 (decoder: start-token bias)
+  const float* bias;       // [kG] bias of steps >= 1
+  float* c;                // [n, kH] cell state: out (encoder), in/out (decoder)
+  const float* h0; int64_t h0_ld;          // decoder: initial hidden rows
+  float* h_out; int64_t h_out_inst_ld;     // step t of instance m at h_out + m*ld + t*kH (enc_out / dec_h)
   __half* scratch;         // [groups][parity 2][hi|lo][128][kH] halfs
+  PointerStepArgs pa;      // decoder only
   unsigned long long* prof;
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// remote arrive that releases this thread's prior global writes at cluster scope (compiles to a GPU-scope membar +
-// arrive; issued by 8 lanes once per step, after the warp's own __threadfence, so it is cheap here)
+// remote arrive that releases this thread's prior writes at cluster scope (compiles to a GPU-scope membar + arrive;
+// cumulative: it also covers the writes of the other lanes that reached the preceding __syncwarp)
 __device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void stg128_u(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
+// Publish index of h'(t): the decoder also publishes its initial hidden state (index 0), so h'(t) has index t+1 there.
+// Index j lives in scratch parity j & 1 and completes phase (j >> 1) & 1 of the a_rdy[j & 1][*] barriers.
+template <bool DEC>
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_constant__ CUtensorMap map_wh_lo,
                      const __grid_constant__ CUtensorMap map_wx_hi, const __grid_constant__ CUtensorMap map_wx_lo,
@@ -96,6 +106,7 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
   const int64_t group = blockIdx.x / CL;
   const int64_t m0 = group * BM;
   float* sbias = reinterpret_cast<float*>(sgen + OFF_BIAS);
+  constexpr int PUB0 = DEC ? 1 : 0;                    // publish index of h'(t) = t + PUB0
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_wh_hi); tma_prefetch_desc(&map_wh_lo);
@@ -106,16 +117,17 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
     for (int s = 0; s < NSLOT; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tfull, 1);
     mbar_init(tempty, EPI_WARPS);
-    mbar_init(x_rdy, 1);
+    mbar_init(x_rdy, DEC ? CL * EPI_WARPS : 1);        // decoder: one arrival per instance of the group (its pointer warp)
     for (int par = 0; par < 2; ++par)
       for (int kb = 0; kb < KB_H; ++kb) mbar_init(a_rdy(par, kb), 2 * EPI_WARPS);   // the two CTAs producing this k-block
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TILE_N);
-  // transformed biases of this CTA's 128 gate columns: (i,f,o) * -log2e, g * -2log2e
-  for (int i = threadIdx.x; i < TILE_N; i += THREADS) {
-    const float b = __ldg(p.bias + rank * TILE_N + i);
-    sbias[i] = b * ((i & 3) == 2 ? -2.0f * kLog2e : -kLog2e);
+  // transformed biases of this CTA's 128 gate columns (two sets: step 0, steps >= 1): (i,f,o) * -log2e, g * -2log2e
+  for (int i = threadIdx.x; i < 2 * TILE_N; i += THREADS) {
+    const int col = i & (TILE_N - 1);
+    const float b = __ldg((i < TILE_N ? p.bias0 : p.bias) + rank * TILE_N + col);
+    sbias[i] = b * ((col & 3) == 2 ? -2.0f * kLog2e : -kLog2e);
   }
 
   auto write_x_rows = [&](const float (*xv)[8]) {
@@ -145,7 +157,7 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
         xv[i][f] = (m < p.n && f < p.F) ? __ldg(p.inputs + m * p.x_inst_ld + (int64_t)t * p.F + f) : 0.f;
     }
   };
-  if (warp == 3) {
+  if (!DEC && warp == 3) {
     float xv[4][8];
     load_x_rows(0, xv);
     write_x_rows(xv);
@@ -172,13 +184,14 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
       tma_load_2d(sbase + OFF_WX_LO, &map_wx_lo, w_full, kH, col0);
       int s = 0; uint32_t ph = 0;
       long long w_rdy = 0;
-      for (int t = 1; t < p.steps; ++t) {
-        const int par = (t - 1) & 1;
-        const uint32_t rph = (uint32_t)((t - 1) >> 1) & 1u;
+      for (int t = DEC ? 0 : 1; t < p.steps; ++t) {
+        const int j = t - 1 + PUB0;                                    // publish index consumed by step t
+        const int par = j & 1;
+        const uint32_t rph = (uint32_t)(j >> 1) & 1u;
         const int row_base = (int)((group * 2 + par) * 2) * BM;       // hi rows; lo rows follow BM later
         for (int kb = 0; kb < KB_H; ++kb) {
           const long long t0 = prof ? clock64() : 0;
-          mbar_wait_cluster(a_rdy(par, kb), rph);                      // both producers of units [64kb, 64kb+64) published h'(t-1)
+          mbar_wait_cluster(a_rdy(par, kb), rph);                      // both producers of units [64kb, 64kb+64) have published
           if (prof) w_rdy += clock64() - t0;
           fence_proxy_async_all();
 #pragma unroll
@@ -204,16 +217,12 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
     long long w_full_c = 0;
     const long long t_begin = clock64();
     for (int t = 0; t < p.steps; ++t) {
-      if (t > 0) mbar_wait(x_rdy, (uint32_t)(t - 1) & 1u);
       mbar_wait(tempty, ((uint32_t)t & 1u) ^ 1u);
       tc_fence_after();
-      if (leader) {
-        mma_f16_ss(tmem_base, ax_lo, wx_hi, idesc, 0u);      // x part first: it does not depend on the exchange
-        mma_f16_ss(tmem_base, ax_hi, wx_hi, idesc, 1u);
-        mma_f16_ss(tmem_base, ax_hi, wx_lo, idesc, 1u);
-      }
-      __syncwarp();
-      if (t > 0) {
+      // MMA order per step = tc_seq.cu's order per tile (h part k-block by k-block: a_lo.w_hi, a_hi.w_hi, a_hi.w_lo;
+      // then the x part), so both scans produce the same bits and a batch can be sharded across them freely.
+      uint32_t acc = 0u;                                     // the first MMA of a step overwrites the accumulator
+      if (DEC || t > 0) {
         for (int kb = 0; kb < KB_H; ++kb) {
           const uint64_t w_hi = smem_desc_k_sw128(sbase + OFF_W_HI + kb * BLK_BYTES);
           const uint64_t w_lo = smem_desc_k_sw128(sbase + OFF_W_LO + kb * BLK_BYTES);
@@ -224,10 +233,12 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
           const uint64_t a_lo = smem_desc_k_sw128(sbase + OFF_RING + s * BLK_BYTES);
           if (leader) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma_f16_ss(tmem_base, a_lo + (uint64_t)(ks * 2), w_hi + (uint64_t)(ks * 2), idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks)
+              mma_f16_ss(tmem_base, a_lo + (uint64_t)(ks * 2), w_hi + (uint64_t)(ks * 2), idesc, ks == 0 ? acc : 1u);
             mma_commit(empty_bar(s));
           }
           __syncwarp();
+          acc = 1u;
           if (++s == NSLOT) { s = 0; ph ^= 1u; }
           t0 = prof ? clock64() : 0;
           mbar_wait(full_bar(s), ph);
@@ -245,6 +256,19 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
           if (++s == NSLOT) { s = 0; ph ^= 1u; }
         }
       }
+      if (!DEC || t > 0) {
+        // x part last.  Decoder: it is the raw row of the previous pick, so the pointer phase of step t-1 overlaps the
+        // exchange and the h-part MMAs of step t.  Encoder: x_rdy was signalled long ago by the x producer.
+        if (DEC) mbar_wait_cluster(x_rdy, (uint32_t)(t - 1) & 1u);
+        else if (t > 0) mbar_wait(x_rdy, (uint32_t)(t - 1) & 1u);
+        tc_fence_after();
+        if (leader) {
+          mma_f16_ss(tmem_base, ax_lo, wx_hi, idesc, acc);
+          mma_f16_ss(tmem_base, ax_hi, wx_hi, idesc, 1u);
+          mma_f16_ss(tmem_base, ax_hi, wx_lo, idesc, 1u);
+        }
+        __syncwarp();
+      }
       if (leader) mma_commit(tfull);
       __syncwarp();
     }
@@ -253,15 +277,17 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
       p.prof[(size_t)blockIdx.x * 8 + 2] = (unsigned long long)w_full_c;
     }
   } else if (warp == 3) {
-    // ================= x producer: raw input row of step t+1 -> fp16 hi/lo x block =================
-    for (int t = 0; t + 1 < p.steps; ++t) {
-      float xv[4][8];
-      load_x_rows(t + 1, xv);
-      mbar_wait(tfull, (uint32_t)t & 1u);             // the MMAs of step t no longer read the x block
-      write_x_rows(xv);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(x_rdy);
+    // ================= x producer (encoder): raw input row of step t+1 -> fp16 hi/lo x block =================
+    if (!DEC) {
+      for (int t = 0; t + 1 < p.steps; ++t) {
+        float xv[4][8];
+        load_x_rows(t + 1, xv);
+        mbar_wait(tfull, (uint32_t)t & 1u);             // the MMAs of step t no longer read the x block
+        write_x_rows(xv);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(x_rdy);
+      }
     }
   } else if (warp >= 4) {
     // ================= epilogue: thread = one instance row x 8 hidden units, cell state in registers ===========
@@ -272,15 +298,51 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
     const bool ok = m < p.n;
     const int u0 = (int)rank * UNITS + grp * 8;                       // first hidden unit of this thread
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 32);
-    const float4* bias4 = reinterpret_cast<const float4*>(sbias) + grp * 8;
     float* const h_row = p.h_out + (ok ? m : 0) * p.h_out_inst_ld + u0;
     __half* const scr = p.scratch + (size_t)group * (2 * 2 * BM * kH) + (size_t)r * kH + u0;
     const uint32_t kb_mine = rank >> 1;
-    float c[8];
+    // split 8 fp32 values to fp16 hi/lo, store them to scratch parity (j & 1) and publish index j to the 8 CTAs
+    auto publish = [&](const float* hv, int j) {
+      uint32_t pk[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) c[u] = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        pk[i] = pack_h2(hv[2 * i], hv[2 * i + 1]);
+        const float2 bk = unpack_h2(pk[i]);
+        pk[4 + i] = pack_h2(hv[2 * i] - bk.x, hv[2 * i + 1] - bk.y);
+      }
+      __half* dst = scr + (size_t)(j & 1) * (2 * BM * kH);
+      stg128_u(dst, pk[0], pk[1], pk[2], pk[3]);                    // hi rows
+      stg128_u(dst + BM * kH, pk[4], pk[5], pk[6], pk[7]);          // lo rows
+      // the warp's stores happen-before the release below through __syncwarp; ONE cumulative release.cluster arrive
+      // per destination CTA (8 lanes in parallel) instead of a GPU-scope fence in every lane
+      __syncwarp();
+      if (lane < CL) {
+        fence_proxy_async_all();
+        mbar_arrive_release_cluster(mapa_rank(a_rdy(j & 1, (int)kb_mine), (uint32_t)lane));
+      }
+      __syncwarp();
+    };
+    float c[8];
+    if (DEC) {
+      if (ok) ldg256(p.c + m * kH + u0, c);
+      else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[u] = 0.f;
+      }
+      float h0v[8];
+      if (ok) ldg256(p.h0 + m * p.h0_ld + u0, h0v);
+      else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) h0v[u] = 0.f;
+      }
+      publish(h0v, 0);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) c[u] = 0.f;
+    }
     long long w_tfull = 0, d_ld = 0, d_cell = 0, d_pub = 0, d_out = 0;
     for (int t = 0; t < p.steps; ++t) {
+      const float4* bias4 = reinterpret_cast<const float4*>(sbias + (t == 0 ? 0 : TILE_N)) + grp * 8;
       const long long t0 = prof ? clock64() : 0;
       mbar_wait(tfull, (uint32_t)t & 1u);
       const long long t1 = prof ? clock64() : 0;
@@ -297,34 +359,62 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
       lstm_cell8(v, bias4, c, cn, hn);
 #pragma unroll
       for (int u = 0; u < 8; ++u) c[u] = cn[u];
-      if (t + 1 < p.steps) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          pk[j] = pack_h2(hn[2 * j], hn[2 * j + 1]);
-          const float2 bk = unpack_h2(pk[j]);
-          pk[4 + j] = pack_h2(hn[2 * j] - bk.x, hn[2 * j + 1] - bk.y);
-        }
-        const long long t3 = prof ? clock64() : 0;
-        if (prof) { d_ld += t2 - t1; d_cell += t3 - t2; }
-        __half* dst = scr + (size_t)(t & 1) * (2 * BM * kH);
-        stg128_u(dst, pk[0], pk[1], pk[2], pk[3]);                    // hi rows
-        stg128_u(dst + BM * kH, pk[4], pk[5], pk[6], pk[7]);          // lo rows
-        // publish: the warp's stores happen-before the release below through __syncwarp; ONE cumulative
-        // release.cluster arrive per destination CTA (8 lanes in parallel) instead of a GPU-scope fence in every lane
-        __syncwarp();
-        if (lane < CL) {
-          fence_proxy_async_all();
-          mbar_arrive_release_cluster(mapa_rank(a_rdy(t & 1, (int)kb_mine), (uint32_t)lane));
-        }
-        __syncwarp();
+      const long long t3 = prof ? clock64() : 0;
+      if (prof) { d_ld += t2 - t1; d_cell += t3 - t2; }
+      if (DEC) {
+        // the query of this step's pointer phase: fp32 h'(t) to dec_h BEFORE the publish (read by other CTAs after it)
+        if (ok) stg256(h_row + (int64_t)t * kH, hn);
+        publish(hn, t + 1);
         if (prof) d_pub += clock64() - t3;
+        // ---- pointer step k = t for instance row 16 * rank + (warp - 4) of the group; the pick's raw row becomes the
+        // x block row of ALL 8 CTAs for step t+1
+        const long long t4 = prof ? clock64() : 0;
+        const int pj = t + 1;
+#pragma unroll
+        for (int kb = 0; kb < KB_H; ++kb) mbar_wait_cluster(a_rdy(pj & 1, kb), (uint32_t)(pj >> 1) & 1u);   // all of h'(t) is in dec_h
+        const int prow = (int)rank * (BM / CL) + (warp - 4);
+        const int64_t b = m0 + prow;
+        int fed = 0;
+        if (b < p.n) {                                                        // warp-uniform
+          const float4* qp = reinterpret_cast<const float4*>(p.h_out + b * p.h_out_inst_ld + (int64_t)t * kH);
+          const float4 q0 = qp[lane], q1 = qp[32 + lane];
+          fed = pointer_step_warp(p.pa, t, b, q0, q1, lane);
+        }
+        if (t + 1 < p.steps) {
+          if (lane < CL) {
+            float xv[8];
+#pragma unroll
+            for (int f = 0; f < 8; ++f)
+              xv[f] = (b < p.n && f < p.F) ? __ldg(p.inputs + (b * p.L + fed) * (int64_t)p.F + f) : 0.f;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              hi[i] = pack_h2(xv[2 * i], xv[2 * i + 1]);
+              const float2 bk = unpack_h2(hi[i]);
+              lo[i] = pack_h2(xv[2 * i] - bk.x, xv[2 * i + 1] - bk.y);
+            }
+            const uint32_t o = (uint32_t)prow * XROW_BYTES;
+            const uint32_t dhi = mapa_rank(sbase + OFF_AX_HI + o, (uint32_t)lane);
+            const uint32_t dlo = mapa_rank(sbase + OFF_AX_LO + o, (uint32_t)lane);
+            st_cluster_v4(dhi, hi[0], hi[1], hi[2], hi[3]);
+            st_cluster_v4(dhi + 16, hi[0], hi[1], hi[2], hi[3]);
+            st_cluster_v4(dlo, lo[0], lo[1], lo[2], lo[3]);
+            st_cluster_v4(dlo + 16, lo[0], lo[1], lo[2], lo[3]);
+            fence_proxy_async_all();
+            mbar_arrive_release_cluster(mapa_rank(x_rdy, (uint32_t)lane));
+          }
+          __syncwarp();
+        }
+        if (prof) d_out += clock64() - t4;
+      } else {
+        if (t + 1 < p.steps) publish(hn, t);
+        if (prof) d_pub += clock64() - t3;
+        const long long t4 = prof ? clock64() : 0;
+        if (ok) stg256(h_row + (int64_t)t * kH, hn);
+        if (prof) d_out += clock64() - t4;
       }
-      const long long t4 = prof ? clock64() : 0;
-      if (ok) stg256(h_row + (int64_t)t * kH, hn);
-      if (prof) d_out += clock64() - t4;
     }
-    if (ok) stg256(p.c_out + m * kH + u0, c);
+    if (ok) stg256(p.c + m * kH + u0, c);
     if (prof && warp == 4 && lane == 0) {
       unsigned long long* o = p.prof + (size_t)blockIdx.x * 8;
       o[3] = (unsigned long long)w_tfull; o[4] = (unsigned long long)d_ld; o[5] = (unsigned long long)d_cell;
@@ -360,7 +450,7 @@ size_t tc_colsplit_scratch_bytes(int64_t n) { return (size_t)ceil_div(n, cs::BM)
 static int max_active_clusters() {
   static const int v = [] {
     using namespace cs;
-    if (cudaFuncSetAttribute(lstm_colsplit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(lstm_colsplit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES;
     cudaLaunchAttribute attr[1];
@@ -368,7 +458,7 @@ static int max_active_clusters() {
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, lstm_colsplit_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&nc, lstm_colsplit_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
     return nc;
   }();
   return v;
@@ -376,8 +466,8 @@ static int max_active_clusters() {
 int tc_colsplit_max_active_clusters() { return max_active_clusters(); }
 
 // GNNPN_COLSPLIT: -1 (default) = automatic, 0 = never, 1 = always.  Automatic: a step of the column-split scan costs
-// ~6.8 us per wave of clusters against ~16.7 us for the CTA-pair scan at any batch up to 18,944, so it is used while
-// the batch fits two waves (measured 2.45x / 1.2x faster at one / two waves, profiles/r01_colsplit_timing.jsonl).
+// ~6.6 us per wave of clusters against ~16.7 us (encoder) / ~39 us (fused decoder) for the CTA-pair scan at any batch
+// up to 18,944, so it is used while the batch fits two waves (profiles/r01_colsplit_timing.jsonl).
 bool tc_colsplit_wanted(int64_t n) {
   const char* e = getenv("GNNPN_COLSPLIT");              // read per call: tests and benches flip it between launches
   const int mode = e ? atoi(e) : -1;
@@ -386,15 +476,16 @@ bool tc_colsplit_wanted(int64_t n) {
   return ceil_div(n, cs::BM) <= 2 * (int64_t)max_active_clusters();
 }
 
-int tc_colsplit_encode(const SeqEncodeArgs& a, void* scratch, cudaStream_t st) {
-  using namespace cs;
-  if (a.F < 1 || a.F > 8 || a.L < 1) return GNNPN_EUNSUPPORTED;
+namespace cs {
+
+template <bool DEC>
+static int launch(const float* packed, Params p, void* scratch, cudaStream_t st) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return GNNPN_EUNSUPPORTED;
-  const int64_t groups = ceil_div(a.n, BM);
+  const int64_t groups = ceil_div(p.n, BM);
   CUtensorMap maps[5];
-  const float* w_hi = a.packed + kOffTc16Hi;
-  const float* w_lo = a.packed + kOffTc16Lo;
+  const float* w_hi = packed + kOffTc16Hi;
+  const float* w_lo = packed + kOffTc16Lo;
   for (int i = 0; i < 4; ++i) {
     cuuint64_t dims[2] = {(cuuint64_t)kKp16, (cuuint64_t)kG};
     cuuint64_t strides[1] = {(cuuint64_t)kKp16 * 2};
@@ -415,16 +506,11 @@ int tc_colsplit_encode(const SeqEncodeArgs& a, void* scratch, cudaStream_t st) {
            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return GNNPN_ESHAPE;
   }
-  Params p{};
-  p.n = a.n; p.steps = a.L; p.F = a.F;
-  p.inputs = a.inputs; p.x_inst_ld = (int64_t)a.L * a.F;
-  p.bias = a.packed + kOffBias;
-  p.c_out = a.c_state;
-  p.h_out = a.enc_out; p.h_out_inst_ld = (int64_t)a.L * kH;
   p.scratch = reinterpret_cast<__half*>(scratch);
+  auto kern = lstm_colsplit_kernel<DEC>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_colsplit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -442,7 +528,7 @@ int tc_colsplit_encode(const SeqEncodeArgs& a, void* scratch, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, lstm_colsplit_kernel, maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], p);
   if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
   const int rc = after_launch();
   if (do_prof) {
@@ -452,14 +538,44 @@ int tc_colsplit_encode(const SeqEncodeArgs& a, void* scratch, cudaStream_t st) {
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (unsigned c = 0; c < grid; ++c)
       for (int i = 0; i < 8; ++i) acc[i] += (double)h[c * 8 + i];
-    fprintf(stderr, "[colsplit prof steps=%d grid=%u max_active_clusters=%d] per-step cycles: mma total %.0f (wait A full %.0f) | tma wait a_rdy %.0f | "
-            "epi wait tmem_full %.0f, tmem ld %.0f, cell %.0f, publish %.0f, h store %.0f\n", a.L, grid, max_active_clusters(),
-            acc[1] / grid / a.L, acc[2] / grid / a.L, acc[0] / grid / a.L, acc[3] / grid / a.L, acc[4] / grid / a.L,
-            acc[5] / grid / a.L, acc[6] / grid / a.L, acc[7] / grid / a.L);
+    const double d = (double)grid * p.steps;
+    fprintf(stderr, "[colsplit prof %s steps=%d grid=%u max_active_clusters=%d] per-step cycles: mma total %.0f (wait A full %.0f) | "
+            "tma wait a_rdy %.0f | epi wait tmem_full %.0f, tmem ld %.0f, cell %.0f, publish %.0f, %s %.0f\n", DEC ? "dec" : "enc",
+            p.steps, grid, max_active_clusters(), acc[1] / d, acc[2] / d, acc[0] / d, acc[3] / d, acc[4] / d, acc[5] / d, acc[6] / d,
+            DEC ? "pointer phase" : "h store", acc[7] / d);
     free(h);
     cudaFree(prof);
   }
   return rc;
+}
+
+}  // namespace cs
+
+int tc_colsplit_encode(const SeqEncodeArgs& a, void* scratch, cudaStream_t st) {
+  if (a.F < 1 || a.F > 8 || a.L < 1) return GNNPN_EUNSUPPORTED;
+  cs::Params p{};
+  p.n = a.n; p.steps = a.L; p.F = a.F; p.L = a.L;
+  p.inputs = a.inputs; p.x_inst_ld = (int64_t)a.L * a.F;
+  p.bias0 = p.bias = a.packed + kOffBias;
+  p.c = a.c_state;
+  p.h_out = a.enc_out; p.h_out_inst_ld = (int64_t)a.L * kH;
+  return cs::launch<false>(a.packed, p, scratch, st);
+}
+
+int tc_colsplit_decode(const SeqDecodeArgs& a, void* scratch, cudaStream_t st) {
+  if (a.F < 1 || a.F > 8 || a.K < 1 || a.N < 1 || a.N > kMaxWindow) return GNNPN_EUNSUPPORTED;
+  cs::Params p{};
+  p.n = a.n; p.steps = a.K; p.F = a.F; p.L = a.L;
+  p.inputs = a.inputs; p.x_inst_ld = (int64_t)a.L * a.F;
+  p.bias0 = a.packed + kOffStart; p.bias = a.packed + kOffBias;
+  p.c = a.c_state;
+  p.h0 = a.enc_out + (int64_t)(a.L - 1) * kH; p.h0_ld = (int64_t)a.L * kH;
+  p.h_out = a.dec_h; p.h_out_inst_ld = (int64_t)a.K * kH;
+  p.pa.enc_out = a.enc_out; p.pa.enc_inst_ld = (int64_t)a.L * kH; p.pa.latent_win = a.latent_win;
+  p.pa.alpha = a.alpha; p.pa.use_tanh = a.use_tanh; p.pa.C = a.C; p.pa.n = a.n; p.pa.L = a.L;
+  p.pa.N = a.N; p.pa.idx_out = a.idx_out; p.pa.win_logits = a.win_logits; p.pa.win_probs = a.win_probs;
+  p.pa.forced = a.forced_idx; p.pa.uniform = a.sample_uniform;
+  return cs::launch<true>(a.packed, p, scratch, st);
 }
 
 }  // namespace gnnpn

@@ -32,6 +32,8 @@ bool tc_colsplit_wanted(int64_t n);
 int tc_colsplit_max_active_clusters();
 size_t tc_colsplit_scratch_bytes(int64_t n);
 int tc_colsplit_encode(const SeqEncodeArgs& a, void* scratch, cudaStream_t st);
+struct SeqDecodeArgs;
+int tc_colsplit_decode(const SeqDecodeArgs& a, void* scratch, cudaStream_t st);
 
 struct SeqDecodeArgs {
   const float* inputs;     // [n, L, F]

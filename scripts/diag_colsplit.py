@@ -37,8 +37,27 @@ if "--time-only" not in sys.argv:
             print("   first bad t:", bad.any(2).any(0).nonzero().flatten()[:5].tolist(), "rows:", bad.any(2).any(1).nonzero().flatten()[:8].tolist(),
                   "units:", bad.any(1).any(0).nonzero().flatten()[:16].tolist())
 
+if "--time-only" not in sys.argv:
+    # full greedy forward (encoder + fused decode) through the module: column-split vs CTA-pair kernels
+    for n, K, N in [(1, 3, 2), (128, 6, 4), (300, 47, 5), (1000, 50, 10), (130, 12, 32)]:
+        x = pn_instances(n, K, N, seed=7).to(dev)
+        mm = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level="High")
+        mm.load_state_dict(reference_shaped_state_dict(256, 8, 78)); mm = mm.cuda().eval()
+        lat = [torch.randn(n, K * N, device=dev) for _ in range(K)]
+        outs = {}
+        for mode in (1, 0):
+            os.environ["GNNPN_COLSPLIT"] = str(mode)
+            with torch.no_grad():
+                _, idx, lg = mm.actor(x, lat, sample="greedy")
+            torch.cuda.synchronize()
+            outs[mode] = (torch.stack(idx).clone(), mm.actor.last["win_logits"].clone(), mm.actor.last["dec_h"].clone(),
+                          mm.actor.last["win_probs"].clone())
+        print(f"decode n={n} K={K} N={N}: picks differ {(outs[1][0] != outs[0][0]).sum().item()}/{outs[0][0].numel()}, "
+              f"dec_h {(outs[1][2]-outs[0][2]).abs().max():.2e}, win_logits {(outs[1][1]-outs[0][1]).abs().max():.2e}, "
+              f"win_probs {(outs[1][3]-outs[0][3]).abs().max():.2e}", flush=True)
+
 rows = []
-for n in [128, 512, 1024, 2048, 4096, 6144, 8192]:
+for n in [128, 1024, 1920, 2048, 3840, 4096, 8192]:
     x = pn_instances(n, 47, 5, seed=5).to(dev)
     ws = ops.pn_workspace(n, 256, dev, "tc")
     enc_out = torch.empty(n, 235, 256, device=dev); c = torch.empty(n, 256, device=dev)
@@ -53,6 +72,19 @@ for n in [128, 512, 1024, 2048, 4096, 6144, 8192]:
         r[name] = sorted(ts[1:])[len(ts[1:]) // 2]
     r["us_per_step_colsplit"] = r["colsplit_ms"] * 1e3 / 235
     r["us_per_step_pair"] = r["pair_ms"] * 1e3 / 235
+    # fused greedy decode (K = 47 steps incl. the pointer phase)
+    dec_h = torch.empty(n, 47, 256, device=dev); idx = torch.empty(47, n, device=dev, dtype=torch.int32)
+    wl = torch.empty(n, 235, device=dev); wp = torch.empty(n, 235, device=dev)
+    for mode, name in ((1, "dec_colsplit_ms"), (0, "dec_pair_ms")):
+        os.environ["GNNPN_COLSPLIT"] = str(mode)
+        ts = []
+        for i in range(5):
+            ops.lstm_encode(x, enc_w, 256, enc_out, c, workspace=ws)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); ops.pn_decode_greedy(x, enc_out, c, dec_w, 47, 5, out=(dec_h, idx, wl, wp), workspace=ws); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        r[name] = sorted(ts[1:])[len(ts[1:]) // 2]
     rows.append(r)
     print(json.dumps(r), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)

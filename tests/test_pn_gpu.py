@@ -18,7 +18,26 @@ LOGIT_TOL = 1e-5
 CUDA_CASES = ["qws_b4", "normal_b2", "small_b16", "sharp_b4", "notanh_b3", "bahdanau_b3", "glimpse_b3", "embed20_b3"]
 
 
-IMPLS = ["tc", "ffma"]        # tcgen05 3xTF32 recurrence (default) and the strict-fp32 FFMA kernels
+# "tc": tcgen05 recurrence as dispatched by default -- at these batch sizes the column-split cluster scan
+# (tc_colsplit.cu); "tc_pair": the same with GNNPN_COLSPLIT=0, i.e. the CTA-pair persistent scan (tc_seq.cu) that large
+# batches use; "ffma": the strict-fp32 FFMA kernels.
+IMPLS = ["tc", "tc_pair", "ffma"]
+
+
+def _select(impl):
+    """Set the scan-kernel knob for `impl` (read by the library on every call) and return the module-level impl."""
+    if impl == "tc_pair":
+        os.environ["GNNPN_COLSPLIT"] = "0"
+        return "tc"
+    os.environ.pop("GNNPN_COLSPLIT", None)
+    return impl
+
+
+@pytest.fixture(autouse=True)
+def _reset_scan_knob():
+    yield
+    os.environ.pop("GNNPN_COLSPLIT", None)
+
 
 
 def _models(name, device="cuda", impl=None):
@@ -32,12 +51,12 @@ def _models(name, device="cuda", impl=None):
                               cfg.tanh_exploration, int(cfg.use_tanh), M.reward, cfg.attention,
                               cfg.s_number, cfg.s_category, use_cuda=True, level=level)
         m.load_state_dict(po.make_state_dict(cfg, seed, gain), strict=True)
-        m.actor.impl = impl
+        m.actor.impl = _select(impl)
         out.append(m.to(device).eval())
     return cfg, x, out[0], out[1]
 
 
-STRESS_FLOOR = {"ffma": 4.0, "tc": 8.0, None: 8.0}   # multiples of the reference's own fp32 noise, stress cases only
+STRESS_FLOOR = {"ffma": 4.0, "tc": 8.0, "tc_pair": 8.0, None: 8.0}   # multiples of the reference's own fp32 noise, stress cases only
 
 
 def _close(a, b, tol=LOGIT_TOL, floor=0.0):
@@ -145,7 +164,7 @@ def test_teacher_forced_steps_against_oracle(n, K, N, gain, impl):
     m = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level="Low")
     m.load_state_dict(sd)
     m = m.cuda().eval()
-    m.actor.impl = impl
+    m.actor.impl = _select(impl)
     with torch.no_grad():
         probs, idx, lg = m.actor(x.cuda(), None, sample="greedy", forced_idxs=[t.cuda() for t in idx_ref])
     idx = torch.stack(idx).cpu().numpy()
@@ -179,7 +198,7 @@ def test_free_running_full_size_properties(impl):
     low.load_state_dict(po.make_state_dict(cfg, 1))
     high.load_state_dict(po.make_state_dict(cfg, 2))
     low, high = low.cuda().eval(), high.cuda().eval()
-    low.actor.impl = high.actor.impl = impl
+    low.actor.impl = high.actor.impl = _select(impl)
 
     def run(xs):
         with torch.no_grad():
@@ -298,7 +317,7 @@ def test_general_variants_teacher_forced_against_oracle(kw, n):
     m.load_state_dict(sd, strict=True)
     m = m.cuda().eval()
     for impl in IMPLS:
-        m.actor.impl = impl
+        m.actor.impl = _select(impl)
         with torch.no_grad():
             probs, idx, lg = m.actor(x.cuda(), None, sample="greedy", forced_idxs=[t.cuda() for t in idx_ref])
         ref_lg = torch.stack(lg_ref).numpy()
@@ -328,3 +347,29 @@ def test_bahdanau_attention_module_against_oracle():
     assert refp.shape == refp_o.shape
     assert _close(refp.cpu().numpy(), refp_o.numpy()).all()
     assert _close(lg.cpu().numpy(), lg_o.numpy()).all()
+
+
+@pytest.mark.parametrize("n,K,N", [(1, 3, 2), (130, 12, 32), (300, 47, 5), (2100, 20, 5)])
+def test_column_split_scan_equals_cta_pair_scan_bitwise(n, K, N):
+    """The small-batch cluster scan (tc_colsplit.cu) issues the same MMA sequence and the same cell / pointer
+    arithmetic as the CTA-pair scan (tc_seq.cu): encodings, decoder states, logits, probabilities and picks are
+    bit-identical, so sharding a batch (which changes the kernel the dispatcher picks) cannot change results.
+    n = 2100 spans 17 clusters = two waves on a B200 (15 co-resident 8-CTA clusters)."""
+    from gnnpn_sc_b200 import modelPN as M
+    from gnnpn_sc_b200.synth import pn_instances
+    from gnnpn_sc_b200.weights import reference_shaped_state_dict
+    x = pn_instances(n, K, N, seed=7).cuda()
+    m = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level="High")
+    m.load_state_dict(reference_shaped_state_dict(256, 8, 78))
+    m = m.cuda().eval()
+    lat = [torch.randn(n, K * N, device="cuda") for _ in range(K)]
+    outs = {}
+    for mode in ("1", "0"):
+        os.environ["GNNPN_COLSPLIT"] = mode
+        with torch.no_grad():
+            _, idx, _ = m.actor(x, lat, sample="greedy")
+        torch.cuda.synchronize()
+        last = m.actor.last
+        outs[mode] = [torch.stack(idx).clone()] + [last[k].clone() for k in ("enc_out", "dec_h", "win_logits", "win_probs")]
+    for a, b in zip(outs["1"], outs["0"]):
+        assert torch.equal(a, b)
