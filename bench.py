@@ -226,6 +226,43 @@ def run_ours(args):
     e2e_ms = timed(lambda: e2e_steps(args.steps), 1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # latency of ONE reference-sized batch (B = 128, trainPNLow.py:221) through the same kernels' entry points: the
+    # dispatcher runs the column-split cluster scan there; GNNPN_COLSPLIT=0 forces the CTA-pair scan for comparison
+    small = None
+    if rank == 0:
+        nb = 128
+        xs = x[:nb].contiguous()
+        enc_s, c_s = torch.empty(nb, L_SEQ, HID, device=dev), torch.empty(nb, HID, device=dev)
+        bufs_s = [(torch.empty(nb, K_TASKS, HID, device=dev), torch.empty(K_TASKS, nb, device=dev, dtype=torch.int32),
+                   torch.empty(nb, L_SEQ, device=dev), torch.empty(nb, L_SEQ, device=dev)) for _ in range(2)]
+        ws_s = ops.pn_workspace(nb, HID, dev, args.kernel)
+
+        def small_step():
+            lat = None
+            for lvl, (ew, dw) in enumerate(((enc_w_lo, dec_w_lo), (enc_w_hi, dec_w_hi))):
+                ops.lstm_encode(xs, ew, HID, enc_s, c_s, workspace=ws_s)
+                _, idx_s, lat, _ = ops.pn_decode_greedy(xs, enc_s, c_s, dw, K_TASKS, N_CAND, latent_win=lat, out=bufs_s[lvl], workspace=ws_s)
+            return ops.pn_reward(xs, idx_s)[2]
+
+        small = {"instances": nb}
+        for key, mode in (("ms", None), ("ms_cta_pair_scan", "0")):
+            if mode is None:
+                os.environ.pop("GNNPN_COLSPLIT", None)
+            else:
+                os.environ["GNNPN_COLSPLIT"] = mode
+            for _ in range(3):
+                small_step()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(10):
+                small_step()
+            t1.record()
+            torch.cuda.synchronize()
+            small[key] = t0.elapsed_time(t1) / 10
+        os.environ.pop("GNNPN_COLSPLIT", None)
+        small["instances_per_s"] = nb / (small["ms"] * 1e-3)
+
     lt = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(lt)
@@ -271,6 +308,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": K_TASKS * n * 4 + n * 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(lt.item()), "clocks": clocks,
+            "small_batch": small,
         }
         print(json.dumps(line))
     if world > 1:

@@ -7,7 +7,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import check, lib
+from ._lib import GnnpnError, check, lib
 
 import os
 
@@ -210,6 +210,27 @@ def pn_reward(inputs, idx, tag: int = 0):
 
 
 # ------------------------------------------------------------------ candidate selection (loadDataPN on the device)
+def woa_fitness(qos: torch.Tensor, idx: torch.Tensor, bounds: torch.Tensor, klen: Optional[torch.Tensor] = None):
+    """``ESWOA.calc`` (WOA.py:87-105) for a batch of positions: ``qos`` f64 [T,4], ``idx`` int32 [P,Kmax] rows of
+    ``qos``, ``bounds`` f64 [P,4] (lo1,hi1,lo2,hi2), ``klen`` int32 [P] or None -> (viol int32 [P], obj f64 [P],
+    fitness f64 [P]); float64 in numpy's operation order (bit-identical to the reference's values)."""
+    if not (qos.is_cuda and idx.is_cuda and bounds.is_cuda):
+        raise GnnpnError("woa_fitness needs CUDA tensors (no CPU fallback)")
+    assert qos.dtype == torch.float64 and bounds.dtype == torch.float64 and idx.dtype == torch.int32
+    qos, idx, bounds = qos.contiguous(), idx.contiguous(), bounds.contiguous()
+    P, Kmax = idx.shape
+    viol = torch.empty(P, device=idx.device, dtype=torch.int32)
+    obj = torch.empty(P, device=idx.device, dtype=torch.float64)
+    fit = torch.empty(P, device=idx.device, dtype=torch.float64)
+    if klen is not None:
+        assert klen.dtype == torch.int32 and klen.is_cuda
+        klen = klen.contiguous()
+    check(lib().gnnpn_woa_fitness_f64(qos.data_ptr(), qos.shape[0], idx.data_ptr(), idx.stride(0), _ptr(klen),
+                                      bounds.data_ptr(), P, Kmax, viol.data_ptr(), obj.data_ptr(), fit.data_ptr(),
+                                      _stream()), "woa_fitness")
+    return viol, obj, fit
+
+
 def select_candidates(scores, svc_qos, cat_ptr, local_bounds, used, global_bounds, N: int, with_category: bool = False,
                       return_picked: bool = False):
     """ML scores ``[n, S]`` -> PN input rows ``[n, K*N, 8(+1)]`` (see ``gnnpn_select_candidates_f32``)."""

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNNPN_ABI_VERSION 4
+#define GNNPN_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define GNNPN_API __attribute__((visibility("default")))
@@ -169,6 +169,18 @@ GNNPN_API int gnnpn_pn_full_logits_f32(const float* enc_out, const float* dec_h,
 GNNPN_API int gnnpn_pn_reward_f32(const float* inputs, const int32_t* idx, int64_t n, int L, int in_features,
                         int K, int tag, int32_t* viol_out, float* obj_out, float* reward_high_out,
                         void* stream);
+
+/* ESWOA fitness (src/baselines/WOA.py:87-105 `ESWOA.calc`, used at :59,78,119,151) for a batch of P whale positions:
+ * float64, every operation in numpy's order (sequential cumprod, np.sum's pairwise scheme), so fitness values and the
+ * search's `bestFitness > fitness` comparisons are bit-identical to the reference's.
+ *   qos    f64 [n_services, 4]  q0..q3 of every candidate service the positions can select
+ *   idx    int32 [P, idx_ld]    row of `qos` chosen for task k of position p (k < klen[p])
+ *   klen   int32 [P] or NULL    tasks per position (NULL: Kmax for all); Kmax <= 512
+ *   bounds f64 [P, 4]           lo1, hi1, lo2, hi2: the instance's two global constraints (loadData.py:279-283)
+ *   viol_out int32 [P], obj_out f64 [P], fit_out f64 [P] = viol + obj   (any may be NULL) */
+GNNPN_API int gnnpn_woa_fitness_f64(const double* qos, int64_t n_services, const int32_t* idx, int64_t idx_ld,
+                          const int32_t* klen, const double* bounds, int64_t P, int Kmax,
+                          int32_t* viol_out, double* obj_out, double* fit_out, void* stream);
 
 /* Host-buffer convenience for non-torch callers: PNLow greedy -> latent -> PNHigh greedy
  * (src/models/trainPNHigh.py:131-144) on pageable or pinned HOST memory; allocates its own device

@@ -1,15 +1,18 @@
-"""CLI of the drop-in: ``python main.py <QWS|qws|Normal> <ML|PNLow|PNHigh|ML+2PN> [epoch ...]``.
+"""CLI of the drop-in: ``python main.py <QWS|qws|Normal> <ML|PNLow|PNHigh|ML+2PN|WOA|ESWOA> [epoch ...]``.
 
 Same dispatch contract as the reference's ``main.py:14-84,216-228`` for the four modes on the accelerated
 path: the ``environment.ini`` section ``<dataset>-<approach>`` is read and its values are passed
 POSITIONALLY (the ini key order is API), trailing epoch selectors can be overridden from argv, and PNHigh
 receives the ``epochML`` value for both ``epochML`` and ``epochPNLow`` (reference quirk, main.py:68,83).
-The CPU metaheuristic baselines (WOA, DAAGA, SDFGA, DPKSD, PDDQN) are outside this repository's scope.
+``WOA`` (= ML+2PN+WOA: ESWOA fine-tuning seeded by the PNHigh picks, main.py:86-104) and ``ESWOA`` (main.py:126-140)
+run the search with its fitness evaluations on the GPU; the other CPU metaheuristic baselines (ML+ESWOA, DAAGA, SDFGA,
+DPKSD, PDDQN) are outside this repository's scope.
 """
 import configparser
 import sys
 
 import src.ML2PN as ML2PN
+import src.baselines.WOA as WOA
 import src.models.trainML as trainML
 import src.models.trainPNHigh as trainPNHigh
 import src.models.trainPNLow as trainPNLow
@@ -21,8 +24,10 @@ CASTS = {
     "PNLow": [INT] * 9 + [FLT, FLT, FLT, INT],
     "PNHigh": [INT] * 9 + [FLT, FLT, FLT, INT, INT],
     "ML+2PN": [INT, INT],
+    "WOA": [INT] * 6 + [FLT, INT, INT, INT],          # reduct is a float in the Normal sections (main.py:102)
+    "ESWOA": [INT] * 6 + [FLT, INT, INT, INT],
 }
-OUT_OF_SCOPE = {"WOA", "DAAGA", "SDFGA", "DPKSD", "PDDQN", "ESWOA", "ML+ESWOA", "ML+2PN+WOA"}
+OUT_OF_SCOPE = {"DAAGA", "SDFGA", "DPKSD", "PDDQN", "ML+ESWOA", "ML+DAAGA", "ML+SDFGA", "ML+DPKSD", "ML+PDDQN"}
 
 
 def section_values(config, dataset, approach, argv):
@@ -38,6 +43,8 @@ def section_values(config, dataset, approach, argv):
             values[-2] = extra[1]
     elif approach == "ML+2PN" and len(extra) == 1:
         values[-1] = extra[0]
+    elif approach == "WOA" and len(extra) == 1:
+        values[-3] = extra[0]                                        # epoch (main.py:89-90)
     return [cast(v) for cast, v in zip(CASTS[approach], values)]
 
 
@@ -60,6 +67,8 @@ def main(argv):
         trainPNLow.PNLow(dataset, *v).start()
     elif approach == "PNHigh":
         trainPNHigh.PNHigh(dataset, *v[:12], v[12], v[12]).start()   # epochML passed twice (main.py:68)
+    elif approach in ("WOA", "ESWOA"):
+        WOA.WOA(dataset, *v).start()
     else:
         ML2PN.check(dataset, v[0], v[1])
 

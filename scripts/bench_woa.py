@@ -1,0 +1,61 @@
+"""ESWOA fine-tuning throughput ([QWS-WOA]: K = 47 tasks, popSize 50, MAX_Iter 250): lock-step batched search with the
+GPU fitness kernel vs the same search with the CPU oracle restating the reference's per-whale numpy `calc`
+(kind = port; bounded sample).  One JSON line.
+
+    python scripts/bench_woa.py [--instances 256] [--cpu-instances 2] [--out gpurun_out/woa.json]"""
+import argparse, copy, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+
+def problems(n, K=47, per=54, seed=0):
+    g = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        services = []
+        for _ in range(K):
+            q = np.stack([g.uniform(0.01, 1, per), g.uniform(0.01, 1, per), g.uniform(0.9, 1, per), g.uniform(0.9, 1, per)], 1)
+            services.append([tuple(float(v) for v in row) for row in q])
+        p2 = float(np.prod([np.mean([s[2] for s in c]) for c in services]))
+        p3 = float(np.prod([np.mean([s[3] for s in c]) for c in services]))
+        sol = [list(c[int(g.integers(0, per))]) for c in services]
+        out.append((services, [[[p2 * 0.98, 1.0]], [[p3 * 1.01, 1.0]]], sol))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--instances", type=int, default=256)
+    ap.add_argument("--cpu-instances", type=int, default=2)
+    ap.add_argument("--pop", type=int, default=50)
+    ap.add_argument("--iters", type=int, default=250)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    import torch
+    from gnnpn_sc_b200 import WOA as W, _lib
+    from oracle import woa_oracle as wo                      # CPU baseline leg only
+    probs = problems(a.instances)
+    W.run_many(copy.deepcopy(probs[:4]), a.pop, 10)          # warm-up (library load, allocator)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count(); t0 = time.perf_counter()
+    res = W.run_many(copy.deepcopy(probs), a.pop, a.iters)
+    torch.cuda.synchronize()
+    gpu_s = time.perf_counter() - t0
+    launches = _lib.launch_count() - l0
+    t0 = time.perf_counter()
+    cpu = W.run_many(copy.deepcopy(probs[: a.cpu_instances]), a.pop, a.iters, fitness=wo.CpuFitness)
+    cpu_s = time.perf_counter() - t0
+    same = all(r[0] == c[0] and r[2] == c[2] for r, c in zip(res, cpu))
+    line = {"config": "eswoa_qws_ml2pn_woa", "K": 47, "candidates_per_task": 54, "popSize": a.pop, "MAX_Iter": a.iters,
+            "instances": a.instances, "gpu_s": gpu_s, "gpu_instances_per_s": a.instances / gpu_s, "fitness_launches": launches,
+            "cpu_port_instances": a.cpu_instances, "cpu_port_s": cpu_s, "cpu_port_instances_per_s": a.cpu_instances / cpu_s,
+            "cpu_cores_used": 1, "trajectories_bit_identical_on_cpu_sample": bool(same),
+            "mean_fitness_gain": float(np.mean([r[2][0] - r[0] if r[2] else 0.0 for r in res]))}
+    print(json.dumps(line))
+    if a.out:
+        with open(a.out, "a") as f:
+            f.write(json.dumps(line) + "\n")
+
+
+if __name__ == "__main__":
+    main()

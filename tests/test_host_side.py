@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     assert declared, "header parse failed"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     L = _lib.lib()                      # CDLL + getattr of every symbol; no compute without a GPU
-    assert L.gnnpn_abi_version() == 4
+    assert L.gnnpn_abi_version() == 5
     assert L.gnnpn_error_string(-2) == b"unsupported shape"
     assert L.gnnpn_pn_packed_lstm_floats(256, 8) == (256 + 32 + 2) * 1024 + 2 * 1024 * 288 + 1024 * 320   # FFMA block, tf32 hi/lo, fp16 hi/lo (halfs)
     # argument errors are detected before any CUDA call, so they are testable on a CPU box
