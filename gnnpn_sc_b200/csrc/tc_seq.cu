@@ -185,9 +185,11 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
   const uint32_t hfull_bar = bar0 + 8u * (2 * MAX_RING + 6);
   const uint32_t hempty_bar = bar0 + 8u * (2 * MAX_RING + 7);
   const uint32_t tmem_slot = bar0 + 8u * (2 * MAX_RING + 8);
+  const uint32_t h_ready_bar = bar0 + 8u * (2 * MAX_RING + 9);   // decoder: h'(t) is in the A tiles (the pointer phase follows)
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   // barriers the MMA issuer (rank 0) waits on collect arrivals from both CTAs of the pair
   const uint32_t a_ready_remote = CG == 2 ? mapa_rank(a_ready_bar, 0) : a_ready_bar;
+  const uint32_t h_ready_remote = CG == 2 ? mapa_rank(h_ready_bar, 0) : h_ready_bar;
   auto arrive_leader = [&](uint32_t local_bar) {
     if (CG == 2) mbar_arrive_cluster(mapa_rank(local_bar, 0)); else mbar_arrive(local_bar);
   };
@@ -208,6 +210,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     for (int s = 0; s < RING; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), CG * EPI_WARPS); }
     mbar_init(a_ready_bar, CG * (EPI_WARPS + (DEC ? 0 : 1)));
+    mbar_init(h_ready_bar, CG * EPI_WARPS);
     mbar_init(mma_done_bar, 1);
     mbar_init(hfull_bar, EPI_WARPS);
     mbar_init(hempty_bar, 1);
@@ -296,39 +299,46 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       const int row_off = (int)rank * SLOT_ROWS;
-      for (int t = 0; t < p.steps; ++t) {
-        for (int it = 0; it < N_TILES; ++it) {
-          const int nt = (it + rot) & (N_TILES - 1);
-          for (int kb = 0; kb < KB_H; ++kb) {
+      auto load_h = [&](int it) {                      // the 8 h-part boxes of tile `it` (hi, lo per k-block)
+        const int nt = (it + rot) & (N_TILES - 1);
+        for (int kb = 0; kb < KB_H; ++kb) {
 #pragma unroll
-            for (int part = 0; part < 2; ++part) {
-              mbar_wait(empty_bar(s), ph ^ 1u);
-              const uint32_t dst = sbase + OFF_RING + s * SLOT_BYTES;
-              if (CG == 2) {
-                if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * SLOT_BYTES);
-                tma_load_2d_cg2(dst, part ? &map_wh_lo : &map_wh_hi, mapa_rank(full_bar(s), 0), kb * 64,
-                                nt * TILE_N + row_off);
-              } else {
-                mbar_arrive_expect_tx(full_bar(s), SLOT_BYTES);
-                tma_load_2d(dst, part ? &map_wh_lo : &map_wh_hi, full_bar(s), kb * 64, nt * TILE_N);
-              }
-              if (++s == RING) { s = 0; ph ^= 1u; }
+          for (int part = 0; part < 2; ++part) {
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t dst = sbase + OFF_RING + s * SLOT_BYTES;
+            if (CG == 2) {
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * SLOT_BYTES);
+              tma_load_2d_cg2(dst, part ? &map_wh_lo : &map_wh_hi, mapa_rank(full_bar(s), 0), kb * 64,
+                              nt * TILE_N + row_off);
+            } else {
+              mbar_arrive_expect_tx(full_bar(s), SLOT_BYTES);
+              tma_load_2d(dst, part ? &map_wh_lo : &map_wh_hi, full_bar(s), kb * 64, nt * TILE_N);
             }
+            if (++s == RING) { s = 0; ph ^= 1u; }
           }
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          const uint32_t dst = sbase + OFF_RING + s * SLOT_BYTES;
-          if (CG == 2) {
-            if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * 2 * SLOT_ROWS * XROW_BYTES);
-            const uint32_t fb = mapa_rank(full_bar(s), 0);
-            tma_load_2d_cg2(dst, &map_wx_hi, fb, kH, nt * TILE_N + row_off);
-            tma_load_2d_cg2(dst + SLOT_ROWS * XROW_BYTES, &map_wx_lo, fb, kH, nt * TILE_N + row_off);
-          } else {
-            mbar_arrive_expect_tx(full_bar(s), 2 * TILE_N * XROW_BYTES);
-            tma_load_2d(dst, &map_wx_hi, full_bar(s), kH, nt * TILE_N);
-            tma_load_2d(dst + TILE_N * XROW_BYTES, &map_wx_lo, full_bar(s), kH, nt * TILE_N);
-          }
-          if (++s == RING) { s = 0; ph ^= 1u; }
         }
+      };
+      auto load_x = [&](int it) {                      // the x-part box (hi | lo) of tile `it`
+        const int nt = (it + rot) & (N_TILES - 1);
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t dst = sbase + OFF_RING + s * SLOT_BYTES;
+        if (CG == 2) {
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * 2 * SLOT_ROWS * XROW_BYTES);
+          const uint32_t fb = mapa_rank(full_bar(s), 0);
+          tma_load_2d_cg2(dst, &map_wx_hi, fb, kH, nt * TILE_N + row_off);
+          tma_load_2d_cg2(dst + SLOT_ROWS * XROW_BYTES, &map_wx_lo, fb, kH, nt * TILE_N + row_off);
+        } else {
+          mbar_arrive_expect_tx(full_bar(s), 2 * TILE_N * XROW_BYTES);
+          tma_load_2d(dst, &map_wx_hi, full_bar(s), kH, nt * TILE_N);
+          tma_load_2d(dst + TILE_N * XROW_BYTES, &map_wx_lo, full_bar(s), kH, nt * TILE_N);
+        }
+        if (++s == RING) { s = 0; ph ^= 1u; }
+      };
+      for (int t = 0; t < p.steps; ++t) {
+        // decoder: the h parts of tiles 0 and 1 come first (issued while the pointer phase still runs), see the MMA warp
+        const int first = DEC ? 2 : 0;
+        if (DEC) { load_h(0); load_h(1); load_x(0); load_x(1); }
+        for (int it = first; it < N_TILES; ++it) { load_h(it); load_x(it); }
       }
     }
   } else if (warp == 1) {
@@ -347,59 +357,86 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
       const bool prof = p.prof != nullptr;
       long long w_aready = 0, w_tempty = 0, w_full = 0;
       const long long t_begin = clock64();
+      auto mma_h = [&](uint32_t d) {                     // h part of one tile: 8 ring slots, 48 MMAs
+        for (int kb = 0; kb < KB_H; ++kb) {
+          const uint64_t a_hi = smem_desc_k_sw128(sbase + OFF_A_HI + kb * BLK_BYTES);
+          const uint64_t a_lo = smem_desc_k_sw128(sbase + OFF_A_LO + kb * BLK_BYTES);
+          mbar_wait_t(full_bar(s), ph, prof, w_full);
+          tc_fence_after();
+          const uint64_t b_hi = smem_desc_k_sw128(sbase + OFF_RING + s * SLOT_BYTES);
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma(d, a_lo + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), (uint32_t)((kb | ks) != 0));
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma(d, a_hi + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), 1u);
+            commit(empty_bar(s));
+          }
+          __syncwarp();
+          if (++s == RING) { s = 0; ph ^= 1u; }
+          mbar_wait_t(full_bar(s), ph, prof, w_full);
+          tc_fence_after();
+          const uint64_t b_lo = smem_desc_k_sw128(sbase + OFF_RING + s * SLOT_BYTES);
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma(d, a_hi + (uint64_t)(ks * 2), b_lo + (uint64_t)(ks * 2), 1u);
+            commit(empty_bar(s));
+          }
+          __syncwarp();
+          if (++s == RING) { s = 0; ph ^= 1u; }
+        }
+      };
+      auto mma_x = [&](uint32_t d, int buf, bool last) {  // x part of one tile, then hand the accumulator to the epilogue
+        mbar_wait_t(full_bar(s), ph, prof, w_full);
+        tc_fence_after();
+        const uint64_t bx_hi = smem_desc_k_sw32(sbase + OFF_RING + s * SLOT_BYTES);
+        const uint64_t bx_lo = smem_desc_k_sw32(sbase + OFF_RING + s * SLOT_BYTES + SLOT_ROWS * XROW_BYTES);
+        if (leader) {
+          mma(d, ax_lo, bx_hi, 1u);
+          mma(d, ax_hi, bx_hi, 1u);
+          mma(d, ax_hi, bx_lo, 1u);
+          commit(empty_bar(s));
+          commit(tfull_bar(buf));
+          if (last) commit(mma_done_bar);
+        }
+        __syncwarp();
+        if (++s == RING) { s = 0; ph ^= 1u; }
+      };
       for (int t = 0; t < p.steps; ++t) {
-        if (t > 0) {
+        int nt0 = 0;
+        if (DEC) {
+          // Only the K = 16 x part of a step depends on the pick.  TMEM has two accumulator buffers, so the h parts of
+          // tiles 0 and 1 (96 of the step's 408 MMAs) are issued as soon as h'(t-1) is in the A tiles, i.e. while the
+          // pointer phase of step t-1 still runs; their x parts follow once the picked rows are in the x block.
+          if (t > 0) {
+            mbar_wait_t<CG == 2>(h_ready_bar, (uint32_t)(t - 1) & 1u, prof, w_aready);
+            tc_fence_after();
+          }
+          for (int b = 0; b < 2; ++b) {
+            mbar_wait_t<CG == 2>(tempty_bar(b), (((uses + b) >> 1) & 1u) ^ 1u, prof, w_tempty);
+            tc_fence_after();
+            mma_h(tmem_base + (uint32_t)(b * TILE_N));
+          }
+          if (t > 0) {
+            mbar_wait_t<CG == 2>(a_ready_bar, (uint32_t)(t - 1) & 1u, prof, w_aready);   // x(t) is in the x block
+            tc_fence_after();
+          }
+          for (int b = 0; b < 2; ++b) mma_x(tmem_base + (uint32_t)(b * TILE_N), b, false);
+          uses += 2;
+          nt0 = 2;
+        } else if (t > 0) {
           mbar_wait_t<CG == 2>(a_ready_bar, (uint32_t)(t - 1) & 1u, prof, w_aready);  // h'(t-1), x(t) are in smem
           tc_fence_after();
         }
-        for (int nt = 0; nt < N_TILES; ++nt, ++uses) {
+        for (int nt = nt0; nt < N_TILES; ++nt, ++uses) {
           const int buf = nt & 1;
           mbar_wait_t<CG == 2>(tempty_bar(buf), ((uses >> 1) & 1u) ^ 1u, prof, w_tempty);
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(buf * TILE_N);
-          for (int kb = 0; kb < KB_H; ++kb) {
-            const uint64_t a_hi = smem_desc_k_sw128(sbase + OFF_A_HI + kb * BLK_BYTES);
-            const uint64_t a_lo = smem_desc_k_sw128(sbase + OFF_A_LO + kb * BLK_BYTES);
-            mbar_wait_t(full_bar(s), ph, prof, w_full);
-            tc_fence_after();
-            const uint64_t b_hi = smem_desc_k_sw128(sbase + OFF_RING + s * SLOT_BYTES);
-            if (leader) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                mma(d, a_lo + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), (uint32_t)((kb | ks) != 0));
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                mma(d, a_hi + (uint64_t)(ks * 2), b_hi + (uint64_t)(ks * 2), 1u);
-              commit(empty_bar(s));
-            }
-            __syncwarp();
-            if (++s == RING) { s = 0; ph ^= 1u; }
-            mbar_wait_t(full_bar(s), ph, prof, w_full);
-            tc_fence_after();
-            const uint64_t b_lo = smem_desc_k_sw128(sbase + OFF_RING + s * SLOT_BYTES);
-            if (leader) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                mma(d, a_hi + (uint64_t)(ks * 2), b_lo + (uint64_t)(ks * 2), 1u);
-              commit(empty_bar(s));
-            }
-            __syncwarp();
-            if (++s == RING) { s = 0; ph ^= 1u; }
-          }
-          mbar_wait_t(full_bar(s), ph, prof, w_full);
-          tc_fence_after();
-          const uint64_t bx_hi = smem_desc_k_sw32(sbase + OFF_RING + s * SLOT_BYTES);
-          const uint64_t bx_lo = smem_desc_k_sw32(sbase + OFF_RING + s * SLOT_BYTES + SLOT_ROWS * XROW_BYTES);
-          if (leader) {
-            mma(d, ax_lo, bx_hi, 1u);
-            mma(d, ax_hi, bx_hi, 1u);
-            mma(d, ax_hi, bx_lo, 1u);
-            commit(empty_bar(s));
-            commit(tfull_bar(buf));
-            if (nt == N_TILES - 1) commit(mma_done_bar);
-          }
-          __syncwarp();
-          if (++s == RING) { s = 0; ph ^= 1u; }
+          mma_h(d);
+          mma_x(d, buf, nt == N_TILES - 1);
         }
       }
       if (prof && leader) {
@@ -529,6 +566,11 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         }
       }
       if (DEC) {
+        // h'(t) is in the A tiles: the MMA warp may start the h parts of the next step's first two tiles now
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(h_ready_remote); else mbar_arrive(h_ready_bar); }
         // ---- pointer step k = t: query = h'(t) (just written to dec_h by this CTA), window rows of enc_out
         const long long tp0 = prof ? clock64() : 0;
         __threadfence_block();
