@@ -231,6 +231,20 @@ def woa_fitness(qos: torch.Tensor, idx: torch.Tensor, bounds: torch.Tensor, klen
     return viol, obj, fit
 
 
+def woa_search(qos, base, size, klen, bounds, pops, best_fit, best_ref, best_vec, seeds, traj):
+    """Device-resident ESWOA search (``gnnpn_woa_search_f64``): all tensors CUDA, updated in place (see the header)."""
+    I, P, KM = pops.shape
+    for x, dt in ((qos, torch.float64), (bounds, torch.float64), (best_fit, torch.float64), (traj, torch.float64),
+                  (base, torch.int32), (size, torch.int32), (klen, torch.int32), (pops, torch.int32),
+                  (best_ref, torch.int32), (best_vec, torch.int32), (seeds, torch.int64)):
+        if not (x.is_cuda and x.is_contiguous() and x.dtype == dt):
+            raise GnnpnError("woa_search needs contiguous CUDA tensors of the declared dtypes (no CPU fallback)")
+    check(lib().gnnpn_woa_search_f64(qos.data_ptr(), qos.shape[0], base.data_ptr(), size.data_ptr(), klen.data_ptr(),
+                                     bounds.data_ptr(), pops.data_ptr(), best_fit.data_ptr(), best_ref.data_ptr(),
+                                     best_vec.data_ptr(), seeds.data_ptr(), traj.data_ptr(), I, P, KM, traj.shape[1],
+                                     _stream()), "woa_search")
+
+
 def select_candidates(scores, svc_qos, cat_ptr, local_bounds, used, global_bounds, N: int, with_category: bool = False,
                       return_picked: bool = False):
     """ML scores ``[n, S]`` -> PN input rows ``[n, K*N, 8(+1)]`` (see ``gnnpn_select_candidates_f32``)."""

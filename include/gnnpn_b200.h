@@ -182,6 +182,22 @@ GNNPN_API int gnnpn_woa_fitness_f64(const double* qos, int64_t n_services, const
                           const int32_t* klen, const double* bounds, int64_t P, int Kmax,
                           int32_t* viol_out, double* obj_out, double* fit_out, void* stream);
 
+/* Device-resident ESWOA search (src/baselines/WOA.py:107-162): one CTA per instance, one thread per whale, all
+ * `iters` iterations in one launch, same sequential semantics as the reference's loop (in-order best-so-far replay,
+ * speculative local phase committed up to the first improvement, bestPops aliasing).  Random numbers are counter-based
+ * Philox4x32-10: key = seeds[I], counter = (slot, whale, phase, iteration), phase 0 = global (slots q / task / candidate),
+ * 1 = exploration skip, 2 = local (slots r / l / p); uniform = ((x0 >> 5) * 2^26 + (x1 >> 6)) / 2^53; integers are
+ * floor(u * n).  The caller initialises the population and the best state (WOA.py:50-85).
+ *   base, size  int32 [I, Kmax]      first `qos` row / length of every task's candidate list (klen[I] tasks used)
+ *   pops        int32 [I, popSize, Kmax] in/out   local candidate index per task (Python index semantics)
+ *   best_fit f64 [I], best_ref int32 [I] (whale whose row IS the best position, or -1), best_vec int32 [I, Kmax]  in/out
+ *   traj        f64 [I, iters]       best fitness after every iteration (`ESWOA.bestFitnesses`)
+ * popSize <= 128, Kmax <= 128. */
+GNNPN_API int gnnpn_woa_search_f64(const double* qos, int64_t n_services, const int32_t* base, const int32_t* size,
+                         const int32_t* klen, const double* bounds, int32_t* pops, double* best_fit,
+                         int32_t* best_ref, int32_t* best_vec, const uint64_t* seeds, double* traj,
+                         int64_t n_instances, int popSize, int Kmax, int iters, void* stream);
+
 /* Host-buffer convenience for non-torch callers: PNLow greedy -> latent -> PNHigh greedy
  * (src/models/trainPNHigh.py:131-144) on pageable or pinned HOST memory; allocates its own device
  * scratch, copies in and out, synchronises.  idx_high_host int32 [K, n]; reward_high_host fp32 [n]. */

@@ -42,12 +42,23 @@ def main():
     torch.cuda.synchronize()
     gpu_s = time.perf_counter() - t0
     launches = _lib.launch_count() - l0
+    # the whole search device-resident (one launch, Philox draws): wall time incl. host-side population init and packing
+    W.run_many_device(copy.deepcopy(probs[:4]), a.pop, 10)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tm = {}
+    dres = W.run_many_device(copy.deepcopy(probs), a.pop, a.iters, timings=tm)
+    torch.cuda.synchronize()
+    dev_s = time.perf_counter() - t0
+    l1 = _lib.launch_count()
     t0 = time.perf_counter()
     cpu = W.run_many(copy.deepcopy(probs[: a.cpu_instances]), a.pop, a.iters, fitness=wo.CpuFitness)
     cpu_s = time.perf_counter() - t0
     same = all(r[0] == c[0] and r[2] == c[2] for r, c in zip(res, cpu))
     line = {"config": "eswoa_qws_ml2pn_woa", "K": 47, "candidates_per_task": 54, "popSize": a.pop, "MAX_Iter": a.iters,
             "instances": a.instances, "gpu_s": gpu_s, "gpu_instances_per_s": a.instances / gpu_s, "fitness_launches": launches,
+            "device_search_s": dev_s, "device_search_kernel_ms": tm.get("search_kernel_ms"), "device_search_instances_per_s": a.instances / dev_s,
+            "device_search_mean_fitness_gain": float(np.mean([r[2][0] - r[0] if r[2] else 0.0 for r in dres])),
             "cpu_port_instances": a.cpu_instances, "cpu_port_s": cpu_s, "cpu_port_instances_per_s": a.cpu_instances / cpu_s,
             "cpu_cores_used": 1, "trajectories_bit_identical_on_cpu_sample": bool(same),
             "mean_fitness_gain": float(np.mean([r[2][0] - r[0] if r[2] else 0.0 for r in res]))}

@@ -178,3 +178,39 @@ def test_load_data_other_matches_reference(tmp_path, golden_dir):
         ref = d["reference"][key]
         assert [[[list(s) for s in c] for c in inst] for inst in feats] == ref["features"], key
         assert cons == ref["constraints"] and mc == ref["minCost"]
+
+
+def test_philox_host_engine_is_deterministic_and_context_addressed(golden_dir):
+    """The counter-based generator gives the same run regardless of how instances are grouped (draws are addressed by
+    (seed, iteration, phase, whale, slot), not by call order across instances)."""
+    from gnnpn_sc_b200.WOA import PhiloxRng, run_many
+    probs = []
+    for name in CASES:
+        inp, services, _ = _load(golden_dir, name)
+        probs.append((services, inp["constraints"], inp["solution"]))
+    mk = lambda: copy.deepcopy(probs)
+    a = run_many(mk(), popSize=10, MAX_Iter=15, fitness=wo.CpuFitness, rngs=[PhiloxRng(7 + k) for k in range(4)])
+    b = [run_many([mk()[k]], popSize=10, MAX_Iter=15, fitness=wo.CpuFitness, rngs=[PhiloxRng(7 + k)])[0] for k in range(4)]
+    assert [x[0] for x in a] == [x[0] for x in b] and [x[2] for x in a] == [x[2] for x in b]
+    u = PhiloxRng(1); u.at(3, 2, 5)
+    v = PhiloxRng(1); v.at(3, 2, 5)
+    assert u.random() == v.random() and 0.0 <= u.random() < 1.0
+
+
+@pytest.mark.gpu
+def test_device_search_equals_host_engine_bitwise(golden_dir):
+    """gnnpn_woa_search_f64 (whole search in one launch) == the host engine driven by the same Philox draws: best-so-far
+    trajectory, final fitness and final position, bit for bit; the host engine itself replays the reference
+    (test_gpu_eswoa_replays_reference_run)."""
+    from gnnpn_sc_b200.WOA import PhiloxRng, run_many, run_many_device
+    probs = []
+    for name in CASES * 3:
+        inp, services, _ = _load(golden_dir, name)
+        probs.append((services, inp["constraints"], inp["solution"]))
+    seeds = [1000 + 17 * k for k in range(len(probs))]
+    for pop, iters in ((12, 40), (50, 30), (128, 12)):
+        dev = run_many_device(copy.deepcopy(probs), popSize=pop, MAX_Iter=iters, seeds=seeds)
+        host = run_many(copy.deepcopy(probs), popSize=pop, MAX_Iter=iters, rngs=[PhiloxRng(s) for s in seeds])
+        for k, (d, h) in enumerate(zip(dev, host)):
+            assert d[2] == h[2], (pop, iters, k, next(i for i, (x, y) in enumerate(zip(d[2], h[2])) if x != y))
+            assert d[0] == h[0] and [tuple(r) for r in d[1]] == [tuple(r) for r in h[1]]
