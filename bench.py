@@ -263,6 +263,28 @@ def run_ours(args):
         os.environ.pop("GNNPN_COLSPLIT", None)
         small["instances_per_s"] = nb / (small["ms"] * 1e-3)
 
+    # second half of BASELINE.json's metric: CSR aggregation GB/s against the HBM peak (one point of the sweep in
+    # scripts/bench_agg.py: E = 2^26 edges, mean degree 16, F = 64, weighted -- 17.9 GB of algorithmic traffic >> L2)
+    agg = None
+    if rank == 0 and not args.no_aggregation:
+        from scripts.bench_agg import make_csr
+        Na, Fa = (1 << 26) // 16, 64
+        rowptr, col, val, Ea = make_csr(Na, 16, 0.0, True, dev)
+        xa = torch.empty(Na, Fa, device=dev).uniform_(-1, 1)
+        ya = torch.empty(Na, Fa, device=dev)
+        for _ in range(3):
+            ops.spmm_csr(rowptr, col, val, xa, out=ya)
+        ts = []
+        for _ in range(5):
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(); ops.spmm_csr(rowptr, col, val, xa, out=ya); t1.record(); torch.cuda.synchronize()
+            ts.append(t0.elapsed_time(t1))
+        ms_a = sorted(ts)[len(ts) // 2]
+        bytes_a = Ea * (8 + 4 * Fa) + Na * 4 * Fa + (Na + 1) * 8
+        agg = {"kernel": "spmm_csr_kernel", "E": Ea, "N": Na, "F": Fa, "ms": ms_a, "algorithmic_bytes": bytes_a,
+               "GBps": bytes_a / ms_a / 1e6, "frac_of_hbm_peak": bytes_a / ms_a / 1e6 / peaks()["hbm_gbs"]}
+        del rowptr, col, val, xa, ya
+
     lt = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(lt)
@@ -308,7 +330,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": K_TASKS * n * 4 + n * 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(lt.item()), "clocks": clocks,
-            "small_batch": small,
+            "small_batch": small, "aggregation": agg,
         }
         print(json.dumps(line))
     if world > 1:
@@ -325,6 +347,7 @@ def main():
                     help="composition instances per GPU per step (default: one full wave, 148 SMs x 128)")
     ap.add_argument("--cpu-batches", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aggregation", action="store_true", help="skip the CSR aggregation GB/s point")
     ap.add_argument("--kernel", default="tc", choices=["tc", "ffma"],
                     help="recurrence kernel: tcgen05 3xTF32 (default) or strict-fp32 FFMA")
     args = ap.parse_args()
