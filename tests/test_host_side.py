@@ -98,3 +98,18 @@ def test_constraint_and_service_arrays_follow_loaddatapn():
                 lo2, hi2, lo3, hi3 = local[b, c]
                 assert (lo2 <= rows[c, :, 3]).all() and (rows[c, :, 3] <= hi2).all()
                 assert (lo3 <= rows[c, :, 4]).all() and (rows[c, :, 4] <= hi3).all()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the one leg that runs on host cores) prints one JSON line with the driver's keys."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-400:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"] == "qws_greedy_pnlow_pnhigh_decode"
