@@ -274,7 +274,7 @@ int gnnpn_lstm_encode_f32(const float* inputs, int64_t n, int L, int in_features
     GNNPN_REQUIRE(workspace_bytes >= tc_lstm_workspace_bytes(n), GNNPN_EWORKSPACE);
     float* scr = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
     SeqEncodeArgs sa{inputs, n, L, in_features, packed, enc_out, c_state, scr};
-    if (tc_colsplit_wanted(n)) return tc_colsplit_encode(sa, scr, st);     // small batch: column-split cluster scan
+    if (tc_colsplit_wanted_encode(n)) return tc_colsplit_encode(sa, scr, st);     // small batch: column-split cluster scan
     return tc_seq_encode(sa, st);
   }
   if (workspace) {

@@ -38,21 +38,28 @@ constexpr int TILE_N = kG / CL;            // 128 gate columns per CTA
 constexpr int UNITS = kH / CL;             // 32 hidden units per CTA
 constexpr int KB_H = kH / 64;              // 4 k-blocks of 64 halfs
 constexpr int BLK_BYTES = 128 * 128;       // [128 rows x 64 halfs]
-constexpr int NSLOT = 5;                   // A ring slots (one per k-block half: lo or hi)
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
 
-constexpr uint32_t OFF_W_HI = 0;
-constexpr uint32_t OFF_W_LO = OFF_W_HI + KB_H * BLK_BYTES;
-constexpr uint32_t OFF_WX_HI = OFF_W_LO + KB_H * BLK_BYTES;
-constexpr uint32_t OFF_WX_LO = OFF_WX_HI + TILE_N * XROW_BYTES;
-constexpr uint32_t OFF_AX_HI = OFF_WX_LO + TILE_N * XROW_BYTES;
-constexpr uint32_t OFF_AX_LO = OFF_AX_HI + BM * XROW_BYTES;
-constexpr uint32_t OFF_RING = OFF_AX_LO + BM * XROW_BYTES;
-constexpr uint32_t OFF_BIAS = OFF_RING + NSLOT * BLK_BYTES;
-constexpr uint32_t OFF_BAR = OFF_BIAS + 2 * TILE_N * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+// G = instance groups of 128 per cluster.  G = 1: lowest latency.  G = 2 (encoder only): two independent groups share the
+// resident weights and are software-pipelined against each other -- while one group's h' is in flight through the exchange
+// (cell epilogue -> publish -> TMA pull, ~8.7k of the 12k cycles of a step) the tensor pipe and the epilogue warps work
+// on the other one.
+template <int G> struct Layout {
+  static constexpr int NSLOT = G == 1 ? 5 : 4;         // A ring slots (one per k-block half: lo or hi)
+  static constexpr uint32_t OFF_W_HI = 0;
+  static constexpr uint32_t OFF_W_LO = OFF_W_HI + KB_H * BLK_BYTES;
+  static constexpr uint32_t OFF_WX_HI = OFF_W_LO + KB_H * BLK_BYTES;
+  static constexpr uint32_t OFF_WX_LO = OFF_WX_HI + TILE_N * XROW_BYTES;
+  static constexpr uint32_t OFF_AX = OFF_WX_LO + TILE_N * XROW_BYTES;       // per group: hi | lo x block
+  static constexpr uint32_t AX_BYTES = 2 * BM * XROW_BYTES;
+  static constexpr uint32_t OFF_RING = OFF_AX + G * AX_BYTES;
+  static constexpr uint32_t OFF_BIAS = OFF_RING + NSLOT * BLK_BYTES;
+  static constexpr uint32_t OFF_BAR = OFF_BIAS + 2 * TILE_N * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+  static_assert(8 * (1 + 2 * NSLOT + G * (3 + 2 * KB_H)) + 4 <= 256, "barrier block overflow");
+};
 constexpr uint32_t W_BYTES = 2 * KB_H * BLK_BYTES + 2 * TILE_N * XROW_BYTES;
 
 struct Params {
@@ -83,29 +90,35 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a,
 }
 
 // Publish index of h'(t): the decoder also publishes its initial hidden state (index 0), so h'(t) has index t+1 there.
-// Index j lives in scratch parity j & 1 and completes phase (j >> 1) & 1 of the a_rdy[j & 1][*] barriers.
-template <bool DEC>
+// Index j lives in scratch parity j & 1 and completes phase (j >> 1) & 1 of the a_rdy[group][j & 1][*] barriers.
+template <bool DEC, int G>
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_constant__ CUtensorMap map_wh_lo,
                      const __grid_constant__ CUtensorMap map_wx_hi, const __grid_constant__ CUtensorMap map_wx_lo,
                      const __grid_constant__ CUtensorMap map_scr, const __grid_constant__ Params p) {
+  static_assert(!DEC || G == 1, "the fused decoder runs one group per cluster");
+  using LY = Layout<G>;
+  constexpr int NSLOT = LY::NSLOT;
+  constexpr int SET_WARPS = EPI_WARPS;                 // every epilogue warp serves every group
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t bar0 = sbase + OFF_BAR;
+  const uint32_t bar0 = sbase + LY::OFF_BAR;
   const uint32_t w_full = bar0;
   auto full_bar = [&](int s) { return bar0 + 8u * (1 + s); };
   auto empty_bar = [&](int s) { return bar0 + 8u * (1 + NSLOT + s); };
-  const uint32_t tfull = bar0 + 8u * (1 + 2 * NSLOT);
-  const uint32_t tempty = tfull + 8u;
-  const uint32_t x_rdy = tfull + 16u;
-  auto a_rdy = [&](int par, int kb) { return tfull + 24u + 8u * (par * KB_H + kb); };
-  const uint32_t tmem_slot = tfull + 24u + 8u * (2 * KB_H);
+  const uint32_t gbar0 = bar0 + 8u * (1 + 2 * NSLOT);                      // per group: tfull, tempty, x_rdy, a_rdy[2][4]
+  auto tfull = [&](int g) { return gbar0 + 8u * (g * (3 + 2 * KB_H)); };
+  auto tempty = [&](int g) { return tfull(g) + 8u; };
+  auto x_rdy = [&](int g) { return tfull(g) + 16u; };
+  auto a_rdy = [&](int g, int par, int kb) { return tfull(g) + 24u + 8u * (par * KB_H + kb); };
+  const uint32_t tmem_slot = gbar0 + 8u * (G * (3 + 2 * KB_H));
+  auto ax_hi_off = [&](int g) { return sbase + LY::OFF_AX + (uint32_t)g * LY::AX_BYTES; };
+  auto ax_lo_off = [&](int g) { return ax_hi_off(g) + BM * XROW_BYTES; };
   const uint32_t rank = cluster_ctarank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t group = blockIdx.x / CL;
-  const int64_t m0 = group * BM;
-  float* sbias = reinterpret_cast<float*>(sgen + OFF_BIAS);
+  const int64_t group0 = (int64_t)(blockIdx.x / CL) * G;                  // first instance group of this cluster
+  float* sbias = reinterpret_cast<float*>(sgen + LY::OFF_BIAS);
   constexpr int PUB0 = DEC ? 1 : 0;                    // publish index of h'(t) = t + PUB0
 
   if (warp == 0 && lane == 0) {
@@ -115,14 +128,16 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
   if (warp == 1 && lane == 0) {
     mbar_init(w_full, 1);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, EPI_WARPS);
-    mbar_init(x_rdy, DEC ? CL * EPI_WARPS : 1);        // decoder: one arrival per instance of the group (its pointer warp)
-    for (int par = 0; par < 2; ++par)
-      for (int kb = 0; kb < KB_H; ++kb) mbar_init(a_rdy(par, kb), 2 * EPI_WARPS);   // the two CTAs producing this k-block
+    for (int g = 0; g < G; ++g) {
+      mbar_init(tfull(g), 1);
+      mbar_init(tempty(g), SET_WARPS);
+      mbar_init(x_rdy(g), DEC ? CL * EPI_WARPS : 1);   // decoder: one arrival per instance of the group (its pointer warp)
+      for (int par = 0; par < 2; ++par)
+        for (int kb = 0; kb < KB_H; ++kb) mbar_init(a_rdy(g, par, kb), 2 * SET_WARPS);   // the two CTAs producing this k-block
+    }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TILE_N);
+  if (warp == 2) tmem_alloc(tmem_slot, G * TILE_N);
   // transformed biases of this CTA's 128 gate columns (two sets: step 0, steps >= 1): (i,f,o) * -log2e, g * -2log2e
   for (int i = threadIdx.x; i < 2 * TILE_N; i += THREADS) {
     const int col = i & (TILE_N - 1);
@@ -130,7 +145,7 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
     sbias[i] = b * ((col & 3) == 2 ? -2.0f * kLog2e : -kLog2e);
   }
 
-  auto write_x_rows = [&](const float (*xv)[8]) {
+  auto write_x_rows = [&](int g, const float (*xv)[8]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = lane + 32 * i;
@@ -142,25 +157,27 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
         lo[j] = pack_h2(xv[i][2 * j] - bk.x, xv[i][2 * j + 1] - bk.y);
       }
       const uint32_t o = (uint32_t)r * XROW_BYTES;
-      st_shared_v4(sbase + OFF_AX_HI + o, hi[0], hi[1], hi[2], hi[3]);
-      st_shared_v4(sbase + OFF_AX_HI + o + 16, hi[0], hi[1], hi[2], hi[3]);
-      st_shared_v4(sbase + OFF_AX_LO + o, lo[0], lo[1], lo[2], lo[3]);
-      st_shared_v4(sbase + OFF_AX_LO + o + 16, lo[0], lo[1], lo[2], lo[3]);
+      st_shared_v4(ax_hi_off(g) + o, hi[0], hi[1], hi[2], hi[3]);
+      st_shared_v4(ax_hi_off(g) + o + 16, hi[0], hi[1], hi[2], hi[3]);
+      st_shared_v4(ax_lo_off(g) + o, lo[0], lo[1], lo[2], lo[3]);
+      st_shared_v4(ax_lo_off(g) + o + 16, lo[0], lo[1], lo[2], lo[3]);
     }
   };
-  auto load_x_rows = [&](int t, float (*xv)[8]) {
+  auto load_x_rows = [&](int g, int t, float (*xv)[8]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int64_t m = m0 + lane + 32 * i;
+      const int64_t m = (group0 + g) * BM + lane + 32 * i;
 #pragma unroll
       for (int f = 0; f < 8; ++f)
         xv[i][f] = (m < p.n && f < p.F) ? __ldg(p.inputs + m * p.x_inst_ld + (int64_t)t * p.F + f) : 0.f;
     }
   };
   if (!DEC && warp == 3) {
-    float xv[4][8];
-    load_x_rows(0, xv);
-    write_x_rows(xv);
+    for (int g = 0; g < G; ++g) {
+      float xv[4][8];
+      load_x_rows(g, 0, xv);
+      write_x_rows(g, xv);
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -172,34 +189,36 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
   const bool prof = p.prof != nullptr;
 
   if (warp == 0) {
-    // ================= TMA: resident weight slice once; then the A operand of every step from the exchange scratch ===
+    // ================= TMA: resident weight slice once; then the A operand of every (step, group) from the exchange scratch
     if (lane == 0) {
       const int col0 = (int)rank * TILE_N;
       mbar_arrive_expect_tx(w_full, W_BYTES);
       for (int kb = 0; kb < KB_H; ++kb) {
-        tma_load_2d(sbase + OFF_W_HI + kb * BLK_BYTES, &map_wh_hi, w_full, kb * 64, col0);
-        tma_load_2d(sbase + OFF_W_LO + kb * BLK_BYTES, &map_wh_lo, w_full, kb * 64, col0);
+        tma_load_2d(sbase + LY::OFF_W_HI + kb * BLK_BYTES, &map_wh_hi, w_full, kb * 64, col0);
+        tma_load_2d(sbase + LY::OFF_W_LO + kb * BLK_BYTES, &map_wh_lo, w_full, kb * 64, col0);
       }
-      tma_load_2d(sbase + OFF_WX_HI, &map_wx_hi, w_full, kH, col0);
-      tma_load_2d(sbase + OFF_WX_LO, &map_wx_lo, w_full, kH, col0);
+      tma_load_2d(sbase + LY::OFF_WX_HI, &map_wx_hi, w_full, kH, col0);
+      tma_load_2d(sbase + LY::OFF_WX_LO, &map_wx_lo, w_full, kH, col0);
       int s = 0; uint32_t ph = 0;
       long long w_rdy = 0;
       for (int t = DEC ? 0 : 1; t < p.steps; ++t) {
         const int j = t - 1 + PUB0;                                    // publish index consumed by step t
         const int par = j & 1;
         const uint32_t rph = (uint32_t)(j >> 1) & 1u;
-        const int row_base = (int)((group * 2 + par) * 2) * BM;       // hi rows; lo rows follow BM later
-        for (int kb = 0; kb < KB_H; ++kb) {
-          const long long t0 = prof ? clock64() : 0;
-          mbar_wait_cluster(a_rdy(par, kb), rph);                      // both producers of units [64kb, 64kb+64) have published
-          if (prof) w_rdy += clock64() - t0;
-          fence_proxy_async_all();
+        for (int g = 0; g < G; ++g) {
+          const int row_base = (int)(((group0 + g) * 2 + par) * 2) * BM;       // hi rows; lo rows follow BM later
+          for (int kb = 0; kb < KB_H; ++kb) {
+            const long long t0 = prof ? clock64() : 0;
+            mbar_wait_cluster(a_rdy(g, par, kb), rph);                   // both producers of units [64kb, 64kb+64) have published
+            if (prof) w_rdy += clock64() - t0;
+            fence_proxy_async_all();
 #pragma unroll
-          for (int part = 0; part < 2; ++part) {                       // lo first: its 4 MMAs free the slot early
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            mbar_arrive_expect_tx(full_bar(s), BLK_BYTES);
-            tma_load_2d(sbase + OFF_RING + s * BLK_BYTES, &map_scr, full_bar(s), kb * 64, row_base + (part ? 0 : BM));
-            if (++s == NSLOT) { s = 0; ph ^= 1u; }
+            for (int part = 0; part < 2; ++part) {                       // lo first: its 4 MMAs free the slot early
+              mbar_wait(empty_bar(s), ph ^ 1u);
+              mbar_arrive_expect_tx(full_bar(s), BLK_BYTES);
+              tma_load_2d(sbase + LY::OFF_RING + s * BLK_BYTES, &map_scr, full_bar(s), kb * 64, row_base + (part ? 0 : BM));
+              if (++s == NSLOT) { s = 0; ph ^= 1u; }
+            }
           }
         }
       }
@@ -209,68 +228,71 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
     // ================= MMA issuer =================
     const uint32_t leader = elect_one();
     const uint32_t idesc = idesc_f16(BM, TILE_N);
-    const uint64_t ax_hi = smem_desc_k_sw32(sbase + OFF_AX_HI), ax_lo = smem_desc_k_sw32(sbase + OFF_AX_LO);
-    const uint64_t wx_hi = smem_desc_k_sw32(sbase + OFF_WX_HI), wx_lo = smem_desc_k_sw32(sbase + OFF_WX_LO);
+    const uint64_t wx_hi = smem_desc_k_sw32(sbase + LY::OFF_WX_HI), wx_lo = smem_desc_k_sw32(sbase + LY::OFF_WX_LO);
     mbar_wait(w_full, 0);
     tc_fence_after();
     int s = 0; uint32_t ph = 0;
     long long w_full_c = 0;
     const long long t_begin = clock64();
     for (int t = 0; t < p.steps; ++t) {
-      mbar_wait(tempty, ((uint32_t)t & 1u) ^ 1u);
-      tc_fence_after();
-      // MMA order per step = tc_seq.cu's order per tile (h part k-block by k-block: a_lo.w_hi, a_hi.w_hi, a_hi.w_lo;
-      // then the x part), so both scans produce the same bits and a batch can be sharded across them freely.
-      uint32_t acc = 0u;                                     // the first MMA of a step overwrites the accumulator
-      if (DEC || t > 0) {
-        for (int kb = 0; kb < KB_H; ++kb) {
-          const uint64_t w_hi = smem_desc_k_sw128(sbase + OFF_W_HI + kb * BLK_BYTES);
-          const uint64_t w_lo = smem_desc_k_sw128(sbase + OFF_W_LO + kb * BLK_BYTES);
-          long long t0 = prof ? clock64() : 0;
-          mbar_wait(full_bar(s), ph);
-          if (prof) w_full_c += clock64() - t0;
-          tc_fence_after();
-          const uint64_t a_lo = smem_desc_k_sw128(sbase + OFF_RING + s * BLK_BYTES);
-          if (leader) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              mma_f16_ss(tmem_base, a_lo + (uint64_t)(ks * 2), w_hi + (uint64_t)(ks * 2), idesc, ks == 0 ? acc : 1u);
-            mma_commit(empty_bar(s));
-          }
-          __syncwarp();
-          acc = 1u;
-          if (++s == NSLOT) { s = 0; ph ^= 1u; }
-          t0 = prof ? clock64() : 0;
-          mbar_wait(full_bar(s), ph);
-          if (prof) w_full_c += clock64() - t0;
-          tc_fence_after();
-          const uint64_t a_hi = smem_desc_k_sw128(sbase + OFF_RING + s * BLK_BYTES);
-          if (leader) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma_f16_ss(tmem_base, a_hi + (uint64_t)(ks * 2), w_hi + (uint64_t)(ks * 2), idesc, 1u);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma_f16_ss(tmem_base, a_hi + (uint64_t)(ks * 2), w_lo + (uint64_t)(ks * 2), idesc, 1u);
-            mma_commit(empty_bar(s));
-          }
-          __syncwarp();
-          if (++s == NSLOT) { s = 0; ph ^= 1u; }
-        }
-      }
-      if (!DEC || t > 0) {
-        // x part last.  Decoder: it is the raw row of the previous pick, so the pointer phase of step t-1 overlaps the
-        // exchange and the h-part MMAs of step t.  Encoder: x_rdy was signalled long ago by the x producer.
-        if (DEC) mbar_wait_cluster(x_rdy, (uint32_t)(t - 1) & 1u);
-        else if (t > 0) mbar_wait(x_rdy, (uint32_t)(t - 1) & 1u);
+      for (int g = 0; g < G; ++g) {
+        const uint32_t d = tmem_base + (uint32_t)(g * TILE_N);
+        const uint64_t ax_hi = smem_desc_k_sw32(ax_hi_off(g)), ax_lo = smem_desc_k_sw32(ax_lo_off(g));
+        mbar_wait(tempty(g), ((uint32_t)t & 1u) ^ 1u);
         tc_fence_after();
-        if (leader) {
-          mma_f16_ss(tmem_base, ax_lo, wx_hi, idesc, acc);
-          mma_f16_ss(tmem_base, ax_hi, wx_hi, idesc, 1u);
-          mma_f16_ss(tmem_base, ax_hi, wx_lo, idesc, 1u);
+        // MMA order per step = tc_seq.cu's order per tile (h part k-block by k-block: a_lo.w_hi, a_hi.w_hi, a_hi.w_lo;
+        // then the x part), so both scans produce the same bits and a batch can be sharded across them freely.
+        uint32_t acc = 0u;                                     // the first MMA of a step overwrites the accumulator
+        if (DEC || t > 0) {
+          for (int kb = 0; kb < KB_H; ++kb) {
+            const uint64_t w_hi = smem_desc_k_sw128(sbase + LY::OFF_W_HI + kb * BLK_BYTES);
+            const uint64_t w_lo = smem_desc_k_sw128(sbase + LY::OFF_W_LO + kb * BLK_BYTES);
+            long long t0 = prof ? clock64() : 0;
+            mbar_wait(full_bar(s), ph);
+            if (prof) w_full_c += clock64() - t0;
+            tc_fence_after();
+            const uint64_t a_lo = smem_desc_k_sw128(sbase + LY::OFF_RING + s * BLK_BYTES);
+            if (leader) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_f16_ss(d, a_lo + (uint64_t)(ks * 2), w_hi + (uint64_t)(ks * 2), idesc, ks == 0 ? acc : 1u);
+              mma_commit(empty_bar(s));
+            }
+            __syncwarp();
+            acc = 1u;
+            if (++s == NSLOT) { s = 0; ph ^= 1u; }
+            t0 = prof ? clock64() : 0;
+            mbar_wait(full_bar(s), ph);
+            if (prof) w_full_c += clock64() - t0;
+            tc_fence_after();
+            const uint64_t a_hi = smem_desc_k_sw128(sbase + LY::OFF_RING + s * BLK_BYTES);
+            if (leader) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) mma_f16_ss(d, a_hi + (uint64_t)(ks * 2), w_hi + (uint64_t)(ks * 2), idesc, 1u);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) mma_f16_ss(d, a_hi + (uint64_t)(ks * 2), w_lo + (uint64_t)(ks * 2), idesc, 1u);
+              mma_commit(empty_bar(s));
+            }
+            __syncwarp();
+            if (++s == NSLOT) { s = 0; ph ^= 1u; }
+          }
         }
+        if (!DEC || t > 0) {
+          // x part last.  Decoder: it is the raw row of the previous pick, so the pointer phase of step t-1 overlaps the
+          // exchange and the h-part MMAs of step t.  Encoder: x_rdy was signalled long ago by the x producer.
+          if (DEC) mbar_wait_cluster(x_rdy(g), (uint32_t)(t - 1) & 1u);
+          else if (t > 0) mbar_wait(x_rdy(g), (uint32_t)(t - 1) & 1u);
+          tc_fence_after();
+          if (leader) {
+            mma_f16_ss(d, ax_lo, wx_hi, idesc, acc);
+            mma_f16_ss(d, ax_hi, wx_hi, idesc, 1u);
+            mma_f16_ss(d, ax_hi, wx_lo, idesc, 1u);
+          }
+          __syncwarp();
+        }
+        if (leader) mma_commit(tfull(g));
         __syncwarp();
       }
-      if (leader) mma_commit(tfull);
-      __syncwarp();
     }
     if (prof && leader) {
       p.prof[(size_t)blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_begin);
@@ -280,29 +302,31 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
     // ================= x producer (encoder): raw input row of step t+1 -> fp16 hi/lo x block =================
     if (!DEC) {
       for (int t = 0; t + 1 < p.steps; ++t) {
-        float xv[4][8];
-        load_x_rows(t + 1, xv);
-        mbar_wait(tfull, (uint32_t)t & 1u);             // the MMAs of step t no longer read the x block
-        write_x_rows(xv);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(x_rdy);
+        for (int g = 0; g < G; ++g) {
+          float xv[4][8];
+          load_x_rows(g, t + 1, xv);
+          mbar_wait(tfull(g), (uint32_t)t & 1u);          // the MMAs of step t no longer read the x block
+          write_x_rows(g, xv);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(x_rdy(g));
+        }
       }
     }
   } else if (warp >= 4) {
     // ================= epilogue: thread = one instance row x 8 hidden units, cell state in registers ===========
+    // All 16 warps serve every group of the cluster in turn (G = 2: group 0 then group 1 of the same step), so a group's
+    // cell epilogue always has the whole SM's MUFU throughput and its publish overlaps the other group's MMAs.
     const int q = warp & 3;
-    const int grp = (warp - 4) >> 2;
+    const int grp = (warp - 4) >> 2;                       // 32-column chunk = 8 hidden units
     const int r = q * 32 + lane;
-    const int64_t m = m0 + r;
-    const bool ok = m < p.n;
-    const int u0 = (int)rank * UNITS + grp * 8;                       // first hidden unit of this thread
-    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 32);
-    float* const h_row = p.h_out + (ok ? m : 0) * p.h_out_inst_ld + u0;
-    __half* const scr = p.scratch + (size_t)group * (2 * 2 * BM * kH) + (size_t)r * kH + u0;
+    const int u0 = (int)rank * UNITS + grp * 8;            // first hidden unit of this thread
     const uint32_t kb_mine = rank >> 1;
-    // split 8 fp32 values to fp16 hi/lo, store them to scratch parity (j & 1) and publish index j to the 8 CTAs
-    auto publish = [&](const float* hv, int j) {
+    const float4* const bias4_0 = reinterpret_cast<const float4*>(sbias) + grp * 8;
+    const float4* const bias4_1 = reinterpret_cast<const float4*>(sbias + TILE_N) + grp * 8;
+    auto row_of = [&](int g) { return (group0 + g) * BM + r; };
+    // split 8 fp32 values to fp16 hi/lo and store them to scratch parity (j & 1) of group g
+    auto stage = [&](int g, const float* hv, int j) {
       uint32_t pk[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -310,24 +334,28 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
         const float2 bk = unpack_h2(pk[i]);
         pk[4 + i] = pack_h2(hv[2 * i] - bk.x, hv[2 * i + 1] - bk.y);
       }
-      __half* dst = scr + (size_t)(j & 1) * (2 * BM * kH);
+      __half* dst = p.scratch + (size_t)(group0 + g) * (2 * 2 * BM * kH) + (size_t)(j & 1) * (2 * BM * kH) + (size_t)r * kH + u0;
       stg128_u(dst, pk[0], pk[1], pk[2], pk[3]);                    // hi rows
       stg128_u(dst + BM * kH, pk[4], pk[5], pk[6], pk[7]);          // lo rows
-      // the warp's stores happen-before the release below through __syncwarp; ONE cumulative release.cluster arrive
-      // per destination CTA (8 lanes in parallel) instead of a GPU-scope fence in every lane
+    };
+    // publish index j of group g to the 8 CTAs: the warp's stores happen-before the release below through __syncwarp; ONE
+    // cumulative release.cluster arrive per destination CTA (8 lanes in parallel) instead of a GPU-scope fence in every lane
+    auto publish = [&](int g, int j) {
       __syncwarp();
       if (lane < CL) {
         fence_proxy_async_all();
-        mbar_arrive_release_cluster(mapa_rank(a_rdy(j & 1, (int)kb_mine), (uint32_t)lane));
+        mbar_arrive_release_cluster(mapa_rank(a_rdy(g, j & 1, (int)kb_mine), (uint32_t)lane));
       }
       __syncwarp();
     };
-    float c[8];
+    float c[G][8];
     if (DEC) {
-      if (ok) ldg256(p.c + m * kH + u0, c);
+      const int64_t m = row_of(0);
+      const bool ok = m < p.n;
+      if (ok) ldg256(p.c + m * kH + u0, c[0]);
       else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) c[u] = 0.f;
+        for (int u = 0; u < 8; ++u) c[0][u] = 0.f;
       }
       float h0v[8];
       if (ok) ldg256(p.h0 + m * p.h0_ld + u0, h0v);
@@ -335,96 +363,112 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
 #pragma unroll
         for (int u = 0; u < 8; ++u) h0v[u] = 0.f;
       }
-      publish(h0v, 0);
+      stage(0, h0v, 0);
+      publish(0, 0);
     } else {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) c[u] = 0.f;
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[g][u] = 0.f;
     }
-    long long w_tfull = 0, d_ld = 0, d_cell = 0, d_pub = 0, d_out = 0;
+    long long w_tfull = 0, d_cell = 0, d_pub = 0, d_out = 0;
     for (int t = 0; t < p.steps; ++t) {
-      const float4* bias4 = reinterpret_cast<const float4*>(sbias + (t == 0 ? 0 : TILE_N)) + grp * 8;
-      const long long t0 = prof ? clock64() : 0;
-      mbar_wait(tfull, (uint32_t)t & 1u);
-      const long long t1 = prof ? clock64() : 0;
-      if (prof) w_tfull += t1 - t0;
-      tc_fence_after();
-      float v[32];
-      tmem_ld_32x32_issue(t_addr, v);
-      tmem_ld_wait(v);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
-      const long long t2 = prof ? clock64() : 0;
-      float cn[8], hn[8];
-      lstm_cell8(v, bias4, c, cn, hn);
+      const float4* bias4 = t == 0 ? bias4_0 : bias4_1;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) c[u] = cn[u];
-      const long long t3 = prof ? clock64() : 0;
-      if (prof) { d_ld += t2 - t1; d_cell += t3 - t2; }
-      if (DEC) {
-        // the query of this step's pointer phase: fp32 h'(t) to dec_h BEFORE the publish (read by other CTAs after it)
-        if (ok) stg256(h_row + (int64_t)t * kH, hn);
-        publish(hn, t + 1);
-        if (prof) d_pub += clock64() - t3;
-        // ---- pointer step k = t for instance row 16 * rank + (warp - 4) of the group; the pick's raw row becomes the
-        // x block row of ALL 8 CTAs for step t+1
-        const long long t4 = prof ? clock64() : 0;
-        const int pj = t + 1;
+      for (int g = 0; g < G; ++g) {
+        const int64_t m = row_of(g);
+        const bool ok = m < p.n;
+        float* const h_dst = p.h_out + (ok ? m : 0) * p.h_out_inst_ld + (int64_t)t * kH + u0;
+        const long long t0 = prof ? clock64() : 0;
+        mbar_wait(tfull(g), (uint32_t)t & 1u);
+        const long long t1 = prof ? clock64() : 0;
+        if (prof && g == 0) w_tfull += t1 - t0;
+        tc_fence_after();
+        float v[32];
+        tmem_ld_32x32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * TILE_N + grp * 32), v);
+        tmem_ld_wait(v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(g));                         // accumulator is in registers
+        float cn[8], hn[8];
+        lstm_cell8(v, bias4, c[g], cn, hn);
 #pragma unroll
-        for (int kb = 0; kb < KB_H; ++kb) mbar_wait_cluster(a_rdy(pj & 1, kb), (uint32_t)(pj >> 1) & 1u);   // all of h'(t) is in dec_h
-        const int prow = (int)rank * (BM / CL) + (warp - 4);
-        const int64_t b = m0 + prow;
-        int fed = 0;
-        if (b < p.n) {                                                        // warp-uniform
-          const float4* qp = reinterpret_cast<const float4*>(p.h_out + b * p.h_out_inst_ld + (int64_t)t * kH);
-          const float4 q0 = qp[lane], q1 = qp[32 + lane];
-          fed = pointer_step_warp(p.pa, t, b, q0, q1, lane);
-        }
-        if (t + 1 < p.steps) {
-          if (lane < CL) {
-            float xv[8];
+        for (int u = 0; u < 8; ++u) c[g][u] = cn[u];
+        const long long t3 = prof ? clock64() : 0;
+        if (prof && g == 0) d_cell += t3 - t1;
+        if (DEC) {
+          // the query of this step's pointer phase: fp32 h'(t) to dec_h BEFORE the publish (read by other CTAs after it)
+          if (ok) stg256(h_dst, hn);
+          stage(0, hn, t + 1);
+          publish(0, t + 1);
+          if (prof) d_pub += clock64() - t3;
+          // ---- pointer step k = t for instance row 16 * rank + (warp - 4) of the group; the pick's raw row becomes the
+          // x block row of ALL 8 CTAs for step t+1
+          const long long t4 = prof ? clock64() : 0;
+          const int pj = t + 1;
 #pragma unroll
-            for (int f = 0; f < 8; ++f)
-              xv[f] = (b < p.n && f < p.F) ? __ldg(p.inputs + (b * p.L + fed) * (int64_t)p.F + f) : 0.f;
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              hi[i] = pack_h2(xv[2 * i], xv[2 * i + 1]);
-              const float2 bk = unpack_h2(hi[i]);
-              lo[i] = pack_h2(xv[2 * i] - bk.x, xv[2 * i + 1] - bk.y);
-            }
-            const uint32_t o = (uint32_t)prow * XROW_BYTES;
-            const uint32_t dhi = mapa_rank(sbase + OFF_AX_HI + o, (uint32_t)lane);
-            const uint32_t dlo = mapa_rank(sbase + OFF_AX_LO + o, (uint32_t)lane);
-            st_cluster_v4(dhi, hi[0], hi[1], hi[2], hi[3]);
-            st_cluster_v4(dhi + 16, hi[0], hi[1], hi[2], hi[3]);
-            st_cluster_v4(dlo, lo[0], lo[1], lo[2], lo[3]);
-            st_cluster_v4(dlo + 16, lo[0], lo[1], lo[2], lo[3]);
-            fence_proxy_async_all();
-            mbar_arrive_release_cluster(mapa_rank(x_rdy, (uint32_t)lane));
+          for (int kb = 0; kb < KB_H; ++kb) mbar_wait_cluster(a_rdy(0, pj & 1, kb), (uint32_t)(pj >> 1) & 1u);   // all of h'(t) is in dec_h
+          const int prow = (int)rank * (BM / CL) + (warp - 4);
+          const int64_t b = group0 * BM + prow;
+          int fed = 0;
+          if (b < p.n) {                                                        // warp-uniform
+            const float4* qp = reinterpret_cast<const float4*>(p.h_out + b * p.h_out_inst_ld + (int64_t)t * kH);
+            const float4 q0 = qp[lane], q1 = qp[32 + lane];
+            fed = pointer_step_warp(p.pa, t, b, q0, q1, lane);
           }
-          __syncwarp();
+          if (t + 1 < p.steps) {
+            if (lane < CL) {
+              float xv[8];
+#pragma unroll
+              for (int f = 0; f < 8; ++f)
+                xv[f] = (b < p.n && f < p.F) ? __ldg(p.inputs + (b * p.L + fed) * (int64_t)p.F + f) : 0.f;
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                hi[i] = pack_h2(xv[2 * i], xv[2 * i + 1]);
+                const float2 bk = unpack_h2(hi[i]);
+                lo[i] = pack_h2(xv[2 * i] - bk.x, xv[2 * i + 1] - bk.y);
+              }
+              const uint32_t o = (uint32_t)prow * XROW_BYTES;
+              const uint32_t dhi = mapa_rank(ax_hi_off(0) + o, (uint32_t)lane);
+              const uint32_t dlo = mapa_rank(ax_lo_off(0) + o, (uint32_t)lane);
+              st_cluster_v4(dhi, hi[0], hi[1], hi[2], hi[3]);
+              st_cluster_v4(dhi + 16, hi[0], hi[1], hi[2], hi[3]);
+              st_cluster_v4(dlo, lo[0], lo[1], lo[2], lo[3]);
+              st_cluster_v4(dlo + 16, lo[0], lo[1], lo[2], lo[3]);
+              fence_proxy_async_all();
+              mbar_arrive_release_cluster(mapa_rank(x_rdy(0), (uint32_t)lane));
+            }
+            __syncwarp();
+          }
+          if (prof) d_out += clock64() - t4;
+        } else {
+          if (t + 1 < p.steps) {
+            stage(g, hn, t);
+            publish(g, t);
+          }
+          if (prof && g == 0) d_pub += clock64() - t3;
+          const long long t4 = prof ? clock64() : 0;
+          if (ok) stg256(h_dst, hn);
+          if (prof && g == 0) d_out += clock64() - t4;
         }
-        if (prof) d_out += clock64() - t4;
-      } else {
-        if (t + 1 < p.steps) publish(hn, t);
-        if (prof) d_pub += clock64() - t3;
-        const long long t4 = prof ? clock64() : 0;
-        if (ok) stg256(h_row + (int64_t)t * kH, hn);
-        if (prof) d_out += clock64() - t4;
       }
     }
-    if (ok) stg256(p.c + m * kH + u0, c);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int64_t m = row_of(g);
+      if (m < p.n) stg256(p.c + m * kH + u0, c[g]);
+    }
     if (prof && warp == 4 && lane == 0) {
       unsigned long long* o = p.prof + (size_t)blockIdx.x * 8;
-      o[3] = (unsigned long long)w_tfull; o[4] = (unsigned long long)d_ld; o[5] = (unsigned long long)d_cell;
+      o[3] = (unsigned long long)w_tfull; o[5] = (unsigned long long)d_cell;
       o[6] = (unsigned long long)d_pub; o[7] = (unsigned long long)d_out;
     }
   }
   __syncwarp();
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 2) tmem_dealloc(tmem_base, TILE_N);
+  if (warp == 2) tmem_dealloc(tmem_base, G * TILE_N);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -444,45 +488,66 @@ static EncodeTiledFn encode_fn() {
 
 }  // namespace cs
 
-size_t tc_colsplit_scratch_bytes(int64_t n) { return (size_t)ceil_div(n, cs::BM) * 2 * 2 * cs::BM * kH * sizeof(__half); }
+size_t tc_colsplit_scratch_bytes(int64_t n) {
+  const int64_t groups = (ceil_div(n, cs::BM) + 1) & ~int64_t(1);          // two-group clusters round the group count up to even
+  return (size_t)groups * 2 * 2 * cs::BM * kH * sizeof(__half);
+}
 
 // how many 8-CTA clusters of this kernel the device can hold at once (GPC packing decides; measured, not assumed)
 static int max_active_clusters() {
   static const int v = [] {
     using namespace cs;
-    if (cudaFuncSetAttribute(lstm_colsplit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return 0;
+    auto kern = lstm_colsplit_kernel<false, 1>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout<1>::SMEM_BYTES) != cudaSuccess) return 0;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Layout<1>::SMEM_BYTES;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, lstm_colsplit_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
     return nc;
   }();
   return v;
 }
 int tc_colsplit_max_active_clusters() { return max_active_clusters(); }
 
-// GNNPN_COLSPLIT: -1 (default) = automatic, 0 = never, 1 = always.  Automatic: a step of the column-split scan costs
-// ~6.6 us per wave of clusters against ~16.7 us (encoder) / ~39 us (fused decoder) for the CTA-pair scan at any batch
-// up to 18,944, so it is used while the batch fits two waves (profiles/r01_colsplit_timing.jsonl).
-bool tc_colsplit_wanted(int64_t n) {
+// GNNPN_COLSPLIT: -1 (default) = automatic, 0 = never, 1 = always; GNNPN_COLSPLIT_G = 1 / 2 forces the groups per cluster of
+// the encoder (default: 2 as soon as one-group clusters would need a second wave).  Automatic (measured on a B200 with 15
+// co-resident clusters, profiles/r01_colsplit_timing.jsonl, r01_pn_batch_sweep.jsonl): a step of the column-split scan
+// costs ~6.6 us per wave (~7 us with two groups per cluster) against ~16.7 us (encoder) / ~37 us (fused decoder) for
+// the CTA-pair scan at any batch up to 18,944.  Encoder: one-group clusters up to 15 groups of 128, two-group clusters up to
+// 30 groups (one wave; two waves of them are slower than the pair scan); decoder: one-group clusters up to two waves.
+static int colsplit_mode() {
   const char* e = getenv("GNNPN_COLSPLIT");              // read per call: tests and benches flip it between launches
-  const int mode = e ? atoi(e) : -1;
+  return e ? atoi(e) : -1;
+}
+bool tc_colsplit_wanted(int64_t n) {                     // fused decoder
+  const int mode = colsplit_mode();
   if (mode == 0) return false;
   if (mode == 1) return true;
   return ceil_div(n, cs::BM) <= 2 * (int64_t)max_active_clusters();
 }
+bool tc_colsplit_wanted_encode(int64_t n) {
+  const int mode = colsplit_mode();
+  if (mode == 0) return false;
+  if (mode == 1) return true;
+  return ceil_div(n, cs::BM) <= 2 * (int64_t)max_active_clusters();
+}
+static int colsplit_groups_per_cluster(int64_t n) {
+  const char* e = getenv("GNNPN_COLSPLIT_G");
+  if (e && (atoi(e) == 1 || atoi(e) == 2)) return atoi(e);
+  return ceil_div(n, cs::BM) > (int64_t)max_active_clusters() ? 2 : 1;
+}
 
 namespace cs {
 
-template <bool DEC>
+template <bool DEC, int G>
 static int launch(const float* packed, Params p, void* scratch, cudaStream_t st) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return GNNPN_EUNSUPPORTED;
-  const int64_t groups = ceil_div(p.n, BM);
+  const int64_t clusters = ceil_div(ceil_div(p.n, BM), G);
   CUtensorMap maps[5];
   const float* w_hi = packed + kOffTc16Hi;
   const float* w_lo = packed + kOffTc16Lo;
@@ -498,7 +563,7 @@ static int launch(const float* packed, Params p, void* scratch, cudaStream_t st)
   }
   {
     // exchange scratch as one 2-D fp16 tensor {kH, groups * 2 parities * (hi|lo) * 128 rows}; box = one k-block
-    cuuint64_t dims[2] = {(cuuint64_t)kH, (cuuint64_t)(groups * 4 * BM)};
+    cuuint64_t dims[2] = {(cuuint64_t)kH, (cuuint64_t)(clusters * G * 4 * BM)};
     cuuint64_t strides[1] = {(cuuint64_t)kH * 2};
     cuuint32_t box[2] = {64u, (cuuint32_t)BM};
     cuuint32_t estr[2] = {1, 1};
@@ -507,15 +572,16 @@ static int launch(const float* packed, Params p, void* scratch, cudaStream_t st)
       return GNNPN_ESHAPE;
   }
   p.scratch = reinterpret_cast<__half*>(scratch);
-  auto kern = lstm_colsplit_kernel<DEC>;
+  auto kern = lstm_colsplit_kernel<DEC, G>;
+  constexpr int SMEM = Layout<G>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   static const int do_prof = getenv("GNNPN_SEQ_PROF") ? atoi(getenv("GNNPN_SEQ_PROF")) : 0;
-  const unsigned grid = (unsigned)(groups * CL);
+  const unsigned grid = (unsigned)(clusters * CL);
   unsigned long long* prof = nullptr;
   if (do_prof) {
     if (cudaMalloc(&prof, (size_t)grid * 8 * 8) != cudaSuccess) return GNNPN_EUNSUPPORTED;
@@ -523,7 +589,7 @@ static int launch(const float* packed, Params p, void* scratch, cudaStream_t st)
   }
   p.prof = prof;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -539,9 +605,9 @@ static int launch(const float* packed, Params p, void* scratch, cudaStream_t st)
     for (unsigned c = 0; c < grid; ++c)
       for (int i = 0; i < 8; ++i) acc[i] += (double)h[c * 8 + i];
     const double d = (double)grid * p.steps;
-    fprintf(stderr, "[colsplit prof %s steps=%d grid=%u max_active_clusters=%d] per-step cycles: mma total %.0f (wait A full %.0f) | "
-            "tma wait a_rdy %.0f | epi wait tmem_full %.0f, tmem ld %.0f, cell %.0f, publish %.0f, %s %.0f\n", DEC ? "dec" : "enc",
-            p.steps, grid, max_active_clusters(), acc[1] / d, acc[2] / d, acc[0] / d, acc[3] / d, acc[4] / d, acc[5] / d, acc[6] / d,
+    fprintf(stderr, "[colsplit prof %s G=%d steps=%d grid=%u max_active_clusters=%d] per-step cycles: mma total %.0f (wait A full %.0f) | "
+            "tma wait a_rdy %.0f | epi (group 0) wait tmem_full %.0f, tmem ld + cell %.0f, publish %.0f, %s %.0f\n", DEC ? "dec" : "enc", G,
+            p.steps, grid, max_active_clusters(), acc[1] / d, acc[2] / d, acc[0] / d, acc[3] / d, acc[5] / d, acc[6] / d,
             DEC ? "pointer phase" : "h store", acc[7] / d);
     free(h);
     cudaFree(prof);
@@ -559,7 +625,8 @@ int tc_colsplit_encode(const SeqEncodeArgs& a, void* scratch, cudaStream_t st) {
   p.bias0 = p.bias = a.packed + kOffBias;
   p.c = a.c_state;
   p.h_out = a.enc_out; p.h_out_inst_ld = (int64_t)a.L * kH;
-  return cs::launch<false>(a.packed, p, scratch, st);
+  return colsplit_groups_per_cluster(a.n) == 2 ? cs::launch<false, 2>(a.packed, p, scratch, st)
+                                               : cs::launch<false, 1>(a.packed, p, scratch, st);
 }
 
 int tc_colsplit_decode(const SeqDecodeArgs& a, void* scratch, cudaStream_t st) {
@@ -575,7 +642,7 @@ int tc_colsplit_decode(const SeqDecodeArgs& a, void* scratch, cudaStream_t st) {
   p.pa.alpha = a.alpha; p.pa.use_tanh = a.use_tanh; p.pa.C = a.C; p.pa.n = a.n; p.pa.L = a.L;
   p.pa.N = a.N; p.pa.idx_out = a.idx_out; p.pa.win_logits = a.win_logits; p.pa.win_probs = a.win_probs;
   p.pa.forced = a.forced_idx; p.pa.uniform = a.sample_uniform;
-  return cs::launch<true>(a.packed, p, scratch, st);
+  return cs::launch<true, 1>(a.packed, p, scratch, st);
 }
 
 }  // namespace gnnpn

@@ -28,7 +28,8 @@ int tc_seq_encode(const SeqEncodeArgs& a, cudaStream_t st);
 
 // Small-batch (latency) variant, tc_colsplit.cu: a cluster of 8 CTAs shares 128 instances and splits the gate
 // columns; `scratch` = tc_colsplit_scratch_bytes(n) bytes (1024-byte aligned) for the h' exchange.
-bool tc_colsplit_wanted(int64_t n);
+bool tc_colsplit_wanted(int64_t n);          // fused decoder
+bool tc_colsplit_wanted_encode(int64_t n);
 int tc_colsplit_max_active_clusters();
 size_t tc_colsplit_scratch_bytes(int64_t n);
 int tc_colsplit_encode(const SeqEncodeArgs& a, void* scratch, cudaStream_t st);

@@ -37,6 +37,7 @@ def _select(impl):
 def _reset_scan_knob():
     yield
     os.environ.pop("GNNPN_COLSPLIT", None)
+    os.environ.pop("GNNPN_COLSPLIT_G", None)
 
 
 
@@ -354,7 +355,8 @@ def test_column_split_scan_equals_cta_pair_scan_bitwise(n, K, N):
     """The small-batch cluster scan (tc_colsplit.cu) issues the same MMA sequence and the same cell / pointer
     arithmetic as the CTA-pair scan (tc_seq.cu): encodings, decoder states, logits, probabilities and picks are
     bit-identical, so sharding a batch (which changes the kernel the dispatcher picks) cannot change results.
-    n = 2100 spans 17 clusters = two waves on a B200 (15 co-resident 8-CTA clusters)."""
+    n = 2100 spans 17 groups: two waves of one-group clusters on a B200 (15 co-resident 8-CTA clusters), or 9 two-group
+    clusters with a phantom 18th group."""
     from gnnpn_sc_b200 import modelPN as M
     from gnnpn_sc_b200.synth import pn_instances
     from gnnpn_sc_b200.weights import reference_shaped_state_dict
@@ -364,12 +366,19 @@ def test_column_split_scan_equals_cta_pair_scan_bitwise(n, K, N):
     m = m.cuda().eval()
     lat = [torch.randn(n, K * N, device="cuda") for _ in range(K)]
     outs = {}
-    for mode in ("1", "0"):
+    # (GNNPN_COLSPLIT, GNNPN_COLSPLIT_G): column-split with one / two instance groups per cluster (encoder), CTA-pair scan
+    for key, (mode, g) in {"cs1": ("1", "1"), "cs2": ("1", "2"), "pair": ("0", None)}.items():
         os.environ["GNNPN_COLSPLIT"] = mode
+        if g is None:
+            os.environ.pop("GNNPN_COLSPLIT_G", None)
+        else:
+            os.environ["GNNPN_COLSPLIT_G"] = g
         with torch.no_grad():
             _, idx, _ = m.actor(x, lat, sample="greedy")
         torch.cuda.synchronize()
         last = m.actor.last
-        outs[mode] = [torch.stack(idx).clone()] + [last[k].clone() for k in ("enc_out", "dec_h", "win_logits", "win_probs")]
-    for a, b in zip(outs["1"], outs["0"]):
-        assert torch.equal(a, b)
+        outs[key] = [torch.stack(idx).clone()] + [last[k].clone() for k in ("enc_out", "dec_h", "win_logits", "win_probs")]
+    os.environ.pop("GNNPN_COLSPLIT_G", None)
+    for key in ("cs1", "cs2"):
+        for a, b in zip(outs[key], outs["pair"]):
+            assert torch.equal(a, b), key
