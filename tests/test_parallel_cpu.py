@@ -86,3 +86,44 @@ def test_reference_import_paths_resolve():
     assert {"Attention", "PointerNet", "CombinatorialRL", "reward"} <= set(dir(m1))
     assert {"Net", "NodeEncoder", "EdgeEncoder"} <= set(dir(m2))
     assert hasattr(t, "PNHigh") and hasattr(e, "check") and hasattr(l, "loadDataPN")
+
+
+def _woa_worker(rank, world, port, out, golden):
+    """ESWOA instances are independent: each rank runs its contiguous block, no collective."""
+    import copy, json
+    import numpy as np
+    from gnnpn_sc_b200.WOA import PhiloxRng, run_many
+    from oracle import woa_oracle as wo
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    probs = []
+    for name in ("woa_small", "woa_tight", "woa_seeded"):
+        with open(os.path.join(golden, name + ".json")) as f:
+            inp = json.load(f)["input"]
+        probs.append(([[tuple(s) for s in c] for c in inp["services"]], inp["constraints"], inp["solution"]))
+    lo, hi = parallel.shard_range(len(probs))
+    res = run_many(copy.deepcopy(probs[lo:hi]), popSize=8, MAX_Iter=12, fitness=wo.CpuFitness,
+                   rngs=[PhiloxRng(50 + k) for k in range(lo, hi)])
+    mine = torch.tensor([r[0] for r in res] + [0.0] * (2 - (hi - lo)), dtype=torch.float64)      # pad ragged shard
+    parts = [torch.empty(2, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, mine)                                                          # reporting only
+    if rank == 0:
+        torch.save(torch.cat(parts)[: len(probs)], out)
+    dist.destroy_process_group()
+
+
+def test_woa_instances_shard_without_communication(tmp_path):
+    import copy, json
+    from gnnpn_sc_b200.WOA import PhiloxRng, run_many
+    from oracle import woa_oracle as wo
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    out = str(tmp_path / "woa.pt")
+    mp.spawn(_woa_worker, args=(2, _free_port(), out, golden), nprocs=2, join=True)
+    got = torch.load(out)
+    probs = []
+    for name in ("woa_small", "woa_tight", "woa_seeded"):
+        with open(os.path.join(golden, name + ".json")) as f:
+            inp = json.load(f)["input"]
+        probs.append(([[tuple(s) for s in c] for c in inp["services"]], inp["constraints"], inp["solution"]))
+    want = run_many(copy.deepcopy(probs), popSize=8, MAX_Iter=12, fitness=wo.CpuFitness, rngs=[PhiloxRng(50 + k) for k in range(3)])
+    assert got.tolist() == [w[0] for w in want]
