@@ -37,22 +37,25 @@ def main():
     probs = problems(a.instances)
     W.run_many(copy.deepcopy(probs[:4]), a.pop, 10)          # warm-up (library load, allocator)
     torch.cuda.synchronize()
+    pc = copy.deepcopy(probs)                                # the engines round / extend their inputs in place
     l0 = _lib.launch_count(); t0 = time.perf_counter()
-    res = W.run_many(copy.deepcopy(probs), a.pop, a.iters)
+    res = W.run_many(pc, a.pop, a.iters)
     torch.cuda.synchronize()
     gpu_s = time.perf_counter() - t0
     launches = _lib.launch_count() - l0
     # the whole search device-resident (one launch, Philox draws): wall time incl. host-side population init and packing
     W.run_many_device(copy.deepcopy(probs[:4]), a.pop, 10)
     torch.cuda.synchronize()
+    pc = copy.deepcopy(probs)
     t0 = time.perf_counter()
     tm = {}
-    dres = W.run_many_device(copy.deepcopy(probs), a.pop, a.iters, timings=tm)
+    dres = W.run_many_device(pc, a.pop, a.iters, timings=tm)
     torch.cuda.synchronize()
     dev_s = time.perf_counter() - t0
     l1 = _lib.launch_count()
+    pc = copy.deepcopy(probs[: a.cpu_instances])
     t0 = time.perf_counter()
-    cpu = W.run_many(copy.deepcopy(probs[: a.cpu_instances]), a.pop, a.iters, fitness=wo.CpuFitness)
+    cpu = W.run_many(pc, a.pop, a.iters, fitness=wo.CpuFitness)
     cpu_s = time.perf_counter() - t0
     same = all(r[0] == c[0] and r[2] == c[2] for r, c in zip(res, cpu))
     line = {"config": "eswoa_qws_ml2pn_woa", "K": 47, "candidates_per_task": 54, "popSize": a.pop, "MAX_Iter": a.iters,
