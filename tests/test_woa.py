@@ -214,3 +214,34 @@ def test_device_search_equals_host_engine_bitwise(golden_dir):
         for k, (d, h) in enumerate(zip(dev, host)):
             assert d[2] == h[2], (pop, iters, k, next(i for i, (x, y) in enumerate(zip(d[2], h[2])) if x != y))
             assert d[0] == h[0] and [tuple(r) for r in d[1]] == [tuple(r) for r in h[1]]
+
+
+@pytest.mark.gpu
+def test_file_level_driver_device_engine(tmp_path):
+    """WOA(..., engine="device"): same files in and out, every instance searched in one launch."""
+    from gnnpn_sc_b200 import WOA as W
+    g = np.random.default_rng(3)
+    K, n = 4, 8
+    svc = {str(c + 1): [[0.0] * 5 + [float(g.uniform(0.05, 1)), float(g.uniform(0.05, 1)), float(g.uniform(0.9, 1)),
+                                     float(g.uniform(0.9, 1))] for _ in range(6)] for c in range(K)}
+    nodef = []
+    for _ in range(n):
+        nodes = [[1] + [0] * K + [0, 0.5, 1.0, 0, 0.5, 1.0]]
+        for c in range(1, K + 1):
+            nodes.append([0] * c + [1] + [0] * (K - c) + [0, 0.0, 1.0, 0, 0.0, 1.0])
+        nodef.append(nodes)
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, "data", "toy"))
+    for name, obj in (("nodefeatures.data", nodef), ("serviceFeature.data", svc), ("minCostList.data", [0.4] * n),
+                      ("labels.data", [[0] * (6 * K)] * n)):
+        with open(os.path.join(root, "data", "toy", name), "w") as f:
+            json.dump(obj, f)
+    out = W.WOA("toy", K, 0, 0, 0, 1, 5, 0, -1, 20, 16, root=root, engine="device").start()
+    with open(os.path.join(root, "solutions", "WOA", "toy", "ESWOA.txt")) as f:
+        saved = json.load(f)
+    assert saved["quality"] == out["quality"] and len(out["quality"]) == n - n // 4 * 3 and all(q > 0 for q in out["quality"])
+    # the search can only improve on the best member of the initial population
+    from gnnpn_sc_b200.WOA import loadDataOther, run_many_device
+    feats, cons, mc = loadDataOther("toy", 0, None, False, root)
+    res = run_many_device([(f, c, None) for f, c in zip(feats, cons)], popSize=16, MAX_Iter=20, seeds=list(range(6, 8)))
+    assert all(r[2][-1] <= r[2][0] for r in res) and [mc[6 + k] / r[0] for k, r in enumerate(res)] == out["quality"]
