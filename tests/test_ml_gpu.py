@@ -10,19 +10,19 @@ from oracle import ml_oracle as mo
 pytestmark = pytest.mark.gpu
 
 
-def _setup(K, S, n_inst, gcn_layers, seed=0):
+def _setup(K, S, n_inst, gcn_layers, seed=0, is_services=True):
     from gnnpn_sc_b200 import synth, loadData, trainML, modelML
     ds = synth.ml_dataset(n_instances=n_inst, K=K, S=S, seed=seed, min_tasks=min(4, K))
     arrays = loadData.ml_arrays(ds)
     samples = trainML.build_samples(arrays)
     torch.manual_seed(seed)
-    ref = mo.NetO(128, S, 20, 2, gcn_layers, isServices=True)
+    ref = mo.NetO(128, S, 20, 2, gcn_layers, isServices=is_services)
     ref.reset_parameters()
     for m in ref.modules():                     # non-trivial eval-mode BatchNorm
         if isinstance(m, torch.nn.BatchNorm1d):
             m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5)
             m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
-    net = modelML.Net(128, S, 20, 2, gcn_layers, isServices=True)
+    net = modelML.Net(128, S, 20, 2, gcn_layers, isServices=is_services)
     missing = net.load_state_dict(ref.state_dict(), strict=True)
     return samples, ref, net.cuda()
 
@@ -46,6 +46,18 @@ def test_net_forward_eval_matches_oracle(K, S, gcn, quirk):
         for r in range(2):                      # same top-10 set unless scores tie within tolerance
             diff = set(top_w[r].tolist()) ^ set(top_g[r].tolist())
             assert all(abs(float(want[r, i]) - float(want[r, top_w[r, -1]])) < 1e-5 for i in diff)
+
+
+def test_net_without_service_graph_branch():
+    """``isServices=False`` (modelML.py:157-162: plain Linear layers instead of GCNConv on the service side) -- never
+    taken by TrainML, but part of the ``Net`` interface."""
+    from gnnpn_sc_b200 import trainML
+    samples, ref, net = _setup(12, 300, 4, 2, is_services=False)
+    ref.eval(); net.eval()
+    with torch.no_grad():
+        want = ref(mo.collate(samples[:2]))
+        got = net(trainML.collate(samples[:2], device="cuda")).cpu()
+    assert got.shape == want.shape and (got - want).abs().max() <= 1e-5
 
 
 def test_net_train_step_gradients_match_oracle():
