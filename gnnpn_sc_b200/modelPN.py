@@ -22,7 +22,7 @@ No CPU fallback: CUDA tensors only, and a missing extension raises.
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 import torch.nn as nn

@@ -3,7 +3,7 @@ device pointers + the current CUDA stream.  Plumbing only -- all arithmetic
 happens in ``libgnnpn_b200.so``.  Every function requires CUDA tensors."""
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

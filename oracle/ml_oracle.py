@@ -27,7 +27,7 @@ from __future__ import annotations
 
 import math
 from types import SimpleNamespace
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 import torch.nn as nn
