@@ -96,6 +96,92 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(
   }
 }
 
+// Categories of at most 64 services (every shipped dataset: ~50 per category) and N <= 32: one WARP per (instance,
+// category), two entries per lane, bitonic network through register shuffles -- no shared memory, no block barriers
+// (the block version above spends its time in 21 __syncthreads stages with a quarter of its threads active).
+constexpr int kSelWarps = 4;
+
+__device__ __forceinline__ void sel_cex(float& k, int& id, float ok, int oid, bool keep_first) {
+  const bool mine_first = sel_before(k, id, ok, oid);
+  const bool other_first = sel_before(ok, oid, k, id);
+  if (keep_first ? other_first : mine_first) { k = ok; id = oid; }
+}
+
+__global__ void __launch_bounds__(32 * kSelWarps) select_candidates_warp_kernel(
+    const float* __restrict__ scores, int64_t scores_ld, const float* __restrict__ svc_qos,
+    const int32_t* __restrict__ cat_ptr, const float* __restrict__ local_bounds, const uint8_t* __restrict__ used,
+    const float* __restrict__ global_bounds, int64_t n, int K, int N, int with_category,
+    float* __restrict__ rows, int32_t* __restrict__ picked) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * kSelWarps + (threadIdx.x >> 5);
+  if (pair >= n * K) return;
+  const int64_t b = pair / K;
+  const int c = (int)(pair - b * K);
+  const int s0 = cat_ptr[c], s1 = cat_ptr[c + 1];
+  const float* lb = local_bounds + (b * K + c) * 4;
+  const float lo2 = lb[0], hi2 = lb[1], lo3 = lb[2], hi3 = lb[3];
+  const bool use = used[b * K + c] != 0;
+  float k[2];
+  int id[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int s = s0 + lane + 32 * h;
+    k[h] = -INFINITY; id[h] = 0x7fffffff;
+    if (use && s < s1) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(svc_qos) + s);
+      if (lo2 <= q.z && q.z <= hi2 && lo3 <= q.w && q.w <= hi3) {
+        k[h] = __ldg(scores + b * scores_ld + s);
+        id[h] = s;
+      }
+    }
+  }
+  const int count = __popc(__ballot_sync(0xffffffffu, id[0] != 0x7fffffff)) + __popc(__ballot_sync(0xffffffffu, id[1] != 0x7fffffff));
+  // bitonic sort of the 64 entries e = lane + 32 h, best first
+#pragma unroll
+  for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride == 32) {                                   // partner = the lane's other entry (size == 64: sorts "up")
+        const float k0 = k[0], k1 = k[1];
+        const int i0 = id[0], i1 = id[1];
+        sel_cex(k[0], id[0], k1, i1, true);
+        sel_cex(k[1], id[1], k0, i0, false);
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int e = lane + 32 * h;
+          const float ok = __shfl_xor_sync(0xffffffffu, k[h], stride);
+          const int oid = __shfl_xor_sync(0xffffffffu, id[h], stride);
+          const bool up = (e & size) == 0;
+          sel_cex(k[h], id[h], ok, oid, ((e & stride) == 0) == up);
+        }
+      }
+    }
+  }
+  const int F = 8 + (with_category ? 1 : 0);
+  float tail[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tail[i] = global_bounds[b * 4 + i];
+  }
+  // row j takes the entry at sorted position j % count (self-duplication padding = cyclic repetition)
+  const int pos = count > 0 ? lane % count : 0;
+  const int v0 = __shfl_sync(0xffffffffu, id[0], pos & 31), v1 = __shfl_sync(0xffffffffu, id[1], pos & 31);
+  if (lane < N) {
+    float* r = rows + ((b * K + c) * (int64_t)N + lane) * F;
+    int sid = -1;
+    float4 q = make_float4(0.f, 1.f, 1.f, 1.f);           // neutral row (loadData.py:148)
+    if (count > 0) {
+      sid = pos < 32 ? v0 : v1;
+      q = __ldg(reinterpret_cast<const float4*>(svc_qos) + sid);
+    }
+    if (with_category) *r++ = (float)c;
+    r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w;
+    r[4] = tail[0]; r[5] = tail[1]; r[6] = tail[2]; r[7] = tail[3];
+    if (picked) picked[(b * K + c) * (int64_t)N + lane] = sid;
+  }
+}
+
 }  // namespace
 }  // namespace gnnpn
 
@@ -111,6 +197,12 @@ extern "C" int gnnpn_select_candidates_f32(const float* scores, int64_t scores_l
   GNNPN_REQUIRE(n >= 0 && n < 65536, GNNPN_ERANGE);
   GNNPN_REQUIRE(aligned16(svc_qos), GNNPN_EALIGN);
   if (n == 0) return GNNPN_OK;
+  if (max_category_size <= 64 && N <= 32) {
+    const int64_t pairs = n * K;
+    select_candidates_warp_kernel<<<(unsigned)ceil_div(pairs, kSelWarps), 32 * kSelWarps, 0, (cudaStream_t)stream>>>(
+        scores, scores_ld, svc_qos, cat_ptr, local_bounds, used, global_bounds, n, K, N, with_category, rows, picked);
+    return after_launch();
+  }
   int P = 32;
   while (P < max_category_size) P <<= 1;
   const size_t smem = (size_t)P * 8;
