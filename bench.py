@@ -88,9 +88,28 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
+REF_MODEL = os.path.join(ROOT, "baseline", "_ref", "src", "models", "modelPN.py")
+
+
+def _load_reference_module():
+    """The UNMODIFIED reference ``src/models/modelPN.py`` (placed under baseline/_ref by
+    baseline/install_reference.py), loaded by path under a private name, or None when it is not installed."""
+    if not os.path.exists(REF_MODEL):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_reference_modelPN", REF_MODEL)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    return ref
+
+
 def cpu_reference_rate(batches: int, batch: int = 128):
-    """The reference's CPU algorithm (oracle port, per-row python loops replayed as in modelPN.py:220-222)
-    on this box's host cores.  Returns (instances/s, seconds per batch list)."""
+    """The reference's own CPU path on this box's host cores: greedy PNLow -> PNHigh + its ``reward()``
+    (trainPNHigh.py:131-144) at the reference's batch size.  Runs the real ``CombinatorialRL`` classes from
+    baseline/_ref when installed (kind "reference"), else the oracle port of the same loop (kind "port").
+    Returns (instances/s, seconds per batch list, kind)."""
+    import contextlib
+    import io
     import torch
     from oracle import pn_oracle as po
     from gnnpn_sc_b200.synth import pn_instances
@@ -98,14 +117,41 @@ def cpu_reference_rate(batches: int, batch: int = 128):
     cfg = po.PNConfig(seq_len=L_SEQ, s_number=N_CAND, s_category=K_TASKS)
     sd_lo, sd_hi = po.make_state_dict(cfg, 1), po.make_state_dict(cfg, 2)
     x = pn_instances(batch, K_TASKS, N_CAND, seed=1234)
+    ref = _load_reference_module()
+    if ref is not None:
+        nets = []
+        for level, sd in (("Low", sd_lo), ("High", sd_hi)):
+            have_cuda = torch.cuda.is_available()
+            if not have_cuda:                                # modelPN.py:151 calls .cuda() unconditionally
+                saved, torch.Tensor.cuda = torch.Tensor.cuda, (lambda self, *a, **k: self)
+            try:
+                m = ref.CombinatorialRL(0, HID, L_SEQ, 0, 10, 1, ref.reward, "Dot", N_CAND, K_TASKS, use_cuda=False,
+                                        level=level)
+            finally:
+                if not have_cuda:
+                    torch.Tensor.cuda = saved
+            m.actor.alpha = m.actor.alpha.cpu()              # CPU run of the reference
+            m.load_state_dict(sd)
+            nets.append(m.eval())
+
+        def one_batch():
+            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):      # reward() prints every batch
+                _, _, _, _, latent = nets[0](x, None, sample="greedy", training="SL")
+                R, _, _, _, _ = nets[1](x, None, latent, sample="greedy", training="RL")
+            return R
+        kind = "reference"
+    else:
+        def one_batch():
+            res = po.greedy_low_high(sd_lo, sd_hi, cfg, x, faithful_loops=True)
+            return po.reward(list(res["actions"]), None, K_TASKS, "High", 0)
+        kind = "port"
     times = []
     for i in range(batches + 1):                       # first batch is warm-up
         t0 = time.perf_counter()
-        res = po.greedy_low_high(sd_lo, sd_hi, cfg, x, faithful_loops=True)
-        po.reward(list(res["actions"]), None, K_TASKS, "High", 0)
+        one_batch()
         if i:
             times.append(time.perf_counter() - t0)
-    return batch / min(times), times
+    return batch / min(times), times, kind
 
 
 def run_reference(args):
@@ -114,7 +160,7 @@ def run_reference(args):
         return
     batch = 128
     t0 = time.perf_counter()
-    rate, times = cpu_reference_rate(args.steps, batch)
+    rate, times, kind = cpu_reference_rate(args.steps, batch)
     ms = 1e3 * statistics.mean(times)
     value = batch / statistics.mean(times)
     line = {
@@ -123,9 +169,12 @@ def run_reference(args):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": WORKLOAD, "instances_per_step": batch, "K": K_TASKS,
                                         "N": N_CAND, "L": L_SEQ, "hidden": HID},
-        "cpu_baseline": {"value": value, "unit": "instances/s", "cores": os.cpu_count(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "instances/s", "cores": os.cpu_count(), "kind": kind,
                          "sample": f"{args.steps} batches of {batch} instances (reference batch size, "
-                                   "trainPNHigh.py:248), torch CPU fp32, all host threads"},
+                                   "trainPNHigh.py:248), " + (
+                                       "the reference's own CombinatorialRL.forward x2 + reward() from baseline/_ref"
+                                       if kind == "reference" else "oracle port of modelPN.py incl. its per-row loops")
+                                   + ", torch CPU fp32, all host threads"},
         "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
@@ -305,10 +354,11 @@ def run_ours(args):
             kname = "lstm_step_ffma_kernel (fp32 FFMA recurrence GEMM + fused cell)"
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, times = cpu_reference_rate(args.cpu_batches)
-            cpu = {"value": rate, "unit": "instances/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"best of {len(times)} batches of 128 instances (reference batch size), "
-                             "oracle port of modelPN.py incl. its per-row python loops, torch CPU fp32"}
+            rate, times, kind = cpu_reference_rate(args.cpu_batches)
+            cpu = {"value": rate, "unit": "instances/s", "cores": os.cpu_count(), "kind": kind,
+                   "sample": f"best of {len(times)} batches of 128 instances (reference batch size), " + (
+                       "the reference's own modelPN.CombinatorialRL x2 + reward() (baseline/_ref)" if kind == "reference"
+                       else "oracle port of modelPN.py incl. its per-row python loops") + ", torch CPU fp32"}
         line = {
             "metric": "composition instances/sec (ML+2PN greedy)", "value": value, "unit": "instances/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

@@ -46,6 +46,8 @@ __device__ __forceinline__ double numpy_sum_f64<0>(const double* a, int n) { ret
 
 constexpr int kMaxTasksWoa = 512;
 
+// MEAN_ALL: `np.average(qos[0])` over all K picks (src/ML2PN.py:6-12, `ML2PN.calc`) instead of sum / #{q0 > 0}
+template <bool MEAN_ALL>
 __global__ void woa_fitness_kernel(const double* __restrict__ qos, const int32_t* __restrict__ idx, int64_t idx_ld,
                                    const int32_t* __restrict__ klen, const double* __restrict__ bounds, int64_t P,
                                    int Kmax, int32_t* __restrict__ viol_out, double* __restrict__ obj_out,
@@ -69,7 +71,7 @@ __global__ void woa_fitness_kernel(const double* __restrict__ qos, const int32_t
   const double* b = bounds + p * 4;
   int viol = 0;
   for (int i = 0; i < 2; ++i) viol += (prod[i] < b[2 * i] || prod[i] > b[2 * i + 1]) ? 1 : 0;
-  double obj = __ddiv_rn(numpy_sum_f64<3>(q0s, K), (double)used);
+  double obj = __ddiv_rn(numpy_sum_f64<3>(q0s, K), (double)(MEAN_ALL ? K : used));
   obj = __dadd_rn(obj, 1.0);
   obj = __dsub_rn(obj, min_q1);
   obj = __ddiv_rn(obj, 2.0);
@@ -271,8 +273,19 @@ extern "C" int gnnpn_woa_fitness_f64(const double* qos, int64_t n_services, cons
   GNNPN_REQUIRE(qos && idx && bounds, GNNPN_ENULL);
   GNNPN_REQUIRE(Kmax >= 1 && Kmax <= kMaxTasksWoa && idx_ld >= Kmax && n_services >= 1 && P >= 0, GNNPN_ESHAPE);
   if (P == 0) return GNNPN_OK;
-  woa_fitness_kernel<<<(unsigned)ceil_div(P, 64), 64, 0, (cudaStream_t)stream>>>(qos, idx, idx_ld, klen, bounds, P, Kmax,
-                                                                                viol_out, obj_out, fit_out);
+  woa_fitness_kernel<false><<<(unsigned)ceil_div(P, 64), 64, 0, (cudaStream_t)stream>>>(qos, idx, idx_ld, klen, bounds, P,
+                                                                                       Kmax, viol_out, obj_out, fit_out);
+  return after_launch();
+}
+
+extern "C" int gnnpn_ml2pn_score_f64(const double* qos, int64_t n_rows, const int32_t* idx, int64_t idx_ld,
+                                     const int32_t* klen, const double* bounds, int64_t P, int Kmax,
+                                     int32_t* viol_out, double* obj_out, double* score_out, void* stream) {
+  GNNPN_REQUIRE(qos && idx && bounds, GNNPN_ENULL);
+  GNNPN_REQUIRE(Kmax >= 1 && Kmax <= kMaxTasksWoa && idx_ld >= Kmax && n_rows >= 1 && P >= 0, GNNPN_ESHAPE);
+  if (P == 0) return GNNPN_OK;
+  woa_fitness_kernel<true><<<(unsigned)ceil_div(P, 64), 64, 0, (cudaStream_t)stream>>>(qos, idx, idx_ld, klen, bounds, P,
+                                                                                      Kmax, viol_out, obj_out, score_out);
   return after_launch();
 }
 

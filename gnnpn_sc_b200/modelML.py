@@ -168,31 +168,67 @@ class Net(nn.Module):
         self.serviceLin.reset_parameters()
 
     # ---- graph structure helpers -------------------------------------------------------------
+    def _cached(self, slot: str, tensors, build):
+        """One-entry cache per ``slot`` keyed on the IDENTITY (+ in-place version) of the source tensors.  The entry
+        holds references to them, so a freed-and-reused device address can never produce a stale hit (a pointer /
+        shape key could: the caching allocator hands the same address to the next batch's ``edge_index``)."""
+        hit = self._csr_cache.get(slot)
+        if hit is not None and len(hit[0]) == len(tensors) and all(
+                (a is b) and (a is None or a._version == v) for (a, v), b in zip(hit[0], tensors)):
+            return hit[1]
+        value = build()
+        self._csr_cache[slot] = ([(t, None if t is None else t._version) for t in tensors], value)
+        return value
+
     def _service_csr(self, data, n_nodes: int, need_transpose: bool):
-        """gcn_norm + CSR of the (static) service graph; rebuilt only when the tensors change."""
+        """gcn_norm + CSR of the service graph; rebuilt whenever ``data`` carries different tensors."""
         ei, ew = data.edge_index_service, data.edge_attr_service
-        key = (ei.data_ptr(), tuple(ei.shape), ei._version, None if ew is None else ew.data_ptr(), n_nodes)
-        hit = self._csr_cache.get("service")
-        if hit is None or hit[0] != key:
-            fwd = _csr(ei, ew, n_nodes, ops.CSR_GCN_NORM)
-            hit = (key, fwd, None)
-            self._csr_cache["service"] = hit
-        if need_transpose and hit[2] is None:
-            fwd = hit[1]
+        entry = self._cached("service", (ei, ew), lambda: {"n": n_nodes, "fwd": _csr(ei, ew, n_nodes, ops.CSR_GCN_NORM),
+                                                           "bwd": None})
+        if entry["n"] != n_nodes:
+            self._csr_cache.pop("service", None)
+            return self._service_csr(data, n_nodes, need_transpose)
+        if need_transpose and entry["bwd"] is None:
+            fwd = entry["fwd"]
             # transpose of the normalised matrix: edge (src=col -> dst=row) becomes (row -> col), same values
             rows = torch.repeat_interleave(torch.arange(n_nodes, device=ei.device),
                                            fwd.rowptr[1:] - fwd.rowptr[:-1])
             t_index = torch.stack([rows, fwd.col.long()])
-            bwd = _csr(t_index, fwd.val, n_nodes, ops.CSR_PLAIN)
-            hit = (key, fwd, bwd)
-            self._csr_cache["service"] = hit
-        return hit[1], hit[2]
+            entry["bwd"] = _csr(t_index, fwd.val, n_nodes, ops.CSR_PLAIN)
+        return entry["fwd"], entry["bwd"]
 
     @staticmethod
     def _membership_csr(seg: torch.Tensor, n_seg: int) -> _Csr:
         """scatter(reduce='mean') as a CSR over (row -> segment) memberships, rows in index order."""
         idx = torch.stack([torch.arange(seg.numel(), device=seg.device), seg.long()])
         return _csr(idx, None, n_seg, ops.CSR_PLAIN)
+
+    def _request_structure(self, data, n_req: int):
+        """(request-graph CSR, request-membership CSR, B): static per collated batch, so built once per ``data``
+        (one ``.item()`` sync and two CSR builds per batch instead of per forward)."""
+        def build():
+            B = int(data.batch.max().item()) + 1 if n_req else 0
+            return _csr(data.edge_index, None, n_req, ops.CSR_PLAIN), self._membership_csr(data.batch, B), B
+        return self._cached("request", (data.edge_index, data.batch), build)
+
+    def _service_membership(self, S: int, B: int, n_svc: int, device) -> _Csr:
+        """serviceBatch = [0..S-1] x B (modelML.py:167-171) as a membership CSR; depends on (S, B, n_svc) only."""
+        key = ("svc_memb", S, B, n_svc, str(device))
+        hit = self._csr_cache.get(key)
+        if hit is None:
+            svc_batch = torch.arange(S, device=device).repeat(B)[:n_svc]
+            hit = self._membership_csr(svc_batch, S)
+            self._csr_cache[key] = hit
+        return hit
+
+    def _eps(self, conv) -> float:
+        """GIN eps as a host float, synchronised only when the parameter changed."""
+        key = ("eps", id(conv))
+        hit = self._csr_cache.get(key)
+        if hit is None or hit[0] is not conv.eps or hit[1] != conv.eps._version:
+            hit = (conv.eps, conv.eps._version, float(conv.eps.detach().item()))
+            self._csr_cache[key] = hit
+        return hit[2]
 
     # ---- forward --------------------------------------------------------------------------------
     def forward(self, data):
@@ -208,17 +244,15 @@ class Net(nn.Module):
         x_raw = data.x.squeeze().float()
         n_req = x_raw.shape[0]
         x = ops.embed_concat(x_raw, self.nodeEncoder.embeddings[0].weight)                 # [n, 28] (26 + pad)
-        req = _csr(data.edge_index, None, n_req, ops.CSR_PLAIN)
+        req, memb, B = self._request_structure(data, n_req)
         for conv, bn in zip(self.nodeConvs, self.nodeBatchNorms):
-            agg = ops.spmm_csr(req.rowptr, req.col, None, x, n_rows=n_req, self_scale=float(1.0 + conv.eps.item()))
+            agg = ops.spmm_csr(req.rowptr, req.col, None, x, n_rows=n_req, self_scale=1.0 + self._eps(conv))
             lin0, bn0, _, lin1 = conv.nn
             s0, t0 = self._fold(bn0)
             h = ops.gemm_bias_act(agg, _pad_w(lin0.weight, agg.shape[1]), bias=lin0.bias, scale=s0, shift=t0, act="relu")
             s1, t1 = self._fold(bn)
             x = ops.gemm_bias_act(h, lin1.weight, bias=lin1.bias, scale=s1, shift=t1, act="relu")
         x = ops.gemm_bias_act(x, self.nodeLin.weight, bias=self.nodeLin.bias)
-        B = int(data.batch.max().item()) + 1 if n_req else 0
-        memb = self._membership_csr(data.batch, B)
         return ops.spmm_csr(memb.rowptr, memb.col, None, x, n_rows=B, mean=True), B        # [B, H]
 
     def _encode_service_nodes(self, data):
@@ -244,8 +278,7 @@ class Net(nn.Module):
         x, B = self._encode_requests(data)
         xs, n_svc = self._encode_service_nodes(data)
         S = self.outChannels
-        svc_batch = torch.arange(S, device=xs.device).repeat(B)[:n_svc]                    # modelML.py:167-171
-        memb_s = self._membership_csr(svc_batch, S)
+        memb_s = self._service_membership(S, B, n_svc, xs.device)                          # modelML.py:167-171
         xs = ops.spmm_csr(memb_s.rowptr, memb_s.col, None, xs, n_rows=S, mean=True)        # [S, H]
         return ops.gemm_bias_act(x, xs, act="sigmoid")                                     # sigmoid(x @ xs^T)
 

@@ -231,6 +231,24 @@ def woa_fitness(qos: torch.Tensor, idx: torch.Tensor, bounds: torch.Tensor, klen
     return viol, obj, fit
 
 
+def ml2pn_score(qos: torch.Tensor, idx: torch.Tensor, bounds: torch.Tensor, klen: torch.Tensor):
+    """``ML2PN.calc`` (ML2PN.py:6-12) for a batch of compositions, float64: same layout as :func:`woa_fitness`, the
+    mean of q0 runs over all ``klen[p]`` picks.  -> (viol int32 [P], obj f64 [P], obj + viol f64 [P])."""
+    if not (qos.is_cuda and idx.is_cuda and bounds.is_cuda and klen.is_cuda):
+        raise GnnpnError("ml2pn_score needs CUDA tensors (no CPU fallback)")
+    assert qos.dtype == torch.float64 and bounds.dtype == torch.float64
+    assert idx.dtype == torch.int32 and klen.dtype == torch.int32
+    qos, idx, bounds, klen = qos.contiguous(), idx.contiguous(), bounds.contiguous(), klen.contiguous()
+    P, Kmax = idx.shape
+    viol = torch.empty(P, device=idx.device, dtype=torch.int32)
+    obj = torch.empty(P, device=idx.device, dtype=torch.float64)
+    score = torch.empty(P, device=idx.device, dtype=torch.float64)
+    check(lib().gnnpn_ml2pn_score_f64(qos.data_ptr(), qos.shape[0], idx.data_ptr(), idx.stride(0), klen.data_ptr(),
+                                      bounds.data_ptr(), P, Kmax, viol.data_ptr(), obj.data_ptr(), score.data_ptr(),
+                                      _stream()), "ml2pn_score")
+    return viol, obj, score
+
+
 def woa_search(qos, base, size, klen, bounds, pops, best_fit, best_ref, best_vec, seeds, traj):
     """Device-resident ESWOA search (``gnnpn_woa_search_f64``): all tensors CUDA, updated in place (see the header)."""
     I, P, KM = pops.shape

@@ -40,28 +40,70 @@ def shard(batch: torch.Tensor) -> torch.Tensor:
     return batch[lo:hi] if _on() else batch
 
 
-def global_mean(x: torch.Tensor) -> torch.Tensor:
-    """Mean over the instances of ALL ranks (sum and count all-reduced, so ragged shards are weighted right)."""
+def _collective_device() -> torch.device:
+    """Tensors handed to a collective must live where the backend works: CUDA for NCCL, host for gloo."""
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def global_mean_count(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(mean, count) over the instances of ALL ranks: sum and count are all-reduced, so ragged -- even empty -- shards
+    are weighted by their size."""
     s = torch.stack([x.sum().float(), torch.tensor(float(x.numel()), device=x.device)])
     if _on():
         dist.all_reduce(s)
-    return s[0] / s[1]
+    return s[0] / s[1], s[1]
 
 
-def allreduce_gradients(params: Iterable[torch.nn.Parameter]) -> None:
-    """Average gradients across ranks through one flat bucket (latency-bound message: one collective)."""
+def global_mean(x: torch.Tensor) -> torch.Tensor:
+    return global_mean_count(x)[0]
+
+
+def broadcast_parameters(params: Iterable[torch.Tensor], src: int = 0) -> None:
+    """Make every replica start from rank ``src``'s weights (one flat broadcast)."""
     if not _on():
         return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
+    ps = [p for p in params]
+    if not ps:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    with torch.no_grad():
+        flat = torch.cat([p.detach().reshape(-1) for p in ps])
+        dist.broadcast(flat, src)
+        off = 0
+        for p in ps:
+            p.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+
+def shared_seed(src: int = 0) -> int:
+    """One random 63-bit seed, drawn on rank ``src`` and broadcast: every rank shuffles the data set identically and
+    ``shard`` then hands each rank its own slice of the SAME permutation."""
+    t = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
+    if _on():
+        t = t.to(_collective_device())
+        dist.broadcast(t, src)
+    return int(t.item())
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], average: bool = True) -> None:
+    """Combine gradients across ranks through one flat bucket (latency-bound message: one collective).  Parameters
+    without a gradient contribute zeros (a rank whose shard was empty still takes part).  ``average=False`` sums --
+    for losses already normalised by the GLOBAL instance count (ragged shards weighted right)."""
+    if not _on():
+        return
+    ps = [p for p in params if p.requires_grad]
+    if not ps:
+        return
+    for p in ps:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
     dist.all_reduce(flat)
-    flat /= world_size()
+    if average:
+        flat /= world_size()
     off = 0
-    for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
+    for p in ps:
+        p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+        off += p.numel()
 
 
 def gather_concat(x: torch.Tensor) -> torch.Tensor:

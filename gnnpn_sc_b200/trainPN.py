@@ -52,7 +52,13 @@ class TrainModel:
         self.train_dataset, self.val_dataset = train_dataset, val_dataset
         self.batch_size, self.threshold, self.epochDiv, self.beta = batch_size, threshold, epochDiv, beta
         self.USE_CUDA, self.dataset, self.serCategory = USE_CUDA, dataset, serCategory
-        self.train_loader = DataLoader(train_dataset, batch_size=batch_size, shuffle=True, num_workers=0)
+        # data parallel: replicas must start identical and shuffle identically (each rank then takes its slice of the
+        # same batch, parallel.shard) -- weights broadcast from rank 0, loader generator seeded with a shared seed
+        parallel.broadcast_parameters(model.actor.parameters())
+        self._loader_gen = torch.Generator()
+        self._loader_gen.manual_seed(parallel.shared_seed())
+        self.train_loader = DataLoader(train_dataset, batch_size=batch_size, shuffle=True, num_workers=0,
+                                       generator=self._loader_gen)
         self.val_loader = DataLoader(val_dataset, batch_size=batch_size, shuffle=False, num_workers=0)
         self.actor_optim = optim.Adam(model.actor.parameters(), lr=lr)
         self.max_grad_norm = max_grad_norm
@@ -62,23 +68,33 @@ class TrainModel:
         self.level = level
 
     def reinforce_step(self, inputs, labs, baseline, first):
-        """One REINFORCE update; returns (mean reward, new baseline)."""
-        latent = None
-        if self.low_model is not None:
-            _, _, _, _, latent = self.low_model(inputs, labs, sample="greedy", training="SL")
-        R, probs, actions, actions_idxs, _ = self.model(inputs, labs, latent)
-        r_mean = parallel.global_mean(R)
-        baseline = r_mean if first else baseline * self.beta + (1. - self.beta) * r_mean
-        advantage = R - baseline
-        logprobs = 0
-        for prob in probs:
-            logprobs = logprobs + torch.log(prob)
-        logprobs = torch.where(logprobs < -1000, torch.zeros_like(logprobs), logprobs)
-        actor_loss = (advantage * logprobs).mean()
+        """One REINFORCE update; returns (mean reward, new baseline).  With several ranks ``inputs`` is this rank's
+        shard (possibly empty for a ragged last batch): the loss is normalised by the GLOBAL batch size and gradients
+        are summed, so the update equals the single-process one on the whole batch."""
+        params = list(self.model.actor.parameters())
         self.actor_optim.zero_grad()
-        actor_loss.backward()
-        parallel.allreduce_gradients(self.model.actor.parameters())
-        torch.nn.utils.clip_grad_norm_(self.model.actor.parameters(), float(self.max_grad_norm), norm_type=2)
+        if inputs.shape[0]:
+            latent = None
+            if self.low_model is not None:
+                # the reference back-propagates into PNLow's graph but never uses that gradient
+                # (trainPNHigh.py:83, optimiser over model.actor only): decode it without autograd
+                with torch.no_grad():
+                    _, _, _, _, latent = self.low_model(inputs, labs, sample="greedy", training="SL")
+            R, probs, actions, actions_idxs, _ = self.model(inputs, labs, latent)
+        else:
+            R, probs = torch.zeros(0, device=inputs.device), []
+        r_mean, n_global = parallel.global_mean_count(R)
+        baseline = r_mean if first else baseline * self.beta + (1. - self.beta) * r_mean
+        if inputs.shape[0]:
+            advantage = R - baseline
+            logprobs = 0
+            for prob in probs:
+                logprobs = logprobs + torch.log(prob)
+            logprobs = torch.where(logprobs < -1000, torch.zeros_like(logprobs), logprobs)
+            actor_loss = (advantage * logprobs).sum() / n_global              # == .mean() on one process
+            actor_loss.backward()
+        parallel.allreduce_gradients(params, average=False)
+        torch.nn.utils.clip_grad_norm_(params, float(self.max_grad_norm), norm_type=2)
         self.actor_optim.step()
         return r_mean, baseline.detach()
 
@@ -89,8 +105,6 @@ class TrainModel:
         for epoch in range(1, n_epochs + 1):
             for batch_id, (sample_batch, labs) in enumerate(self.train_loader):
                 self.model.train()
-                if self.low_model is not None:
-                    self.low_model.train()
                 inputs = parallel.shard(sample_batch).cuda(non_blocking=True)
                 r_mean, baseline = self.reinforce_step(inputs, labs, baseline, batch_id == 0)
                 self.train_tour.append(float(r_mean))
@@ -135,7 +149,8 @@ class TrainModel:
             json.dump(allActions, f)
         if not high:
             with open(os.path.join(self.out_dir, f"allR{n}.txt"), "w") as f:
-                json.dump(allR, f)
+                if allR:                                                    # trainPNLow.py:123-141
+                    json.dump({"quality": allR, "averageQ": sum(allR) / len(allR)}, f)
         print(time.time() - t0)
         with open(os.path.join(self.out_dir, f"val{n}.txt"), "w") as f:
             json.dump(self.val_tour, f)

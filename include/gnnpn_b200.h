@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNNPN_ABI_VERSION 5
+#define GNNPN_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define GNNPN_API __attribute__((visibility("default")))
@@ -181,6 +181,13 @@ GNNPN_API int gnnpn_pn_reward_f32(const float* inputs, const int32_t* idx, int64
 GNNPN_API int gnnpn_woa_fitness_f64(const double* qos, int64_t n_services, const int32_t* idx, int64_t idx_ld,
                           const int32_t* klen, const double* bounds, int64_t P, int Kmax,
                           int32_t* viol_out, double* obj_out, double* fit_out, void* stream);
+
+/* `ML2PN.calc` (src/ML2PN.py:6-12) for a batch of compositions, float64 in numpy's operation order: same layout as
+ * gnnpn_woa_fitness_f64, but the objective is 0.5*(np.average(q0) + 1 - np.min(q1)) -- the mean runs over ALL klen[p]
+ * picks, not over those with q0 > 0 -- and score = obj + #violated global constraints. */
+GNNPN_API int gnnpn_ml2pn_score_f64(const double* qos, int64_t n_rows, const int32_t* idx, int64_t idx_ld,
+                          const int32_t* klen, const double* bounds, int64_t P, int Kmax,
+                          int32_t* viol_out, double* obj_out, double* score_out, void* stream);
 
 /* Device-resident ESWOA search (src/baselines/WOA.py:107-162): one CTA per instance, one thread per whale, all
  * `iters` iterations in one launch, same sequential semantics as the reference's loop (in-order best-so-far replay,

@@ -63,6 +63,51 @@ def test_data_parallel_step_equals_single_process(tmp_path):
     assert torch.equal(got["gathered"], x[:, 0])
 
 
+def _ragged_worker(rank, world, port, out, n):
+    """The trainer's recipe (trainPN.TrainModel.reinforce_step): different initial weights and RNG state per rank,
+    a batch of ``n`` rows that does not divide by the world size (n = 1: rank 1's shard is EMPTY)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                           # replicas start DIFFERENT ...
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    parallel.broadcast_parameters(model.parameters())       # ... and are made identical
+    seed = parallel.shared_seed()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, 6, generator=g)
+    R = torch.randn(n, generator=g)
+    xs, Rs = parallel.shard(x), parallel.shard(R)
+    r_mean, n_global = parallel.global_mean_count(Rs)
+    if xs.shape[0]:
+        loss = ((Rs - r_mean) * model(xs).squeeze(1)).sum() / n_global
+        loss.backward()
+    parallel.allreduce_gradients(list(model.parameters()), average=False)
+    flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    w0 = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    torch.save({"grad": flat, "r_mean": r_mean, "w0": w0, "seed": seed, "n_local": xs.shape[0]}, f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [7, 1])
+def test_ragged_and_empty_shards_equal_single_process(tmp_path, n):
+    out = str(tmp_path / "ragged.pt")
+    mp.spawn(_ragged_worker, args=(2, _free_port(), out, n), nprocs=2, join=True)
+    a, b = torch.load(out + ".0"), torch.load(out + ".1")
+    assert a["n_local"] + b["n_local"] == n and (n != 1 or b["n_local"] == 0)
+    assert torch.equal(a["w0"], b["w0"])                    # broadcast: replicas identical
+    assert a["seed"] == b["seed"]
+    assert torch.equal(a["grad"], b["grad"])
+    torch.manual_seed(100)                                   # rank 0's initial weights
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, 6, generator=g)
+    R = torch.randn(n, generator=g)
+    loss = ((R - R.mean()) * model(x).squeeze(1)).mean()
+    loss.backward()
+    want = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert torch.allclose(a["r_mean"], R.mean(), atol=1e-7)
+    assert torch.allclose(a["grad"], want, atol=1e-6)       # global-count weighting: ragged shards exact
+
+
 def test_main_reads_ini_positionally():
     import configparser
     import main

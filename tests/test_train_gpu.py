@@ -92,20 +92,20 @@ def test_pnlow_then_pnhigh_trainers_and_ml2pn(tmp_path):
     # PNLow's weights are not stepped by PNHigh training (only model.actor is in the optimiser, trainPNHigh.py:62)
     after = th.low_model.state_dict()
     assert all(torch.equal(before[k].cpu(), after[k].cpu()) for k in before)
-    # ML2PN scoring of the saved picks == oracle objective (+ violations)
+    # ML2PN scoring of the saved picks == ML2PN.calc restated (oracle/ml2pn_oracle.py), float64 EXACT; a pick with
+    # q0 == 0 is injected: ML2PN.calc averages over all real picks (np.average), unlike modelPN.calc
     from gnnpn_sc_b200 import ML2PN
+    from oracle import ml2pn_oracle as mo
     x = torch.tensor(data[0])[48:, :, 1:]                                  # validation quarter
-    cons = x[:, 0, 4:8].numpy()
+    cons = x[:, 0, 4:8].double().numpy()
+    acts_h[1][0][0] = 0.0
     got = ML2PN.composition_scores(acts_h, K, cons)
-    a = np.asarray(acts_h, dtype=np.float32)                                # [K, n, 8]
-    for i in range(a.shape[1]):
-        rows = a[:, i, :]
-        real = rows[rows[:, :4].sum(axis=1) != 3]
-        obj = 0.5 * (np.average(real[:, 0]) + 1 - np.min(real[:, 1]))
-        for j, (lo, hi) in enumerate(((cons[i, 0], cons[i, 1]), (cons[i, 2], cons[i, 3]))):
-            pr = np.cumprod(real[:, 2 + j])[-1]
-            obj += float(pr < lo or pr > hi)
-        assert abs(got[i] - obj) < 1e-6
+    want = mo.scores(acts_h, K, cons.tolist())
+    assert np.array_equal(got, want)
+    with open(os.path.join(root, "solutions", "PNLow", "toy", "allR1.txt")) as f:
+        allR = json.load(f)                                                # trainPNLow.py:123-141
+    assert set(allR) == {"quality", "averageQ"} and len(allR["quality"]) == 16
+    assert allR["averageQ"] == sum(allR["quality"]) / 16
 
 
 def test_reinforce_step_reduces_loss_surrogate():
