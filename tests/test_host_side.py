@@ -18,7 +18,9 @@ def test_library_exports_every_declared_symbol():
     assert declared, "header parse failed"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     L = _lib.lib()                      # CDLL + getattr of every symbol; no compute without a GPU
-    assert L.gnnpn_abi_version() == 5
+    with open(os.path.join(ROOT, "include", "gnnpn_b200.h")) as f:
+        version = int(re.search(r"#define GNNPN_ABI_VERSION (\d+)", f.read()).group(1))
+    assert L.gnnpn_abi_version() == version
     assert L.gnnpn_error_string(-2) == b"unsupported shape"
     assert L.gnnpn_pn_packed_lstm_floats(256, 8) == (256 + 32 + 2) * 1024 + 2 * 1024 * 288 + 1024 * 320   # FFMA block, tf32 hi/lo, fp16 hi/lo (halfs)
     # argument errors are detected before any CUDA call, so they are testable on a CPU box
@@ -111,5 +113,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    installed = os.path.exists(os.path.join(root, "baseline", "_ref", "src", "models", "modelPN.py"))
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == ("reference" if installed else "port")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"] == "qws_greedy_pnlow_pnhigh_decode"
