@@ -210,12 +210,15 @@ def run_ours(args):
     enc_w_hi, dec_w_hi = high.actor._packed_weights()
 
     # persistent device buffers for the HBM-resident loop (no allocation inside the timed region)
-    enc_out = torch.empty(n, L_SEQ, HID, device=dev)
+    ws = ops.pn_workspace(n, HID, dev, args.kernel)
+    # encodings layout the dispatcher wants for this batch: blocked (pointer dots fused into the decoder's cell
+    # epilogue) when the batch runs on the persistent CTA-pair scan
+    layout = ops.pn_enc_layout(n, L_SEQ, FEAT, K_TASKS, N_CAND, ws is not None)
+    enc_out = ops.enc_out_empty(n, L_SEQ, HID, layout, dev)
     c = torch.empty(n, HID, device=dev)
     bufs = [(torch.empty(n, K_TASKS, HID, device=dev), torch.empty(K_TASKS, n, device=dev, dtype=torch.int32),
              torch.empty(n, L_SEQ, device=dev), torch.empty(n, L_SEQ, device=dev)) for _ in range(2)]
-    ws = ops.pn_workspace(n, HID, dev, args.kernel)
-    enc_ev = []
+    enc_ev, dec_ev = [], []
 
     def device_step(record: bool):
         lat = None
@@ -223,11 +226,16 @@ def run_ours(args):
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            ops.lstm_encode(x, ew, HID, enc_out, c, workspace=ws)
+            ops.lstm_encode(x, ew, HID, enc_out, c, workspace=ws, layout=layout)
             if record:
                 e1.record()
                 enc_ev.append((e0, e1))
-            _, idx, wl, _ = ops.pn_decode_greedy(x, enc_out, c, dw, K_TASKS, N_CAND, latent_win=lat, out=bufs[lvl], workspace=ws)
+            _, idx, wl, _ = ops.pn_decode_greedy(x, enc_out, c, dw, K_TASKS, N_CAND, latent_win=lat, out=bufs[lvl],
+                                                 workspace=ws, enc_layout=layout)
+            if record:
+                e2 = torch.cuda.Event(enable_timing=True)
+                e2.record()
+                dec_ev.append((e1, e2))
             lat = wl
         return ops.pn_reward(x, idx)[2], idx
 
@@ -268,7 +276,8 @@ def run_ours(args):
     ms_total = timed(lambda: device_step(True), args.steps)
     launches = _lib.launch_count() - launches0
     enc_launch_ms = sum(a.elapsed_time(b) for a, b in enc_ev) / len(enc_ev)        # avg encoder-scan launch, ms
-    seq_on = args.kernel == "tc" and (int(os.environ.get("GNNPN_SEQ", "3")) & 1)
+    dec_launch_ms = sum(a.elapsed_time(b) for a, b in dec_ev) / len(dec_ev)        # avg fused-decode launch, ms
+    seq_on = args.kernel == "tc" and (ops.get_option("persistent") & 1)
     enc_ms = enc_launch_ms / L_SEQ                                                 # per recurrence step
 
     e2e_steps(max(1, min(args.warmup, 2)))
@@ -281,7 +290,7 @@ def run_ours(args):
     if rank == 0:
         nb = 128
         xs = x[:nb].contiguous()
-        enc_s, c_s = torch.empty(nb, L_SEQ, HID, device=dev), torch.empty(nb, HID, device=dev)
+        c_s = torch.empty(nb, HID, device=dev)
         bufs_s = [(torch.empty(nb, K_TASKS, HID, device=dev), torch.empty(K_TASKS, nb, device=dev, dtype=torch.int32),
                    torch.empty(nb, L_SEQ, device=dev), torch.empty(nb, L_SEQ, device=dev)) for _ in range(2)]
         ws_s = ops.pn_workspace(nb, HID, dev, args.kernel)
@@ -289,16 +298,16 @@ def run_ours(args):
         def small_step():
             lat = None
             for lvl, (ew, dw) in enumerate(((enc_w_lo, dec_w_lo), (enc_w_hi, dec_w_hi))):
-                ops.lstm_encode(xs, ew, HID, enc_s, c_s, workspace=ws_s)
-                _, idx_s, lat, _ = ops.pn_decode_greedy(xs, enc_s, c_s, dw, K_TASKS, N_CAND, latent_win=lat, out=bufs_s[lvl], workspace=ws_s)
+                ops.lstm_encode(xs, ew, HID, enc_s, c_s, workspace=ws_s, layout=lay_s)
+                _, idx_s, lat, _ = ops.pn_decode_greedy(xs, enc_s, c_s, dw, K_TASKS, N_CAND, latent_win=lat,
+                                                        out=bufs_s[lvl], workspace=ws_s, enc_layout=lay_s)
             return ops.pn_reward(xs, idx_s)[2]
 
         small = {"instances": nb}
-        for key, mode in (("ms", None), ("ms_cta_pair_scan", "0")):
-            if mode is None:
-                os.environ.pop("GNNPN_COLSPLIT", None)
-            else:
-                os.environ["GNNPN_COLSPLIT"] = mode
+        for key, mode in (("ms", -1), ("ms_cta_pair_scan", 0)):
+            ops.set_option("scan", mode)
+            lay_s = ops.pn_enc_layout(nb, L_SEQ, FEAT, K_TASKS, N_CAND, ws_s is not None)
+            enc_s = ops.enc_out_empty(nb, L_SEQ, HID, lay_s, dev)
             for _ in range(3):
                 small_step()
             torch.cuda.synchronize()
@@ -309,7 +318,7 @@ def run_ours(args):
             t1.record()
             torch.cuda.synchronize()
             small[key] = t0.elapsed_time(t1) / 10
-        os.environ.pop("GNNPN_COLSPLIT", None)
+        ops.set_option("scan", -1)
         small["instances_per_s"] = nb / (small["ms"] * 1e-3)
 
     # second half of BASELINE.json's metric: CSR aggregation GB/s against the HBM peak (one point of the sweep in

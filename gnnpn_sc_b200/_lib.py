@@ -28,10 +28,15 @@ SIGNATURES = {
     "gnnpn_launch_count": (C.c_uint64, []),
     "gnnpn_pn_packed_lstm_floats": (C.c_size_t, [_i, _i]),
     "gnnpn_pn_pack_lstm_f32": (_i, [_p] * 7 + [_i, _i, _p, _p]),
-    "gnnpn_lstm_encode_f32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p, C.c_size_t, _p]),
+    "gnnpn_set_option": (_i, [C.c_char_p, _i]),
+    "gnnpn_get_option": (_i, [C.c_char_p, C.POINTER(_i)]),
+    "gnnpn_pn_enc_layout": (_i, [_i64, _i, _i, _i, _i, _i]),
+    "gnnpn_pn_enc_out_floats": (C.c_size_t, [_i64, _i, _i, _i]),
+    "gnnpn_pn_enc_to_rowmajor_f32": (_i, [_p, _i64, _i, _i, _p, _p]),
+    "gnnpn_lstm_encode_f32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p, C.c_size_t, _i, _p]),
     "gnnpn_pn_workspace_bytes": (C.c_size_t, [_i64, _i]),
     "gnnpn_pn_decode_greedy_f32": (_i, [_p, _p, _p, _p, _f, _p, _i, _p, _i, _f, _i64, _i, _i, _i, _i, _i,
-                                        _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+                                        _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _i, _p]),
     "gnnpn_pn_att_block_floats": (C.c_size_t, [_i]),
     "gnnpn_pn_decode_general_workspace_bytes": (C.c_size_t, [_i64, _i, _i, _i, _i, _i, _i]),
     "gnnpn_pn_decode_general_f32": (_i, [_p, _p, _p, _p, _f, _p, _i, _p, _i, _i, _f, _i64, _i, _i, _i, _i, _i,
@@ -85,6 +90,17 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib().gnnpn_error_string(rc).decode()
         raise GnnpnError(f"{what or 'gnnpn call'} failed: {msg} (code {rc})")
+
+
+def set_option(name: str, value: int) -> None:
+    """``gnnpn_set_option``: "scan" (-1 auto / 0 CTA-pair / 1 column-split), "scan_groups", "persistent", "prof"."""
+    check(lib().gnnpn_set_option(name.encode(), int(value)), f"set_option({name})")
+
+
+def get_option(name: str) -> int:
+    v = _i(0)
+    check(lib().gnnpn_get_option(name.encode(), C.byref(v)), f"get_option({name})")
+    return int(v.value)
 
 
 def launch_count() -> int:

@@ -1,10 +1,39 @@
 // Library-wide C ABI plumbing: version, error strings, launch counter, GEMM dispatch,
 // host-buffer convenience entry for the PNLow -> PNHigh greedy decode.
+#include <stdlib.h>
+#include <string.h>
 #include <vector>
 #include "common.cuh"
+#include "options.cuh"
 
 namespace gnnpn {
 std::atomic<uint64_t> g_launch_count{0};
+
+// initial option values come from the environment, read once at load time
+static void env_int(const char* name, std::atomic<int>& dst) {
+  const char* e = getenv(name);
+  if (e && *e) dst.store(atoi(e), std::memory_order_relaxed);
+}
+Options& options() {
+  static Options* o = [] {
+    Options* x = new Options();
+    env_int("GNNPN_COLSPLIT", x->scan);
+    env_int("GNNPN_COLSPLIT_G", x->scan_groups);
+    env_int("GNNPN_SEQ", x->persistent);
+    env_int("GNNPN_SEQ_PROF", x->prof);
+    return x;
+  }();
+  return *o;
+}
+static std::atomic<int>* option_slot(const char* name) {
+  if (!name) return nullptr;
+  Options& o = options();
+  if (!strcmp(name, "scan")) return &o.scan;
+  if (!strcmp(name, "scan_groups")) return &o.scan_groups;
+  if (!strcmp(name, "persistent")) return &o.persistent;
+  if (!strcmp(name, "prof")) return &o.prof;
+  return nullptr;
+}
 int launch_gemm_ffma(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                      const float* scale, const float* shift, int act, float* C, int64_t ldc, int64_t M, int N,
                      int K, cudaStream_t st);
@@ -27,6 +56,20 @@ extern "C" {
 int gnnpn_abi_version(void) { return GNNPN_ABI_VERSION; }
 
 uint64_t gnnpn_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
+
+int gnnpn_set_option(const char* name, int value) {
+  std::atomic<int>* s = option_slot(name);
+  if (!s) return GNNPN_EUNSUPPORTED;
+  s->store(value, std::memory_order_relaxed);
+  return GNNPN_OK;
+}
+
+int gnnpn_get_option(const char* name, int* value) {
+  std::atomic<int>* s = option_slot(name);
+  if (!s || !value) return s ? GNNPN_ENULL : GNNPN_EUNSUPPORTED;
+  *value = s->load(std::memory_order_relaxed);
+  return GNNPN_OK;
+}
 
 const char* gnnpn_error_string(int code) {
   switch (code) {
@@ -105,7 +148,7 @@ int gnnpn_pn_greedy_low_high_host(const float* inputs_host, int64_t n, int L, in
   CUDA_TRY(cudaStreamCreate(&st));
   CUDA_TRY(cudaMalloc(&d_pk, 4 * pfloats * sizeof(float)));   // enc/dec blocks of low and high
   CUDA_TRY(cudaMalloc(&d_in, chunk * L * F * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&d_enc, chunk * (size_t)L * H * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d_enc, gnnpn_pn_enc_out_floats(chunk, L, H, GNNPN_ENC_BLOCKED128) * sizeof(float)));
   CUDA_TRY(cudaMalloc(&d_c, chunk * H * sizeof(float)));
   CUDA_TRY(cudaMalloc(&d_dech, chunk * (size_t)K * H * sizeof(float)));
   CUDA_TRY(cudaMalloc(&d_wl_lo, chunk * L * sizeof(float)));
@@ -121,14 +164,15 @@ int gnnpn_pn_greedy_low_high_host(const float* inputs_host, int64_t n, int L, in
                            cudaMemcpyHostToDevice, st));
   for (int64_t s = 0; s < n; s += chunk) {
     const int64_t m = (n - s) < chunk ? (n - s) : chunk;
+    const int layout = gnnpn_pn_enc_layout(m, L, F, K, N, 1);
     CUDA_TRY(cudaMemcpyAsync(d_in, inputs_host + s * L * F, m * L * F * sizeof(float), cudaMemcpyHostToDevice, st));
     for (int level = 0; level < 2; ++level) {
       const float* pk = d_pk + (size_t)level * 2 * pfloats;
-      RC_TRY(gnnpn_lstm_encode_f32(d_in, m, L, F, H, pk, d_enc, d_c, d_ws, ws_bytes, st));
+      RC_TRY(gnnpn_lstm_encode_f32(d_in, m, L, F, H, pk, d_enc, d_c, d_ws, ws_bytes, layout, st));
       RC_TRY(gnnpn_pn_decode_greedy_f32(d_in, d_enc, d_c, level ? d_wl_lo : nullptr, alpha, pk + pfloats,
                                         GNNPN_ATT_DOT, nullptr, use_tanh, C, m, L, F, H, K, N, d_dech,
                                         level ? d_idx_hi : d_idx_lo, level ? d_wl_hi : d_wl_lo, d_wp, nullptr,
-                                        nullptr, d_ws, ws_bytes, st));
+                                        nullptr, d_ws, ws_bytes, layout, st));
     }
     RC_TRY(gnnpn_pn_reward_f32(d_in, d_idx_hi, m, L, F, K, 0, nullptr, nullptr, d_rew, st));
     // device layout is [K, m]; the host result is [K, n]: copy row by row

@@ -7,6 +7,7 @@
 #include "tc_lstm.cuh"
 #include "tc_seq.cuh"
 #include "pointer.cuh"
+#include "options.cuh"
 
 namespace gnnpn {
 namespace {
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) pointer_step_dot_kernel(
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= pa.n) return;
   const float4* qp = reinterpret_cast<const float4*>(q + b * q_ld);
-  const float4 q0 = __ldg(qp + lane), q1 = __ldg(qp + 32 + lane);
+  const float4 q0 = __ldg(qp + 2 * lane), q1 = __ldg(qp + 2 * lane + 1);     // the lane's floats [8*lane, 8*lane+8)
   const int fed = pointer_step_warp(pa, k, b, q0, q1, lane);
   if (a_hi_next && lane < F) {
     // tensor-core path: the chosen candidate's raw row becomes columns [H, H+F) of the next step's A operand
@@ -130,11 +131,11 @@ __global__ void __launch_bounds__(256) full_logits_dot_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int l = l0 + warp; l < min(L, l0 + 32); l += 8) {
     const float4* rp = reinterpret_cast<const float4*>(enc_out + (b * L + l) * (int64_t)kH);
-    const float4 r0 = __ldg(rp + lane), r1 = __ldg(rp + 32 + lane);
+    const float4 r0 = __ldg(rp + 2 * lane), r1 = __ldg(rp + 2 * lane + 1);   // canonical dot: lane owns floats [8*lane, +8)
     for (int k = 0; k < K; ++k) {
-      const float4 a0 = reinterpret_cast<const float4*>(sq + k * kH)[lane];
-      const float4 a1 = reinterpret_cast<const float4*>(sq + k * kH)[32 + lane];
-      const float d = warp_sum(dot8(r0, r1, a0, a1));
+      const float4 a0 = reinterpret_cast<const float4*>(sq + k * kH)[2 * lane];
+      const float4 a1 = reinterpret_cast<const float4*>(sq + k * kH)[2 * lane + 1];
+      const float d = dot_reduce(dot8(r0, r1, a0, a1), lane);
       if (lane == 0) out[((int64_t)k * n + b) * L + l] = use_tanh ? C * tanhf(d) : d;
     }
   }
@@ -221,14 +222,22 @@ __global__ void reward_kernel(const float* __restrict__ inputs, const int32_t* _
   }
 }
 
-// GNNPN_SEQ: bit 0 = persistent encoder scan, bit 1 = persistent fused decode (default 3); 0 selects the
-// one-launch-per-step kernels (kept as the A/B reference for the persistent ones)
-int seq_mode() {
-  static const int m = [] {
-    const char* e = getenv("GNNPN_SEQ");
-    return e ? atoi(e) : 3;
-  }();
-  return m;
+// option "persistent": bit 0 = persistent encoder scan, bit 1 = persistent fused decode (default 3); 0 selects the
+// one-launch-per-step kernels (kept for inputs wider than 8 columns and as the A/B reference)
+int seq_mode() { return options().persistent.load(std::memory_order_relaxed); }
+
+// blocked encodings -> row-major [n, L, kH]; one thread per float4 of the output (coalesced writes)
+__global__ void enc_unblock_kernel(const float* __restrict__ blk, int64_t n, int L, float* __restrict__ out) {
+  const int64_t total = n * L * (kH / 4);
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(e % (kH / 4));
+    const int64_t bl = e / (kH / 4);
+    const int l = (int)(bl % L);
+    const int64_t b = bl / L;
+    const int u = c4 * 4, nt = u >> 5, g = (u >> 3) & 3, half = (u >> 2) & 1;
+    const int64_t src = ((((b >> 7) * L + l) * 8 + nt) * 4 + g) * 1024 + half * 512 + (b & 127) * 4;
+    reinterpret_cast<float4*>(out)[e] = __ldg(reinterpret_cast<const float4*>(blk + src));
+  }
 }
 
 }  // namespace
@@ -258,9 +267,33 @@ int gnnpn_pn_pack_lstm_f32(const float* w_ih, const float* w_hh, const float* b_
   return after_launch();
 }
 
+int gnnpn_pn_enc_layout(int64_t n, int L, int in_features, int K, int N, int has_workspace) {
+  (void)L; (void)K;
+  if (!has_workspace || seq_mode() != 3 || in_features < 1 || in_features > 8) return GNNPN_ENC_ROWMAJOR;
+  if (!tc_seq_fused_decode_supported(N)) return GNNPN_ENC_ROWMAJOR;
+  if (tc_colsplit_wanted(n) || tc_colsplit_wanted_encode(n)) return GNNPN_ENC_ROWMAJOR;   // small batch: cluster scan
+  return GNNPN_ENC_BLOCKED128;
+}
+
+size_t gnnpn_pn_enc_out_floats(int64_t n, int L, int hidden, int layout) {
+  if (n < 0 || L < 1 || hidden != kH) return 0;
+  const int64_t rows = layout == GNNPN_ENC_BLOCKED128 ? (n + 127) / 128 * 128 : n;
+  return (size_t)rows * L * kH;
+}
+
+int gnnpn_pn_enc_to_rowmajor_f32(const float* enc_blocked, int64_t n, int L, int hidden, float* enc_out, void* stream) {
+  GNNPN_REQUIRE(enc_blocked && enc_out, GNNPN_ENULL);
+  GNNPN_REQUIRE(hidden == kH && L >= 1 && n >= 0, GNNPN_ESHAPE);
+  GNNPN_REQUIRE(aligned16(enc_blocked) && aligned16(enc_out), GNNPN_EALIGN);
+  if (n == 0) return GNNPN_OK;
+  enc_unblock_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(enc_blocked, n, L, enc_out);
+  return after_launch();
+}
+
 int gnnpn_lstm_encode_f32(const float* inputs, int64_t n, int L, int in_features, int hidden,
                           const float* packed, float* enc_out, float* c_state, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+                          size_t workspace_bytes, int enc_layout, void* stream) {
+  GNNPN_REQUIRE(enc_layout == GNNPN_ENC_ROWMAJOR || enc_layout == GNNPN_ENC_BLOCKED128, GNNPN_ESHAPE);
   GNNPN_REQUIRE(inputs && packed && enc_out && c_state, GNNPN_ENULL);
   GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= kXPad && L >= 1 && n >= 0, GNNPN_ESHAPE);
   GNNPN_REQUIRE(n < (1ll << 31), GNNPN_ERANGE);
@@ -273,10 +306,12 @@ int gnnpn_lstm_encode_f32(const float* inputs, int64_t n, int L, int in_features
                   GNNPN_EALIGN);
     GNNPN_REQUIRE(workspace_bytes >= tc_lstm_workspace_bytes(n), GNNPN_EWORKSPACE);
     float* scr = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
-    SeqEncodeArgs sa{inputs, n, L, in_features, packed, enc_out, c_state, scr};
+    SeqEncodeArgs sa{inputs, n, L, in_features, packed, enc_out, c_state, scr, enc_layout};
+    if (enc_layout == GNNPN_ENC_BLOCKED128) return tc_seq_encode(sa, st);         // the CTA-pair scan owns this layout
     if (tc_colsplit_wanted_encode(n)) return tc_colsplit_encode(sa, scr, st);     // small batch: column-split cluster scan
     return tc_seq_encode(sa, st);
   }
+  GNNPN_REQUIRE(enc_layout == GNNPN_ENC_ROWMAJOR, GNNPN_EUNSUPPORTED);
   if (workspace) {
     // ---- tcgen05 recurrence, one launch per step: [h|x] kept as hi/lo pairs in two ping-pong buffers
     TcLstmPlan plan;
@@ -316,7 +351,8 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
                                int64_t n, int L, int in_features, int hidden, int K, int N,
                                float* dec_h, int32_t* idx_out, float* win_logits, float* win_probs,
                                const int32_t* forced_idx, const float* sample_uniform, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               size_t workspace_bytes, int enc_layout, void* stream) {
+  GNNPN_REQUIRE(enc_layout == GNNPN_ENC_ROWMAJOR || enc_layout == GNNPN_ENC_BLOCKED128, GNNPN_ESHAPE);
   GNNPN_REQUIRE(inputs && enc_out && c_state && packed && dec_h && idx_out && win_logits && win_probs,
                 GNNPN_ENULL);
   GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= kXPad, GNNPN_ESHAPE);
@@ -336,11 +372,14 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
                       (reinterpret_cast<uintptr_t>(dec_h) & 31u) == 0, GNNPN_EALIGN);
     SeqDecodeArgs sa{inputs, enc_out, c_state, latent_win, alpha, packed, use_tanh, C, n, L, in_features, K, N,
                      dec_h, idx_out, win_logits, win_probs, forced_idx, sample_uniform,
-                     reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023))};
+                     reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023)),
+                     enc_layout};
     GNNPN_REQUIRE(workspace_bytes >= tc_lstm_workspace_bytes(n), GNNPN_EWORKSPACE);
+    if (enc_layout == GNNPN_ENC_BLOCKED128) return tc_seq_decode(sa, st);          // fused pointer dots (CTA-pair scan)
     if (tc_colsplit_wanted(n)) return tc_colsplit_decode(sa, sa.c_scratch, st);    // small batch: column-split cluster scan
     return tc_seq_decode(sa, st);
   }
+  GNNPN_REQUIRE(enc_layout == GNNPN_ENC_ROWMAJOR, GNNPN_EUNSUPPORTED);
   TcLstmPlan plan;
   TcLstmStep ts{};
   LstmStepArgs a{};

@@ -7,7 +7,7 @@
 //   * any window width N (scale-up: N = 1000) and up to 32 raw input columns (embedding_size = 20).
 // One launch per piece and per step (LSTM cell, [query GEMM, glimpse] x n_glimpses, query GEMM, pointer); one CTA
 // per composition instance in the attention kernels.  For Dot / no glimpse / N <= 32 the pointer arithmetic is the
-// same as pointer_step_warp's (dot8 + warp_sum, fmaf latent, sequential softmax sum) -> bit-identical picks / logits.
+// same as pointer_step_warp's (canonical dot, fmaf latent, sequential softmax sum) -> bit-identical picks / logits.
 #include <math.h>
 #include <cuda_fp16.h>
 #include "lstm_step.cuh"
@@ -144,16 +144,18 @@ __global__ void __launch_bounds__(kAttThreads) pointer_general_kernel(const Poin
   __shared__ int s_pick;
   const int64_t b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Dot: canonical pointer dot (pointer.cuh), lane owns floats [8*lane, 8*lane+8); Bahdanau: float4 lane / 32+lane
   const float4* qp = reinterpret_cast<const float4*>(p.g.q + b * p.g.q_ld);
-  const float4 q0 = qp[lane], q1 = qp[32 + lane];
+  const int i0 = BAHD ? lane : 2 * lane, i1 = BAHD ? 32 + lane : 2 * lane + 1;
+  const float4 q0 = qp[i0], q1 = qp[i1];
   float4 v0 = make_float4(0, 0, 0, 0), v1 = v0;
   if (BAHD) { v0 = __ldg(reinterpret_cast<const float4*>(p.g.V) + lane); v1 = __ldg(reinterpret_cast<const float4*>(p.g.V) + 32 + lane); }
   const float* base = p.g.rows + (b * (int64_t)p.g.L + (int64_t)k * N) * kH;
   const int64_t wbase = b * (int64_t)p.g.L + (int64_t)k * N;
   for (int j = warp; j < N; j += kAttWarps) {
     const float4* rp = reinterpret_cast<const float4*>(base + (int64_t)j * kH);
-    const float4 r0 = ldg_stream(rp + lane), r1 = ldg_stream(rp + 32 + lane);
-    const float d = warp_sum(BAHD ? bahdanau8(r0, r1, q0, q1, v0, v1) : dot8(r0, r1, q0, q1));
+    const float4 r0 = ldg_stream(rp + i0), r1 = ldg_stream(rp + i1);
+    const float d = BAHD ? warp_sum(bahdanau8(r0, r1, q0, q1, v0, v1)) : dot_reduce(dot8(r0, r1, q0, q1), lane);
     if (lane == 0) {
       const float l = p.use_tanh ? p.C * tanhf(d) : d;
       p.win_logits[wbase + j] = l;

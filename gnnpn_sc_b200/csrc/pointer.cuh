@@ -33,13 +33,41 @@ struct PointerStepArgs {
 };
 // The decode step k is passed separately so that the argument block itself can stay in constant memory.
 
-// <row, q> over the 8 elements a lane owns, explicit fma chain so every kernel that forms a
-// pointer logit rounds identically (window logits == the same entries of the full logits).
+// ---- canonical pointer-logit dot product ------------------------------------------------------------------
+// Every kernel that forms a Dot pointer logit <row, q> rounds in THIS order, so window logits == the same entries of
+// the dense logits == the fused decoders' values, bit for bit, whichever kernel a batch is dispatched to:
+//   the 256 hidden units are indexed u = 32*nt + 8*g + i   (nt = 0..7 "tile", g = 0..3 "group", i = 0..7)
+//   s[nt][g] = r_u0*q_u0, then fmaf over i = 1..7                       (8 consecutive units)
+//   p[g]     = ((((s[0][g] + s[1][g]) + s[2][g]) + ... ) + s[7][g])     (sequential over the tiles)
+//   dot      = (p[0] + p[1]) + (p[2] + p[3])
+// It is the order the persistent tcgen05 decoder meets for free: its epilogue thread (instance, g) produces the h'
+// units of accumulator tile nt as exactly those 8 consecutive values (tc_seq.cu).  A warp computes one row with lane
+// l = 4*nt + g owning the 32 contiguous bytes [8l, 8l+8) of the row and of the query (one 256-bit load each).
 __device__ __forceinline__ float dot8(const float4 r0, const float4 r1, const float4 q0, const float4 q1) {
-  float s = r0.x * q0.x;
+  float s = __fmul_rn(r0.x, q0.x);
   s = fmaf(r0.y, q0.y, s); s = fmaf(r0.z, q0.z, s); s = fmaf(r0.w, q0.w, s);
   s = fmaf(r1.x, q1.x, s); s = fmaf(r1.y, q1.y, s); s = fmaf(r1.z, q1.z, s); s = fmaf(r1.w, q1.w, s);
   return s;
+}
+// s = this lane's s[nt][g] (lane = 4*nt + g)  ->  the canonical dot, in every lane
+__device__ __forceinline__ float dot_reduce(float s, int lane) {
+  const int g = lane & 3;
+  float p = __shfl_sync(0xffffffffu, s, g);
+#pragma unroll
+  for (int nt = 1; nt < 8; ++nt) p = __fadd_rn(p, __shfl_sync(0xffffffffu, s, 4 * nt + g));
+  const float a = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 1));          // p0+p1 | p2+p3 (commutative: both lanes agree)
+  return __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 2));
+}
+// the lane's 8 consecutive floats of a 256-float row: streaming (read-once) and coherent variants
+__device__ __forceinline__ void ldg_row8_stream(const float* row, int lane, float4& a, float4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(row + 8 * lane));
+}
+__device__ __forceinline__ void ld_row8(const float* row, int lane, float4& a, float4& b) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(row + 8 * lane) : "memory");
 }
 
 // Second half of the pointer step, from the window logit pre-activations: lane j (< N) holds d_j = <row_j, q> in
@@ -93,7 +121,7 @@ __device__ __forceinline__ int pointer_finish_warp(const PointerStepArgs& a, int
   return a.forced ? a.forced[(int64_t)k * a.n + b] : k * N + best_j;
 }
 
-// q0/q1: the lane's 8 query elements (float4 index lane and 32+lane of the 256-float query).
+// q0/q1: the lane's 8 query elements (floats [8*lane, 8*lane+8) of the 256-float query).
 // Returns, in every lane, the position fed to the next decoder step (the pick, or forced[b]).
 __device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int k, int64_t b, const float4 q0,
                                                  const float4 q1, int lane) {
@@ -106,14 +134,14 @@ __device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int k
     for (int u = 0; u < 4; ++u) {
       part[u] = 0.f;
       if (j0 + u < N) {
-        const float4* rp = reinterpret_cast<const float4*>(base + (int64_t)(j0 + u) * kH);
-        const float4 r0 = ldg_stream(rp + lane), r1 = ldg_stream(rp + 32 + lane);
+        float4 r0, r1;
+        ldg_row8_stream(base + (int64_t)(j0 + u) * kH, lane, r0, r1);
         part[u] = dot8(r0, r1, q0, q1);
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float d = warp_sum(part[u]);
+      const float d = dot_reduce(part[u], lane);
       if (lane == j0 + u) my_d = d;
     }
   }
@@ -128,7 +156,7 @@ __device__ __forceinline__ int pointer_step_warp(const PointerStepArgs& a, int k
 // instances overlap the butterfly reductions.  The logit pre-activations are parked lane-wise: instance i,
 // candidate j -> register i / IPP, lane (i % IPP) * SEG + j  (SEG = 8, 16 or 32 lanes per instance, IPP = 32 / SEG).
 // Phase 2 then runs tanh / latent / softmax / pick for IPP instances at once with SEG-wide segmented shuffles.
-// Per candidate the arithmetic is exactly that of pointer_step_warp (dot8 + warp_sum, fmaf latent, sequential
+// Per candidate the arithmetic is exactly that of pointer_step_warp (canonical dot, fmaf latent, sequential
 // softmax sum in candidate order) -> same bits.
 // `feed(i, b, fed, j)` is called by every lane of a pass with the position fed to the next step for ITS instance
 // (i = instance slot 0..7, j = lane index inside the segment); slots >= count must be ignored by the callee.
@@ -152,8 +180,8 @@ __device__ __forceinline__ void pointer_steps_batched(const PointerStepArgs& a, 
   const float* qrow = q_base + b0 * q_ld;
 #pragma unroll 1
   for (int i = 0; i < count; ++i) {
-    const float4 q0 = reinterpret_cast<const float4*>(qrow)[lane];        // coherent loads: written earlier in this
-    const float4 q1 = reinterpret_cast<const float4*>(qrow)[32 + lane];   // launch by this CTA
+    float4 q0, q1;
+    ld_row8(qrow, lane, q0, q1);                                          // coherent loads: written earlier in this launch
     const int slot = i / IPP, base = (i % IPP) * SEG;
 #pragma unroll 1
     for (int j0 = 0; j0 < N; j0 += CH) {
@@ -161,16 +189,14 @@ __device__ __forceinline__ void pointer_steps_batched(const PointerStepArgs& a, 
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
         const int j = j0 + u < N ? j0 + u : N - 1;                        // clamp: every register is always written
-        const float4* rp = reinterpret_cast<const float4*>(rows + (int64_t)j * kH);
-        r0[u] = ldg_stream(rp + lane);
-        r1[u] = ldg_stream(rp + 32 + lane);
+        ldg_row8_stream(rows + (int64_t)j * kH, lane, r0[u], r1[u]);
       }
       float part[CH];
 #pragma unroll
       for (int u = 0; u < CH; ++u) part[u] = dot8(r0[u], r1[u], q0, q1);
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
-        const float d = warp_sum(part[u]);
+        const float d = dot_reduce(part[u], lane);
         const bool mine = j0 + u < N && lane == base + j0 + u;
 #pragma unroll
         for (int r = 0; r < PASSES; ++r) dv[r] = (mine && slot == r) ? d : dv[r];   // selects: dv stays in registers

@@ -24,6 +24,7 @@
 #include "tc_lstm.cuh"
 #include "tc_seq.cuh"
 #include "tc_seq_dev.cuh"
+#include "options.cuh"
 #include "pointer.cuh"
 
 namespace gnnpn {
@@ -412,8 +413,8 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
           const int64_t b = group0 * BM + prow;
           int fed = 0;
           if (b < p.n) {                                                        // warp-uniform
-            const float4* qp = reinterpret_cast<const float4*>(p.h_out + b * p.h_out_inst_ld + (int64_t)t * kH);
-            const float4 q0 = qp[lane], q1 = qp[32 + lane];
+            float4 q0, q1;
+            ld_row8(p.h_out + b * p.h_out_inst_ld + (int64_t)t * kH, lane, q0, q1);
             fed = pointer_step_warp(p.pa, t, b, q0, q1, lane);
           }
           if (t + 1 < p.steps) {
@@ -519,10 +520,7 @@ int tc_colsplit_max_active_clusters() { return max_active_clusters(); }
 // costs ~6.6 us per wave (~7 us with two groups per cluster) against ~16.7 us (encoder) / ~37 us (fused decoder) for
 // the CTA-pair scan at any batch up to 18,944.  Encoder: one-group clusters up to 15 groups of 128, two-group clusters up to
 // 30 groups (one wave; two waves of them are slower than the pair scan); decoder: one-group clusters up to two waves.
-static int colsplit_mode() {
-  const char* e = getenv("GNNPN_COLSPLIT");              // read per call: tests and benches flip it between launches
-  return e ? atoi(e) : -1;
-}
+static int colsplit_mode() { return options().scan.load(std::memory_order_relaxed); }   // gnnpn_set_option("scan", ..)
 bool tc_colsplit_wanted(int64_t n) {                     // fused decoder
   const int mode = colsplit_mode();
   if (mode == 0) return false;
@@ -536,8 +534,8 @@ bool tc_colsplit_wanted_encode(int64_t n) {
   return ceil_div(n, cs::BM) <= 2 * (int64_t)max_active_clusters();
 }
 static int colsplit_groups_per_cluster(int64_t n) {
-  const char* e = getenv("GNNPN_COLSPLIT_G");
-  if (e && (atoi(e) == 1 || atoi(e) == 2)) return atoi(e);
+  const int g = options().scan_groups.load(std::memory_order_relaxed);
+  if (g == 1 || g == 2) return g;
   return ceil_div(n, cs::BM) > (int64_t)max_active_clusters() ? 2 : 1;
 }
 
@@ -580,7 +578,7 @@ static int launch(const float* packed, Params p, void* scratch, cudaStream_t st)
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  static const int do_prof = getenv("GNNPN_SEQ_PROF") ? atoi(getenv("GNNPN_SEQ_PROF")) : 0;
+  const int do_prof = options().prof.load(std::memory_order_relaxed);
   const unsigned grid = (unsigned)(clusters * CL);
   unsigned long long* prof = nullptr;
   if (do_prof) {

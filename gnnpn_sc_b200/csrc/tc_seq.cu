@@ -13,9 +13,23 @@
 //   * h'(t) of tiles 0..6 cannot be written over A while the MMAs of step t still read it: it is staged in the
 //     other 256 TMEM columns (tcgen05.st) and copied to shared memory once the last MMA of the step has retired.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = x producer (encoder inputs),
-// 4..19 = epilogue (TMEM lane quarter = warp & 3, column group = (warp - 4) / 4) and, in the decoder, the
-// pointer phase (each warp owns 8 instances: rows streamed per instance, softmax / pick for 4 instances at once,
-// pointer.cuh::pointer_steps_batched).
+// 4..19 = epilogue (TMEM lane quarter = warp & 3, column group = (warp - 4) / 4).
+//
+// Encodings layout (template parameter NR, SeqParams::enc_layout):
+//   NR == 0  row-major enc_out [n, L, H] (GNNPN_ENC_ROWMAJOR).  Encoder: h' tiles leave by TMA store.  Decoder: a
+//            separate pointer phase after each step's cell epilogue (each epilogue warp owns 8 instances, window rows
+//            streamed per instance, pointer.cuh::pointer_steps_batched) -- the step is MMA phase + pointer phase.
+//   NR >= 1  blocked encodings (GNNPN_ENC_BLOCKED128): per block of 128 instances
+//            [L][8 tiles][4 groups][2 halves][128 instances][4 floats], unit = 32*tile + 8*group + 4*half + i -- exactly
+//            the (thread = instance, 8 units per tile) ownership of the epilogue.  The encoder writes it with coalesced
+//            128-bit stores.  In the decoder (NR = row capacity of the window, N <= NR) the pointer dot products are
+//            FUSED INTO THE CELL EPILOGUE: when thread (instance r, group g) has produced the 8 h' units of tile nt
+//            it multiplies them into the matching 8 floats of each of the N window rows of ITS instance (a warp's
+//            load is 512 contiguous bytes; the rows were L2-prefetched two tiles ahead), in pointer.cuh's canonical
+//            order.  The window rows stream from HBM UNDER the step's MMAs; after the last tile the four group
+//            partials are combined through shared memory and one thread per instance finishes the step (C*tanh,
+//            latent, softmax, first-max pick / draw, next input row) while the tensor cores already run the h parts
+//            of the next step's first two tiles.  No separate pointer phase remains.
 // Cross-CTA mbarrier arrives use .release.cta semantics on purpose (see mbar_arrive_cluster).
 #include <stdio.h>
 #include <stdlib.h>
@@ -28,6 +42,7 @@
 #include "tc_seq.cuh"
 #include "pointer.cuh"
 #include "tc_seq_dev.cuh"
+#include "options.cuh"
 
 namespace gnnpn {
 namespace tc {
@@ -74,8 +89,7 @@ struct SeqParams {
   const float* h0; int64_t h0_ld;          // initial hidden rows or nullptr (zeros)
   float* h_out; int64_t h_out_inst_ld;     // step t of instance m at h_out + m*ld + t*kH
   PointerStepArgs pa;      // decoder only
-  int rotate;
-  int dec_flags;          // bit 1: batched two-phase pointer step (default); 0: one instance at a time (A/B reference)
+  int enc_layout;          // GNNPN_ENC_ROWMAJOR / GNNPN_ENC_BLOCKED128 of h_out (encoder) or pa.enc_out (decoder)
   unsigned long long* prof; // debug (GNNPN_SEQ_PROF): per-CTA wait-cycle counters, 16 per CTA, or nullptr
   float* c_scr;            // blocked cell-state scratch, 128*kH floats per CTA (coalesced 128-bit accesses)
 };
@@ -109,20 +123,7 @@ __device__ __forceinline__ void pointer_phase(const SeqParams& p, int t, int rr0
   const int count = left <= 0 ? 0 : (left < BM / EPI_WARPS ? (int)left : BM / EPI_WARPS);
   const bool feed_next = t + 1 < p.steps;
   const float* q_base = p.h_out + (int64_t)t * kH;
-  if (!(p.dec_flags & 2)) {
-    // reference form: one instance at a time (kept for A/B runs, GNNPN_SEQ_DEC=0)
-    for (int i = 0; i < count; ++i) {
-      const float4* qp = reinterpret_cast<const float4*>(q_base + (b0 + i) * p.h_out_inst_ld);
-      const float4 q0 = qp[lane], q1 = qp[32 + lane];
-      const int fed = pointer_step_warp(pa, t, b0 + i, q0, q1, lane);
-      if (feed_next && lane < 8) {
-        const float xv = lane < p.F ? __ldg(p.inputs + ((b0 + i) * p.L + fed) * (int64_t)p.F + lane) : 0.f;
-        store_ax(sgen, rr0 + i, lane, xv);
-      }
-    }
-    return;
-  }
-  // batched form: the raw rows of the picks (next decoder inputs) of a whole pass are fetched together and written
+  // the raw rows of the picks (next decoder inputs) of a whole pass are fetched together and written
   // to the x block after the last pass, so their latency is paid once
   float pend_x[kWarpInstances];
 #pragma unroll
@@ -158,13 +159,93 @@ __device__ __forceinline__ void pointer_phase(const SeqParams& p, int t, int rr0
 }
 
 
+// ---- blocked encodings (GNNPN_ENC_BLOCKED128) ------------------------------------------------------------------
+// float offset of (block of 128 instances, position l, tile nt, group g); + half * 512 + row * 4 inside
+constexpr int64_t ENC_BLK_ROW = 8 * 4 * 2 * BM * 4;              // floats between consecutive positions l (= BM * kH)
+__host__ __device__ inline int64_t enc_blk_off(int64_t block, int L, int64_t l, int nt, int g) {
+  return (block * L + l) * ENC_BLK_ROW + (int64_t)(nt * 4 + g) * (2 * BM * 4);
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Last part of a fused decode step (NR >= 1), executed by ONE thread per instance (the group-0 epilogue thread of row
+// rr): d[j] = canonical dot <enc_out[b, kN+j], h'(k)>.  Same arithmetic, operation by operation, as
+// pointer_finish_warp (C*tanhf, fmaf latent, expf(w - max), sequential sum in candidate order, first maximal
+// probability, inverse-CDF draw) -- a thread-serial loop instead of warp shuffles.  Writes win_logits / win_probs /
+// idx_out and the x block row of the next step.
+template <int NR>
+__device__ __forceinline__ void pointer_finish_thread(const SeqParams& p, int k, int rr, int64_t b, bool ok,
+                                                      const float (&d)[NR], uint32_t sbase) {
+  const PointerStepArgs& a = p.pa;
+  const int N = a.N;
+  const int64_t wpos = (ok ? b : 0) * a.L + (int64_t)k * N;
+  float w[NR];
+  float lat[NR];
+#pragma unroll
+  for (int j = 0; j < NR; ++j) lat[j] = (a.latent_win && j < N) ? __ldg(a.latent_win + wpos + j) : 0.f;
+  const float uu = a.uniform ? __ldg(a.uniform + (int64_t)k * a.n + (ok ? b : 0)) : 0.f;
+  const int forced = a.forced ? a.forced[(int64_t)k * a.n + (ok ? b : 0)] : -1;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    w[j] = -INFINITY;
+    if (j < N) {
+      const float l = a.use_tanh ? a.C * tanhf(d[j]) : d[j];
+      if (ok) a.win_logits[wpos + j] = l;
+      w[j] = a.latent_win ? fmaf(a.alpha, lat[j], l) : l;
+      mx = fmaxf(mx, w[j]);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    if (j < N) { w[j] = expf(w[j] - mx); s += w[j]; }
+  }
+  float best = -1.f, cum = 0.f;
+  int best_j = 0, pick = -1, last_pos = 0;
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    if (j < N) {
+      const float pj = w[j] / s;
+      if (ok) a.win_probs[wpos + j] = pj;
+      if (pj > best) { best = pj; best_j = j; }            // ascending j, strict >: first maximum (torch.max tie rule)
+      cum += pj;
+      if (pj > 0.f) last_pos = j;
+      if (pick < 0 && uu < cum) pick = j;
+    }
+  }
+  if (a.uniform) best_j = pick < 0 ? last_pos : pick;
+  if (ok) a.idx_out[(int64_t)k * a.n + b] = k * N + best_j;
+  if (k + 1 < p.steps) {
+    const int fed = a.forced ? forced : k * N + best_j;
+    float xv[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) xv[f] = (ok && f < p.F) ? __ldg(p.inputs + (b * p.L + fed) * (int64_t)p.F + f) : 0.f;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = pack_h2(xv[2 * j], xv[2 * j + 1]);
+      const float2 bk = unpack_h2(hi[j]);
+      lo[j] = pack_h2(xv[2 * j] - bk.x, xv[2 * j + 1] - bk.y);
+    }
+    const uint32_t o = (uint32_t)rr * XROW_BYTES;
+    st_shared_v4(sbase + OFF_AX_HI + o, hi[0], hi[1], hi[2], hi[3]);
+    st_shared_v4(sbase + OFF_AX_HI + o + 16, hi[0], hi[1], hi[2], hi[3]);
+    st_shared_v4(sbase + OFF_AX_LO + o, lo[0], lo[1], lo[2], lo[3]);
+    st_shared_v4(sbase + OFF_AX_LO + o + 16, lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // CG = 1: one CTA per 128 instances, cta_group::1 MMAs (M=128, N=128).
 // CG = 2: CTA pair (cluster of 2 = one TPC), cta_group::2 MMAs (M=256: 128 instances per CTA, N=128): each CTA
 //         streams only HALF of every weight tile (64 of the 128 gate columns) and the tensor cores read the
 //         other half from the peer -- half the L2->SM weight traffic, half the B-operand shared-memory reads,
 //         twice the ring depth.  CTA rank 0 issues the MMAs for the pair; both CTAs run producer / epilogue.
-template <bool DEC, int CG>
+template <bool DEC, int CG, int NR>
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_constant__ CUtensorMap map_wh_lo,
                 const __grid_constant__ CUtensorMap map_wx_hi, const __grid_constant__ CUtensorMap map_wx_lo,
@@ -197,14 +278,14 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
-  // every CTA walks the 8 N tiles in a rotated order so the CTAs do not all pull the same weight lines from
-  // the same L2 slices at the same time
-  const int rot = p.rotate ? (int)(blockIdx.x & (N_TILES - 1)) : 0;
+  constexpr bool BLK = NR > 0;                         // blocked encodings (see the file header)
+  constexpr bool FUSED = DEC && BLK;                   // pointer dots fused into the cell epilogue
+  const bool cta_ok = m0 < p.n;                        // a pair's second CTA may be all padding
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_wh_hi); tma_prefetch_desc(&map_wh_lo);
     tma_prefetch_desc(&map_wx_hi); tma_prefetch_desc(&map_wx_lo);
-    if (!DEC) tma_prefetch_desc(&map_h);
+    if (!DEC && !BLK) tma_prefetch_desc(&map_h);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < RING; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -221,11 +302,18 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
   // ---- initial A operand: h(-1) split to fp16 hi/lo (zeros for the encoder), x block of step 0
   {
     for (int it = threadIdx.x; it < BM * 32; it += THREADS) {       // (row, 8-unit chunk)
-      const int r = it >> 5, ch = it & 31;
+      const int r = FUSED ? (it & (BM - 1)) : (it >> 5), ch = FUSED ? (it >> 7) : (it & 31);
       uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
-      if (p.h0 && m0 + r < p.n) {
+      if (FUSED ? cta_ok : (p.h0 && m0 + r < p.n)) {
         float hv[8];
-        ldg256(p.h0 + (m0 + r) * p.h0_ld + ch * 8, hv);
+        if (FUSED) {
+          // decoder start state = the encoder's last hidden state (modelPN.py:191,205): position L-1 of the block
+          const float* e = p.pa.enc_out + enc_blk_off(blockIdx.x, p.L, p.L - 1, ch >> 2, ch & 3) + r * 4;
+          const float4 a = ldg128(e), b = ldg128(e + BM * 4);
+          hv[0] = a.x; hv[1] = a.y; hv[2] = a.z; hv[3] = a.w; hv[4] = b.x; hv[5] = b.y; hv[6] = b.z; hv[7] = b.w;
+        } else {
+          ldg256(p.h0 + (m0 + r) * p.h0_ld + ch * 8, hv);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           hi[j] = pack_h2(hv[2 * j], hv[2 * j + 1]);
@@ -293,6 +381,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  if (warp < 4) {
+  if constexpr (FUSED) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");   // role warpgroup hands registers to the epilogue
   if (warp == 0) {
     // ================= TMA producer: weights, the same 72 boxes every step (each CTA of a pair loads its
     // half of the gate columns of every box and signals the leader's barrier) =================
@@ -300,7 +390,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
       int s = 0; uint32_t ph = 0;
       const int row_off = (int)rank * SLOT_ROWS;
       auto load_h = [&](int it) {                      // the 8 h-part boxes of tile `it` (hi, lo per k-block)
-        const int nt = (it + rot) & (N_TILES - 1);
+        const int nt = it;
         for (int kb = 0; kb < KB_H; ++kb) {
 #pragma unroll
           for (int part = 0; part < 2; ++part) {
@@ -319,7 +409,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         }
       };
       auto load_x = [&](int it) {                      // the x-part box (hi | lo) of tile `it`
-        const int nt = (it + rot) & (N_TILES - 1);
+        const int nt = it;
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t dst = sbase + OFF_RING + s * SLOT_BYTES;
         if (CG == 2) {
@@ -446,11 +536,11 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     }
   } else if (warp == 2) {
     // ================= h' store issuer (encoder): one TMA store per tile, [128 instances x 32 units] -> enc_out ====
-    if (!DEC && lane == 0) {
+    if (!DEC && !BLK && lane == 0) {
       uint32_t g = 0;
       for (int t = 0; t < p.steps; ++t) {
         for (int it = 0; it < N_TILES; ++it, ++g) {
-          const int nt = (it + rot) & (N_TILES - 1);
+          const int nt = it;
           mbar_wait(hfull_bar, g & 1u);
           tma_store_3d(&map_h, sbase + OFF_HBUF, nt * 32, t, (int)m0);
           bulk_commit();
@@ -473,8 +563,11 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         if (lane == 0) { if (CG == 2) mbar_arrive_cluster(a_ready_remote); else mbar_arrive(a_ready_bar); }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ================= epilogue: thread = one instance (TMEM lane), 32 gate columns = 8 hidden units per tile ====
+    // (fused decoder: a chunk of window-row slices, 40 registers, is in flight next to the cell arithmetic)
+    if constexpr (FUSED) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
     const int r = q * 32 + lane;                       // row inside the CTA
@@ -485,6 +578,16 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     float* const h_row = p.h_out + (ok ? m : 0) * p.h_out_inst_ld;
     // blocked scratch: float4 index (((cta*8 + nt)*4 + grp)*2 + half)*128 + row  -> a warp touches 512 contiguous bytes
     float* const c_blk = p.c_scr + ((int64_t)blockIdx.x * (BM * kH) + (int64_t)grp * (2 * BM * 4) + r * 4);
+    // blocked encodings of this thread: + position * ENC_BLK_ROW + nt * (4 * 2 * BM * 4) [+ BM * 4 for the second half]
+    const int64_t blk_thread = enc_blk_off(blockIdx.x, p.L, 0, 0, grp) + r * 4;
+    float* const e_out = BLK && !DEC ? p.h_out + blk_thread : nullptr;
+    const float* const e_in = FUSED ? p.pa.enc_out + blk_thread : nullptr;
+    const int N = DEC ? p.pa.N : 0;
+    constexpr int NRA = NR > 0 ? NR : 1;
+    constexpr int CHK = (NR % 5 == 0) ? 5 : 4;          // window rows in flight per thread (8 registers each)
+    float acc[NRA];                                    // FUSED: running p[g] of the canonical dot, per window row
+#pragma unroll
+    for (int j = 0; j < NRA; ++j) acc[j] = 0.f;
     uint32_t uses = 0;
     const bool prof = p.prof != nullptr;
     long long w_tfull = 0, w_hempty = 0, w_ptr = 0;
@@ -492,9 +595,21 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     for (int t = 0; t < p.steps; ++t) {
       const float4* bias4 = reinterpret_cast<const float4*>(sbias + (t == 0 ? 0 : kG));
       const bool last = t == p.steps - 1;
+      const float* const e_win = FUSED ? e_in + (int64_t)t * N * ENC_BLK_ROW : nullptr;     // window rows of step t
+      if (FUSED && cta_ok && t == 0) {
+        // L2 prefetch of the first two tiles' slices of window 0 (later slices are requested two tiles ahead below)
+        for (int j = 0; j < N; ++j)
+          if ((lane & 7) == 0) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              prefetch_l2(e_win + (int64_t)j * ENC_BLK_ROW + a * (4 * 2 * BM * 4));
+              prefetch_l2(e_win + (int64_t)j * ENC_BLK_ROW + a * (4 * 2 * BM * 4) + BM * 4);
+            }
+          }
+      }
       for (int it = 0; it < N_TILES; ++it, ++uses) {
         const int buf = it & 1;
-        const int nt = (it + rot) & (N_TILES - 1);      // which 128 gate columns this tile holds
+        const int nt = it;                             // which 128 gate columns this tile holds
         const int u0 = nt * 32 + grp * 8;              // first hidden unit of this thread's chunk
         float* const c_t = c_blk + nt * (4 * 2 * BM * 4);
         float c_old[8];
@@ -508,6 +623,18 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
 #pragma unroll
           for (int u = 0; u < 8; ++u) c_old[u] = 0.f;
         }
+        if (FUSED && cta_ok && (lane & 7) == 0) {
+          // L2 prefetch, two tiles ahead: tile it+2 of this window, or tile it-6 of the next step's window
+          const int nt2 = (it + 2) & (N_TILES - 1);
+          const bool wrap = it + 2 >= N_TILES;
+          if (!wrap || !last) {
+            const float* pf = e_win + (wrap ? (int64_t)N * ENC_BLK_ROW : 0) + nt2 * (4 * 2 * BM * 4);
+            for (int j = 0; j < N; ++j) {
+              prefetch_l2(pf + (int64_t)j * ENC_BLK_ROW);
+              prefetch_l2(pf + (int64_t)j * ENC_BLK_ROW + BM * 4);
+            }
+          }
+        }
         mbar_wait_t(tfull_bar(buf), (uses >> 1) & 1u, prof, w_tfull);
         tc_fence_after();
         float v[32];
@@ -518,6 +645,18 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         if (lane == 0) arrive_leader(tempty_bar(buf));  // accumulators are in registers: MMA may reuse the buffer
         float cn[8], hn[8];
         lstm_cell8(v, bias4 + u0, c_old, cn, hn);
+        // FUSED: first chunk of this tile's window-row slices (requested here, consumed after the h' bookkeeping)
+        float4 ea[CHK], eb[CHK];
+        if (FUSED && cta_ok) {
+#pragma unroll
+          for (int u = 0; u < CHK; ++u) {
+            if (u < N) {
+              const float* e = e_win + (int64_t)u * ENC_BLK_ROW + nt * (4 * 2 * BM * 4);
+              ea[u] = ldg_stream(reinterpret_cast<const float4*>(e));
+              eb[u] = ldg_stream(reinterpret_cast<const float4*>(e + BM * 4));
+            }
+          }
+        }
         if (!last) {
           stg128(c_t, cn[0], cn[1], cn[2], cn[3]);
           stg128(c_t + BM * 4, cn[4], cn[5], cn[6], cn[7]);
@@ -526,6 +665,13 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         }
         if (DEC) {
           if (ok) stg256(h_row + (int64_t)t * kH + u0, hn);
+        } else if (BLK) {
+          // blocked encodings: the thread's 8 units of position t, coalesced across the warp (512 B per store)
+          if (cta_ok) {
+            float* e = e_out + (int64_t)t * ENC_BLK_ROW + nt * (4 * 2 * BM * 4);
+            stg128(e, hn[0], hn[1], hn[2], hn[3]);
+            stg128(e + BM * 4, hn[4], hn[5], hn[6], hn[7]);
+          }
         } else {
           // fp32 h' -> 128B-swizzled [128 x 32] tile; the store issuer (warp 2) sends it to enc_out by TMA
           mbar_wait_t(hempty_bar, (uses & 1u) ^ 1u, prof, w_hempty);   // the previous tile's store has left shared memory
@@ -563,19 +709,68 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
             st_shared_v4(sbase + OFF_A_HI + off, sg[0], sg[1], sg[2], sg[3]);
             st_shared_v4(sbase + OFF_A_LO + off, sg[4], sg[5], sg[6], sg[7]);
           }
+          if (DEC) {
+            // h'(t) is in the A tiles: the MMA warp may start the h parts of the next step's first two tiles now
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(h_ready_remote); else mbar_arrive(h_ready_bar); }
+          }
+        }
+        if (FUSED && cta_ok) {
+          // canonical dot (pointer.cuh): s[nt][g] = fma chain over the 8 units, p[g] sequential over the tiles
+#pragma unroll
+          for (int j0 = 0; j0 < NR; j0 += CHK) {
+            if (j0 > 0) {
+#pragma unroll
+              for (int u = 0; u < CHK; ++u) {
+                if (j0 + u < NR && j0 + u < N) {
+                  const float* e = e_win + (int64_t)(j0 + u) * ENC_BLK_ROW + nt * (4 * 2 * BM * 4);
+                  ea[u] = ldg_stream(reinterpret_cast<const float4*>(e));
+                  eb[u] = ldg_stream(reinterpret_cast<const float4*>(e + BM * 4));
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < CHK; ++u) {
+              if (j0 + u < NR && j0 + u < N) {
+                // dot8's operand order: row element first, query element second
+                float sj = __fmul_rn(ea[u].x, hn[0]);
+                sj = fmaf(ea[u].y, hn[1], sj); sj = fmaf(ea[u].z, hn[2], sj); sj = fmaf(ea[u].w, hn[3], sj);
+                sj = fmaf(eb[u].x, hn[4], sj); sj = fmaf(eb[u].y, hn[5], sj); sj = fmaf(eb[u].z, hn[6], sj);
+                sj = fmaf(eb[u].w, hn[7], sj);
+                acc[j0 + u] = it == 0 ? sj : __fadd_rn(acc[j0 + u], sj);
+              }
+            }
+          }
         }
       }
-      if (DEC) {
-        // h'(t) is in the A tiles: the MMA warp may start the h parts of the next step's first two tiles now
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(h_ready_remote); else mbar_arrive(h_ready_bar); }
+      if (DEC && !FUSED) {
         // ---- pointer step k = t: query = h'(t) (just written to dec_h by this CTA), window rows of enc_out
         const long long tp0 = prof ? clock64() : 0;
         __threadfence_block();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
         pointer_phase(p, t, (warp - 4) * (BM / EPI_WARPS), m0, lane, sgen);
+        if (prof) w_ptr += clock64() - tp0;
+      }
+      if (FUSED) {
+        // ---- combine the four group partials of every instance and finish the step (one thread per instance)
+        const long long tp0 = prof ? clock64() : 0;
+        float* const part = reinterpret_cast<float*>(sgen + OFF_HBUF);      // [3 groups][NR][128 rows]
+        if (grp > 0) {
+#pragma unroll
+          for (int j = 0; j < NR; ++j)
+            if (j < N) part[((grp - 1) * NR + j) * BM + r] = acc[j];
+        }
+        named_bar_sync(1 + q, 128);                     // the four warps that own this quarter's rows
+        if (grp == 0) {
+          float d[NRA];
+#pragma unroll
+          for (int j = 0; j < NR; ++j)
+            d[j] = j < N ? __fadd_rn(__fadd_rn(acc[j], part[(0 * NR + j) * BM + r]),
+                                      __fadd_rn(part[(1 * NR + j) * BM + r], part[(2 * NR + j) * BM + r])) : 0.f;
+          pointer_finish_thread<NRA>(p, t, r, m, ok, d, sbase);
+        }
         if (prof) w_ptr += clock64() - tp0;
       }
       fence_proxy_async_smem();
@@ -608,16 +803,7 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// GNNPN_SEQ_CG=1 selects the single-CTA variant (cta_group::1); default is the CTA pair
-static int seq_cta_group() {
-  static const int cg = [] {
-    const char* e = getenv("GNNPN_SEQ_CG");
-    return (e && atoi(e) == 1) ? 1 : 2;
-  }();
-  return cg;
-}
-
-template <bool DEC, int CG>
+template <bool DEC, int CG, int NR>
 int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return GNNPN_EUNSUPPORTED;
@@ -636,8 +822,8 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return GNNPN_ESHAPE;
   }
-  CUtensorMap map_h;
-  {
+  CUtensorMap map_h = maps[0];                         // only the row-major encoder stores through it
+  if (!DEC && NR == 0) {
     // h_out as a 3-D tensor {unit, step, instance}; box = 32 units x 1 step x 128 instances, 128B swizzle
     const int64_t T = p.h_out_inst_ld / kH;
     cuuint64_t dims[3] = {(cuuint64_t)kH, (cuuint64_t)T, (cuuint64_t)p.n};
@@ -650,11 +836,7 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
       return GNNPN_ESHAPE;
   }
   SeqParams pp = p;
-  static const int rotate = getenv("GNNPN_SEQ_ROT") ? atoi(getenv("GNNPN_SEQ_ROT")) : 0;
-  pp.rotate = rotate;
-  static const int dec_flags = getenv("GNNPN_SEQ_DEC") ? atoi(getenv("GNNPN_SEQ_DEC")) : 2;
-  pp.dec_flags = dec_flags;
-  auto kern = lstm_seq_kernel<DEC, CG>;
+  auto kern = lstm_seq_kernel<DEC, CG, NR>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -662,7 +844,7 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
     configured = true;
   }
   const unsigned grid = (unsigned)(ceil_div(p.n, BM * CG) * CG);
-  static const int do_prof = getenv("GNNPN_SEQ_PROF") ? atoi(getenv("GNNPN_SEQ_PROF")) : 0;
+  const int do_prof = options().prof.load(std::memory_order_relaxed);
   unsigned long long* prof = nullptr;
   if (do_prof) {                                       // debug only: synchronous, allocates
     if (cudaMalloc(&prof, (size_t)grid * 16 * 8) != cudaSuccess) return GNNPN_EUNSUPPORTED;
@@ -689,8 +871,8 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
       for (int i = 0; i < 8; ++i) acc[i] += (double)hbuf[c * 16 + i];
     }
     if (!leaders) leaders = 1;
-    fprintf(stderr, "[seq prof %s cg=%d steps=%d grid=%u] per-step cycles: mma total %.0f (wait a_ready %.0f, tmem_empty %.0f, "
-            "B full %.0f) | epi total %.0f (wait tmem_full %.0f, h buf %.0f, pointer %.0f)\n", DEC ? "dec" : "enc", CG,
+    fprintf(stderr, "[seq prof %s cg=%d nr=%d steps=%d grid=%u] per-step cycles: mma total %.0f (wait a_ready %.0f, tmem_empty %.0f, "
+            "B full %.0f) | epi total %.0f (wait tmem_full %.0f, h buf %.0f, pointer %.0f)\n", DEC ? "dec" : "enc", CG, NR,
             p.steps, grid, acc[0] / leaders / p.steps, acc[1] / leaders / p.steps, acc[2] / leaders / p.steps,
             acc[3] / leaders / p.steps, acc[4] / grid / p.steps, acc[5] / grid / p.steps, acc[6] / grid / p.steps,
             acc[7] / grid / p.steps);
@@ -698,11 +880,6 @@ int launch_seq_cg(const float* packed, const SeqParams& p, cudaStream_t st) {
     cudaFree(prof);
   }
   return rc_launch;
-}
-
-template <bool DEC>
-int launch_seq(const float* packed, const SeqParams& p, cudaStream_t st) {
-  return seq_cta_group() == 2 ? launch_seq_cg<DEC, 2>(packed, p, st) : launch_seq_cg<DEC, 1>(packed, p, st);
 }
 
 }  // namespace seq
@@ -717,8 +894,12 @@ int tc_seq_encode(const SeqEncodeArgs& a, cudaStream_t st) {
   p.h0 = nullptr; p.h0_ld = 0;
   p.h_out = a.enc_out; p.h_out_inst_ld = (int64_t)a.L * kH;
   p.c_scr = a.c_scratch;
-  return seq::launch_seq<false>(a.packed, p, st);
+  p.enc_layout = a.enc_layout;
+  if (a.enc_layout == GNNPN_ENC_BLOCKED128) return seq::launch_seq_cg<false, 2, 1>(a.packed, p, st);
+  return seq::launch_seq_cg<false, 2, 0>(a.packed, p, st);
 }
+
+bool tc_seq_fused_decode_supported(int N) { return N >= 1 && N <= 10; }
 
 int tc_seq_decode(const SeqDecodeArgs& a, cudaStream_t st) {
   if (a.F < 1 || a.F > 8 || a.K < 1 || a.N < 1 || a.N > kMaxWindow) return GNNPN_EUNSUPPORTED;
@@ -727,14 +908,23 @@ int tc_seq_decode(const SeqDecodeArgs& a, cudaStream_t st) {
   p.inputs = a.inputs; p.x_inst_ld = (int64_t)a.L * a.F;
   p.bias0 = a.packed + kOffStart; p.bias = a.packed + kOffBias;
   p.c = a.c_state; p.c_zero_init = 0;
-  p.h0 = a.enc_out + (int64_t)(a.L - 1) * kH; p.h0_ld = (int64_t)a.L * kH;
   p.h_out = a.dec_h; p.h_out_inst_ld = (int64_t)a.K * kH;
   p.pa.enc_out = a.enc_out; p.pa.enc_inst_ld = (int64_t)a.L * kH; p.pa.latent_win = a.latent_win;
   p.pa.alpha = a.alpha; p.pa.use_tanh = a.use_tanh; p.pa.C = a.C; p.pa.n = a.n; p.pa.L = a.L;
   p.pa.N = a.N; p.pa.idx_out = a.idx_out; p.pa.win_logits = a.win_logits; p.pa.win_probs = a.win_probs;
   p.pa.forced = a.forced_idx; p.pa.uniform = a.sample_uniform;
   p.c_scr = a.c_scratch;
-  return seq::launch_seq<true>(a.packed, p, st);
+  p.enc_layout = a.enc_layout;
+  if (a.enc_layout == GNNPN_ENC_BLOCKED128) {
+    // blocked encodings: the pointer dots ride in the cell epilogue (row capacity 5 / 8 / 10 of the window)
+    if (!tc_seq_fused_decode_supported(a.N)) return GNNPN_EUNSUPPORTED;
+    p.h0 = nullptr; p.h0_ld = 0;                         // read from the block's position L-1 inside the kernel
+    if (a.N == 5) return seq::launch_seq_cg<true, 2, 5>(a.packed, p, st);
+    if (a.N <= 8) return seq::launch_seq_cg<true, 2, 8>(a.packed, p, st);
+    return seq::launch_seq_cg<true, 2, 10>(a.packed, p, st);
+  }
+  p.h0 = a.enc_out + (int64_t)(a.L - 1) * kH; p.h0_ld = (int64_t)a.L * kH;
+  return seq::launch_seq_cg<true, 2, 0>(a.packed, p, st);
 }
 
 }  // namespace gnnpn

@@ -19,9 +19,10 @@ struct SeqEncodeArgs {
   int L;
   int F;                   // <= 8
   const float* packed;     // packed LSTM block (uses the bias and the fp16 hi/lo operand blocks)
-  float* enc_out;          // [n, L, kH]
+  float* enc_out;          // [n, L, kH], or the blocked layout (gnnpn_pn_enc_out_floats) when enc_layout says so
   float* c_state;          // [n, kH] out
   float* c_scratch;        // tc_seq_scratch_floats(n) floats
+  int enc_layout;          // GNNPN_ENC_ROWMAJOR / GNNPN_ENC_BLOCKED128 (CTA-pair scan only)
 };
 // returns GNNPN_EUNSUPPORTED when the shape is outside what the persistent kernel covers
 int tc_seq_encode(const SeqEncodeArgs& a, cudaStream_t st);
@@ -54,7 +55,9 @@ struct SeqDecodeArgs {
   const int32_t* forced_idx;     // [K, n] or nullptr
   const float* sample_uniform;   // [K, n] or nullptr
   float* c_scratch;              // tc_seq_scratch_floats(n) floats
+  int enc_layout;                // layout of enc_out
 };
+bool tc_seq_fused_decode_supported(int N);     // blocked-layout decoder (pointer dots fused into the cell epilogue)
 int tc_seq_decode(const SeqDecodeArgs& a, cudaStream_t st);
 
 }  // namespace gnnpn

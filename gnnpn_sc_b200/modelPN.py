@@ -77,6 +77,17 @@ class WindowLogits(_StepList):
         self.window = window
 
 
+class _Last(dict):
+    """Device-side results of the most recent forward.  ``["enc_out"]`` is the reference's ``[B, L, H]`` tensor
+    (modelPN.py:191); when the kernels kept the encodings in the blocked layout it is converted on first use."""
+
+    def __getitem__(self, key):
+        if key == "enc_out" and not dict.__contains__(self, "enc_out"):
+            B, L, H = dict.__getitem__(self, "enc_shape")
+            dict.__setitem__(self, "enc_out", ops.enc_to_rowmajor(dict.__getitem__(self, "enc_buf"), B, L, H))
+        return dict.__getitem__(self, key)
+
+
 def _window_of(latent, K: int, N: int) -> torch.Tensor:
     """Compact ``[B, L]`` latent from whatever the caller passed (our lazy list or the reference's dense list)."""
     if isinstance(latent, WindowLogits):
@@ -233,7 +244,10 @@ class PointerNet(nn.Module):
         att = self.pointer.name
         with torch.no_grad():
             ws = ops.pn_workspace(B, self.hidden_size, x.device, self.impl)
-            enc_out, c = ops.lstm_encode(x, enc_w, self.hidden_size, workspace=ws)
+            # batches the CTA-pair scan takes keep their encodings in the blocked layout (pointer dots fused into the
+            # decoder's cell epilogue); ``self.last["enc_out"]`` / the dense logits convert lazily
+            layout = ops.pn_enc_layout(B, L, x.shape[2], K, N, ws is not None) if fast else ops.ENC_ROWMAJOR
+            enc_out, c = ops.lstm_encode(x, enc_w, self.hidden_size, workspace=ws, layout=layout)
             lat = _window_of(latent, K, N) if latent else None
             forced = None if forced_idxs is None else torch.stack([t.to(torch.int32) for t in forced_idxs])
             # sample != "greedy": multinomial draw per step (modelPN.py:227-228) as an inverse-CDF pick in the kernel
@@ -242,7 +256,8 @@ class PointerNet(nn.Module):
             if fast:
                 dec_h, idx, win_logits, win_probs = ops.pn_decode_greedy(
                     x, enc_out, c, dec_w, K, N, latent_win=lat, alpha=float(self.alpha), attention="Dot",
-                    use_tanh=use_tanh, C=C, forced_idx=forced, workspace=ws, sample_uniform=uniform)
+                    use_tanh=use_tanh, C=C, forced_idx=forced, workspace=ws, sample_uniform=uniform, enc_layout=layout,
+                    hidden=self.hidden_size)
                 dec_q = dec_h
             else:
                 blocks = None
@@ -254,15 +269,20 @@ class PointerNet(nn.Module):
                     att_params=blocks, n_glimpses=self.n_glimpses, use_tanh=use_tanh, C=C, forced_idx=forced,
                     sample_uniform=uniform, use_tc=ws is not None)
         idx64 = idx.long()
-        self.last = {"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "enc_out": enc_out, "dec_h": dec_h,
-                     "dec_q": dec_q, "latent_win": lat}
+        self.last = _Last({"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "dec_h": dec_h,
+                           "dec_q": dec_q, "latent_win": lat, "enc_buf": enc_out, "enc_layout": layout,
+                           "enc_shape": (B, L, self.hidden_size)})
+        if layout == ops.ENC_ROWMAJOR:
+            self.last["enc_out"] = enc_out
+        last = self.last
 
         fed = idx if forced is None else forced.contiguous()     # the picks the visited mask follows
 
         def dense_logits():
             if att == "Dot":
-                return ops.pn_full_logits(enc_out, dec_q, fed, "Dot", None, use_tanh, C)
-            return ops.pn_full_logits_bahdanau(ops.pn_ref_transform(enc_out, ptr_blk), qw, ptr_blk, fed, use_tanh, C)
+                return ops.pn_full_logits(last["enc_out"], dec_q, fed, "Dot", None, use_tanh, C)
+            return ops.pn_full_logits_bahdanau(ops.pn_ref_transform(last["enc_out"], ptr_blk), qw, ptr_blk, fed,
+                                               use_tanh, C)
 
         def dense_probs():      # exactly zero outside window k
             out = torch.zeros(K, B, L, device=x.device, dtype=torch.float32)

@@ -7,7 +7,7 @@ from typing import Optional
 
 import torch
 
-from ._lib import GnnpnError, check, lib
+from ._lib import GnnpnError, check, get_option, lib, set_option  # noqa: F401  (re-exported)
 
 import os
 
@@ -17,6 +17,7 @@ DEFAULT_IMPL = os.environ.get("GNNPN_IMPL", "tc")
 TC_GEMM_MIN_ROWS = 512          # below this the tile pipeline cannot fill; the FFMA kernel is used
 ATT = {"Dot": 0, "Bahdanau": 1}
 CSR_PLAIN, CSR_GCN_NORM = 0, 1
+ENC_ROWMAJOR, ENC_BLOCKED128 = 0, 1     # include/gnnpn_b200.h: layouts of the encoder -> decoder encodings buffer
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -64,28 +65,50 @@ def _ws(ws):
     return (None, 0) if ws is None else (ws.data_ptr(), ws.numel())
 
 
+def pn_enc_layout(n: int, L: int, F: int, K: int, N: int, has_workspace: bool = True) -> int:
+    """Layout the dispatcher wants for the (lstm_encode, pn_decode_greedy) pair of a batch: ``ENC_BLOCKED128`` when the
+    batch runs on the persistent CTA-pair scan (pointer dots fused into the decoder's cell epilogue), else row-major."""
+    return int(lib().gnnpn_pn_enc_layout(n, L, F, K, N, int(bool(has_workspace))))
+
+
+def enc_out_empty(n: int, L: int, hidden: int, layout: int, device) -> torch.Tensor:
+    """Encodings buffer for ``lstm_encode``: ``[n, L, H]`` (row-major) or the flat blocked buffer."""
+    if layout == ENC_ROWMAJOR:
+        return torch.empty(n, L, hidden, device=device, dtype=torch.float32)
+    return torch.empty(int(lib().gnnpn_pn_enc_out_floats(n, L, hidden, layout)), device=device, dtype=torch.float32)
+
+
+def enc_to_rowmajor(enc_blocked: torch.Tensor, n: int, L: int, hidden: int = 256) -> torch.Tensor:
+    """Blocked encodings -> the reference's ``[n, L, H]`` tensor (modelPN.py:191)."""
+    out = torch.empty(n, L, hidden, device=enc_blocked.device, dtype=torch.float32)
+    check(lib().gnnpn_pn_enc_to_rowmajor_f32(enc_blocked.data_ptr(), n, L, hidden, out.data_ptr(), _stream()),
+          "enc_to_rowmajor")
+    return out
+
+
 def lstm_encode(inputs: torch.Tensor, packed: torch.Tensor, hidden: int = 256,
                 enc_out: Optional[torch.Tensor] = None, c_state: Optional[torch.Tensor] = None,
-                workspace: Optional[torch.Tensor] = None):
+                workspace: Optional[torch.Tensor] = None, layout: int = ENC_ROWMAJOR):
     x = _f32(inputs, "inputs")
     n, L, F = x.shape
     if enc_out is None:
-        enc_out = torch.empty(n, L, hidden, device=x.device, dtype=torch.float32)
+        enc_out = enc_out_empty(n, L, hidden, layout, x.device)
     if c_state is None:
         c_state = torch.empty(n, hidden, device=x.device, dtype=torch.float32)
     check(lib().gnnpn_lstm_encode_f32(x.data_ptr(), n, L, F, hidden, packed.data_ptr(), enc_out.data_ptr(),
-                                      c_state.data_ptr(), *_ws(workspace), _stream()), "lstm_encode")
+                                      c_state.data_ptr(), *_ws(workspace), int(layout), _stream()), "lstm_encode")
     return enc_out, c_state
 
 
 def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, latent_win=None, alpha: float = 1.0,
                      attention: str = "Dot", att_params=None, use_tanh: bool = True, C: float = 10.0,
                      forced_idx=None, out=None, workspace: Optional[torch.Tensor] = None,
-                     sample_uniform: Optional[torch.Tensor] = None):
-    """Returns (dec_h [n,K,H], idx int32 [K,n], win_logits [n,L], win_probs [n,L]).  ``c_state`` is updated in place."""
+                     sample_uniform: Optional[torch.Tensor] = None, enc_layout: int = ENC_ROWMAJOR, hidden: int = 256):
+    """Returns (dec_h [n,K,H], idx int32 [K,n], win_logits [n,L], win_probs [n,L]).  ``c_state`` is updated in place.
+    ``enc_out`` is in ``enc_layout`` (as produced by ``lstm_encode(..., layout=enc_layout)``)."""
     x = _f32(inputs, "inputs")
     n, L, F = x.shape
-    H = enc_out.shape[2]
+    H = enc_out.shape[2] if enc_layout == ENC_ROWMAJOR else hidden
     dev = x.device
     if out is None:
         dec_h = torch.empty(n, K, H, device=dev, dtype=torch.float32)
@@ -107,7 +130,7 @@ def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, laten
         x.data_ptr(), enc_out.data_ptr(), c_state.data_ptr(), _ptr(latent_win), float(alpha),
         packed_dec.data_ptr(), ATT[attention], _ptr(att_params), int(bool(use_tanh)), float(C),
         n, L, F, H, K, N, dec_h.data_ptr(), idx.data_ptr(), wl.data_ptr(), wp.data_ptr(),
-        _ptr(forced_idx), _ptr(sample_uniform), *_ws(workspace), _stream()), "pn_decode_greedy")
+        _ptr(forced_idx), _ptr(sample_uniform), *_ws(workspace), int(enc_layout), _stream()), "pn_decode_greedy")
     return dec_h, idx, wl, wp
 
 

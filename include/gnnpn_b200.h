@@ -54,6 +54,16 @@ GNNPN_API const char* gnnpn_error_string(int code);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 GNNPN_API uint64_t gnnpn_launch_count(void);
 
+/* Process-wide run-time options (dispatch overrides for tests / benches / profiling; defaults need no call):
+ *   "scan"         -1 auto by batch size (default) | 0 CTA-pair scan | 1 column-split cluster scan
+ *   "scan_groups"   0 auto | 1 | 2 instance groups per column-split cluster
+ *   "persistent"    bit 0: encoder, bit 1: decoder run as one persistent launch (default 3; 0 = one launch per step)
+ *   "prof"          1: in-kernel wait-cycle counters printed to stderr (debug; makes the call synchronous)
+ * Initial values are taken once, at load time, from GNNPN_COLSPLIT / GNNPN_COLSPLIT_G / GNNPN_SEQ / GNNPN_SEQ_PROF.
+ * Unknown name -> GNNPN_EUNSUPPORTED. */
+GNNPN_API int gnnpn_set_option(const char* name, int value);
+GNNPN_API int gnnpn_get_option(const char* name, int* value);
+
 /* ---------------------------------------------------------------------------
  * Pointer network  (reference: src/models/modelPN.py)
  * ------------------------------------------------------------------------- */
@@ -77,14 +87,34 @@ GNNPN_API int gnnpn_pn_pack_lstm_f32(const float* w_ih, const float* w_hh, const
                            const float* w_embed, const float* b_embed, const float* start_input,
                            int hidden, int in_features, float* packed, void* stream);
 
+/* Layout of the encodings buffer handed from gnnpn_lstm_encode_f32 to gnnpn_pn_decode_greedy_f32.
+ *   GNNPN_ENC_ROWMAJOR    fp32 [n, L, H] (what modelPN.py:191 returns; every other entry point takes this one)
+ *   GNNPN_ENC_BLOCKED128  blocks of 128 instances, fp32 [ceil(n/128)][L][8 tiles][4 groups][2 halves][128][4] with hidden
+ *                         unit = 32*tile + 8*group + 4*half + i: the ownership (thread = instance, 8 units per
+ *                         accumulator tile) of the persistent CTA-pair scan's epilogue.  The encoder writes it with
+ *                         coalesced 128-bit stores and the decoder folds the pointer dot products into its cell
+ *                         epilogue, so the window rows stream from HBM under the step's MMAs (no separate attention
+ *                         phase).  Only valid for the pair (encode, decode_greedy) on the same n.
+ * gnnpn_pn_enc_layout() returns the layout the dispatcher wants for a batch (blocked for batches that run on the
+ * CTA-pair scan: F <= 8, window N <= 10, workspace given, more instances than the column-split cluster scan takes);
+ * gnnpn_pn_enc_out_floats() the buffer size; gnnpn_pn_enc_to_rowmajor_f32() converts a blocked buffer to [n, L, H]
+ * (for callers that want modelPN.py:191's tensor, e.g. the dense logits of gnnpn_pn_full_logits_f32). */
+#define GNNPN_ENC_ROWMAJOR 0
+#define GNNPN_ENC_BLOCKED128 1
+GNNPN_API int gnnpn_pn_enc_layout(int64_t n, int L, int in_features, int K, int N, int has_workspace);
+GNNPN_API size_t gnnpn_pn_enc_out_floats(int64_t n, int L, int hidden, int layout);
+GNNPN_API int gnnpn_pn_enc_to_rowmajor_f32(const float* enc_blocked, int64_t n, int L, int hidden, float* enc_out,
+                                 void* stream);
+
 /* Encoder: embedding2 + nn.LSTM over L steps (modelPN.py:190-191).
  *   inputs  fp32 [n, L, F]          (F = in_features, 8 when embedding_size == 0)
- *   enc_out fp32 [n, L, H]          every hidden state
+ *   enc_out fp32 [n, L, H]          every hidden state (or the blocked layout, gnnpn_pn_enc_out_floats() floats)
  *   c_state fp32 [n, H]             final cell state (also scratch during the scan)
- * The final hidden state is enc_out[:, L-1, :]. */
+ * The final hidden state is enc_out[:, L-1, :].  enc_layout = GNNPN_ENC_BLOCKED128 needs a workspace and F <= 8
+ * (else GNNPN_EUNSUPPORTED). */
 GNNPN_API int gnnpn_lstm_encode_f32(const float* inputs, int64_t n, int L, int in_features, int hidden,
                           const float* packed_encoder, float* enc_out, float* c_state,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          void* workspace, size_t workspace_bytes, int enc_layout, void* stream);
 
 /* Scratch for the tensor-core (tcgen05, 3xTF32) recurrence: the tf32 hi/lo split of [h | x] of the
  * current and next step, 4 * n * (H + 32) floats.  Passing workspace == NULL to encode/decode selects
@@ -94,7 +124,7 @@ GNNPN_API size_t gnnpn_pn_workspace_bytes(int64_t n, int hidden);
 /* Fused greedy pointer decode: K x { decoder LSTM cell -> pointer logits on window k ->
  * C*tanh -> (+ alpha*latent) -> window/visited mask -> softmax -> first-max index -> gather
  * next decoder input }  (modelPN.py:204-239 with sample="greedy"), batched over n instances.
- *   enc_out      fp32 [n, L, H]     from gnnpn_lstm_encode_f32
+ *   enc_out      fp32 [n, L, H]     from gnnpn_lstm_encode_f32, in the layout `enc_layout` names
  *   c_state      fp32 [n, H]        in: encoder final cell state; out: decoder final cell state
  *   latent_win   fp32 [n, L] or NULL   PNLow's step-(l/N) logit at position l (only the window
  *                                   slice of latent[k] can influence a pick)
@@ -116,7 +146,7 @@ GNNPN_API int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_o
                                int64_t n, int L, int in_features, int hidden, int K, int N,
                                float* dec_h, int32_t* idx_out, float* win_logits, float* win_probs,
                                const int32_t* forced_idx, const float* sample_uniform,
-                               void* workspace, size_t workspace_bytes, void* stream);
+                               void* workspace, size_t workspace_bytes, int enc_layout, void* stream);
 
 /* ---- general decode: every PointerNet variant outside the fused fast path above --------------------------
  * Attention parameter block (gnnpn_pn_att_block_floats(H) floats per Attention module, modelPN.py:83-91):

@@ -27,16 +27,19 @@ os.makedirs(os.path.dirname(a.out), exist_ok=True)
 with open(a.out, "w") as f:
     for n in [int(s) for s in a.sizes.split(",")]:
         x = pn_instances(n, K, N, seed=3).to(dev)
-        enc, c = torch.empty(n, L, H, device=dev), torch.empty(n, H, device=dev)
+        c = torch.empty(n, H, device=dev)
         bufs = [(torch.empty(n, K, H, device=dev), torch.empty(K, n, device=dev, dtype=torch.int32),
                  torch.empty(n, L, device=dev), torch.empty(n, L, device=dev)) for _ in range(2)]
         ws = ops.pn_workspace(n, H, dev, "tc")
+        lay = ops.pn_enc_layout(n, L, F, K, N, True)
+        enc = ops.enc_out_empty(n, L, H, lay, dev)
 
         def step():
             lat = None
             for lvl, (ew, dw) in enumerate(w):
-                ops.lstm_encode(x, ew, H, enc, c, workspace=ws)
-                _, idx, lat, _ = ops.pn_decode_greedy(x, enc, c, dw, K, N, latent_win=lat, out=bufs[lvl], workspace=ws)
+                ops.lstm_encode(x, ew, H, enc, c, workspace=ws, layout=lay)
+                _, idx, lat, _ = ops.pn_decode_greedy(x, enc, c, dw, K, N, latent_win=lat, out=bufs[lvl], workspace=ws,
+                                                      enc_layout=lay)
             return ops.pn_reward(x, idx)[2]
 
         for _ in range(2):
@@ -49,7 +52,7 @@ with open(a.out, "w") as f:
             ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[2]
         groups = (n + 127) // 128
-        line = {"n": n, "ms": ms, "instances_per_s": n / ms * 1e3, "scan": "column-split" if groups <= 30 else "cta-pair",
+        line = {"n": n, "ms": ms, "instances_per_s": n / ms * 1e3, "scan": "cta-pair (blocked encodings, fused pointer dots)" if lay == ops.ENC_BLOCKED128 else "column-split",
                 "groups_of_128": groups}
         print(json.dumps(line), flush=True)
         f.write(json.dumps(line) + "\n")

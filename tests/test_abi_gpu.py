@@ -38,13 +38,14 @@ def test_argument_errors_are_reported_before_any_launch():
     before = lib.gnnpn_launch_count()
     call = lambda **kw: lib.gnnpn_lstm_encode_f32(
         kw.get("x", x.data_ptr()), kw.get("n", n), L, kw.get("F", F), kw.get("H", H), enc.data_ptr(),
-        kw.get("out", out.data_ptr()), c.data_ptr(), ws.data_ptr(), kw.get("wsb", ws.numel()), st)
+        kw.get("out", out.data_ptr()), c.data_ptr(), ws.data_ptr(), kw.get("wsb", ws.numel()), kw.get("layout", 0), st)
     assert call(x=None) == -1                                   # GNNPN_ENULL
     assert call(H=128) == -2                                    # GNNPN_ESHAPE: hidden_size != 256
     assert call(F=33) == -2                                     # more raw columns than the packed block holds
     assert call(out=out.data_ptr() + 4) == -3                   # GNNPN_EALIGN
     assert call(wsb=16) == -4                                   # GNNPN_EWORKSPACE
     assert call(n=1 << 31) == -5                                # GNNPN_ERANGE
+    assert call(layout=7) == -2                                 # unknown encodings layout
     assert lib.gnnpn_launch_count() == before                   # nothing was launched
     assert call(n=0) == 0                                       # empty batch: success, no launch
     assert lib.gnnpn_launch_count() == before

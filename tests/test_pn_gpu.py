@@ -19,25 +19,27 @@ CUDA_CASES = ["qws_b4", "normal_b2", "small_b16", "sharp_b4", "notanh_b3", "bahd
 
 
 # "tc": tcgen05 recurrence as dispatched by default -- at these batch sizes the column-split cluster scan
-# (tc_colsplit.cu); "tc_pair": the same with GNNPN_COLSPLIT=0, i.e. the CTA-pair persistent scan (tc_seq.cu) that large
-# batches use; "ffma": the strict-fp32 FFMA kernels.
+# (tc_colsplit.cu); "tc_pair": the same with option scan=0, i.e. the CTA-pair persistent scan (tc_seq.cu: blocked
+# encodings, pointer dots fused into the decoder's cell epilogue) that large batches use; "ffma": the strict-fp32 kernels.
 IMPLS = ["tc", "tc_pair", "ffma"]
 
 
 def _select(impl):
-    """Set the scan-kernel knob for `impl` (read by the library on every call) and return the module-level impl."""
+    """Set the scan-kernel option for `impl` (gnnpn_set_option) and return the module-level impl."""
+    from gnnpn_sc_b200 import ops
     if impl == "tc_pair":
-        os.environ["GNNPN_COLSPLIT"] = "0"
+        ops.set_option("scan", 0)
         return "tc"
-    os.environ.pop("GNNPN_COLSPLIT", None)
+    ops.set_option("scan", -1)
     return impl
 
 
 @pytest.fixture(autouse=True)
 def _reset_scan_knob():
     yield
-    os.environ.pop("GNNPN_COLSPLIT", None)
-    os.environ.pop("GNNPN_COLSPLIT_G", None)
+    from gnnpn_sc_b200 import ops
+    ops.set_option("scan", -1)
+    ops.set_option("scan_groups", 0)
 
 
 
@@ -253,9 +255,9 @@ def test_host_buffer_c_abi_matches_module_path():
 def test_argument_errors_are_reported_not_thrown():
     from gnnpn_sc_b200 import _lib, modelPN as M
     L = _lib.lib()
-    assert L.gnnpn_lstm_encode_f32(None, 1, 1, 8, 256, None, None, None, None, 0, None) == -1       # GNNPN_ENULL
+    assert L.gnnpn_lstm_encode_f32(None, 1, 1, 8, 256, None, None, None, None, 0, 0, None) == -1    # GNNPN_ENULL
     t = torch.zeros(16, device="cuda")
-    assert L.gnnpn_lstm_encode_f32(t.data_ptr(), 1, 1, 8, 128, t.data_ptr(), t.data_ptr(), t.data_ptr(), None, 0, None) == -2
+    assert L.gnnpn_lstm_encode_f32(t.data_ptr(), 1, 1, 8, 128, t.data_ptr(), t.data_ptr(), t.data_ptr(), None, 0, 0, None) == -2
     with pytest.raises(RuntimeError):
         m = M.CombinatorialRL(0, 256, 6, 0, 10, 1, M.reward, "Dot", 2, 3).cuda()
         m(torch.zeros(2, 6, 8), None, sample="greedy", training="SL")                       # CPU tensor -> loud error
@@ -366,19 +368,17 @@ def test_column_split_scan_equals_cta_pair_scan_bitwise(n, K, N):
     m = m.cuda().eval()
     lat = [torch.randn(n, K * N, device="cuda") for _ in range(K)]
     outs = {}
-    # (GNNPN_COLSPLIT, GNNPN_COLSPLIT_G): column-split with one / two instance groups per cluster (encoder), CTA-pair scan
-    for key, (mode, g) in {"cs1": ("1", "1"), "cs2": ("1", "2"), "pair": ("0", None)}.items():
-        os.environ["GNNPN_COLSPLIT"] = mode
-        if g is None:
-            os.environ.pop("GNNPN_COLSPLIT_G", None)
-        else:
-            os.environ["GNNPN_COLSPLIT_G"] = g
+    # options (scan, scan_groups): column-split with one / two instance groups per cluster (encoder), CTA-pair scan
+    from gnnpn_sc_b200 import ops
+    for key, (mode, g) in {"cs1": (1, 1), "cs2": (1, 2), "pair": (0, 0)}.items():
+        ops.set_option("scan", mode)
+        ops.set_option("scan_groups", g)
         with torch.no_grad():
             _, idx, _ = m.actor(x, lat, sample="greedy")
         torch.cuda.synchronize()
         last = m.actor.last
         outs[key] = [torch.stack(idx).clone()] + [last[k].clone() for k in ("enc_out", "dec_h", "win_logits", "win_probs")]
-    os.environ.pop("GNNPN_COLSPLIT_G", None)
+        assert last["enc_layout"] == (ops.ENC_BLOCKED128 if key == "pair" else ops.ENC_ROWMAJOR)
     for key in ("cs1", "cs2"):
         for a, b in zip(outs[key], outs["pair"]):
             assert torch.equal(a, b), key
