@@ -216,7 +216,9 @@ def run_ours(args):
     layout = ops.pn_enc_layout(n, L_SEQ, FEAT, K_TASKS, N_CAND, ws is not None)
     enc_out = ops.enc_out_empty(n, L_SEQ, HID, layout, dev)
     c = torch.empty(n, HID, device=dev)
-    bufs = [(torch.empty(n, K_TASKS, HID, device=dev), torch.empty(K_TASKS, n, device=dev, dtype=torch.int32),
+    # decoder hidden states (dec_h) are a by-product nobody reads in this loop: the fused decoder keeps them on chip
+    bufs = [(torch.empty(n, K_TASKS, HID, device=dev) if layout == ops.ENC_ROWMAJOR else None,
+             torch.empty(K_TASKS, n, device=dev, dtype=torch.int32),
              torch.empty(n, L_SEQ, device=dev), torch.empty(n, L_SEQ, device=dev)) for _ in range(2)]
     enc_ev, dec_ev = [], []
 

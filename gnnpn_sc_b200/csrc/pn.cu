@@ -234,8 +234,8 @@ __global__ void enc_unblock_kernel(const float* __restrict__ blk, int64_t n, int
     const int64_t bl = e / (kH / 4);
     const int l = (int)(bl % L);
     const int64_t b = bl / L;
-    const int u = c4 * 4, nt = u >> 5, g = (u >> 3) & 3, half = (u >> 2) & 1;
-    const int64_t src = ((((b >> 7) * L + l) * 8 + nt) * 4 + g) * 1024 + half * 512 + (b & 127) * 4;
+    const int u = c4 * 4, nt = u >> 5, g = (u >> 3) & 3;
+    const int64_t src = ((((b >> 7) * L + l) * 8 + nt) * 4 + g) * 1024 + (b & 127) * 8 + (u & 7);
     reinterpret_cast<float4*>(out)[e] = __ldg(reinterpret_cast<const float4*>(blk + src));
   }
 }
@@ -353,14 +353,14 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
                                const int32_t* forced_idx, const float* sample_uniform, void* workspace,
                                size_t workspace_bytes, int enc_layout, void* stream) {
   GNNPN_REQUIRE(enc_layout == GNNPN_ENC_ROWMAJOR || enc_layout == GNNPN_ENC_BLOCKED128, GNNPN_ESHAPE);
-  GNNPN_REQUIRE(inputs && enc_out && c_state && packed && dec_h && idx_out && win_logits && win_probs,
-                GNNPN_ENULL);
+  GNNPN_REQUIRE(inputs && enc_out && c_state && packed && idx_out && win_logits && win_probs, GNNPN_ENULL);
+  GNNPN_REQUIRE(dec_h || enc_layout == GNNPN_ENC_BLOCKED128, GNNPN_ENULL);   // optional only in the fused decoder
   GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= kXPad, GNNPN_ESHAPE);
   GNNPN_REQUIRE(K >= 1 && N >= 1 && N <= kMaxWindow && (int64_t)K * N == L, GNNPN_ESHAPE);
   GNNPN_REQUIRE(n >= 0 && n < (1ll << 31), GNNPN_ERANGE);
   GNNPN_REQUIRE(attention == GNNPN_ATT_DOT, GNNPN_EUNSUPPORTED);
   (void)att_params;
-  GNNPN_REQUIRE(aligned16(enc_out) && aligned16(dec_h) && aligned16(c_state) && aligned16(packed), GNNPN_EALIGN);
+  GNNPN_REQUIRE(aligned16(enc_out) && aligned16(dec_h) && aligned16(c_state) && aligned16(packed), GNNPN_EALIGN);   // NULL dec_h passes
   if (n == 0) return GNNPN_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const float* bias = packed + kOffBias;

@@ -20,13 +20,13 @@
 //            separate pointer phase after each step's cell epilogue (each epilogue warp owns 8 instances, window rows
 //            streamed per instance, pointer.cuh::pointer_steps_batched) -- the step is MMA phase + pointer phase.
 //   NR >= 1  blocked encodings (GNNPN_ENC_BLOCKED128): per block of 128 instances
-//            [L][8 tiles][4 groups][2 halves][128 instances][4 floats], unit = 32*tile + 8*group + 4*half + i -- exactly
-//            the (thread = instance, 8 units per tile) ownership of the epilogue.  The encoder writes it with coalesced
-//            128-bit stores.  In the decoder (NR = row capacity of the window, N <= NR) the pointer dot products are
+//            [L][8 tiles][4 groups][128 instances][8 floats], unit = 32*tile + 8*group + i -- exactly the
+//            (thread = instance, 8 units per tile) ownership of the epilogue.  The encoder writes it with coalesced
+//            256-bit stores.  In the decoder (NR = row capacity of the window, N <= NR) the pointer dot products are
 //            FUSED INTO THE CELL EPILOGUE: when thread (instance r, group g) has produced the 8 h' units of tile nt
 //            it multiplies them into the matching 8 floats of each of the N window rows of ITS instance (a warp's
-//            load is 512 contiguous bytes; the rows were L2-prefetched two tiles ahead), in pointer.cuh's canonical
-//            order.  The window rows stream from HBM UNDER the step's MMAs; after the last tile the four group
+//            load is 1 KB contiguous; the otherwise idle warp 3 bulk-prefetches every 16 KB (row, tile) slice into L2
+//            two tiles ahead), in pointer.cuh's canonical order.  The window rows stream from HBM UNDER the step's MMAs; after the last tile the four group
 //            partials are combined through shared memory and one thread per instance finishes the step (C*tanh,
 //            latent, softmax, first-max pick / draw, next input row) while the tensor cores already run the h parts
 //            of the next step's first two tiles.  No separate pointer phase remains.
@@ -160,12 +160,42 @@ __device__ __forceinline__ void pointer_phase(const SeqParams& p, int t, int rr0
 
 
 // ---- blocked encodings (GNNPN_ENC_BLOCKED128) ------------------------------------------------------------------
-// float offset of (block of 128 instances, position l, tile nt, group g); + half * 512 + row * 4 inside
-constexpr int64_t ENC_BLK_ROW = 8 * 4 * 2 * BM * 4;              // floats between consecutive positions l (= BM * kH)
+// float offset of (block of 128 instances, position l, tile nt, group g); + row * 8 inside (8 consecutive units)
+constexpr int64_t ENC_BLK_ROW = 8 * 4 * BM * 8;                  // floats between consecutive positions l (= BM * kH)
+constexpr int ENC_BLK_TILE = 4 * BM * 8;                         // floats of one (position, tile): 16 KB, contiguous
 __host__ __device__ inline int64_t enc_blk_off(int64_t block, int L, int64_t l, int nt, int g) {
-  return (block * L + l) * ENC_BLK_ROW + (int64_t)(nt * 4 + g) * (2 * BM * 4);
+  return (block * L + l) * ENC_BLK_ROW + (int64_t)(nt * 4 + g) * (BM * 8);
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// L2 residency control.  The fused decoder streams 97 MB of window rows per step through L2 next to a 19 MB cell-state
+// scratch that is re-read every step: the rows are loaded evict-first (read once), the scratch evict-last -- without
+// the hints the scratch is evicted and costs 1.8 GB of extra DRAM traffic per launch (ncu, profiles/).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void ldg256_stream(const float* p, float4& a, float4& b, uint64_t pol) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ float4 ldg128_hint(const float* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void stg128_hint(float* p, float a, float b, float c, float d, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -308,9 +338,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         float hv[8];
         if (FUSED) {
           // decoder start state = the encoder's last hidden state (modelPN.py:191,205): position L-1 of the block
-          const float* e = p.pa.enc_out + enc_blk_off(blockIdx.x, p.L, p.L - 1, ch >> 2, ch & 3) + r * 4;
-          const float4 a = ldg128(e), b = ldg128(e + BM * 4);
-          hv[0] = a.x; hv[1] = a.y; hv[2] = a.z; hv[3] = a.w; hv[4] = b.x; hv[5] = b.y; hv[6] = b.z; hv[7] = b.w;
+          ldg256(p.pa.enc_out + enc_blk_off(blockIdx.x, p.L, p.L - 1, ch >> 2, ch & 3) + r * 8, hv);
         } else {
           ldg256(p.h0 + (m0 + r) * p.h0_ld + ch * 8, hv);
         }
@@ -551,6 +579,28 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
       bulk_wait0();
     }
   } else if (warp == 3) {
+    if (FUSED) {
+      // ================= L2 prefetcher (fused decoder): the 16 KB slice (window row j, tile nt) of this CTA's block is
+      // contiguous; it is requested two tiles before the epilogue multiplies it, paced by the MMA's tile barriers
+      if (lane == 0 && cta_ok) {
+        constexpr int dist = 2;      // measured: 1 tile ahead 40.1k cycles / step, 2: 39.7k, 3: 51.8k, none: 46.0k (profiles/)
+        const float* const blk = p.pa.enc_out + enc_blk_off(blockIdx.x, p.L, 0, 0, 0);
+        const int N = p.pa.N;
+        for (int a = 0; a < dist; ++a)
+          for (int j = 0; j < N; ++j) bulk_prefetch_l2(blk + (int64_t)j * ENC_BLK_ROW + a * ENC_BLK_TILE, ENC_BLK_TILE * 4);
+        uint32_t uses = 0;
+        for (int t = 0; t < p.steps; ++t) {
+          for (int it = 0; it < N_TILES; ++it, ++uses) {
+            mbar_wait(tfull_bar(it & 1), (uses >> 1) & 1u);      // tile `it` of step t is multiplied: the epilogue starts on it
+            const int nt2 = (it + dist) & (N_TILES - 1);
+            const int t2 = t + (it + dist >= N_TILES ? 1 : 0);
+            if (t2 < p.steps)
+              for (int j = 0; j < N; ++j)
+                bulk_prefetch_l2(blk + ((int64_t)t2 * N + j) * ENC_BLK_ROW + nt2 * ENC_BLK_TILE, ENC_BLK_TILE * 4);
+          }
+        }
+      }
+    }
     // ================= x producer (encoder): raw input row of step t+1 -> fp16 hi/lo x block =================
     if (!DEC) {
       for (int t = 0; t + 1 < p.steps; ++t) {
@@ -578,8 +628,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     float* const h_row = p.h_out + (ok ? m : 0) * p.h_out_inst_ld;
     // blocked scratch: float4 index (((cta*8 + nt)*4 + grp)*2 + half)*128 + row  -> a warp touches 512 contiguous bytes
     float* const c_blk = p.c_scr + ((int64_t)blockIdx.x * (BM * kH) + (int64_t)grp * (2 * BM * 4) + r * 4);
-    // blocked encodings of this thread: + position * ENC_BLK_ROW + nt * (4 * 2 * BM * 4) [+ BM * 4 for the second half]
-    const int64_t blk_thread = enc_blk_off(blockIdx.x, p.L, 0, 0, grp) + r * 4;
+    // blocked encodings of this thread (8 consecutive units): + position * ENC_BLK_ROW + nt * ENC_BLK_TILE
+    const int64_t blk_thread = enc_blk_off(blockIdx.x, p.L, 0, 0, grp) + r * 8;
     float* const e_out = BLK && !DEC ? p.h_out + blk_thread : nullptr;
     const float* const e_in = FUSED ? p.pa.enc_out + blk_thread : nullptr;
     const int N = DEC ? p.pa.N : 0;
@@ -588,6 +638,18 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
     float acc[NRA];                                    // FUSED: running p[g] of the canonical dot, per window row
 #pragma unroll
     for (int j = 0; j < NRA; ++j) acc[j] = 0.f;
+    // FUSED: the first CHK window-row slices of the NEXT tile are requested as soon as the current tile's dots have
+    // consumed the registers, i.e. a whole tile (barrier wait + cell arithmetic) before they are used
+    float4 ea[CHK], eb[CHK];
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const bool keep_c = FUSED;
+    const bool do_dot = FUSED && cta_ok;
+    auto request_rows = [&](int t_, int nt_) {
+#pragma unroll
+      for (int u = 0; u < CHK; ++u)
+        if (u < N) ldg256_stream(e_in + ((int64_t)t_ * N + u) * ENC_BLK_ROW + nt_ * ENC_BLK_TILE, ea[u], eb[u], pol_stream);
+    };
+    if (do_dot) request_rows(0, 0);
     uint32_t uses = 0;
     const bool prof = p.prof != nullptr;
     long long w_tfull = 0, w_hempty = 0, w_ptr = 0;
@@ -596,17 +658,6 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
       const float4* bias4 = reinterpret_cast<const float4*>(sbias + (t == 0 ? 0 : kG));
       const bool last = t == p.steps - 1;
       const float* const e_win = FUSED ? e_in + (int64_t)t * N * ENC_BLK_ROW : nullptr;     // window rows of step t
-      if (FUSED && cta_ok && t == 0) {
-        // L2 prefetch of the first two tiles' slices of window 0 (later slices are requested two tiles ahead below)
-        for (int j = 0; j < N; ++j)
-          if ((lane & 7) == 0) {
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-              prefetch_l2(e_win + (int64_t)j * ENC_BLK_ROW + a * (4 * 2 * BM * 4));
-              prefetch_l2(e_win + (int64_t)j * ENC_BLK_ROW + a * (4 * 2 * BM * 4) + BM * 4);
-            }
-          }
-      }
       for (int it = 0; it < N_TILES; ++it, ++uses) {
         const int buf = it & 1;
         const int nt = it;                             // which 128 gate columns this tile holds
@@ -614,7 +665,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         float* const c_t = c_blk + nt * (4 * 2 * BM * 4);
         float c_old[8];
         if (t > 0) {
-          const float4 a = ldg128(c_t), b = ldg128(c_t + BM * 4);
+          const float4 a = keep_c ? ldg128_hint(c_t, pol_keep) : ldg128(c_t);
+          const float4 b = keep_c ? ldg128_hint(c_t + BM * 4, pol_keep) : ldg128(c_t + BM * 4);
           c_old[0] = a.x; c_old[1] = a.y; c_old[2] = a.z; c_old[3] = a.w;
           c_old[4] = b.x; c_old[5] = b.y; c_old[6] = b.z; c_old[7] = b.w;
         } else if (ok && !p.c_zero_init) {
@@ -622,18 +674,6 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         } else {
 #pragma unroll
           for (int u = 0; u < 8; ++u) c_old[u] = 0.f;
-        }
-        if (FUSED && cta_ok && (lane & 7) == 0) {
-          // L2 prefetch, two tiles ahead: tile it+2 of this window, or tile it-6 of the next step's window
-          const int nt2 = (it + 2) & (N_TILES - 1);
-          const bool wrap = it + 2 >= N_TILES;
-          if (!wrap || !last) {
-            const float* pf = e_win + (wrap ? (int64_t)N * ENC_BLK_ROW : 0) + nt2 * (4 * 2 * BM * 4);
-            for (int j = 0; j < N; ++j) {
-              prefetch_l2(pf + (int64_t)j * ENC_BLK_ROW);
-              prefetch_l2(pf + (int64_t)j * ENC_BLK_ROW + BM * 4);
-            }
-          }
         }
         mbar_wait_t(tfull_bar(buf), (uses >> 1) & 1u, prof, w_tfull);
         tc_fence_after();
@@ -645,33 +685,20 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
         if (lane == 0) arrive_leader(tempty_bar(buf));  // accumulators are in registers: MMA may reuse the buffer
         float cn[8], hn[8];
         lstm_cell8(v, bias4 + u0, c_old, cn, hn);
-        // FUSED: first chunk of this tile's window-row slices (requested here, consumed after the h' bookkeeping)
-        float4 ea[CHK], eb[CHK];
-        if (FUSED && cta_ok) {
-#pragma unroll
-          for (int u = 0; u < CHK; ++u) {
-            if (u < N) {
-              const float* e = e_win + (int64_t)u * ENC_BLK_ROW + nt * (4 * 2 * BM * 4);
-              ea[u] = ldg_stream(reinterpret_cast<const float4*>(e));
-              eb[u] = ldg_stream(reinterpret_cast<const float4*>(e + BM * 4));
-            }
-          }
-        }
-        if (!last) {
+        if (!last && keep_c) {
+          stg128_hint(c_t, cn[0], cn[1], cn[2], cn[3], pol_keep);
+          stg128_hint(c_t + BM * 4, cn[4], cn[5], cn[6], cn[7], pol_keep);
+        } else if (!last) {
           stg128(c_t, cn[0], cn[1], cn[2], cn[3]);
           stg128(c_t + BM * 4, cn[4], cn[5], cn[6], cn[7]);
         } else if (ok) {
           stg256(c_row + u0, cn);
         }
         if (DEC) {
-          if (ok) stg256(h_row + (int64_t)t * kH + u0, hn);
+          if (ok && p.h_out) stg256(h_row + (int64_t)t * kH + u0, hn);        // dec_h is optional in the fused decoder
         } else if (BLK) {
-          // blocked encodings: the thread's 8 units of position t, coalesced across the warp (512 B per store)
-          if (cta_ok) {
-            float* e = e_out + (int64_t)t * ENC_BLK_ROW + nt * (4 * 2 * BM * 4);
-            stg128(e, hn[0], hn[1], hn[2], hn[3]);
-            stg128(e + BM * 4, hn[4], hn[5], hn[6], hn[7]);
-          }
+          // blocked encodings: the thread's 8 units of position t, coalesced across the warp (1 KB per store)
+          if (cta_ok) stg256(e_out + (int64_t)t * ENC_BLK_ROW + nt * ENC_BLK_TILE, hn);
         } else {
           // fp32 h' -> 128B-swizzled [128 x 32] tile; the store issuer (warp 2) sends it to enc_out by TMA
           mbar_wait_t(hempty_bar, (uses & 1u) ^ 1u, prof, w_hempty);   // the previous tile's store has left shared memory
@@ -717,18 +744,15 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
             if (lane == 0) { if (CG == 2) mbar_arrive_cluster(h_ready_remote); else mbar_arrive(h_ready_bar); }
           }
         }
-        if (FUSED && cta_ok) {
+        if (do_dot) {
           // canonical dot (pointer.cuh): s[nt][g] = fma chain over the 8 units, p[g] sequential over the tiles
 #pragma unroll
           for (int j0 = 0; j0 < NR; j0 += CHK) {
             if (j0 > 0) {
 #pragma unroll
               for (int u = 0; u < CHK; ++u) {
-                if (j0 + u < NR && j0 + u < N) {
-                  const float* e = e_win + (int64_t)(j0 + u) * ENC_BLK_ROW + nt * (4 * 2 * BM * 4);
-                  ea[u] = ldg_stream(reinterpret_cast<const float4*>(e));
-                  eb[u] = ldg_stream(reinterpret_cast<const float4*>(e + BM * 4));
-                }
+                if (j0 + u < NR && j0 + u < N)
+                  ldg256_stream(e_win + (int64_t)(j0 + u) * ENC_BLK_ROW + nt * ENC_BLK_TILE, ea[u], eb[u], pol_stream);
               }
             }
 #pragma unroll
@@ -743,6 +767,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
               }
             }
           }
+          if (it + 1 < N_TILES) request_rows(t, it + 1);
+          else if (!last) request_rows(t + 1, 0);
         }
       }
       if (DEC && !FUSED) {

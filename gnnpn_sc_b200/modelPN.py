@@ -85,6 +85,12 @@ class _Last(dict):
         if key == "enc_out" and not dict.__contains__(self, "enc_out"):
             B, L, H = dict.__getitem__(self, "enc_shape")
             dict.__setitem__(self, "enc_out", ops.enc_to_rowmajor(dict.__getitem__(self, "enc_buf"), B, L, H))
+        if key in ("dec_h", "dec_q") and not dict.__contains__(self, key):
+            # the fused decoder does not write its hidden states: replay the decode teacher-forced on the same picks
+            # with the output enabled (same kernels, same arithmetic -> the states the picks were made from)
+            dec_h = dict.__getitem__(self, "replay_dec_h")()
+            dict.__setitem__(self, "dec_h", dec_h)
+            dict.__setitem__(self, "dec_q", dec_h)
         return dict.__getitem__(self, key)
 
 
@@ -253,12 +259,22 @@ class PointerNet(nn.Module):
             # sample != "greedy": multinomial draw per step (modelPN.py:227-228) as an inverse-CDF pick in the kernel
             uniform = None if sample == "greedy" else torch.rand(K, B, device=x.device, generator=self.generator)
             ptr_blk = qw = None
+            replay = None
             if fast:
-                dec_h, idx, win_logits, win_probs = ops.pn_decode_greedy(
-                    x, enc_out, c, dec_w, K, N, latent_win=lat, alpha=float(self.alpha), attention="Dot",
-                    use_tanh=use_tanh, C=C, forced_idx=forced, workspace=ws, sample_uniform=uniform, enc_layout=layout,
-                    hidden=self.hidden_size)
+                lazy_h = layout == ops.ENC_BLOCKED128          # fused decoder: hidden states stay on chip
+                c_enc = c.clone() if lazy_h else None
+                kw = dict(latent_win=lat, alpha=float(self.alpha), attention="Dot", use_tanh=use_tanh, C=C,
+                          workspace=ws, sample_uniform=uniform, enc_layout=layout, hidden=self.hidden_size)
+                dec_h, idx, win_logits, win_probs = ops.pn_decode_greedy(x, enc_out, c, dec_w, K, N, forced_idx=forced,
+                                                                         want_dec_h=not lazy_h, **kw)
                 dec_q = dec_h
+                if lazy_h:
+                    fed_picks = idx if forced is None else forced
+
+                    def replay():
+                        with torch.no_grad():
+                            return ops.pn_decode_greedy(x, enc_out, c_enc.clone(), dec_w, K, N, forced_idx=fed_picks,
+                                                        want_dec_h=True, **kw)[0]
             else:
                 blocks = None
                 if att == "Bahdanau":
@@ -269,18 +285,21 @@ class PointerNet(nn.Module):
                     att_params=blocks, n_glimpses=self.n_glimpses, use_tanh=use_tanh, C=C, forced_idx=forced,
                     sample_uniform=uniform, use_tc=ws is not None)
         idx64 = idx.long()
-        self.last = _Last({"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "dec_h": dec_h,
-                           "dec_q": dec_q, "latent_win": lat, "enc_buf": enc_out, "enc_layout": layout,
-                           "enc_shape": (B, L, self.hidden_size)})
+        self.last = _Last({"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "latent_win": lat,
+                           "enc_buf": enc_out, "enc_layout": layout, "enc_shape": (B, L, self.hidden_size)})
         if layout == ops.ENC_ROWMAJOR:
             self.last["enc_out"] = enc_out
+        if dec_h is not None:
+            self.last["dec_h"], self.last["dec_q"] = dec_h, dec_q
+        else:
+            self.last["replay_dec_h"] = replay
         last = self.last
 
         fed = idx if forced is None else forced.contiguous()     # the picks the visited mask follows
 
         def dense_logits():
             if att == "Dot":
-                return ops.pn_full_logits(last["enc_out"], dec_q, fed, "Dot", None, use_tanh, C)
+                return ops.pn_full_logits(last["enc_out"], last["dec_q"], fed, "Dot", None, use_tanh, C)
             return ops.pn_full_logits_bahdanau(ops.pn_ref_transform(last["enc_out"], ptr_blk), qw, ptr_blk, fed,
                                                use_tanh, C)
 

@@ -103,15 +103,17 @@ def lstm_encode(inputs: torch.Tensor, packed: torch.Tensor, hidden: int = 256,
 def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, latent_win=None, alpha: float = 1.0,
                      attention: str = "Dot", att_params=None, use_tanh: bool = True, C: float = 10.0,
                      forced_idx=None, out=None, workspace: Optional[torch.Tensor] = None,
-                     sample_uniform: Optional[torch.Tensor] = None, enc_layout: int = ENC_ROWMAJOR, hidden: int = 256):
-    """Returns (dec_h [n,K,H], idx int32 [K,n], win_logits [n,L], win_probs [n,L]).  ``c_state`` is updated in place.
-    ``enc_out`` is in ``enc_layout`` (as produced by ``lstm_encode(..., layout=enc_layout)``)."""
+                     sample_uniform: Optional[torch.Tensor] = None, enc_layout: int = ENC_ROWMAJOR, hidden: int = 256,
+                     want_dec_h: bool = True):
+    """Returns (dec_h [n,K,H] | None, idx int32 [K,n], win_logits [n,L], win_probs [n,L]).  ``c_state`` is updated in
+    place.  ``enc_out`` is in ``enc_layout`` (as produced by ``lstm_encode(..., layout=enc_layout)``).  With blocked
+    encodings the decoder hidden states need not be written to memory: ``want_dec_h=False`` (or ``out[0] is None``)."""
     x = _f32(inputs, "inputs")
     n, L, F = x.shape
     H = enc_out.shape[2] if enc_layout == ENC_ROWMAJOR else hidden
     dev = x.device
     if out is None:
-        dec_h = torch.empty(n, K, H, device=dev, dtype=torch.float32)
+        dec_h = torch.empty(n, K, H, device=dev, dtype=torch.float32) if (want_dec_h or enc_layout == ENC_ROWMAJOR) else None
         idx = torch.empty(K, n, device=dev, dtype=torch.int32)
         wl = torch.empty(n, L, device=dev, dtype=torch.float32)
         wp = torch.empty(n, L, device=dev, dtype=torch.float32)
@@ -129,7 +131,7 @@ def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, laten
     check(lib().gnnpn_pn_decode_greedy_f32(
         x.data_ptr(), enc_out.data_ptr(), c_state.data_ptr(), _ptr(latent_win), float(alpha),
         packed_dec.data_ptr(), ATT[attention], _ptr(att_params), int(bool(use_tanh)), float(C),
-        n, L, F, H, K, N, dec_h.data_ptr(), idx.data_ptr(), wl.data_ptr(), wp.data_ptr(),
+        n, L, F, H, K, N, _ptr(dec_h), idx.data_ptr(), wl.data_ptr(), wp.data_ptr(),
         _ptr(forced_idx), _ptr(sample_uniform), *_ws(workspace), int(enc_layout), _stream()), "pn_decode_greedy")
     return dec_h, idx, wl, wp
 

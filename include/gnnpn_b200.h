@@ -89,8 +89,8 @@ GNNPN_API int gnnpn_pn_pack_lstm_f32(const float* w_ih, const float* w_hh, const
 
 /* Layout of the encodings buffer handed from gnnpn_lstm_encode_f32 to gnnpn_pn_decode_greedy_f32.
  *   GNNPN_ENC_ROWMAJOR    fp32 [n, L, H] (what modelPN.py:191 returns; every other entry point takes this one)
- *   GNNPN_ENC_BLOCKED128  blocks of 128 instances, fp32 [ceil(n/128)][L][8 tiles][4 groups][2 halves][128][4] with hidden
- *                         unit = 32*tile + 8*group + 4*half + i: the ownership (thread = instance, 8 units per
+ *   GNNPN_ENC_BLOCKED128  blocks of 128 instances, fp32 [ceil(n/128)][L][8 tiles][4 groups][128 instances][8] with hidden
+ *                         unit = 32*tile + 8*group + i: the ownership (thread = instance, 8 units per
  *                         accumulator tile) of the persistent CTA-pair scan's epilogue.  The encoder writes it with
  *                         coalesced 128-bit stores and the decoder folds the pointer dot products into its cell
  *                         epilogue, so the window rows stream from HBM under the step's MMAs (no separate attention
@@ -129,7 +129,8 @@ GNNPN_API size_t gnnpn_pn_workspace_bytes(int64_t n, int hidden);
  *   latent_win   fp32 [n, L] or NULL   PNLow's step-(l/N) logit at position l (only the window
  *                                   slice of latent[k] can influence a pick)
  *   att_params   NULL for Dot; for Bahdanau a packed block, see gnnpn_pn_pack_bahdanau_f32
- *   dec_h        fp32 [n, K, H]     out: decoder hidden state (= attention query) of every step
+ *   dec_h        fp32 [n, K, H]     out: decoder hidden state (= attention query) of every step; may be NULL with
+ *                                   enc_layout = GNNPN_ENC_BLOCKED128 (the fused decoder does not need it in memory)
  *   idx_out      int32 [K, n]       out: selected position in [k*N, (k+1)*N)
  *   win_logits   fp32 [n, L]        out: this network's pointer logit at position l taken at step l/N
  *   win_probs    fp32 [n, L]        out: softmax probability at position l at step l/N

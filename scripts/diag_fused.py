@@ -54,8 +54,11 @@ ws = ops.pn_workspace(n, 256, dev, "tc")
 c = torch.empty(n, 256, device=dev)
 out = (torch.empty(n, K, 256, device=dev), torch.empty(K, n, device=dev, dtype=torch.int32),
        torch.empty(n, K * N, device=dev), torch.empty(n, K * N, device=dev))
-for lay, name in ((ops.ENC_BLOCKED128, "blocked/fused"), (ops.ENC_ROWMAJOR, "row-major/pointer phase")):
+variants = [(ops.ENC_BLOCKED128, "blocked/fused, dec_h not stored", False), (ops.ENC_BLOCKED128, "blocked/fused, dec_h stored", True),
+            (ops.ENC_ROWMAJOR, "row-major/pointer phase", True)]
+for lay, name, with_h in variants:
     ops.set_option("scan", 0)
+    out = (torch.empty(n, K, 256, device=dev) if with_h else None,) + tuple(out[1:])
     enc = ops.enc_out_empty(n, K * N, 256, lay, dev)
     te, td = [], []
     for i in range(6):

@@ -378,7 +378,8 @@ def test_column_split_scan_equals_cta_pair_scan_bitwise(n, K, N):
         torch.cuda.synchronize()
         last = m.actor.last
         outs[key] = [torch.stack(idx).clone()] + [last[k].clone() for k in ("enc_out", "dec_h", "win_logits", "win_probs")]
-        assert last["enc_layout"] == (ops.ENC_BLOCKED128 if key == "pair" else ops.ENC_ROWMAJOR)
+        # the pair scan keeps blocked encodings / fused pointer dots for windows of up to 10 candidates
+        assert last["enc_layout"] == (ops.ENC_BLOCKED128 if key == "pair" and N <= 10 else ops.ENC_ROWMAJOR)
     for key in ("cs1", "cs2"):
         for a, b in zip(outs[key], outs["pair"]):
             assert torch.equal(a, b), key
