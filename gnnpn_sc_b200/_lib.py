@@ -30,6 +30,8 @@ SIGNATURES = {
     "gnnpn_pn_pack_lstm_f32": (_i, [_p] * 7 + [_i, _i, _p, _p]),
     "gnnpn_set_option": (_i, [C.c_char_p, _i]),
     "gnnpn_get_option": (_i, [C.c_char_p, C.POINTER(_i)]),
+    "gnnpn_pn_input_limit": (_f, []),
+    "gnnpn_pn_check_inputs_f32": (_i, [_p, _i64, _p, _p]),
     "gnnpn_pn_enc_layout": (_i, [_i64, _i, _i, _i, _i, _i]),
     "gnnpn_pn_enc_out_floats": (C.c_size_t, [_i64, _i, _i, _i]),
     "gnnpn_pn_enc_to_rowmajor_f32": (_i, [_p, _i64, _i, _i, _p, _p]),

@@ -17,7 +17,10 @@
 //     sigmoid; each warp's [32 x 32] result tile leaves through shared memory and a TMA store) while the MMAs of
 //     tile i+1 run;
 //   * persistent grid: one CTA pair per TPC (74 pairs), tiles strided over the pairs.
-// Input range: |a| < 4095 (fp16 after the 2^4 pre-scale); the ML stage feeds O(1) features / BatchNorm outputs.
+// Input range: |a| < 4095 (fp16 after the 2^4 pre-scale); the ML stage feeds O(1) features / BatchNorm outputs.  The
+// converters check every value they touch; when one is outside the range (or not finite) they raise a flag in the
+// workspace and launch_node_transform's guarded strict-fp32 FFMA pass (gemm_ffma.cu) recomputes C -- on the device,
+// no host round trip; it returns immediately when the flag is clear (the normal case).
 // Shapes outside (K > 256, N > 256, N % 16 != 0, K % 4 != 0) use the 3xTF32 mainloop in tc_kernels.cu.
 #include <stdlib.h>
 #include <cuda_fp16.h>
@@ -26,6 +29,9 @@
 #include "tc_seq_dev.cuh"
 
 namespace gnnpn {
+int launch_gemm_ffma_if(const int* only_if, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                        const float* scale, const float* shift, int act, float* C, int64_t ldc, int64_t M, int N,
+                        int K, cudaStream_t st);
 namespace tc {
 int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f16);
 }
@@ -76,6 +82,7 @@ struct Params {
   int64_t n_tiles;         // 256-row pair tiles
   int c_vec;               // 0: TMA stores through shared memory; 8 / 4 / 1: direct 256-bit / 128-bit / scalar row stores
   const float2* st_tab;    // [MAX_N] per column {s', t'}: out = act(acc * s' + t')
+  int* status;             // workspace word: set to 1 when an input value is outside the fp16-split range
 };
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
@@ -202,6 +209,7 @@ node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid
       }
     };
     int s = 0; uint32_t ph = 0;
+    bool out_of_range = false;
     auto convert_block = [&](const float (*v)[8]) {
       mbar_wait(a_empty(s), ph ^ 1u);
       const uint32_t st = sbase + OFF_A + (uint32_t)s * 2 * BLK_BYTES;
@@ -212,6 +220,7 @@ node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float a = v[i][2 * j] * kScale, b = v[i][2 * j + 1] * kScale;
+          out_of_range |= !(fmaxf(fabsf(a), fabsf(b)) < 65504.0f);      // also catches NaN / inf
           hi[j] = pack_h2(a, b);
           const float2 bk = unpack_h2(hi[j]);
           lo[j] = pack_h2(a - bk.x, b - bk.y);
@@ -234,6 +243,7 @@ node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid
       load_block(g + 2, b0);
       convert_block(b1);
     }
+    if (out_of_range) atomicOr(p.status, 1);
   } else if (warp >= 4 + CONV_WARPS) {
     // ================= epilogue: thread = one row, 32-column chunks grp, grp+2, ... =================
     const int e = warp - (4 + CONV_WARPS);
@@ -319,8 +329,9 @@ node_transform_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid
 // W [N, K] fp32 -> fp16 hi/lo [N, Kp] (x 2^4), K zero-padded to Kp
 __global__ void split_w_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, int Kp, __half* __restrict__ hi,
                                __half* __restrict__ lo, const float* __restrict__ bias, const float* __restrict__ scale,
-                               const float* __restrict__ shift, float2* __restrict__ st_tab) {
+                               const float* __restrict__ shift, float2* __restrict__ st_tab, int* __restrict__ status) {
   const int total = N * Kp;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *status = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < MAX_N; i += gridDim.x * blockDim.x) {
     const bool in = i < N;
     const float b = (in && bias) ? bias[i] : 0.f;
@@ -346,7 +357,7 @@ bool node_transform_supported(int64_t M, int N, int K) {
 
 size_t node_transform_workspace_bytes(int N, int K) {
   const int Kp = round_up(K, nt::KB);
-  return (size_t)2 * N * Kp * sizeof(__half) + nt::MAX_N * sizeof(float2) + 1024;
+  return (size_t)2 * N * Kp * sizeof(__half) + nt::MAX_N * sizeof(float2) + 16 + 1024;
 }
 
 int launch_node_transform(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
@@ -358,7 +369,8 @@ int launch_node_transform(const float* A, int64_t lda, const float* W, int64_t l
   __half* w_hi = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   __half* w_lo = w_hi + (size_t)N * Kp;
   float2* st_tab = reinterpret_cast<float2*>(w_lo + (size_t)N * Kp);            // 16-byte aligned: N * Kp * 2 is a multiple of 2 KB
-  split_w_kernel<<<(N * Kp + 255) / 256, 256, 0, st>>>(W, ldw, N, K, Kp, w_hi, w_lo, bias, scale, shift, st_tab);
+  int* status = reinterpret_cast<int*>(st_tab + MAX_N);
+  split_w_kernel<<<(N * Kp + 255) / 256, 256, 0, st>>>(W, ldw, N, K, Kp, w_hi, w_lo, bias, scale, shift, st_tab, status);
   int rc = after_launch();
   if (rc) return rc;
   CUtensorMap maps[2];
@@ -370,6 +382,7 @@ int launch_node_transform(const float* A, int64_t lda, const float* W, int64_t l
   const uintptr_t ca = reinterpret_cast<uintptr_t>(C);
   p.c_vec = ((ldc & 7) == 0 && (ca & 31u) == 0) ? 8 : ((ldc & 3) == 0 && (ca & 15u) == 0) ? 4 : 1;
   p.st_tab = st_tab;
+  p.status = status;
   CUtensorMap map_c;
   static const int direct = getenv("GNNPN_GEMM_DIRECT_STORE") ? atoi(getenv("GNNPN_GEMM_DIRECT_STORE")) : 0;   // A/B knob
   if (p.c_vec >= 4 && !direct) {
@@ -402,7 +415,10 @@ int launch_node_transform(const float* A, int64_t lda, const float* W, int64_t l
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, node_transform_kernel, maps[0], maps[1], map_c, p);
   if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
-  return after_launch();
+  if ((rc = after_launch())) return rc;
+  // inputs outside the fp16-split range (|a| >= 4095, NaN, inf): the converters raised *status and the strict-fp32
+  // pass below recomputes C; with the flag clear its grid returns immediately
+  return launch_gemm_ffma_if(status, A, lda, W, ldw, bias, scale, shift, act, C, ldc, M, N, K, st);
 }
 
 }  // namespace gnnpn

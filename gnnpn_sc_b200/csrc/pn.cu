@@ -226,6 +226,14 @@ __global__ void reward_kernel(const float* __restrict__ inputs, const int32_t* _
 // one-launch-per-step kernels (kept for inputs wider than 8 columns and as the A/B reference)
 int seq_mode() { return options().persistent.load(std::memory_order_relaxed); }
 
+// raw input range check: *flag |= 1 if any value is NaN / inf or has |x| >= limit
+__global__ void check_inputs_kernel(const float* __restrict__ x, int64_t count, float limit, int32_t* __restrict__ flag) {
+  bool bad = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    bad |= !(fabsf(__ldg(x + i)) < limit);
+  if (bad) atomicOr(flag, 1);
+}
+
 // blocked encodings -> row-major [n, L, kH]; one thread per float4 of the output (coalesced writes)
 __global__ void enc_unblock_kernel(const float* __restrict__ blk, int64_t n, int L, float* __restrict__ out) {
   const int64_t total = n * L * (kH / 4);
@@ -264,6 +272,18 @@ int gnnpn_pn_pack_lstm_f32(const float* w_ih, const float* w_hh, const float* b_
   pack_lstm_kernel<<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(w_ih, w_hh, b_ih, b_hh, w_embed, b_embed,
                                                                   start_input, hidden, in_features, kXPad, kKp,
                                                                   packed);
+  return after_launch();
+}
+
+float gnnpn_pn_input_limit(void) { return 65504.0f; }
+
+int gnnpn_pn_check_inputs_f32(const float* inputs, int64_t count, int32_t* flag, void* stream) {
+  GNNPN_REQUIRE(inputs && flag, GNNPN_ENULL);
+  GNNPN_REQUIRE(count >= 0, GNNPN_ESHAPE);
+  if (count == 0) return GNNPN_OK;
+  const int64_t blocks = ceil_div(count, 256 * 8);
+  check_inputs_kernel<<<(unsigned)(blocks < 8 * kNumSMs ? blocks : 8 * kNumSMs), 256, 0, (cudaStream_t)stream>>>(
+      inputs, count, gnnpn_pn_input_limit(), flag);
   return after_launch();
 }
 

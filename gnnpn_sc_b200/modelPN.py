@@ -204,6 +204,7 @@ class PointerNet(nn.Module):
         self.impl = None                          # None -> ops.DEFAULT_IMPL ("tc"); "ffma" = strict-fp32 kernels
         self.generator = None                     # optional torch.Generator (cuda) for sample="sample"
         self.force_general = False                # route a fast-path configuration through the general kernels (tests)
+        self.check_inputs = True                  # range-check the raw rows of every batch (one tiny kernel + one sync)
 
     # -- packed weights are a cache over the parameters; rebuilt when any of them changes
     def _packed_weights(self):
@@ -244,6 +245,7 @@ class PointerNet(nn.Module):
             raise RuntimeError("PointerNet.forward needs CUDA tensors: the B200 path has no CPU fallback")
         K, N = self.serCategory, self.serNumber
         x = self._kernel_inputs(inputs)
+        range_flag = ops.pn_check_inputs(x) if (self.check_inputs and self.impl != "ffma") else None
         fast = self._fast_path(x.shape[2])
         enc_w, dec_w = self._packed_weights()
         use_tanh, C = bool(self.pointer.use_tanh), float(self.pointer.C)
@@ -284,6 +286,11 @@ class PointerNet(nn.Module):
                     x, enc_out, c, dec_w, K, N, latent_win=lat, alpha=float(self.alpha), attention=att,
                     att_params=blocks, n_glimpses=self.n_glimpses, use_tanh=use_tanh, C=C, forced_idx=forced,
                     sample_uniform=uniform, use_tc=ws is not None)
+        if range_flag is not None and int(range_flag.item()):
+            raise ops.GnnpnError(
+                "PointerNet.forward: an input value is NaN / inf or |x| >= 65504 -- outside the range of the fp16-split "
+                "tensor-core LSTM (GNNPN_ERANGE).  Normalise the QoS columns (the reference's data is min-max scaled) "
+                "or set actor.impl = 'ffma' for the strict-fp32 kernels.")
         idx64 = idx.long()
         self.last = _Last({"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "latent_win": lat,
                            "enc_buf": enc_out, "enc_layout": layout, "enc_shape": (B, L, self.hidden_size)})

@@ -65,6 +65,15 @@ def _ws(ws):
     return (None, 0) if ws is None else (ws.data_ptr(), ws.numel())
 
 
+def pn_check_inputs(inputs: torch.Tensor) -> torch.Tensor:
+    """int32 [1] device flag: 1 when a raw input value is NaN / inf / outside the fp16-split range of the LSTM kernels
+    (``gnnpn_pn_input_limit()``).  Asynchronous; the caller decides when to read it."""
+    x = _f32(inputs, "inputs")
+    flag = torch.zeros(1, device=x.device, dtype=torch.int32)
+    check(lib().gnnpn_pn_check_inputs_f32(x.data_ptr(), x.numel(), flag.data_ptr(), _stream()), "pn_check_inputs")
+    return flag
+
+
 def pn_enc_layout(n: int, L: int, F: int, K: int, N: int, has_workspace: bool = True) -> int:
     """Layout the dispatcher wants for the (lstm_encode, pn_decode_greedy) pair of a batch: ``ENC_BLOCKED128`` when the
     batch runs on the persistent CTA-pair scan (pointer dots fused into the decoder's cell epilogue), else row-major."""

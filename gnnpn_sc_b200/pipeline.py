@@ -16,6 +16,7 @@ import torch
 class GreedyLowHigh:
     def __init__(self, low, high, device=None):
         self.low, self.high = low.eval(), high.eval()
+        self.high.actor.check_inputs = False      # PNHigh decodes the rows PNLow has just range-checked
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.type != "cuda":
             raise RuntimeError("GreedyLowHigh needs a CUDA device: the B200 path has no CPU fallback")
@@ -106,6 +107,7 @@ class ML2PN:
     def __init__(self, net, low, high, service_sample, serviceFeature, device=None):
         self.device = torch.device(device if device is not None else "cuda")
         self.net, self.low, self.high = net.eval(), low.eval(), high.eval()
+        self.high.actor.check_inputs = False      # same rows as PNLow
         qos, ptr = service_arrays(serviceFeature)
         self.svc_qos = torch.from_numpy(qos).to(self.device)
         self.cat_ptr = torch.from_numpy(ptr).to(self.device)

@@ -106,6 +106,13 @@ GNNPN_API size_t gnnpn_pn_enc_out_floats(int64_t n, int L, int hidden, int layou
 GNNPN_API int gnnpn_pn_enc_to_rowmajor_f32(const float* enc_blocked, int64_t n, int L, int hidden, float* enc_out,
                                  void* stream);
 
+/* Input range of the tensor-core LSTM kernels: the raw rows are split into fp16 hi/lo pairs, so |x| must stay below
+ * gnnpn_pn_input_limit() (65504; min-max-normalised QoS values are in [0, 1]).  gnnpn_pn_check_inputs_f32 ORs 1 into the
+ * device word *flag (caller zeroes it) when any of `count` values is NaN, infinite or at / above the limit; the
+ * Python modules call it on every batch and raise instead of decoding garbage (GNNPN_ERANGE semantics, asynchronous). */
+GNNPN_API float gnnpn_pn_input_limit(void);
+GNNPN_API int gnnpn_pn_check_inputs_f32(const float* inputs, int64_t count, int32_t* flag, void* stream);
+
 /* Encoder: embedding2 + nn.LSTM over L steps (modelPN.py:190-191).
  *   inputs  fp32 [n, L, F]          (F = in_features, 8 when embedding_size == 0)
  *   enc_out fp32 [n, L, H]          every hidden state (or the blocked layout, gnnpn_pn_enc_out_floats() floats)

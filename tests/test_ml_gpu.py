@@ -99,3 +99,62 @@ def test_trainml_smoke(tmp_path):
     with open(os.path.join(tmp_path, "solutions", "ML", "tiny", "testServices-epoch1.txt")) as f:
         rank = json.load(f)
     assert len(rank) == 16 and sorted(rank[0]) == list(range(60))
+
+
+def _reference_test_loop(x, y, log=(1, 5)):
+    """trainML.py:49-72 restated on CPU tensors: per-row descending sort, P@k counting, list of index lists."""
+    idx_list, total = [], [[] for _ in log]
+    for _x, _y in zip(x, y):
+        pat = [0] * len(log)
+        _, indices = _x.sort(dim=0, descending=True, stable=True)      # the reference's CPU sort keeps ties in index order
+        for k in range(len(log)):
+            for idx in indices[:log[k]]:
+                if _y[idx] == 1:
+                    pat[k] += 1
+        idx_list.append(indices.numpy().tolist())
+        for k in range(len(log)):
+            total[k].append(pat[k] / log[k])
+    return idx_list, [float(np.average(t)) for t in total]
+
+
+def test_ranking_and_precision_at_k_match_reference_loop_with_ties():
+    """f3: the batched device ranking / P@1 / P@5 of TrainML.test against the reference's per-row python loop
+    (trainML.py:49-72) on the SAME scores, with exact ties injected (scores quantised to 1/8 and constant rows)."""
+    from gnnpn_sc_b200 import trainML
+    g = torch.Generator().manual_seed(3)
+    B, S = 48, 257
+    x = torch.rand(B, S, generator=g)
+    x[: B // 2] = (x[: B // 2] * 8).floor() / 8          # many exact ties
+    x[0] = 0.5                                            # all equal: ranking = index order, P@k = label prefix
+    y = (torch.rand(B, S, generator=g) < 0.05).float()
+    y[0, :5] = torch.tensor([1, 0, 1, 0, 0.])
+    order, (p1, p5) = trainML.precision_at(x.cuda(), y.cuda())
+    want_idx, (w1, w5) = _reference_test_loop(x, y)
+    assert order.cpu().numpy().tolist() == want_idx
+    assert abs(float(p1.mean()) - w1) < 1e-7 and abs(float(p5.mean()) - w5) < 1e-7
+    assert order[0].cpu().tolist() == list(range(S)) and float(p1[0]) == 1.0 and abs(float(p5[0]) - 0.4) < 1e-7
+
+
+def test_trainml_test_rankings_and_file_layout(tmp_path):
+    """TrainML.test end to end: rankings == descending stable sort of the model's own scores, P@k == the reference loop
+    on them; testServices-epoch{e}.txt = train rankings (loader order) + validation rankings, S ints per instance
+    (trainML.py:146-149)."""
+    import json, os
+    from gnnpn_sc_b200 import synth, loadData, trainML
+    ds = synth.ml_dataset(n_instances=12, K=6, S=60, seed=2, min_tasks=3)
+    t = trainML.TrainML("tiny", 2, 2, 128, 20, 0.0, 0.001, 1, root=str(tmp_path))
+    t.start(arrays=loadData.ml_arrays(ds))
+    idx, (p1, p5) = t.test(t.val_loader)
+    scores, labels = [], []
+    t.model.eval()
+    with torch.no_grad():
+        for data in t.val_loader:
+            d = trainML._to(data, t.device)
+            scores.append(t.model(d).view(d.num_graphs, -1).cpu())
+            labels.append(d.y.view(d.num_graphs, -1).cpu())
+    want_idx, (w1, w5) = _reference_test_loop(torch.cat(scores), torch.cat(labels))
+    assert idx == want_idx and abs(p1 - w1) < 1e-6 and abs(p5 - w5) < 1e-6
+    with open(os.path.join(tmp_path, "solutions", "ML", "tiny", "testServices-epoch0.txt")) as f:
+        rank = json.load(f)
+    assert len(rank) == 12 and all(sorted(r) == list(range(60)) for r in rank)
+    assert rank[9:] == idx                               # validation quarter last, in loader order

@@ -72,3 +72,68 @@ def test_segment_mean_and_aggregate_sum():
     assert (got.double() - ref).abs().max() <= 1e-6
     ei, w = _graph(n, 400, 8)
     assert (mo.aggregate_sum(x, ei, w).double() - _dense_adj(ei, w, n) @ x.double()).abs().max() <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# hand-derived known-answer tests (tests/ml_kats.py): the restatement against arithmetic done on paper
+# ---------------------------------------------------------------------------------------------------------------------
+import ml_kats as kat
+
+
+def _close_fr(got, want, tol=2e-7):
+    return abs(float(got) - float(want)) <= tol * max(1.0, abs(float(want)))
+
+
+def test_kat_gcn_norm_existing_duplicate_and_zero_weight_self_loops():
+    ei = torch.tensor([[s for s, _, _ in kat.GCN_EDGES], [d for _, d, _ in kat.GCN_EDGES]])
+    w = torch.tensor([x for _, _, x in kat.GCN_EDGES])
+    ei2, norm = mo.gcn_norm(ei, w, kat.GCN_N)
+    assert list(zip(ei2[0].tolist(), ei2[1].tolist())) == kat.GCN_EDGE_ORDER          # kept edges, then loops 0..n-1
+    for (s, d), v in zip(kat.GCN_EDGE_ORDER, norm.tolist()):
+        assert _close_fr(v, kat.GCN_NORM[(s, d)]), ((s, d), v)
+    assert norm[-1].item() == 0.0                                                      # deg = 0 -> inf -> 0, not NaN
+
+
+def test_kat_gcn_conv_layer():
+    conv = mo.GCNConvO(2, 2)
+    conv.weight.data = torch.eye(2)
+    conv.bias.data = torch.tensor(kat.GCN_BIAS)
+    ei = torch.tensor([[s for s, _, _ in kat.GCN_EDGES], [d for _, d, _ in kat.GCN_EDGES]])
+    w = torch.tensor([x for _, _, x in kat.GCN_EDGES])
+    with torch.no_grad():
+        out = conv(torch.tensor(kat.GCN_X), ei, w)
+    for i in range(kat.GCN_N):
+        for c in range(2):
+            assert _close_fr(out[i, c].item(), kat.GCN_OUT[i][c], 3e-7), (i, c, out[i, c].item())
+
+
+def test_kat_gin_eps_and_multi_edges():
+    conv = mo.GINConvO(torch.nn.Sequential(torch.nn.Identity()), True)
+    conv.eps.data.fill_(kat.GIN_EPS)
+    ei = torch.tensor([[s for s, _ in kat.GIN_EDGES], [d for _, d in kat.GIN_EDGES]])
+    with torch.no_grad():
+        pre = conv(torch.tensor(kat.GIN_X).view(-1, 1), ei).view(-1)
+    assert pre.tolist() == [float(v) for v in kat.GIN_PRE]                             # small integers / halves: exact
+
+
+def test_kat_segment_mean_with_empty_segments():
+    out = mo.segment_mean(torch.tensor(kat.MEAN_X).view(-1, 1), torch.tensor(kat.MEAN_SEG), kat.MEAN_SEGMENTS)
+    assert out.view(-1).tolist() == kat.MEAN_OUT
+
+
+def test_kat_collation_inc_rule_oracle_and_product():
+    from types import SimpleNamespace
+    from gnnpn_sc_b200 import trainML
+    svc = torch.tensor([[s for s, _ in kat.COLLATE_SVC_EDGES], [d for _, d in kat.COLLATE_SVC_EDGES]])
+    samples = []
+    for n, edges in zip(kat.COLLATE_REQ_NODES, kat.COLLATE_REQ_EDGES):
+        samples.append(SimpleNamespace(
+            x=torch.zeros(n, 7), y=torch.zeros(kat.COLLATE_S),
+            edge_index=torch.tensor([[s for s, _ in edges], [d for _, d in edges]]),
+            x_service=torch.zeros(kat.COLLATE_S, 5), edge_index_service=svc, edge_attr_service=torch.ones(2)))
+    for collate in (mo.collate, trainML.collate):
+        b = collate(samples, True)
+        assert b.edge_index.tolist() == kat.COLLATE_EDGE_INDEX and b.batch.tolist() == kat.COLLATE_BATCH
+        assert b.edge_index_service.tolist() == kat.COLLATE_SVC_FAITHFUL               # shifted by 3 request nodes
+        assert collate(samples, False).edge_index_service.tolist() == kat.COLLATE_SVC_SANE
+        assert b.x_service.shape[0] == 2 * kat.COLLATE_S

@@ -13,6 +13,8 @@ import torch
 from oracle import make_golden as mg
 from oracle import pn_oracle as po
 
+from conftest import record_parity
+
 pytestmark = pytest.mark.gpu
 LOGIT_TOL = 1e-5
 CUDA_CASES = ["qws_b4", "normal_b2", "small_b16", "sharp_b4", "notanh_b3", "bahdanau_b3", "glimpse_b3", "embed20_b3"]
@@ -59,14 +61,15 @@ def _models(name, device="cuda", impl=None):
     return cfg, x, out[0], out[1]
 
 
-STRESS_FLOOR = {"ffma": 4.0, "tc": 8.0, "tc_pair": 8.0, None: 8.0}   # multiples of the reference's own fp32 noise, stress cases only
+STRESS_FLOOR = {"ffma": 2.0, "tc": 4.0, "tc_pair": 4.0, None: 4.0}   # multiples of the reference's own fp32 noise, stress cases only
 
 
 def _close(a, b, tol=LOGIT_TOL, floor=0.0):
     """|a-b| <= max(tol * max(1,|b|), floor).  `floor` = 4x the reference's own fp32-vs-fp64 deviation, used only
     on stress cases whose weights (LSTM matrices x3) amplify rounding noise beyond 1e-5 for ANY fp32 evaluation
     order -- there the reference's own fp32 run is 1.2e-5..2.3e-5 away from its fp64 run.  The tcgen05 path
-    (3xTF32 with the tensor core's truncating fp32 accumulation, MUFU-based activations) gets 8x, FFMA 4x."""
+    (3xFP16 split with the tensor core's truncating fp32 accumulation, MUFU-based activations) gets 4x, FFMA 2x
+    (achieved on a B200: 2.7x and 1.2x, profiles/r02_parity.json)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return np.abs(a - b) <= np.maximum(tol * np.maximum(1.0, np.abs(b)), floor)
 
@@ -118,6 +121,10 @@ def test_greedy_low_high_matches_reference_fixture(name, impl, golden_dir):
         noise = _reference_noise(g, key)
         err = np.abs(dense[fin] - ref[fin]).max()
         print(f"{name}/{key}[{impl}]: max |dlogit| {err:.2e} (reference's own fp32 noise vs its fp64 run: {noise:.2e})")
+        record_parity(f"fixture_{name}_{key}_{impl}", max_abs_dlogit=err, reference_fp32_vs_fp64_noise=noise,
+                      max_rel=float((np.abs(dense[fin] - ref[fin]) / np.maximum(1.0, np.abs(ref[fin]))).max()),
+                      allowed=("1e-5*max(1,|ref|)" if noise <= LOGIT_TOL / 2 else f"{STRESS_FLOOR[impl]}x reference noise"),
+                      pick_flips=flips)
         assert _close(dense[fin], ref[fin], floor=STRESS_FLOOR[impl] * noise if noise > LOGIT_TOL / 2 else 0.0).all(), err
     assert _close(torch.stack(ap_lo).cpu().numpy(), g["action_probs_low"]).all()
     assert _close(torch.stack(ap_hi).cpu().numpy(), g["action_probs_high"]).all()
