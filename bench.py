@@ -55,6 +55,24 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
 
 
+def decode_roofline(n, dec_launch_ms, pk, layout):
+    """HBM roofline of the fused pointer decode (one launch = K steps: LSTM cell + window dots + softmax + pick).
+    ALGORITHMIC bytes per instance: every encoding row read once (L*H*4), the window logits and
+    probabilities written once (2*L*4), PNLow's latent window read by PNHigh (L*4, averaged over the two networks: L*2),
+    picks (K*4), the picked raw rows (K*F*4) and the cell state in / out (2*H*4).  The decoder hidden states are not
+    written by the fused decoder (nobody reads them in this loop)."""
+    per_inst = L_SEQ * HID * 4 + 2 * L_SEQ * 4 + L_SEQ * 2 + K_TASKS * 4 + K_TASKS * FEAT * 4 + 2 * HID * 4
+    if layout == 0:
+        per_inst += K_TASKS * HID * 4                       # row-major path also writes dec_h
+    gbs = n * per_inst / (dec_launch_ms * 1e-3) / 1e9
+    return {"kernel": "lstm_seq_kernel<true,2,5> (persistent tcgen05 decoder: K steps in one launch, pointer dot products "
+                      "fused into the cell epilogue over blocked encodings, thread-per-instance softmax / pick)"
+                      if layout else "lstm_seq_kernel<true,2,0> (persistent decoder + separate pointer phase)",
+            "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+            "avg_launch_ms": dec_launch_ms, "algorithmic_bytes_per_launch": n * per_inst, "traffic": None,
+            "peak_source": pk["src"] + ": MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -181,6 +199,88 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ----------------------------------------------------------------------------- full ML+2PN pipeline (BASELINE config 3)
+PIPE_SHAPES = {"normal": dict(K=50, N=10, S=2500, gcn=4, dist="normal"),      # environment.ini [Normal-*]
+               "qws": dict(K=47, N=5, S=2507, gcn=2, dist="qws")}              # environment.ini [QWS-*]
+
+
+def pipeline_block(dev, shape: str, n: int, steps: int, warmup: int):
+    """`main.py <ds> ML+2PN` as one device-resident pipeline on n request instances: Net scores (modelML.py:131-176) ->
+    per-category top-N feasible candidates (loadData.py:99-150) -> PNLow greedy -> PNHigh greedy (trainPNHigh.py:131-144)
+    -> objective (ML2PN.py:6-12).  `value`: inputs resident in HBM, the ML stage INSIDE the timed region; `e2e`: request
+    graphs + constraint tensors uploaded from pinned host memory and the chosen services + objective read back, every step.
+    256 distinct synthetic request graphs (gnnpn_sc_b200.synth) are tiled to n instances; every instance is computed."""
+    import torch
+    from gnnpn_sc_b200 import synth, loadData, trainML, modelML, ops, modelPN as M
+    from gnnpn_sc_b200.pipeline import ML2PN, constraint_arrays, low_high
+    from gnnpn_sc_b200.weights import reference_shaped_state_dict
+    cfg = PIPE_SHAPES[shape]
+    K, N, S = cfg["K"], cfg["N"], cfg["S"]
+    ds = synth.ml_dataset(n_instances=256, K=K, S=S, seed=3, dist=cfg["dist"])
+    samples = trainML.build_samples(loadData.ml_arrays(ds))
+    reps = (n + len(samples) - 1) // len(samples)
+    samples_n, nodef = (samples * reps)[:n], (ds["nodefeatures"] * reps)[:n]
+    torch.manual_seed(0)
+    net = modelML.Net(128, S, 20, 2, cfg["gcn"], isServices=True).to(dev)
+    net.reset_parameters()
+    net.eval()
+    pn = []
+    for level, seed in (("Low", 1), ("High", 2)):
+        m = M.CombinatorialRL(0, HID, K * N, 0, 10, 1, M.reward, "Dot", N, K, level=level)
+        m.load_state_dict(reference_shaped_state_dict(HID, FEAT, seed))
+        pn.append(m.to(dev).eval())
+    svc = type(samples[0])(**{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in vars(samples[0]).items()})
+    pipe = ML2PN(net, pn[0], pn[1], svc, ds["serviceFeature"], dev)
+    host = trainML.collate_requests(samples_n, pin=True)
+    cons_host = [torch.from_numpy(a).pin_memory() for a in constraint_arrays(nodef, K)]
+    h2d = sum(t.numel() * t.element_size() for t in (host.x, host.edge_index, host.batch, *cons_host))
+
+    def upload():
+        b = type(host)(x=host.x.to(dev, non_blocking=True), edge_index=host.edge_index.to(dev, non_blocking=True),
+                       batch=host.batch.to(dev, non_blocking=True), num_graphs=host.num_graphs)
+        return b, [t.to(dev, non_blocking=True) for t in cons_host]
+
+    batch, cons = upload()
+    out = {}
+
+    def device_step():
+        out.update(pipe.compose(batch, *cons))
+
+    def e2e_step():
+        b, c = upload()
+        r = pipe.compose(b, *c)
+        return r["services"].to(torch.int32).cpu(), r["objective"].cpu()
+
+    def timed(fn, k):
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(k):
+            fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / k
+
+    for _ in range(warmup):
+        device_step()
+    ms = timed(device_step, steps)
+    stage = {
+        "net_scores": timed(lambda: net.score_requests(batch, pipe.service_enc), steps),
+        "select_candidates": timed(lambda: ops.select_candidates(out["scores"], pipe.svc_qos, pipe.cat_ptr, *cons, N), steps),
+        "pnlow_pnhigh": timed(lambda: low_high(pn[0], pn[1], out["rows"], pipe._side), steps),
+        "objective": timed(lambda: ops.pn_reward(out["rows"], out["idx_high"].to(torch.int32)), steps),
+    }
+    e2e_step()
+    e2e_ms = timed(e2e_step, max(2, steps // 2))
+    d2h = n * K * 4 + n * 4
+    return {"workload": f"ml2pn_pipeline_{shape}", "K": K, "N": N, "L": K * N, "S": S, "gcn_layers": cfg["gcn"],
+            "instances": n, "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "instances/s", "stage_ms": stage,
+            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "instances/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "mean_violations": float(out["violations"].float().mean()), "mean_objective": float(out["objective"].mean()),
+            "note": "ML stage inside the timed region; stage_ms are the stages timed in isolation (same inputs)"}
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -221,6 +321,7 @@ def run_ours(args):
              torch.empty(K_TASKS, n, device=dev, dtype=torch.int32),
              torch.empty(n, L_SEQ, device=dev), torch.empty(n, L_SEQ, device=dev)) for _ in range(2)]
     enc_ev, dec_ev = [], []
+    enc_mib = (enc_out.numel() * 4) >> 20
 
     def device_step(record: bool):
         lat = None
@@ -345,6 +446,12 @@ def run_ours(args):
                "GBps": bytes_a / ms_a / 1e6, "frac_of_hbm_peak": bytes_a / ms_a / 1e6 / peaks()["hbm_gbs"]}
         del rowptr, col, val, xa, ya
 
+    pipeline = None
+    if rank == 0 and world == 1 and not args.no_pipeline:
+        del enc_out, bufs                                    # the pipeline allocates its own encodings (2 x 9.7 GB at Normal)
+        torch.cuda.empty_cache()
+        pipeline = [pipeline_block(dev, shape, n, max(3, args.steps // 2), 2) for shape in ("normal", "qws")]
+
     lt = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(lt)
@@ -377,7 +484,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "instances_per_gpu_per_step": n, "K": K_TASKS, "N": N_CAND,
                        "L": L_SEQ, "hidden": HID, "kernel": args.kernel, "parallelism": f"instance-sharded x{world}, no collective",
-                       "l2": f"working set {(enc_out.numel() * 4) >> 20} MiB of encodings per step >> 126 MB L2"},
+                       "l2": f"working set {enc_mib} MiB of encodings per step >> 126 MB L2"},
             "roofline": {"kernel": kname, "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(n), "avg_launch_ms": enc_launch_ms if seq_on else enc_ms,
@@ -387,11 +494,12 @@ def run_ours(args):
                          "peak_source": f"{pk['src']}: fp32-accuracy GEMM -> TF32 dense proxy = 1/2 bf16 sustained "
                                         f"({pk['bf16_sustained']:.0f} TFLOP/s, SURVEY 8d); the 3 fp16 passes the split "
                                         "issues are not counted in `achieved`"},
+            "roofline_decode": decode_roofline(n, dec_launch_ms, pk, layout),
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": K_TASKS * n * 4 + n * 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(lt.item()), "clocks": clocks,
-            "small_batch": small, "aggregation": agg,
+            "small_batch": small, "aggregation": agg, "pipeline": pipeline,
         }
         print(json.dumps(line))
     if world > 1:
@@ -409,6 +517,7 @@ def main():
     ap.add_argument("--cpu-batches", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aggregation", action="store_true", help="skip the CSR aggregation GB/s point")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the full ML+2PN pipeline block (BASELINE config 3)")
     ap.add_argument("--kernel", default="tc", choices=["tc", "ffma"],
                     help="recurrence kernel: tcgen05 3xTF32 (default) or strict-fp32 FFMA")
     args = ap.parse_args()

@@ -207,7 +207,9 @@ class Net(nn.Module):
         """(request-graph CSR, request-membership CSR, B): static per collated batch, so built once per ``data``
         (one ``.item()`` sync and two CSR builds per batch instead of per forward)."""
         def build():
-            B = int(data.batch.max().item()) + 1 if n_req else 0
+            B = getattr(data, "num_graphs", None)           # known on the host for collated batches: no device sync
+            if B is None:
+                B = int(data.batch.max().item()) + 1 if n_req else 0
             return _csr(data.edge_index, None, n_req, ops.CSR_PLAIN), self._membership_csr(data.batch, B), B
         return self._cached("request", (data.edge_index, data.batch), build)
 

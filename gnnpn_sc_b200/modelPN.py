@@ -235,27 +235,51 @@ class PointerNet(nn.Module):
         return (not self.force_general and self.embedding_size == 0 and self.n_glimpses == 0
                 and self.pointer.name == "Dot" and self.serNumber <= 32 and F <= 8)
 
-    def forward(self, inputs, latent, sample="sample", forced_idxs=None):
-        """inputs [B, L, F] -> (prev_probs, prev_idxs, prev_logits), K-long each (modelPN.py:241)."""
+    def encode(self, inputs):
+        """The encoder half of ``forward`` (modelPN.py:183-191: embedding + encoder LSTM), enqueued on the CURRENT stream.
+        Returns an opaque handle for ``forward(..., encoded=handle)``.  The two networks of the ML+2PN decode read the
+        same rows and their encoders are independent, so a caller can run them concurrently on two streams (batches
+        that do not fill the machine finish in the time of one encoder; gnnpn_sc_b200.pipeline does)."""
         B, L, _ = inputs.shape
         assert L == self.seq_len
-        if self.pointer.name not in ("Dot", "Bahdanau"):
-            raise NotImplementedError(self.pointer.name)
         if not inputs.is_cuda:
             raise RuntimeError("PointerNet.forward needs CUDA tensors: the B200 path has no CPU fallback")
         K, N = self.serCategory, self.serNumber
         x = self._kernel_inputs(inputs)
         range_flag = ops.pn_check_inputs(x) if (self.check_inputs and self.impl != "ffma") else None
         fast = self._fast_path(x.shape[2])
-        enc_w, dec_w = self._packed_weights()
-        use_tanh, C = bool(self.pointer.use_tanh), float(self.pointer.C)
-        att = self.pointer.name
+        enc_w, _ = self._packed_weights()
         with torch.no_grad():
             ws = ops.pn_workspace(B, self.hidden_size, x.device, self.impl)
             # batches the CTA-pair scan takes keep their encodings in the blocked layout (pointer dots fused into the
             # decoder's cell epilogue); ``self.last["enc_out"]`` / the dense logits convert lazily
             layout = ops.pn_enc_layout(B, L, x.shape[2], K, N, ws is not None) if fast else ops.ENC_ROWMAJOR
             enc_out, c = ops.lstm_encode(x, enc_w, self.hidden_size, workspace=ws, layout=layout)
+        return {"x": x, "ws": ws, "layout": layout, "enc_out": enc_out, "c": c, "range_flag": range_flag, "fast": fast,
+                "stream": torch.cuda.current_stream(x.device)}
+
+    def forward(self, inputs, latent, sample="sample", forced_idxs=None, encoded=None):
+        """inputs [B, L, F] -> (prev_probs, prev_idxs, prev_logits), K-long each (modelPN.py:241)."""
+        B, L, _ = inputs.shape
+        assert L == self.seq_len
+        if self.pointer.name not in ("Dot", "Bahdanau"):
+            raise NotImplementedError(self.pointer.name)
+        K, N = self.serCategory, self.serNumber
+        if encoded is None:
+            encoded = self.encode(inputs)
+        else:
+            cur = torch.cuda.current_stream(inputs.device)
+            if encoded["stream"] != cur:                   # encoded on a side stream: order after it, keep its buffers alive
+                cur.wait_stream(encoded["stream"])
+                for t in (encoded["x"], encoded["ws"], encoded["enc_out"], encoded["c"]):
+                    if t is not None:
+                        t.record_stream(cur)
+        x, ws, layout, enc_out, c = (encoded[k] for k in ("x", "ws", "layout", "enc_out", "c"))
+        range_flag, fast = encoded["range_flag"], encoded["fast"]
+        _, dec_w = self._packed_weights()
+        use_tanh, C = bool(self.pointer.use_tanh), float(self.pointer.C)
+        att = self.pointer.name
+        with torch.no_grad():
             lat = _window_of(latent, K, N) if latent else None
             forced = None if forced_idxs is None else torch.stack([t.to(torch.int32) for t in forced_idxs])
             # sample != "greedy": multinomial draw per step (modelPN.py:227-228) as an inverse-CDF pick in the kernel
@@ -375,9 +399,10 @@ class CombinatorialRL(nn.Module):
         self.actor = PointerNet(embedding_size, hidden_size, seq_len, n_glimpses, tanh_exploration, use_tanh,
                                 attention, sNumber, sCategory, use_cuda, level=level, mask=mask)
 
-    def forward(self, inputs, labs, latent=None, sample="sample", training="RL"):
-        """-> (R | probs, action_probs, actions, action_idxs, latent_p), lists of length K (modelPN.py:282-306)."""
-        probs, action_idxs, logits = self.actor(inputs, latent, sample=sample)
+    def forward(self, inputs, labs, latent=None, sample="sample", training="RL", encoded=None):
+        """-> (R | probs, action_probs, actions, action_idxs, latent_p), lists of length K (modelPN.py:282-306).
+        ``encoded``: optional handle from ``self.actor.encode(inputs)`` (encoder already enqueued, maybe on another stream)."""
+        probs, action_idxs, logits = self.actor(inputs, latent, sample=sample, encoded=encoded)
         latent_p = logits.copy()
         idx = torch.stack(action_idxs)                                              # [K, B] int64
         B = inputs.shape[0]

@@ -21,6 +21,7 @@ class GreedyLowHigh:
         if self.device.type != "cuda":
             raise RuntimeError("GreedyLowHigh needs a CUDA device: the B200 path has no CPU fallback")
         self._copy = torch.cuda.Stream(self.device)
+        self._side = torch.cuda.Stream(self.device)   # PNHigh's encoder runs here, next to PNLow's on the main stream
         self._stage = [None, None]            # device staging buffers (double buffer)
         self._ready = [torch.cuda.Event(), torch.cuda.Event()]
         self._consumed = [None, None]
@@ -53,14 +54,28 @@ class GreedyLowHigh:
                 self._upload(cur_slot ^ 1, nxt)
             main.wait_event(self._ready[cur_slot])
             x = self._stage[cur_slot]
-            _, _, _, _, latent = self.low(x, None, sample="greedy", training="SL")
-            R, _, _, idx, _ = self.high(x, None, latent, sample="greedy", training="RL")
+            latent, R, idx = low_high(self.low, self.high, x, self._side)
             idx32 = torch.stack(idx).to(torch.int32)
             ev = torch.cuda.Event()
             ev.record(main)
             self._consumed[cur_slot] = ev
             yield idx32.cpu(), R.cpu()                    # device->host reads synchronise this batch
             slot = cur_slot ^ 1
+
+
+def low_high(low, high, x, side_stream):
+    """PNLow greedy -> latent -> PNHigh greedy on the rows ``x`` (trainPNHigh.py:131-144).  The two encoders are independent
+    (same rows, different weights): PNHigh's is enqueued on ``side_stream`` and runs concurrently with PNLow's whenever the
+    batch leaves SMs free (one encoder occupies ceil(n / 128) SMs); the decoders follow on the current stream.
+    Returns (latent, reward, K-list of picks)."""
+    main = torch.cuda.current_stream(x.device)
+    side_stream.wait_stream(main)                         # x is ready on the main stream
+    with torch.cuda.stream(side_stream):
+        enc_hi = high.actor.encode(x)
+    enc_lo = low.actor.encode(x)
+    _, _, _, _, latent = low(x, None, sample="greedy", training="SL", encoded=enc_lo)
+    R, _, _, idx, _ = high(x, None, latent, sample="greedy", training="RL", encoded=enc_hi)
+    return latent, R, idx
 
 
 # ----------------------------------------------------------------------------- ML -> candidates -> 2PN on the device
@@ -114,6 +129,7 @@ class ML2PN:
         self.K = len(ptr) - 1
         self.N = low.sNumber
         self.service_enc = net.service_encodings(service_sample)          # static: encoded once
+        self._side = torch.cuda.Stream(self.device)
 
     @torch.no_grad()
     def compose(self, request_batch, local_bounds, used, global_bounds):
@@ -123,8 +139,7 @@ class ML2PN:
         scores = self.net.score_requests(request_batch, self.service_enc)                     # [B, S]
         rows, picked = ops.select_candidates(scores, self.svc_qos, self.cat_ptr, local_bounds, used, global_bounds,
                                              self.N, with_category=False, return_picked=True)  # [B, K*N, 8]
-        _, _, _, _, latent = self.low(rows, None, sample="greedy", training="SL")
-        R, _, actions, idx, _ = self.high(rows, None, latent, sample="greedy", training="RL")
+        latent, R, idx = low_high(self.low, self.high, rows, self._side)
         idx = torch.stack(idx)                                                                # [K, B]
         services = picked.gather(1, idx.t())                                                  # chosen service per task (-1: unused)
         viol, obj, _ = ops.pn_reward(rows, idx.to(torch.int32))

@@ -65,6 +65,24 @@ def collate(samples: Sequence[SimpleNamespace], faithful_quirk: bool = True, dev
     return b
 
 
+def collate_requests(samples: Sequence[SimpleNamespace], device=None, pin: bool = False) -> SimpleNamespace:
+    """Request side only (x, edge_index, batch, num_graphs) of a collated batch -- what ``Net.score_requests`` reads.  The
+    service graph is static and encoded once (``Net.service_encodings``), so it is not replicated per sample."""
+    sizes = [s.x.shape[0] for s in samples]
+    offs = torch.tensor([0] + sizes[:-1]).cumsum(0)
+    b = SimpleNamespace(
+        x=torch.cat([s.x for s in samples]),
+        edge_index=torch.cat([s.edge_index + int(o) for s, o in zip(samples, offs)], 1),
+        batch=torch.repeat_interleave(torch.arange(len(samples)), torch.tensor(sizes)),
+        num_graphs=len(samples))
+    for k, v in list(vars(b).items()):
+        if torch.is_tensor(v):
+            if pin:
+                v = v.pin_memory()
+            setattr(b, k, v.to(device, non_blocking=True) if device is not None else v)
+    return b
+
+
 class _Loader:
     def __init__(self, samples, batch_size, shuffle, faithful_quirk=True):
         self.samples, self.batch_size, self.shuffle, self.quirk = samples, batch_size, shuffle, faithful_quirk
