@@ -506,6 +506,103 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- scale-up workload (BASELINE config 4)
+def run_scaleup(args):
+    """100 abstract tasks x 1000 candidates per task (L = 100,000), instance-sharded over the ranks with no collective
+    (SURVEY 8e): every rank decodes its own block PNLow -> PNHigh -> objective.  One step = one pass over n instances per
+    GPU; the encodings are 102 MB per instance, so a 180 GB GPU holds one network's encodings of ~1,500 instances at a
+    time (PNLow's are released before PNHigh's are produced).  Latency-bound: 100,000 dependent LSTM steps per network."""
+    import torch
+    import torch.distributed as dist
+    from gnnpn_sc_b200 import _lib, modelPN as M
+    from gnnpn_sc_b200.synth import pn_instances
+    from gnnpn_sc_b200.weights import reference_shaped_state_dict
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, N = 100, 1000
+    L = K * N
+    n = args.instances if args.instances != 18944 else 1280          # 10 groups of 128: 131 GB of encodings (one network at a time)
+    x_host = pn_instances(n, K, N, seed=77 + rank).pin_memory()
+    nets = []
+    for level, seed in (("Low", 1), ("High", 2)):
+        m = M.CombinatorialRL(0, HID, L, 0, 10, 1, M.reward, "Dot", N, K, level=level)
+        m.load_state_dict(reference_shaped_state_dict(HID, FEAT, seed))
+        m.actor.check_inputs = False
+        nets.append(m.to(dev).eval())
+    low, high = nets
+    # one encodings buffer, shared: PNLow's encodings are dead once its decode is enqueued (same stream order)
+    low.actor.enc_buffer = high.actor.enc_buffer = torch.empty(n * L * HID, device=dev)
+
+    def step(x):
+        with torch.no_grad():
+            _, _, _, _, latent = low(x, None, sample="greedy", training="SL")
+            lat = M.WindowLogits(K, latent.window, None)      # keep only the compact window: PNLow's encodings are freed
+            del latent
+            low.actor.last = None
+            R, _, _, idx, _ = high(x, None, lat, sample="greedy", training="RL")
+            high.actor.last = None
+        return R, torch.stack(idx).to(torch.int32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            fn()
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    x = x_host.to(dev)
+    for _ in range(args.warmup):
+        step(x)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ms = timed(lambda: step(x), args.steps) / args.steps
+    launches = _lib.launch_count() - launches0
+
+    def e2e():
+        R, idx = step(x_host.to(dev, non_blocking=True))
+        return R.cpu(), idx.cpu()
+    e2e_ms = timed(e2e, max(1, args.steps // 2)) / max(1, args.steps // 2)
+    clocks = sampler.stop() if rank == 0 else None
+    lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(lt)
+    if rank == 0:
+        value = world * n / (ms * 1e-3)
+        print(json.dumps({
+            "metric": "composition instances/sec (ML+2PN greedy)", "value": value, "unit": "instances/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "scaleup_100x1000_greedy_pnlow_pnhigh_decode", "instances_per_gpu_per_step": n, "K": K,
+                       "N": N, "L": L, "hidden": HID, "parallelism": f"instance-sharded x{world}, no collective",
+                       "l2": f"{n * L * HID * 4 >> 30} GiB of encodings per network per step >> 126 MB L2"},
+            "per_gpu_instances_per_s": value / world,
+            "latency": {"dependent_lstm_steps_per_network": L + K, "us_per_encoder_step": ms * 1e3 / (2 * (L + K)),
+                        "note": "column-split cluster scan (8-CTA clusters); step time bounds the whole pass"},
+            "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": "instances/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": K * n * 4 + n * 4},
+            "gpu_launches": int(lt.item()), "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -520,9 +617,13 @@ def main():
     ap.add_argument("--no-pipeline", action="store_true", help="skip the full ML+2PN pipeline block (BASELINE config 3)")
     ap.add_argument("--kernel", default="tc", choices=["tc", "ffma"],
                     help="recurrence kernel: tcgen05 3xTF32 (default) or strict-fp32 FFMA")
+    ap.add_argument("--workload", default="qws", choices=["qws", "scaleup"],
+                    help="qws: the headline (BASELINE config 2/3); scaleup: 100 tasks x 1000 candidates (config 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "scaleup":
+        run_scaleup(args)
     else:
         run_ours(args)
 

@@ -205,6 +205,7 @@ class PointerNet(nn.Module):
         self.generator = None                     # optional torch.Generator (cuda) for sample="sample"
         self.force_general = False                # route a fast-path configuration through the general kernels (tests)
         self.check_inputs = True                  # range-check the raw rows of every batch (one tiny kernel + one sync)
+        self.enc_buffer = None                    # optional caller-owned encodings buffer (reused when large enough)
 
     # -- packed weights are a cache over the parameters; rebuilt when any of them changes
     def _packed_weights(self):
@@ -254,7 +255,14 @@ class PointerNet(nn.Module):
             # batches the CTA-pair scan takes keep their encodings in the blocked layout (pointer dots fused into the
             # decoder's cell epilogue); ``self.last["enc_out"]`` / the dense logits convert lazily
             layout = ops.pn_enc_layout(B, L, x.shape[2], K, N, ws is not None) if fast else ops.ENC_ROWMAJOR
-            enc_out, c = ops.lstm_encode(x, enc_w, self.hidden_size, workspace=ws, layout=layout)
+            buf = None
+            if self.enc_buffer is not None:
+                # a caller-owned buffer (e.g. shared by PNLow and PNHigh at the scale-up size, where one network's
+                # encodings are ~100 GB and the caching allocator would fragment)
+                need = B * L * self.hidden_size if layout == ops.ENC_ROWMAJOR else None
+                if need is not None and self.enc_buffer.numel() >= need:
+                    buf = self.enc_buffer.view(-1)[:need].view(B, L, self.hidden_size)
+            enc_out, c = ops.lstm_encode(x, enc_w, self.hidden_size, enc_out=buf, workspace=ws, layout=layout)
         return {"x": x, "ws": ws, "layout": layout, "enc_out": enc_out, "c": c, "range_flag": range_flag, "fast": fast,
                 "stream": torch.cuda.current_stream(x.device)}
 

@@ -314,6 +314,7 @@ def test_general_kernels_equal_fused_path_bitwise(impl):
     (dict(s_category=4, s_number=6, n_glimpses=2), 20),                           # two Dot glimpses
     (dict(s_category=7, s_number=3, embedding_size=20, attention="Bahdanau"), 19),
     (dict(s_category=3, s_number=1000), 6),                                       # scale-up window width (BASELINE config 4)
+    (dict(s_category=12, s_number=1000), 20),                                     # 12,000 encoder steps, 12 decode steps of 1000 candidates
 ])
 def test_general_variants_teacher_forced_against_oracle(kw, n):
     from gnnpn_sc_b200 import modelPN as M
