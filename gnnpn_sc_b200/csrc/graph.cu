@@ -129,34 +129,17 @@ CsrWorkspace csr_layout(int64_t Nn, int64_t E, int mode) {
 // Neighbour (col,val) pairs are staged 32 at a time per group through shared memory, gathers are
 // issued UNROLL rows ahead, accumulation is strictly sequential in CSR order per feature
 // (mul_rn then add_rn: bit-identical to the CPU index_add_ oracle).
+// --- shared pieces: one group's accumulation over the edge range [beg, end), and the row epilogue
 template <int GROUP, int VPL, int UNROLL>
-__global__ void __launch_bounds__(256) spmm_csr_kernel(
-    const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
-    const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t n_rows, int F4,
-    float self_scale, int mean, const float* __restrict__ bias, const float* __restrict__ scale,
-    const float* __restrict__ shift, int act) {
-  constexpr int GROUPS_PER_CTA = 256 / GROUP;
-  __shared__ int32_t s_col[GROUPS_PER_CTA][32];
-  __shared__ float s_val[GROUPS_PER_CTA][32];
-
-  const int gl = threadIdx.x % GROUP;                 // lane inside the group
-  const int grp = threadIdx.x / GROUP;                // group inside the CTA
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane / GROUP * GROUP));
-  const int64_t row = (int64_t)blockIdx.x * GROUPS_PER_CTA + grp;
-  if (row >= n_rows) return;
-
-  float4 acc[VPL];
-#pragma unroll
-  for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  const int64_t beg = rowptr[row], end = rowptr[row + 1];
+__device__ __forceinline__ void spmm_accumulate(float4 (&acc)[VPL], int64_t beg, int64_t end, const int32_t* __restrict__ col,
+                                                const float* __restrict__ val, const float* __restrict__ x, int64_t ldx,
+                                                int F4, int32_t* s_col, float* s_val, int gl, unsigned gmask) {
   for (int64_t e0 = beg; e0 < end; e0 += 32) {
     const int cnt = (int)min((int64_t)32, end - e0);
     __syncwarp(gmask);
     for (int i = gl; i < cnt; i += GROUP) {
-      s_col[grp][i] = __ldg(col + e0 + i);
-      s_val[grp][i] = val ? __ldg(val + e0 + i) : 1.0f;
+      s_col[i] = __ldg(col + e0 + i);
+      s_val[i] = val ? __ldg(val + e0 + i) : 1.0f;
     }
     __syncwarp(gmask);
     for (int j0 = 0; j0 < cnt; j0 += UNROLL) {
@@ -165,8 +148,8 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         const int j = min(j0 + u, cnt - 1);
-        w[u] = s_val[grp][j];
-        const float4* src = reinterpret_cast<const float4*>(x + (int64_t)s_col[grp][j] * ldx);
+        w[u] = s_val[j];
+        const float4* src = reinterpret_cast<const float4*>(x + (int64_t)s_col[j] * ldx);
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
           const int c4 = gl + v * GROUP;
@@ -187,40 +170,178 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(
       }
     }
   }
+}
 
-  const float inv_cnt_den = mean ? (float)max((int64_t)1, end - beg) : 1.0f;
+struct SpmmEpilogue {
+  float self_scale; int mean; const float* bias; const float* scale; const float* shift; int act;
+};
+
+template <int GROUP, int VPL>
+__device__ __forceinline__ void spmm_finish_row(const float4 (&acc)[VPL], int64_t row, int64_t degree,
+                                                const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
+                                                int64_t ldy, int F4, const SpmmEpilogue& ep, int gl) {
+  const float inv_cnt_den = ep.mean ? (float)max((int64_t)1, degree) : 1.0f;
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
     const int c4 = gl + v * GROUP;
     if (c4 >= F4) continue;
     float4 r = acc[v];
-    if (self_scale != 0.f) {
+    if (ep.self_scale != 0.f) {
       const float4 xi = __ldg(reinterpret_cast<const float4*>(x + row * ldx) + c4);
-      r.x = __fadd_rn(r.x, __fmul_rn(self_scale, xi.x));
-      r.y = __fadd_rn(r.y, __fmul_rn(self_scale, xi.y));
-      r.z = __fadd_rn(r.z, __fmul_rn(self_scale, xi.z));
-      r.w = __fadd_rn(r.w, __fmul_rn(self_scale, xi.w));
+      r.x = __fadd_rn(r.x, __fmul_rn(ep.self_scale, xi.x));
+      r.y = __fadd_rn(r.y, __fmul_rn(ep.self_scale, xi.y));
+      r.z = __fadd_rn(r.z, __fmul_rn(ep.self_scale, xi.z));
+      r.w = __fadd_rn(r.w, __fmul_rn(ep.self_scale, xi.w));
     }
-    if (mean) {
+    if (ep.mean) {
       r.x = __fdiv_rn(r.x, inv_cnt_den); r.y = __fdiv_rn(r.y, inv_cnt_den);
       r.z = __fdiv_rn(r.z, inv_cnt_den); r.w = __fdiv_rn(r.w, inv_cnt_den);
     }
-    if (bias) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    if (ep.bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias) + c4);
       r.x = __fadd_rn(r.x, b.x); r.y = __fadd_rn(r.y, b.y); r.z = __fadd_rn(r.z, b.z); r.w = __fadd_rn(r.w, b.w);
     }
-    if (scale) {
-      const float4 s = __ldg(reinterpret_cast<const float4*>(scale) + c4);
-      const float4 t = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+    if (ep.scale) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(ep.scale) + c4);
+      const float4 t = __ldg(reinterpret_cast<const float4*>(ep.shift) + c4);
       r.x = fmaf(r.x, s.x, t.x); r.y = fmaf(r.y, s.y, t.y); r.z = fmaf(r.z, s.z, t.z); r.w = fmaf(r.w, s.w, t.w);
     }
-    if (act == GNNPN_ACT_RELU) {
+    if (ep.act == GNNPN_ACT_RELU) {
       r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
-    } else if (act == GNNPN_ACT_SIGMOID) {
+    } else if (ep.act == GNNPN_ACT_SIGMOID) {
       r.x = sigmoid_accurate(r.x); r.y = sigmoid_accurate(r.y);
       r.z = sigmoid_accurate(r.z); r.w = sigmoid_accurate(r.w);
     }
     reinterpret_cast<float4*>(y + row * ldy)[c4] = r;
+  }
+}
+
+// long_threshold > 0: rows with more edges are left to the split path below (hub rows of a skewed graph)
+template <int GROUP, int VPL, int UNROLL>
+__global__ void __launch_bounds__(256) spmm_csr_kernel(
+    const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+    const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t n_rows, int F4,
+    const SpmmEpilogue ep, int64_t long_threshold) {
+  constexpr int GROUPS_PER_CTA = 256 / GROUP;
+  __shared__ int32_t s_col[GROUPS_PER_CTA][32];
+  __shared__ float s_val[GROUPS_PER_CTA][32];
+
+  const int gl = threadIdx.x % GROUP;                 // lane inside the group
+  const int grp = threadIdx.x / GROUP;                // group inside the CTA
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane / GROUP * GROUP));
+  const int64_t row = (int64_t)blockIdx.x * GROUPS_PER_CTA + grp;
+  if (row >= n_rows) return;
+  const int64_t beg = rowptr[row], end = rowptr[row + 1];
+  if (long_threshold > 0 && end - beg > long_threshold) return;
+
+  float4 acc[VPL];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  spmm_accumulate<GROUP, VPL, UNROLL>(acc, beg, end, col, val, x, ldx, F4, s_col[grp], s_val[grp], gl, gmask);
+  spmm_finish_row<GROUP, VPL>(acc, row, end - beg, x, ldx, y, ldy, F4, ep, gl);
+}
+
+// ---- long-row splitting (hub destinations: a service used by 10^5 compositions would otherwise be ONE group's
+// sequential walk).  Rows with more than T edges are cut into chunks of T consecutive edges; every chunk is summed by
+// one group exactly like a short row (sequential in CSR order), the chunk sums are then added in chunk order.
+// Deterministic (fixed order, no atomics in the arithmetic); rows of <= T edges stay bit-identical to index_add_ order,
+// split rows differ from the strictly sequential sum by re-association only (~1e-7 relative; tests bound it by 1e-5).
+struct LongRowPlan {
+  int* counters;          // [0] number of long rows, [1] number of chunks
+  int64_t* row;           // [max_long] row id per slot
+  int* chunk_base;        // [max_long] first chunk of the slot's row
+  int* chunk_slot;        // [max_chunks] slot a chunk belongs to
+  float* partial;         // [max_chunks, F]
+  int max_long, max_chunks;
+};
+
+__global__ void find_long_rows_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int64_t T, LongRowPlan p) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t d = rowptr[r + 1] - rowptr[r];
+    if (d <= T) continue;
+    const int nch = (int)((d + T - 1) / T);
+    const int slot = atomicAdd(p.counters, 1);
+    const int cb = atomicAdd(p.counters + 1, nch);
+    if (slot >= p.max_long || cb + nch > p.max_chunks) continue;        // cannot happen: both bounds follow from nnz / T
+    p.row[slot] = r;
+    p.chunk_base[slot] = cb;
+    for (int i = 0; i < nch; ++i) p.chunk_slot[cb + i] = slot;
+  }
+}
+
+template <int GROUP, int VPL, int UNROLL>
+__global__ void __launch_bounds__(256) spmm_chunk_kernel(
+    const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+    const float* __restrict__ x, int64_t ldx, int F4, int64_t T, const LongRowPlan p) {
+  constexpr int GROUPS_PER_CTA = 256 / GROUP;
+  __shared__ int32_t s_col[GROUPS_PER_CTA][32];
+  __shared__ float s_val[GROUPS_PER_CTA][32];
+  const int gl = threadIdx.x % GROUP, grp = threadIdx.x / GROUP;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane / GROUP * GROUP));
+  const int n_chunks = min(p.counters[1], p.max_chunks);
+  for (int c = blockIdx.x * GROUPS_PER_CTA + grp; c < n_chunks; c += gridDim.x * GROUPS_PER_CTA) {
+    const int slot = p.chunk_slot[c];
+    const int64_t row = p.row[slot];
+    const int64_t beg = rowptr[row] + (int64_t)(c - p.chunk_base[slot]) * T;
+    const int64_t end = min(beg + T, rowptr[row + 1]);
+    float4 acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    spmm_accumulate<GROUP, VPL, UNROLL>(acc, beg, end, col, val, x, ldx, F4, s_col[grp], s_val[grp], gl, gmask);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c4 = gl + v * GROUP;
+      if (c4 < F4) reinterpret_cast<float4*>(p.partial + (int64_t)c * F4 * 4)[c4] = acc[v];
+    }
+  }
+}
+
+template <int GROUP, int VPL>
+__global__ void __launch_bounds__(256) spmm_combine_kernel(
+    const int64_t* __restrict__ rowptr, const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
+    int F4, int64_t T, const SpmmEpilogue ep, const LongRowPlan p) {
+  constexpr int GROUPS_PER_CTA = 256 / GROUP;
+  const int gl = threadIdx.x % GROUP, grp = threadIdx.x / GROUP;
+  const int n_long = min(p.counters[0], p.max_long);
+  for (int s = blockIdx.x * GROUPS_PER_CTA + grp; s < n_long; s += gridDim.x * GROUPS_PER_CTA) {
+    const int64_t row = p.row[s];
+    const int64_t d = rowptr[row + 1] - rowptr[row];
+    const int nch = (int)((d + T - 1) / T), cb = p.chunk_base[s];
+    float4 acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // chunk order = edge order; 8 chunk sums are requested together (independent loads) and then added in order, so a
+    // hub row of 10^3..10^4 chunks is not a chain of that many dependent L2 round trips
+    constexpr int CU = 8 / VPL;            // 8 float4 loads in flight per lane
+    for (int i0 = 0; i0 < nch; i0 += CU) {
+      float4 q[CU][VPL];
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        const int i = min(i0 + u, nch - 1);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c4 = gl + v * GROUP;
+          q[u][v] = c4 < F4 ? __ldcs(reinterpret_cast<const float4*>(p.partial + (int64_t)(cb + i) * F4 * 4) + c4)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        if (i0 + u < nch) {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            if (i0 + u == 0) acc[v] = q[u][v];
+            else {
+              acc[v].x = __fadd_rn(acc[v].x, q[u][v].x); acc[v].y = __fadd_rn(acc[v].y, q[u][v].y);
+              acc[v].z = __fadd_rn(acc[v].z, q[u][v].z); acc[v].w = __fadd_rn(acc[v].w, q[u][v].w);
+            }
+          }
+        }
+      }
+    }
+    spmm_finish_row<GROUP, VPL>(acc, row, d, x, ldx, y, ldy, F4, ep, gl);
   }
 }
 
@@ -247,13 +368,25 @@ __global__ void embed_concat_kernel(const float* __restrict__ x, int64_t n, int 
 
 template <int GROUP, int VPL, int UNROLL>
 int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx,
-                float* y, int64_t ldy, int64_t n_rows, int F4, float self_scale, int mean, const float* bias,
-                const float* scale, const float* shift, int act, cudaStream_t st) {
+                float* y, int64_t ldy, int64_t n_rows, int F4, const SpmmEpilogue& ep, int64_t T, const LongRowPlan* plan,
+                cudaStream_t st) {
   constexpr int GROUPS_PER_CTA = 256 / GROUP;
   const int64_t blocks = ceil_div(n_rows, GROUPS_PER_CTA);
   if (blocks > 0x7fffffffll) return GNNPN_ERANGE;
-  spmm_csr_kernel<GROUP, VPL, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(
-      rowptr, col, val, x, ldx, y, ldy, n_rows, F4, self_scale, mean, bias, scale, shift, act);
+  int rc;
+  if (plan) {
+    cudaMemsetAsync(plan->counters, 0, 2 * sizeof(int), st);
+    const int64_t fb = ceil_div(n_rows, 256);
+    find_long_rows_kernel<<<(unsigned)(fb < 8 * kNumSMs ? fb : 8 * kNumSMs), 256, 0, st>>>(rowptr, n_rows, T, *plan);
+    if ((rc = after_launch())) return rc;
+  }
+  spmm_csr_kernel<GROUP, VPL, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, ldx, y, ldy, n_rows, F4, ep,
+                                                                       plan ? T : 0);
+  if ((rc = after_launch()) || !plan) return rc;
+  // persistent grids: they read the chunk / row counts on the device and return at once when there is no long row
+  spmm_chunk_kernel<GROUP, VPL, UNROLL><<<8 * kNumSMs, 256, 0, st>>>(rowptr, col, val, x, ldx, F4, T, *plan);
+  if ((rc = after_launch())) return rc;
+  spmm_combine_kernel<GROUP, VPL><<<kNumSMs, 256, 0, st>>>(rowptr, x, ldx, y, ldy, F4, T, ep, *plan);
   return after_launch();
 }
 
@@ -335,20 +468,11 @@ int gnnpn_embed_concat_f32(const float* x, int64_t n, int n_cols, const float* t
   return after_launch();
 }
 
-int gnnpn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val, const float* x,
-                       int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int F, float self_scale, int mean,
-                       const float* bias, const float* scale, const float* shift, int act, void* stream) {
-  GNNPN_REQUIRE(rowptr && (col || n_rows == 0) && x && y, GNNPN_ENULL);
-  GNNPN_REQUIRE(F >= 4 && F % 4 == 0 && F <= 1024 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= F && ldy >= F,
-                GNNPN_ESHAPE);
-  GNNPN_REQUIRE((scale == nullptr) == (shift == nullptr), GNNPN_ENULL);
-  GNNPN_REQUIRE(aligned16(x) && aligned16(y) && aligned16(bias) && aligned16(scale) && aligned16(shift),
-                GNNPN_EALIGN);
-  if (n_rows == 0) return GNNPN_OK;
-  cudaStream_t st = (cudaStream_t)stream;
+static int spmm_dispatch(const int64_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx, float* y,
+                         int64_t ldy, int64_t n_rows, int F, const SpmmEpilogue& ep, int64_t T, const LongRowPlan* plan,
+                         cudaStream_t st) {
   const int F4 = F / 4;
-#define GNNPN_SPMM(G, V, U) \
-  return launch_spmm<G, V, U>(rowptr, col, val, x, ldx, y, ldy, n_rows, F4, self_scale, mean, bias, scale, shift, act, st)
+#define GNNPN_SPMM(G, V, U) return launch_spmm<G, V, U>(rowptr, col, val, x, ldx, y, ldy, n_rows, F4, ep, T, plan, st)
   if (F4 <= 8) GNNPN_SPMM(8, 1, 8);
   if (F4 <= 16) GNNPN_SPMM(16, 1, 8);
   if (F4 <= 32) GNNPN_SPMM(32, 1, 8);
@@ -356,6 +480,59 @@ int gnnpn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* v
   if (F4 <= 128) GNNPN_SPMM(32, 4, 2);
   GNNPN_SPMM(32, 8, 1);
 #undef GNNPN_SPMM
+}
+
+#define GNNPN_SPMM_CHECKS                                                                                        \
+  GNNPN_REQUIRE(rowptr && (col || n_rows == 0) && x && y, GNNPN_ENULL);                                            \
+  GNNPN_REQUIRE(F >= 4 && F % 4 == 0 && F <= 1024 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= F && ldy >= F,         \
+                GNNPN_ESHAPE);                                                                                     \
+  GNNPN_REQUIRE((scale == nullptr) == (shift == nullptr), GNNPN_ENULL);                                            \
+  GNNPN_REQUIRE(aligned16(x) && aligned16(y) && aligned16(bias) && aligned16(scale) && aligned16(shift), GNNPN_EALIGN)
+
+int gnnpn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val, const float* x,
+                       int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int F, float self_scale, int mean,
+                       const float* bias, const float* scale, const float* shift, int act, void* stream) {
+  GNNPN_SPMM_CHECKS;
+  if (n_rows == 0) return GNNPN_OK;
+  const SpmmEpilogue ep{self_scale, mean, bias, scale, shift, act};
+  return spmm_dispatch(rowptr, col, val, x, ldx, y, ldy, n_rows, F, ep, 0, nullptr, (cudaStream_t)stream);
+}
+
+static void split_bounds(int64_t nnz, int64_t T, int64_t* max_long, int64_t* max_chunks) {
+  *max_long = nnz / (T + 1) + 1;                 // a long row has at least T + 1 edges
+  *max_chunks = nnz / T + *max_long + 1;         // sum of ceil(d / T) over the long rows
+}
+
+size_t gnnpn_spmm_csr_split_workspace_bytes(int64_t nnz, int F, int64_t long_row_threshold) {
+  if (nnz < 0 || F < 4 || long_row_threshold < 32) return 0;
+  int64_t ml, mc;
+  split_bounds(nnz, long_row_threshold, &ml, &mc);
+  return 256 + (size_t)ml * 16 + (size_t)mc * 4 + 256 + (size_t)mc * F * 4;
+}
+
+int gnnpn_spmm_csr_split_f32(const int64_t* rowptr, const int32_t* col, const float* val, const float* x,
+                             int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int64_t nnz, int F, float self_scale,
+                             int mean, const float* bias, const float* scale, const float* shift, int act,
+                             int64_t long_row_threshold, void* workspace, size_t workspace_bytes, void* stream) {
+  GNNPN_SPMM_CHECKS;
+  GNNPN_REQUIRE(workspace, GNNPN_ENULL);
+  GNNPN_REQUIRE(long_row_threshold >= 32 && nnz >= 0, GNNPN_ESHAPE);
+  GNNPN_REQUIRE(nnz < (1ll << 31) * (int64_t)32, GNNPN_ERANGE);
+  GNNPN_REQUIRE(workspace_bytes >= gnnpn_spmm_csr_split_workspace_bytes(nnz, F, long_row_threshold), GNNPN_EWORKSPACE);
+  GNNPN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, GNNPN_EALIGN);
+  if (n_rows == 0) return GNNPN_OK;
+  int64_t ml, mc;
+  split_bounds(nnz, long_row_threshold, &ml, &mc);
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  LongRowPlan plan{};
+  plan.counters = reinterpret_cast<int*>(w);            w += 256;
+  plan.row = reinterpret_cast<int64_t*>(w);             w += (size_t)ml * 8;
+  plan.chunk_base = reinterpret_cast<int*>(w);          w += (size_t)ml * 8;     // keeps the next array 8-byte aligned
+  plan.chunk_slot = reinterpret_cast<int*>(w);          w += ((size_t)mc * 4 + 255) & ~size_t(255);
+  plan.partial = reinterpret_cast<float*>(w);
+  plan.max_long = (int)ml; plan.max_chunks = (int)mc;
+  const SpmmEpilogue ep{self_scale, mean, bias, scale, shift, act};
+  return spmm_dispatch(rowptr, col, val, x, ldx, y, ldy, n_rows, F, ep, long_row_threshold, &plan, (cudaStream_t)stream);
 }
 
 }  // extern "C"

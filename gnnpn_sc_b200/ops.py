@@ -356,13 +356,33 @@ def embed_concat(x: torch.Tensor, table: torch.Tensor, pad_to: int = 4) -> torch
     return out
 
 
+SPLIT_MIN_NNZ = 1 << 22          # below this the three extra (tiny) launches of the split path cost more than a hub row
+SPLIT_THRESHOLD = 256            # edges per chunk: a chunk is one lane group's sequential walk (32 rounds of 8 gathers)
+
+
 def spmm_csr(rowptr, col, val, x, n_rows: Optional[int] = None, self_scale: float = 0.0, mean: bool = False,
-             bias=None, scale=None, shift=None, act=None, out=None) -> torch.Tensor:
+             bias=None, scale=None, shift=None, act=None, out=None, long_row_threshold: Optional[int] = None,
+             workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CSR aggregation.  ``long_row_threshold``: rows with more edges are split into chunks (hub destinations of a skewed
+    graph, ``gnnpn_spmm_csr_split_f32``); None = ``SPLIT_THRESHOLD`` for graphs of at least ``SPLIT_MIN_NNZ`` edges, no splitting below;
+    0 = never."""
     x = _f32(x, "x")
     F = x.shape[1]
     assert F % 4 == 0, "feature dim must be padded to a multiple of 4"
     n_rows = rowptr.numel() - 1 if n_rows is None else n_rows
     y = torch.empty(n_rows, F, device=x.device, dtype=torch.float32) if out is None else out
+    nnz = int(col.numel())
+    if long_row_threshold is None:
+        long_row_threshold = SPLIT_THRESHOLD if nnz >= SPLIT_MIN_NNZ else 0
+    if long_row_threshold:
+        need = int(lib().gnnpn_spmm_csr_split_workspace_bytes(nnz, F, int(long_row_threshold)))
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, device=x.device, dtype=torch.uint8)
+        check(lib().gnnpn_spmm_csr_split_f32(rowptr.data_ptr(), col.data_ptr(), _ptr(val), x.data_ptr(), x.stride(0),
+                                             y.data_ptr(), y.stride(0), n_rows, nnz, F, float(self_scale), int(mean),
+                                             _ptr(bias), _ptr(scale), _ptr(shift), ACT[act], int(long_row_threshold),
+                                             workspace.data_ptr(), workspace.numel(), _stream()), "spmm_csr_split")
+        return y
     check(lib().gnnpn_spmm_csr_f32(rowptr.data_ptr(), col.data_ptr(), _ptr(val), x.data_ptr(), x.stride(0),
                                    y.data_ptr(), y.stride(0), n_rows, F, float(self_scale), int(mean),
                                    _ptr(bias), _ptr(scale), _ptr(shift), ACT[act], _stream()), "spmm_csr")

@@ -306,6 +306,19 @@ GNNPN_API int gnnpn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, cons
                        float self_scale, int mean, const float* bias, const float* scale,
                        const float* shift, int act, void* stream);
 
+/* Same aggregation with LONG-ROW SPLITTING for skewed in-degree distributions (hub destinations: the service co-usage
+ * graph of src/loadData.py:55-65 gives popular services rows of 10^4..10^5 edges).  Rows with more than
+ * `long_row_threshold` (>= 32) edges are cut into chunks of that many consecutive edges, each chunk is summed by one lane
+ * group like a short row, and the chunk sums are added in chunk order: deterministic, no atomics in the arithmetic.
+ * Rows at or below the threshold stay bit-identical to gnnpn_spmm_csr_f32 (index_add_ order); split rows differ from the
+ * strictly sequential sum by re-association only.  `nnz` = rowptr[n_rows] (known to the caller, not read from the
+ * device); workspace: gnnpn_spmm_csr_split_workspace_bytes(nnz, F, threshold) bytes, 256-byte aligned. */
+GNNPN_API size_t gnnpn_spmm_csr_split_workspace_bytes(int64_t nnz, int F, int64_t long_row_threshold);
+GNNPN_API int gnnpn_spmm_csr_split_f32(const int64_t* rowptr, const int32_t* col, const float* val, const float* x,
+                             int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int64_t nnz, int F, float self_scale,
+                             int mean, const float* bias, const float* scale, const float* shift, int act,
+                             int64_t long_row_threshold, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Node transform: C[M,N] = act( (A[M,K] . W[N,K]^T + bias[N]) * scale[N] + shift[N] )
  * (nn.Linear / GCNConv's X.W, modelML.py:77-93,98-106,164-165; bias/scale/shift may be NULL).
  * fp32 in/out.  With a workspace of gnnpn_gemm_workspace_bytes() the contraction runs on tcgen05

@@ -240,3 +240,41 @@ def test_kat_gin_and_segment_mean_on_device():
     xm[:, 0] = torch.tensor(kat.MEAN_X)
     out = ops.spmm_csr(rp, col, None, xm.cuda(), n_rows=kat.MEAN_SEGMENTS, mean=True).cpu()[:, 0]
     assert out.tolist() == kat.MEAN_OUT                                    # empty segments -> 0, not NaN
+
+
+def test_long_row_split_hub_destinations():
+    """Skewed in-degrees (hub rows): rows at or below the threshold are bit-identical to the index_add_ order oracle, split
+    rows agree to 1e-5 (re-association of chunk sums only), the result is deterministic, and the fused epilogue (mean,
+    bias, ReLU) is applied once per row."""
+    from gnnpn_sc_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n, F, T = 3000, 64, 256
+    deg = torch.randint(0, 40, (n,), generator=g)
+    deg[7], deg[1500], deg[2999] = 120000, 5000, 257                       # hubs; 257 = just above the threshold
+    deg[11] = 256                                                          # exactly at the threshold: not split
+    dst = torch.repeat_interleave(torch.arange(n), deg)
+    src = torch.randint(0, n, (dst.numel(),), generator=g)
+    w = torch.rand(dst.numel(), generator=g) + 0.05
+    x = torch.randn(n, F, generator=g)
+    ei = torch.stack([src, dst])
+    ref = mo.aggregate_sum(x, ei, w)                                       # sequential fp32 in edge order per row
+    ref64 = torch.zeros(n, F, dtype=torch.float64).index_add_(0, dst, w.double().view(-1, 1) * x.double()[src])
+    rp, col, val = ops.csr_build(ei.cuda(), w.cuda(), n, ops.CSR_PLAIN)
+    y = ops.spmm_csr(rp, col, val, x.cuda(), long_row_threshold=T).cpu()
+    y2 = ops.spmm_csr(rp, col, val, x.cuda(), long_row_threshold=T).cpu()
+    assert torch.equal(y, y2)                                              # deterministic
+    short = deg <= T
+    assert torch.equal(y[short], ref[short])                              # bit-identical where no split happened
+    scale = (w.double().view(-1, 1) * x.double()[src]).abs()
+    mag = torch.zeros(n, F, dtype=torch.float64).index_add_(0, dst, scale).clamp(min=1)
+    err = ((y.double() - ref64).abs() / mag).max().item()
+    err_seq = ((ref.double() - ref64).abs() / mag).max().item()
+    record_parity("spmm_long_row_split", max_err_over_summed_magnitude=err, sequential_fp32_err=err_seq, tolerance=1e-5,
+                  max_in_degree=120000, threshold=T)
+    assert err <= 1e-5, err
+    bias = torch.randn(F, generator=g)
+    ym = ops.spmm_csr(rp, col, val, x.cuda(), mean=True, bias=bias.cuda(), act="relu", long_row_threshold=T).cpu()
+    want = torch.relu(ref64 / deg.clamp(min=1).double().view(-1, 1) + bias.double())
+    assert ((ym.double() - want).abs() / want.abs().clamp(min=1)).max() <= 1e-5
+    y0 = ops.spmm_csr(rp, col, val, x.cuda(), long_row_threshold=0).cpu()  # unsplit path: whole matrix bit-identical
+    assert torch.equal(y0, ref)
