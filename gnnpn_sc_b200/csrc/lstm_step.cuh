@@ -26,10 +26,13 @@ struct LstmStepArgs {
   const float* P;         // packed [(kH + kXPad)][kG]
   const float* bias;      // [kG]
   float* c;               // [M, kH] in/out
+  const float* c_in;      // optional: read the old cell state from here instead of `c` (c is then write-only)
   float* h_out;           // [M, kH] rows h_out_ld apart
   int64_t h_out_ld;
   int M;
   int first;              // 1: h_in = 0 and c = 0 (first encoder step)
+  // training replay (pn_train.cu): optional per-step saves for the backward pass, or nullptr
+  float* gates_out;       // [M, kG] post-activation gates, columns 4j+{i,f,g,o}
 };
 
 int launch_lstm_step(const LstmStepArgs& a, cudaStream_t stream);

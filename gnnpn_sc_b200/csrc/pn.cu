@@ -448,6 +448,61 @@ int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_out, float*
   return GNNPN_OK;
 }
 
+// Differentiable replay, forward half (see pn_train.cu): strict-fp32 FFMA LSTM steps + pointer steps, teacher-forced on
+// the picks `idx`, saving the post-activation gates and the cell state of every step for the backward pass.
+int gnnpn_pn_train_forward_f32(const float* inputs, const float* packed_enc, const float* packed_dec, const int32_t* idx,
+                               const float* latent_win, float alpha, int use_tanh, float C, int64_t n, int L,
+                               int in_features, int hidden, int K, int N, float* enc_out, float* gates_e, float* c_e,
+                               float* dec_h, float* gates_d, float* c_d, float* win_logits, float* win_probs,
+                               int32_t* idx_free, void* stream) {
+  GNNPN_REQUIRE(inputs && packed_enc && packed_dec && idx && enc_out && gates_e && c_e && dec_h && gates_d && c_d &&
+                    win_logits && win_probs && idx_free, GNNPN_ENULL);
+  GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= 8 && K >= 1 && N >= 1 && N <= kMaxWindow &&
+                    (int64_t)K * N == L && n >= 0 && n < (1ll << 31), GNNPN_ESHAPE);
+  GNNPN_REQUIRE(aligned16(enc_out) && aligned16(dec_h) && aligned16(gates_e) && aligned16(gates_d), GNNPN_EALIGN);
+  if (n == 0) return GNNPN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  LstmStepArgs a{};
+  a.x = inputs; a.x_inst_ld = (int64_t)L * in_features; a.F = in_features; a.use_x = 1; a.gather = nullptr;
+  a.P = packed_enc; a.bias = packed_enc + kOffBias; a.M = (int)n;
+  a.h_in_ld = a.h_out_ld = (int64_t)L * kH;
+  for (int t = 0; t < L; ++t) {
+    a.first = t == 0;
+    a.h_in = t == 0 ? nullptr : enc_out + (int64_t)(t - 1) * kH;
+    a.h_out = enc_out + (int64_t)t * kH;
+    a.x_row = t;
+    a.gates_out = gates_e + (size_t)t * n * kG;
+    a.c = c_e + (size_t)t * n * kH;                                  // this step's slot of the saved cell states
+    a.c_in = t == 0 ? nullptr : c_e + (size_t)(t - 1) * n * kH;
+    if ((rc = launch_lstm_step(a, st))) return rc;
+  }
+  a.P = packed_dec; a.x_row = -1; a.first = 0; a.h_out_ld = (int64_t)K * kH;
+  for (int k = 0; k < K; ++k) {
+    if (k == 0) {
+      a.h_in = enc_out + (int64_t)(L - 1) * kH; a.h_in_ld = (int64_t)L * kH;
+      a.use_x = 0; a.bias = packed_dec + kOffStart; a.gather = nullptr;
+    } else {
+      a.h_in = dec_h + (int64_t)(k - 1) * kH; a.h_in_ld = (int64_t)K * kH;
+      a.use_x = 1; a.bias = packed_dec + kOffBias; a.gather = idx + (int64_t)(k - 1) * n;
+    }
+    a.h_out = dec_h + (int64_t)k * kH;
+    a.gates_out = gates_d + (size_t)k * n * kG;
+    a.c = c_d + (size_t)k * n * kH;
+    a.c_in = k == 0 ? c_e + (size_t)(L - 1) * n * kH : c_d + (size_t)(k - 1) * n * kH;
+    if ((rc = launch_lstm_step(a, st))) return rc;
+    PointerStepArgs pa;
+    pa.enc_out = enc_out; pa.enc_inst_ld = (int64_t)L * kH; pa.latent_win = latent_win; pa.alpha = alpha;
+    pa.use_tanh = use_tanh; pa.C = C; pa.n = n; pa.L = L; pa.N = N;
+    pa.idx_out = idx_free; pa.win_logits = win_logits; pa.win_probs = win_probs;
+    pa.forced = idx; pa.uniform = nullptr;
+    pointer_step_dot_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(pa, k, dec_h + (int64_t)k * kH, (int64_t)K * kH,
+                                                                     inputs, in_features, nullptr, nullptr, 0, 0);
+    if ((rc = after_launch())) return rc;
+  }
+  return GNNPN_OK;
+}
+
 int gnnpn_pn_full_logits_f32(const float* enc_out, const float* dec_h, const int32_t* idx,
                              int attention, const float* att_params, int use_tanh, float C,
                              int64_t n, int L, int hidden, int K, float* logits_full, void* stream) {

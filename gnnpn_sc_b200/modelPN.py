@@ -206,6 +206,7 @@ class PointerNet(nn.Module):
         self.force_general = False                # route a fast-path configuration through the general kernels (tests)
         self.check_inputs = True                  # range-check the raw rows of every batch (one tiny kernel + one sync)
         self.enc_buffer = None                    # optional caller-owned encodings buffer (reused when large enough)
+        self.replay_impl = "own"                  # REINFORCE gradient: "own" = library kernels (fast configuration), "torch"
 
     # -- packed weights are a cache over the parameters; rebuilt when any of them changes
     def _packed_weights(self):
@@ -360,8 +361,16 @@ class PointerNet(nn.Module):
         the windows -- outside window k the reference's probabilities are exactly 0 and carry no gradient
         (modelPN.py:220-224) -- so the gradient equals the reference's.  Encoder via nn.LSTM (cuDNN), K cell steps;
         glimpses (when configured) attend over all positions with the cumulative visited mask as in modelPN.py:208-211."""
-        # strict fp32 (set process-wide in gnnpn_sc_b200/__init__.py: cuDNN's TF32 default would put ~5e-4 relative
-        # error into forward AND backward of the nn.LSTM calls below)
+        if self.replay_impl != "torch" and self._fast_path(inputs.shape[2]):
+            # the library's own forward-with-saves + BPTT kernels (Dot attention, no glimpse, embedding_size = 0)
+            e, d = self.encoder, self.decoder
+            probs = _ReplayFn.apply(self, inputs.detach().float().contiguous(), idx.to(torch.int32).contiguous(),
+                                    latent_win, self.embedding2.weight, self.embedding2.bias, self.decoder_start_input,
+                                    e.weight_ih_l0, e.weight_hh_l0, e.bias_ih_l0, e.bias_hh_l0,
+                                    d.weight_ih_l0, d.weight_hh_l0, d.bias_ih_l0, d.bias_hh_l0)
+            return list(probs.unbind(0))
+        # torch replay (every other variant: Bahdanau, glimpses, category embedding).  Strict fp32 (set process-wide in
+        # gnnpn_sc_b200/__init__.py: cuDNN's TF32 default would put ~5e-4 relative error into the nn.LSTM calls below)
         B, L, _ = inputs.shape
         K, N = self.serCategory, self.serNumber
         rows = torch.arange(B, device=inputs.device)
@@ -389,6 +398,66 @@ class PointerNet(nn.Module):
             visited = visited.clone()
             visited[rows, idx[k]] = True
         return out
+
+
+# --------------------------------------------------------------------------- REINFORCE replay on the library's kernels
+class _ReplayFn(torch.autograd.Function):
+    """Probabilities of the sampled picks, differentiable w.r.t. every actor parameter, on this library's kernels
+    (``gnnpn_pn_train_forward_f32`` / ``gnnpn_pn_train_backward_f32`` + ``gnnpn_gemm_f32_bias_act`` for the weight-gradient
+    contractions): the gradient trainPNLow.py:88-96 obtains from torch autograd over its K-step python graph.
+    Layout shuffles (transposes, shifts) are torch copy kernels; every contraction and the BPTT run in the library."""
+
+    @staticmethod
+    def forward(ctx, actor, x, idx, latent_win, emb_w, emb_b, start, e_ih, e_hh, e_bih, e_bhh, d_ih, d_hh, d_bih, d_bhh):
+        K, N = actor.serCategory, actor.serNumber
+        enc_w, dec_w = actor._packed_weights()
+        use_tanh, C = bool(actor.pointer.use_tanh), float(actor.pointer.C)
+        sv = ops.pn_train_forward(x, enc_w, dec_w, idx, K, N, latent_win=latent_win, alpha=float(actor.alpha),
+                                  use_tanh=use_tanh, C=C, hidden=actor.hidden_size)
+        ctx.sv, ctx.x, ctx.cfg = sv, x, (K, N, use_tanh, C)
+        ctx.save_for_backward(emb_w, emb_b, start, e_ih, e_hh, d_ih, d_hh)
+        return sv["win_probs"].gather(1, idx.t().long()).t().contiguous()            # [K, B]
+
+    @staticmethod
+    def backward(ctx, grad_p):
+        emb_w, emb_b, start, e_ih, e_hh, d_ih, d_hh = ctx.saved_tensors
+        sv, x = ctx.sv, ctx.x
+        K, N, use_tanh, C = ctx.cfg
+        n, L, H = sv["enc_out"].shape
+        F = x.shape[2]
+        idx = sv["idx"].long()                                                       # [K, n]
+        dGe, dGd = ops.pn_train_backward(sv, grad_p.contiguous(), e_hh.detach(), d_hh.detach(), K, N,
+                                         use_tanh, C)
+        mm = lambda a, w: ops.gemm_bias_act(a, w, impl="ffma")                       # a @ w.T (small operands)
+        rows = torch.arange(n, device=x.device)
+        enc_lnh = sv["enc_out"].permute(1, 0, 2)                                     # [L, n, H]
+        dec_knh = sv["dec_h"].permute(1, 0, 2)                                       # [K, n, H]
+
+        def contract(dG_T, h_prev, x_in):
+            """One tensor-core GEMM per LSTM: dG_T [4H, T*n] against the step inputs [h(t-1) | x(t) | 1] laid out
+            [H + F + 1 (padded to 16), T*n]  ->  dW_hh [4H, H], dM = d(W_ih . W_emb) [4H, F], db = row sums [4H]."""
+            T = h_prev.shape[0]
+            ops_in = torch.zeros(H + 16, T * n, device=x.device)
+            ops_in[:H] = h_prev.reshape(T * n, H).t()
+            ops_in[H:H + F] = x_in.reshape(T * n, F).t()
+            ops_in[H + F] = 1.0
+            out = ops.gemm_bias_act(dG_T, ops_in, impl="tc")                         # [4H, H + 16]
+            return out[:, :H].contiguous(), out[:, H:H + F].contiguous(), out[:, H + F].contiguous()
+
+        h_prev_e = torch.cat([torch.zeros_like(enc_lnh[:1]), enc_lnh[:-1]])          # [L, n, H]
+        dWhh_e, dM_e, db_e = contract(dGe, h_prev_e, x.permute(1, 0, 2))
+        h_prev_d = torch.cat([enc_lnh[-1:], dec_knh[:-1]])                           # [K, n, H]
+        x_d = torch.cat([torch.zeros(1, n, F, device=x.device), x[rows.unsqueeze(0), idx[:-1]]])   # step 0: no input term
+        dWhh_d, dM_d, db_dec = contract(dGd, h_prev_d, x_d)
+        s0, db_d = dGd[:, :n].sum(1), dGd[:, n:].sum(1)                              # step 0 uses the start-token bias
+        # unfold M = W_ih . W_emb,  b = b_ih + b_hh + W_ih . b_emb,  start bias = b_ih + b_hh + W_ih . start
+        e_ih_t, d_ih_t = e_ih.t().contiguous(), d_ih.t().contiguous()                # [H, 4H]
+        dWih_e = mm(dM_e, emb_w) + torch.outer(db_e, emb_b)
+        dWih_d = mm(dM_d, emb_w) + torch.outer(db_d, emb_b) + torch.outer(s0, start)
+        d_emb_w = mm(e_ih_t, dM_e.t().contiguous()) + mm(d_ih_t, dM_d.t().contiguous())
+        d_emb_b = (mm(e_ih_t, db_e.view(1, -1)) + mm(d_ih_t, db_d.view(1, -1))).view(-1)
+        d_start = mm(d_ih_t, s0.view(1, -1)).view(-1)
+        return (None, None, None, None, d_emb_w, d_emb_b, d_start, dWih_e, dWhh_e, db_e, db_e, dWih_d, dWhh_d, db_dec, db_dec)
 
 
 # --------------------------------------------------------------------------- CombinatorialRL

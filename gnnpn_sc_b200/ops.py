@@ -145,6 +145,44 @@ def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, laten
     return dec_h, idx, wl, wp
 
 
+def pn_train_forward(inputs, packed_enc, packed_dec, idx, K: int, N: int, latent_win=None, alpha: float = 1.0,
+                     use_tanh: bool = True, C: float = 10.0, hidden: int = 256):
+    """Differentiable replay, forward half (``gnnpn_pn_train_forward_f32``).  Returns the dict of saved tensors."""
+    x = _f32(inputs, "inputs")
+    n, L, F = x.shape
+    dev, H = x.device, hidden
+    f = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+    sv = {"enc_out": f(n, L, H), "gates_e": f(L, n, 4 * H), "c_e": f(L, n, H), "dec_h": f(n, K, H),
+          "gates_d": f(K, n, 4 * H), "c_d": f(K, n, H), "win_logits": f(n, L), "win_probs": f(n, L),
+          "idx": idx.to(torch.int32).contiguous()}
+    idx_free = torch.empty(K, n, device=dev, dtype=torch.int32)
+    lat = None if latent_win is None else _f32(latent_win, "latent_win")
+    check(lib().gnnpn_pn_train_forward_f32(
+        x.data_ptr(), packed_enc.data_ptr(), packed_dec.data_ptr(), sv["idx"].data_ptr(), _ptr(lat), float(alpha),
+        int(bool(use_tanh)), float(C), n, L, F, H, K, N, sv["enc_out"].data_ptr(), sv["gates_e"].data_ptr(),
+        sv["c_e"].data_ptr(), sv["dec_h"].data_ptr(), sv["gates_d"].data_ptr(), sv["c_d"].data_ptr(),
+        sv["win_logits"].data_ptr(), sv["win_probs"].data_ptr(), idx_free.data_ptr(), _stream()), "pn_train_forward")
+    return sv
+
+
+def pn_train_backward(sv, grad_p, w_hh_enc, w_hh_dec, K: int, N: int, use_tanh: bool = True, C: float = 10.0):
+    """Backward half (``gnnpn_pn_train_backward_f32``): -> (dG_enc_T [4H, L*n], dG_dec_T [4H, K*n])."""
+    n, L, H = sv["enc_out"].shape
+    dev = sv["enc_out"].device
+    dGe = torch.empty(4 * H, L * n, device=dev, dtype=torch.float32)
+    dGd = torch.empty(4 * H, K * n, device=dev, dtype=torch.float32)
+    nws = int(lib().gnnpn_pn_train_backward_workspace_floats(n, L, K, H))
+    ws = torch.empty(nws, device=dev, dtype=torch.float32)
+    gp = _f32(grad_p, "grad_p")
+    check(lib().gnnpn_pn_train_backward_f32(
+        sv["enc_out"].data_ptr(), sv["gates_e"].data_ptr(), sv["c_e"].data_ptr(), sv["dec_h"].data_ptr(),
+        sv["gates_d"].data_ptr(), sv["c_d"].data_ptr(), sv["win_logits"].data_ptr(), sv["win_probs"].data_ptr(),
+        sv["idx"].data_ptr(), gp.data_ptr(), _f32(w_hh_enc, "w_hh").data_ptr(), _f32(w_hh_dec, "w_hh").data_ptr(),
+        int(bool(use_tanh)), float(C), n, L, H, K, N, dGe.data_ptr(), dGd.data_ptr(), ws.data_ptr(), ws.numel(),
+        _stream()), "pn_train_backward")
+    return dGe, dGd
+
+
 def att_block(W_query_w, W_query_b, W_ref_w, W_ref_b, V) -> torch.Tensor:
     """One Attention module's Bahdanau parameters in the layout of ``gnnpn_pn_att_block_floats``."""
     H = V.numel()

@@ -156,6 +156,32 @@ GNNPN_API int gnnpn_pn_decode_greedy_f32(const float* inputs, const float* enc_o
                                const int32_t* forced_idx, const float* sample_uniform,
                                void* workspace, size_t workspace_bytes, int enc_layout, void* stream);
 
+/* ---- REINFORCE training: differentiable replay of a sampled decode (src/models/trainPNLow.py:77-106,
+ * trainPNHigh.py:77-112 back-propagate sum_k log p_k(a_k) with torch autograd through the K-step python graph).
+ * Dot attention, no glimpses, embedding_size = 0, N <= 32 (what every reference call site trains).
+ *
+ * forward: strict-fp32 LSTM steps + pointer steps teacher-forced on the picks `idx` int32 [K, n], saving for the backward
+ *   enc_out [n,L,H], gates_e [L,n,4H] (post-activation, columns 4j+{i,f,g,o}), c_e [L,n,H], dec_h [n,K,H],
+ *   gates_d [K,n,4H], c_d [K,n,H], win_logits / win_probs [n,L]; idx_free int32 [K,n] scratch (the free choices).
+ * backward: grad_p fp32 [K,n] = dLoss/dp_k[idx_k] ->
+ *   dG_enc_T [4H, L*n], dG_dec_T [4H, K*n]: gradients w.r.t. the gate pre-activations, TORCH gate order (row = gate*H +
+ *   unit), column = step*n + instance.  The weight gradients are contractions of these with the step inputs
+ *   (dW_hh = dG_T . h(t-1), d(W_ih.W_embed) = dG_T . x(t), db = row sums), run by the caller through
+ *   gnnpn_gemm_f32_bias_act.  w_hh_* = weight_hh_l0 as torch stores it, fp32 [4H, H].
+ *   workspace: gnnpn_pn_train_backward_workspace_floats(n, L, K, H) floats, 16-byte aligned. */
+GNNPN_API int gnnpn_pn_train_forward_f32(const float* inputs, const float* packed_enc, const float* packed_dec,
+                               const int32_t* idx, const float* latent_win, float alpha, int use_tanh, float C,
+                               int64_t n, int L, int in_features, int hidden, int K, int N, float* enc_out,
+                               float* gates_e, float* c_e, float* dec_h, float* gates_d, float* c_d,
+                               float* win_logits, float* win_probs, int32_t* idx_free, void* stream);
+GNNPN_API size_t gnnpn_pn_train_backward_workspace_floats(int64_t n, int L, int K, int hidden);
+GNNPN_API int gnnpn_pn_train_backward_f32(const float* enc_out, const float* gates_e, const float* c_e, const float* dec_h,
+                                const float* gates_d, const float* c_d, const float* win_logits,
+                                const float* win_probs, const int32_t* idx, const float* grad_p,
+                                const float* w_hh_enc, const float* w_hh_dec, int use_tanh, float C, int64_t n,
+                                int L, int hidden, int K, int N, float* dG_enc_T, float* dG_dec_T, float* workspace,
+                                size_t workspace_floats, void* stream);
+
 /* ---- general decode: every PointerNet variant outside the fused fast path above --------------------------
  * Attention parameter block (gnnpn_pn_att_block_floats(H) floats per Attention module, modelPN.py:83-91):
  *   [ W_query.weight H x H (out, in) | W_query.bias H | W_ref.weight H x H (Conv1d kernel 1 -> out, in) | W_ref.bias H | V H ]

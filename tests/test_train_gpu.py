@@ -38,26 +38,39 @@ def test_sampled_decode_follows_the_window_distribution():
     assert len(set(idx[0].tolist())) > 1                                   # actually stochastic
 
 
-def test_replay_gradient_equals_oracle_autograd():
-    """d/dtheta of sum_k log p_k(action_k) through replay_action_probs == autograd through the oracle's graph."""
+@pytest.mark.parametrize("impl,K,N,B,high", [("own", 6, 4, 16, False), ("own", 6, 4, 16, True), ("own", 47, 5, 40, True),
+                                              ("own", 5, 10, 130, False), ("torch", 6, 4, 16, False)])
+def test_replay_gradient_equals_oracle_autograd(impl, K, N, B, high):
+    """d/dtheta of sum_k log p_k(action_k) through replay_action_probs == autograd through the oracle's graph.
+    impl = "own": forward-with-saves + BPTT on the library's kernels (gnnpn_pn_train_*); "torch": the torch replay kept
+    for the non-default variants.  `high`: with PNLow's latent added to the logits (trainPNHigh.py:83-84)."""
     from gnnpn_sc_b200.synth import pn_instances
-    K, N, B = 6, 4, 16
+    from conftest import record_parity
     cfg, sd, m = _model(K, N, seed=5)
     x = pn_instances(B, K, N, seed=2)
+    g = torch.Generator().manual_seed(9)
+    latent = [torch.randn(B, K * N, generator=g) for _ in range(K)] if high else None
     sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    probs, idx, _ = po.pointer_forward(sd_g, cfg, x, None, "greedy")
-    logp = sum(torch.log(p[torch.arange(B), a]) for p, a in zip(probs, idx)).sum()
+    probs, idx, _ = po.pointer_forward(sd_g, cfg, x, latent, "greedy")
+    w = torch.rand(B, generator=g) - 0.3                                   # per-instance advantage
+    logp = (w * sum(torch.log(p[torch.arange(B), a]) for p, a in zip(probs, idx))).sum()
     logp.backward()
     m.train()
+    m.actor.replay_impl = impl
     idx_c = torch.stack(idx).cuda()
-    ap = m.actor.replay_action_probs(x.cuda(), idx_c, None)
-    sum(torch.log(p) for p in ap).sum().backward()
+    lat_win = None
+    if high:
+        dense = torch.stack(latent)                                        # [K, B, L] -> compact window form [B, L]
+        lat_win = dense.view(K, B, K, N).diagonal(dim1=0, dim2=2).permute(0, 2, 1).reshape(B, K * N).contiguous().cuda()
+    ap = m.actor.replay_action_probs(x.cuda(), idx_c, lat_win)
+    (w.cuda() * sum(torch.log(p) for p in ap)).sum().backward()
     worst = 0.0
     for name, p in m.named_parameters():
         g_ref = sd_g[name].grad
         d = (p.grad.cpu() - g_ref).abs().max() / g_ref.abs().max().clamp(min=1e-3)
         worst = max(worst, float(d))
-    print(f"replay gradient max relative deviation vs oracle autograd: {worst:.2e}")
+    print(f"replay gradient [{impl}, K={K}, N={N}, B={B}, high={high}] max relative deviation vs oracle autograd: {worst:.2e}")
+    record_parity(f"reinforce_gradient_{impl}_K{K}_N{N}_B{B}_{'high' if high else 'low'}", max_rel_dev=worst, tolerance=1e-4)
     assert worst < 1e-4
 
 
