@@ -63,6 +63,8 @@ SIGNATURES = {
     "gnnpn_spmm_csr_split_workspace_bytes": (C.c_size_t, [_i64, _i, _i64]),
     "gnnpn_spmm_csr_split_f32": (_i, [_p, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i, _f, _i, _p, _p, _p, _i, _i64, _p,
                                       C.c_size_t, _p]),
+    "gnnpn_bn_train_forward_f32": (_i, [_p, _i64, _i64, _i, _p, _p, _f, _f, _i, _p, _i64, _p, _p, _p, _p, _p]),
+    "gnnpn_bn_train_backward_f32": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i, _p, _p, _p, _i, _p, _i64, _p, _p, _p]),
     "gnnpn_gemm_workspace_bytes": (C.c_size_t, [_i64, _i, _i]),
     "gnnpn_gemm_f32_bias_act": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _p, _i64, _i64, _i, _i, _p, C.c_size_t, _p]),
 }

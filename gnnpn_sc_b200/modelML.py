@@ -10,9 +10,9 @@ torch_geometric / torch_scatter.  ``forward`` runs on the sm_100a kernels of ``l
 * ``gnnpn_spmm_csr_f32``      GIN sum + (1+eps)x, GCN normalised sum + bias + BN + ReLU, scatter-mean
 * ``gnnpn_gemm_f32_bias_act`` every Linear / X.W with bias, eval-BatchNorm and ReLU/sigmoid folded in
 
-Inference (``eval()`` / no grad) is entirely on those kernels.  With gradients enabled (``TrainML.train``)
-the aggregations still run on the CUDA CSR kernels, forward and backward (``_Aggregate``), while the dense
-transforms and train-mode BatchNorm use torch ops so autograd can differentiate them.
+Inference (``eval()`` / no grad) is entirely on those kernels.  With gradients enabled (``TrainML.train``) the
+aggregations, every dense transform and train-mode BatchNorm + ReLU run on the library's kernels too, forward and
+backward, wrapped in ``torch.autograd.Function`` (``_Aggregate``, ``_MatmulNT``, ``_BatchNormAct``).
 No CPU fallback: CUDA tensors only.
 """
 from __future__ import annotations
@@ -54,6 +54,66 @@ class _Aggregate(torch.autograd.Function):
     def backward(ctx, gy):
         b = ctx.bwd
         return ops.spmm_csr(b.rowptr, b.col, b.val, gy.contiguous(), n_rows=b.n), None, None
+
+
+def _gemm_nt(a: torch.Tensor, b: torch.Tensor, bias=None) -> torch.Tensor:
+    """a [M,K] @ b[N,K]^T (+ bias) through ``gnnpn_gemm_f32_bias_act``: the tcgen05 kernels when the shape allows (rows >=
+    512, K % 4 == 0, N % 16 == 0), the strict-fp32 FFMA kernel otherwise."""
+    a, b = a.contiguous(), b.contiguous()
+    M, K = a.shape
+    N = b.shape[0]
+    tc_ok = M >= ops.TC_GEMM_MIN_ROWS and K % 4 == 0 and N % 16 == 0
+    return ops.gemm_bias_act(a, b, bias=bias, impl="tc" if tc_ok else "ffma")
+
+
+class _MatmulNT(torch.autograd.Function):
+    """C = A . B^T (+ bias) with every contraction -- forward, dA = dC . B, dB = dC^T . A -- on the library's GEMM
+    kernels (the reference trains through torch.nn.Linear / PyG GCNConv's ``x @ weight``, modelML.py:77-104,164-176)."""
+
+    @staticmethod
+    def forward(ctx, a, b, bias):
+        ctx.save_for_backward(a, b)
+        ctx.has_bias = bias is not None
+        return _gemm_nt(a.detach(), b.detach(), None if bias is None else bias.detach())
+
+    @staticmethod
+    def backward(ctx, dc):
+        a, b = ctx.saved_tensors
+        dc = dc.contiguous()
+        da = _gemm_nt(dc, b.t()) if ctx.needs_input_grad[0] else None                  # [M,N] . [N,K]
+        db = _gemm_nt(dc.t(), a.t()) if ctx.needs_input_grad[1] else None             # [N,M] . [M,K]
+        dbias = dc.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return da, db, dbias
+
+
+class _BatchNormAct(torch.autograd.Function):
+    """Train-mode BatchNorm1d (+ fused ReLU) on ``gnnpn_bn_train_forward_f32`` / ``gnnpn_bn_train_backward_f32``."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, bn, relu):
+        y = y.contiguous()
+        out, mean, rstd = ops.bn_train_forward(y, gamma.detach(), beta.detach(), bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+                                               relu, bn.running_mean if bn.track_running_stats else None,
+                                               bn.running_var if bn.track_running_stats else None)
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        ctx.save_for_backward(y, out, gamma, mean, rstd)
+        ctx.relu = relu
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, out, gamma, mean, rstd = ctx.saved_tensors
+        dx, dg, db = ops.bn_train_backward(y, out, dout.contiguous(), gamma.detach(), mean, rstd, ctx.relu)
+        return dx, dg, db, None, None
+
+
+def _linear(x, lin: "Linear"):
+    return _MatmulNT.apply(x, lin.weight, lin.bias)
+
+
+def _bn_act(y, bn: "BatchNorm1d", relu: bool = True):
+    return _BatchNormAct.apply(y, bn.weight, bn.bias, bn, relu)
 
 
 def _pad4(x: torch.Tensor) -> torch.Tensor:
@@ -308,8 +368,10 @@ class Net(nn.Module):
         return _bn_fold(bn)
 
     def _forward_train(self, data):
-        """Autograd path (TrainML.train, trainML.py:34-47): CUDA CSR kernels for every aggregation, forward and
-        backward; dense transforms + train-mode BatchNorm in torch."""
+        """Autograd path (TrainML.train, trainML.py:34-47) on the library's kernels, forward AND backward: CSR
+        aggregations (``_Aggregate``), every dense transform (``_MatmulNT`` -> gnnpn_gemm_f32_bias_act) and train-mode
+        BatchNorm + ReLU (``_BatchNormAct`` -> gnnpn_bn_train_*).  Embedding lookups, the segment mean, the sigmoid and
+        the loss stay element-wise / indexing torch ops."""
         x_raw = data.x.squeeze().float()
         n_req = x_raw.shape[0]
         x = torch.cat((self.nodeEncoder(x_raw[:, 0].view(-1, 1).long()), x_raw[:, 1:]), -1)
@@ -318,7 +380,9 @@ class Net(nn.Module):
         for conv, bn in zip(self.nodeConvs, self.nodeBatchNorms):
             xp = _pad4(x)
             agg = _Aggregate.apply(xp, req, req_t)[:, : x.shape[1]] + (1 + conv.eps) * x
-            x = F.dropout(F.relu(bn(conv.nn(agg))), self.dropout, training=True)
+            lin0, bn0, _, lin1 = conv.nn                                    # Linear, BatchNorm1d, ReLU, Linear
+            h = _bn_act(_linear(agg, lin0), bn0, relu=True)
+            x = F.dropout(_bn_act(_linear(h, lin1), bn, relu=True), self.dropout, training=True)
         xs_raw = data.x_service.squeeze().float()
         n_svc = xs_raw.shape[0]
         xs = torch.cat((self.serviceEncoder(xs_raw[:, 0].view(-1, 1).long()), xs_raw[:, 1:]), -1)
@@ -327,19 +391,19 @@ class Net(nn.Module):
         for i in range(self.numLayersGCN):
             if self.isService:
                 conv = self.serviceConvs[i]
-                xs = _Aggregate.apply(xs @ conv.weight, svc, svc_t) + conv.bias
+                xs = _Aggregate.apply(_MatmulNT.apply(xs, conv.weight.t(), None), svc, svc_t) + conv.bias
             else:
-                xs = self.noServicesLins[i](xs)
-            xs = F.dropout(F.relu(self.serviceBatchNorms[i](xs)), self.dropout, training=True)
-        xs = self.serviceLin(xs)
-        x = self.nodeLin(x)
+                xs = _linear(xs, self.noServicesLins[i])
+            xs = F.dropout(_bn_act(xs, self.serviceBatchNorms[i], relu=True), self.dropout, training=True)
+        xs = _linear(xs, self.serviceLin)
+        x = _linear(x, self.nodeLin)
         B = int(data.batch.max().item()) + 1
         ones = torch.ones(n_req, device=x.device)
         x = torch.zeros(B, x.shape[1], device=x.device).index_add_(0, data.batch, x) / \
             torch.zeros(B, device=x.device).index_add_(0, data.batch, ones).clamp(min=1).view(-1, 1)
         S = self.outChannels
         xs = xs.view(-1, S, xs.shape[1]).mean(0) if n_svc % S == 0 else xs
-        return self.sigmoid(x @ xs.t())
+        return self.sigmoid(_MatmulNT.apply(x, xs, None))
 
 
 def _pad_w(w: torch.Tensor, k: int) -> torch.Tensor:

@@ -445,3 +445,32 @@ def gemm_bias_act(a, w, bias=None, scale=None, shift=None, act=None, out=None, i
                                         _ptr(scale), _ptr(shift), ACT[act], c.data_ptr(), c.stride(0),
                                         M, N, K, *_ws(ws), _stream()), "gemm_bias_act")
     return c
+
+
+# ------------------------------------------------------------------ train-mode BatchNorm (+ReLU)
+def bn_train_forward(y, gamma, beta, eps: float, momentum: float, relu: bool, running_mean=None, running_var=None):
+    """-> (out [M,C], save_mean [C], save_rstd [C]); running statistics are updated in place (torch semantics)."""
+    y = _f32(y, "y")
+    M, Cc = y.shape
+    out = torch.empty_like(y)
+    mean = torch.empty(Cc, device=y.device, dtype=torch.float32)
+    rstd = torch.empty(Cc, device=y.device, dtype=torch.float32)
+    check(lib().gnnpn_bn_train_forward_f32(y.data_ptr(), y.stride(0), M, Cc, _ptr(gamma), _ptr(beta), float(eps),
+                                           float(momentum), int(bool(relu)), out.data_ptr(), out.stride(0),
+                                           mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var),
+                                           _stream()), "bn_train_forward")
+    return out, mean, rstd
+
+
+def bn_train_backward(y, out, dout, gamma, mean, rstd, relu: bool):
+    """-> (dx [M,C], dgamma [C], dbeta [C])."""
+    dout = _f32(dout, "dout")
+    M, Cc = y.shape
+    dx = torch.empty_like(y)
+    dg = torch.empty(Cc, device=y.device, dtype=torch.float32)
+    db = torch.empty(Cc, device=y.device, dtype=torch.float32)
+    check(lib().gnnpn_bn_train_backward_f32(y.data_ptr(), y.stride(0), out.data_ptr(), out.stride(0), dout.data_ptr(),
+                                            dout.stride(0), M, Cc, _ptr(gamma), mean.data_ptr(), rstd.data_ptr(),
+                                            int(bool(relu)), dx.data_ptr(), dx.stride(0), dg.data_ptr(), db.data_ptr(),
+                                            _stream()), "bn_train_backward")
+    return dx, dg, db

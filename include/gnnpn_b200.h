@@ -345,6 +345,21 @@ GNNPN_API int gnnpn_spmm_csr_split_f32(const int64_t* rowptr, const int32_t* col
                              int mean, const float* bias, const float* scale, const float* shift, int act,
                              int64_t long_row_threshold, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Train-mode BatchNorm1d (+ optional fused ReLU) for the ML stage's training path (torch.nn.BatchNorm1d in training mode,
+ * src/models/modelML.py:75-93,98-104 under TrainML.train, trainML.py:34-47).
+ * forward : batch mean / biased variance per channel over the M rows of y [M, C] (two passes), out = act((y - mean) * rstd
+ *           * gamma + beta); save_mean / save_rstd [C] for the backward; running_mean / running_var (may be NULL) updated
+ *           with `momentum` and the unbiased variance, as torch does.
+ * backward: dout masked by the ReLU (out > 0), dgamma = sum dout * xhat, dbeta = sum dout,
+ *           dx = gamma * rstd * (dout - dbeta / M - xhat * dgamma / M).  Deterministic (fixed-order reductions). */
+GNNPN_API int gnnpn_bn_train_forward_f32(const float* y, int64_t ldy, int64_t M, int C, const float* gamma, const float* beta,
+                               float eps, float momentum, int relu, float* out, int64_t ldo, float* save_mean,
+                               float* save_rstd, float* running_mean, float* running_var, void* stream);
+GNNPN_API int gnnpn_bn_train_backward_f32(const float* y, int64_t ldy, const float* out, int64_t ldo, const float* dout,
+                                int64_t ldd, int64_t M, int C, const float* gamma, const float* save_mean,
+                                const float* save_rstd, int relu, float* dx, int64_t ldx, float* dgamma, float* dbeta,
+                                void* stream);
+
 /* Node transform: C[M,N] = act( (A[M,K] . W[N,K]^T + bias[N]) * scale[N] + shift[N] )
  * (nn.Linear / GCNConv's X.W, modelML.py:77-93,98-106,164-165; bias/scale/shift may be NULL).
  * fp32 in/out.  With a workspace of gnnpn_gemm_workspace_bytes() the contraction runs on tcgen05
