@@ -33,14 +33,14 @@ FLOPS_PER_INSTANCE_STEP = 2 * HID * 4 * HID + 2 * FEAT * 4 * HID   # h.W_hh^T + 
 ISSUED_OVER_ALGORITHMIC = 3 * (HID + 16) / (HID + FEAT)            # a_lo.w_hi + a_hi.w_hi + a_hi.w_lo, x padded to 16
 
 
-def ncu_traffic(n: int):
+def ncu_traffic(n: int, key: str = "encoder_dram_bytes"):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
     capture (profiles/*_seq_traffic.json), per launch; only reported when it was captured at this n."""
-    p = os.path.join(ROOT, "profiles", "r01_seq_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_seq_traffic.json")
     try:
         with open(p) as f:
             d = json.load(f)
-        return d["encoder_dram_bytes"] if int(d["instances"]) == int(n) else None
+        return d[key] if int(d["instances"]) == int(n) else None
     except (OSError, KeyError, ValueError):
         return None
 
@@ -69,7 +69,8 @@ def decode_roofline(n, dec_launch_ms, pk, layout):
                       "fused into the cell epilogue over blocked encodings, thread-per-instance softmax / pick)"
                       if layout else "lstm_seq_kernel<true,2,0> (persistent decoder + separate pointer phase)",
             "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-            "avg_launch_ms": dec_launch_ms, "algorithmic_bytes_per_launch": n * per_inst, "traffic": None,
+            "avg_launch_ms": dec_launch_ms, "algorithmic_bytes_per_launch": n * per_inst,
+            "traffic": ncu_traffic(n, "decoder_dram_bytes") if layout else None,
             "peak_source": pk["src"] + ": MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"}
 
 

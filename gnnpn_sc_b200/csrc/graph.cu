@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(
 }
 
 // ---- long-row splitting (hub destinations: a service used by 10^5 compositions would otherwise be ONE group's
-// sequential walk).  Rows with more than T edges are cut into chunks of T consecutive edges; every chunk is summed by
-// one group exactly like a short row (sequential in CSR order), the chunk sums are then added in chunk order.
+// sequential walk).  Rows with more than T edges are cut into chunks of Tc = T / 8 consecutive edges; every chunk is summed
+// by one group exactly like a short row (sequential in CSR order), the chunk sums are then added in chunk order.
 // Deterministic (fixed order, no atomics in the arithmetic); rows of <= T edges stay bit-identical to index_add_ order,
 // split rows differ from the strictly sequential sum by re-association only (~1e-7 relative; tests bound it by 1e-5).
 struct LongRowPlan {
@@ -256,11 +256,12 @@ struct LongRowPlan {
   int max_long, max_chunks;
 };
 
-__global__ void find_long_rows_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int64_t T, LongRowPlan p) {
+__global__ void find_long_rows_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int64_t T, int64_t Tc,
+                                      LongRowPlan p) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
     const int64_t d = rowptr[r + 1] - rowptr[r];
     if (d <= T) continue;
-    const int nch = (int)((d + T - 1) / T);
+    const int nch = (int)((d + Tc - 1) / Tc);
     const int slot = atomicAdd(p.counters, 1);
     const int cb = atomicAdd(p.counters + 1, nch);
     if (slot >= p.max_long || cb + nch > p.max_chunks) continue;        // cannot happen: both bounds follow from nnz / T
@@ -366,6 +367,8 @@ __global__ void embed_concat_kernel(const float* __restrict__ x, int64_t n, int 
   }
 }
 
+inline int64_t chunk_len(int64_t T) { return T / 8 < 32 ? 32 : T / 8; }    // edges per chunk of a split row
+
 template <int GROUP, int VPL, int UNROLL>
 int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx,
                 float* y, int64_t ldy, int64_t n_rows, int F4, const SpmmEpilogue& ep, int64_t T, const LongRowPlan* plan,
@@ -377,16 +380,16 @@ int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* val, con
   if (plan) {
     cudaMemsetAsync(plan->counters, 0, 2 * sizeof(int), st);
     const int64_t fb = ceil_div(n_rows, 256);
-    find_long_rows_kernel<<<(unsigned)(fb < 8 * kNumSMs ? fb : 8 * kNumSMs), 256, 0, st>>>(rowptr, n_rows, T, *plan);
+    find_long_rows_kernel<<<(unsigned)(fb < 8 * kNumSMs ? fb : 8 * kNumSMs), 256, 0, st>>>(rowptr, n_rows, T, chunk_len(T), *plan);
     if ((rc = after_launch())) return rc;
   }
   spmm_csr_kernel<GROUP, VPL, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, ldx, y, ldy, n_rows, F4, ep,
                                                                        plan ? T : 0);
   if ((rc = after_launch()) || !plan) return rc;
   // persistent grids: they read the chunk / row counts on the device and return at once when there is no long row
-  spmm_chunk_kernel<GROUP, VPL, UNROLL><<<8 * kNumSMs, 256, 0, st>>>(rowptr, col, val, x, ldx, F4, T, *plan);
+  spmm_chunk_kernel<GROUP, VPL, UNROLL><<<8 * kNumSMs, 256, 0, st>>>(rowptr, col, val, x, ldx, F4, chunk_len(T), *plan);
   if ((rc = after_launch())) return rc;
-  spmm_combine_kernel<GROUP, VPL><<<kNumSMs, 256, 0, st>>>(rowptr, x, ldx, y, ldy, F4, T, ep, *plan);
+  spmm_combine_kernel<GROUP, VPL><<<kNumSMs, 256, 0, st>>>(rowptr, x, ldx, y, ldy, F4, chunk_len(T), ep, *plan);
   return after_launch();
 }
 
@@ -500,7 +503,7 @@ int gnnpn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* v
 
 static void split_bounds(int64_t nnz, int64_t T, int64_t* max_long, int64_t* max_chunks) {
   *max_long = nnz / (T + 1) + 1;                 // a long row has at least T + 1 edges
-  *max_chunks = nnz / T + *max_long + 1;         // sum of ceil(d / T) over the long rows
+  *max_chunks = nnz / chunk_len(T) + *max_long + 1;      // sum of ceil(d / Tc) over the long rows
 }
 
 size_t gnnpn_spmm_csr_split_workspace_bytes(int64_t nnz, int F, int64_t long_row_threshold) {

@@ -583,7 +583,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_cons
       // ================= L2 prefetcher (fused decoder): the 16 KB slice (window row j, tile nt) of this CTA's block is
       // contiguous; it is requested two tiles before the epilogue multiplies it, paced by the MMA's tile barriers
       if (lane == 0 && cta_ok) {
-        constexpr int dist = 2;      // measured: 1 tile ahead 40.1k cycles / step, 2: 39.7k, 3: 51.8k, none: 46.0k (profiles/)
+        // tiles ahead.  N = 5 (QWS): 1 tile ahead 40.1k cycles / step, 2: 39.7k, 3: 51.8k, none: 46.0k (profiles/).  Wider
+        // windows keep the prefetched-but-unused footprint (dist x N x 16 KB per CTA) at the same ~24 MB: at N = 10 two tiles
+        // ahead made the kernel re-read 35 % of the rows from DRAM (ncu: 13.1 GB for 9.7 GB algorithmic)
+        const int dist = p.pa.N > 5 ? 1 : 2;
         const float* const blk = p.pa.enc_out + enc_blk_off(blockIdx.x, p.L, 0, 0, 0);
         const int N = p.pa.N;
         for (int a = 0; a < dist; ++a)

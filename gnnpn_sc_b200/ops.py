@@ -395,7 +395,8 @@ def embed_concat(x: torch.Tensor, table: torch.Tensor, pad_to: int = 4) -> torch
 
 
 SPLIT_MIN_NNZ = 1 << 22          # below this the three extra (tiny) launches of the split path cost more than a hub row
-SPLIT_THRESHOLD = 256            # edges per chunk: a chunk is one lane group's sequential walk (32 rounds of 8 gathers)
+SPLIT_THRESHOLD = 2048           # rows with more edges are split, into chunks of threshold / 8 = 256 edges (one lane group's
+                                 # sequential walk of 32 rounds of 8 gathers); the QWS co-usage graph's largest row has 1,378 edges
 
 
 def spmm_csr(rowptr, col, val, x, n_rows: Optional[int] = None, self_scale: float = 0.0, mean: bool = False,

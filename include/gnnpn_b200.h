@@ -334,8 +334,8 @@ GNNPN_API int gnnpn_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, cons
 
 /* Same aggregation with LONG-ROW SPLITTING for skewed in-degree distributions (hub destinations: the service co-usage
  * graph of src/loadData.py:55-65 gives popular services rows of 10^4..10^5 edges).  Rows with more than
- * `long_row_threshold` (>= 32) edges are cut into chunks of that many consecutive edges, each chunk is summed by one lane
- * group like a short row, and the chunk sums are added in chunk order: deterministic, no atomics in the arithmetic.
+ * `long_row_threshold` (>= 32) edges are cut into chunks of threshold / 8 consecutive edges, each chunk is summed by one
+ * lane group like a short row, and the chunk sums are added in chunk order: deterministic, no atomics in the arithmetic.
  * Rows at or below the threshold stay bit-identical to gnnpn_spmm_csr_f32 (index_add_ order); split rows differ from the
  * strictly sequential sum by re-association only.  `nnz` = rowptr[n_rows] (known to the caller, not read from the
  * device); workspace: gnnpn_spmm_csr_split_workspace_bytes(nnz, F, threshold) bytes, 256-byte aligned. */

@@ -248,7 +248,7 @@ def test_long_row_split_hub_destinations():
     bias, ReLU) is applied once per row."""
     from gnnpn_sc_b200 import ops
     g = torch.Generator().manual_seed(5)
-    n, F, T = 3000, 64, 256
+    n, F, T = 3000, 64, 256                                               # rows > 256 edges split into chunks of 32
     deg = torch.randint(0, 40, (n,), generator=g)
     deg[7], deg[1500], deg[2999] = 120000, 5000, 257                       # hubs; 257 = just above the threshold
     deg[11] = 256                                                          # exactly at the threshold: not split
