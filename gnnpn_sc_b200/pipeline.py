@@ -132,16 +132,30 @@ class ML2PN:
         self._side = torch.cuda.Stream(self.device)
 
     @torch.no_grad()
-    def compose(self, request_batch, local_bounds, used, global_bounds):
+    def compose(self, request_batch, local_bounds, used, global_bounds, stage_events=None):
         """``request_batch``: collated request graphs (x, edge_index, batch) on the device; constraint tensors from
-        ``constraint_arrays``.  Returns scores, PN rows, picked service ids per row, PNHigh picks and objective."""
+        ``constraint_arrays``.  Returns scores, PN rows, picked service ids per row, PNHigh picks and objective.
+        ``stage_events``: optional list that receives five CUDA events recorded on the current stream at the stage
+        boundaries (start, scores, candidates, PNLow+PNHigh, objective) -- bench.py's per-stage times."""
         from . import ops
+
+        def mark():
+            if stage_events is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                stage_events.append(ev)
+
+        mark()
         scores = self.net.score_requests(request_batch, self.service_enc)                     # [B, S]
+        mark()
         rows, picked = ops.select_candidates(scores, self.svc_qos, self.cat_ptr, local_bounds, used, global_bounds,
                                              self.N, with_category=False, return_picked=True)  # [B, K*N, 8]
+        mark()
         latent, R, idx = low_high(self.low, self.high, rows, self._side)
         idx = torch.stack(idx)                                                                # [K, B]
         services = picked.gather(1, idx.t())                                                  # chosen service per task (-1: unused)
+        mark()
         viol, obj, _ = ops.pn_reward(rows, idx.to(torch.int32))
+        mark()
         return {"scores": scores, "rows": rows, "picked": picked, "idx_high": idx, "services": services,
                 "reward": R, "violations": viol, "objective": obj}
