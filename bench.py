@@ -265,16 +265,16 @@ def pipeline_block(dev, shape: str, n: int, steps: int, warmup: int):
     for _ in range(warmup):
         device_step()
     ms = timed(device_step, steps)
-    # per-stage times from CUDA events recorded INSIDE compose at the stage boundaries (same runs as a whole step)
+    # per-stage times from CUDA events recorded INSIDE compose at the stage boundaries, steady state: the steps run back
+    # to back (no host sync between them, as in the whole-step timing above); the first one only fills the queue
     names = ("net_scores", "select_candidates", "pnlow_pnhigh", "objective")
-    acc = dict.fromkeys(names, 0.0)
-    for _ in range(steps):
+    runs = []
+    for _ in range(steps + 1):
         evs = []
         out.update(pipe.compose(batch, *cons, stage_events=evs))
-        torch.cuda.synchronize()
-        for i, k in enumerate(names):
-            acc[k] += evs[i].elapsed_time(evs[i + 1]) / steps
-    stage = acc
+        runs.append(evs)
+    torch.cuda.synchronize()
+    stage = {k: sum(evs[i].elapsed_time(evs[i + 1]) for evs in runs[1:]) / steps for i, k in enumerate(names)}
     e2e_step()
     e2e_ms = timed(e2e_step, max(2, steps // 2))
     d2h = n * K * 4 + n * 4

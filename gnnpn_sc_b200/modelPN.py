@@ -206,6 +206,8 @@ class PointerNet(nn.Module):
         self.force_general = False                # route a fast-path configuration through the general kernels (tests)
         self.check_inputs = True                  # range-check the raw rows of every batch (one tiny kernel + one sync)
         self.enc_buffer = None                    # optional caller-owned encodings buffer (reused when large enough)
+        self.defer_range_check = False            # True: forward leaves the range flag in ``last["range_flag"]`` (no sync);
+                                                  # the caller reads it with ``raise_if_out_of_range`` when convenient
         self.replay_impl = "own"                  # REINFORCE gradient: "own" = library kernels (fast configuration), "torch"
 
     # -- packed weights are a cache over the parameters; rebuilt when any of them changes
@@ -260,9 +262,11 @@ class PointerNet(nn.Module):
             if self.enc_buffer is not None:
                 # a caller-owned buffer (e.g. shared by PNLow and PNHigh at the scale-up size, where one network's
                 # encodings are ~100 GB and the caching allocator would fragment)
-                need = B * L * self.hidden_size if layout == ops.ENC_ROWMAJOR else None
-                if need is not None and self.enc_buffer.numel() >= need:
-                    buf = self.enc_buffer.view(-1)[:need].view(B, L, self.hidden_size)
+                need = ops.enc_out_floats(B, L, self.hidden_size, layout)
+                if self.enc_buffer.numel() >= need:
+                    buf = self.enc_buffer.view(-1)[:need]
+                    if layout == ops.ENC_ROWMAJOR:
+                        buf = buf.view(B, L, self.hidden_size)
             enc_out, c = ops.lstm_encode(x, enc_w, self.hidden_size, enc_out=buf, workspace=ws, layout=layout)
         return {"x": x, "ws": ws, "layout": layout, "enc_out": enc_out, "c": c, "range_flag": range_flag, "fast": fast,
                 "stream": torch.cuda.current_stream(x.device)}
@@ -319,14 +323,12 @@ class PointerNet(nn.Module):
                     x, enc_out, c, dec_w, K, N, latent_win=lat, alpha=float(self.alpha), attention=att,
                     att_params=blocks, n_glimpses=self.n_glimpses, use_tanh=use_tanh, C=C, forced_idx=forced,
                     sample_uniform=uniform, use_tc=ws is not None)
-        if range_flag is not None and int(range_flag.item()):
-            raise ops.GnnpnError(
-                "PointerNet.forward: an input value is NaN / inf or |x| >= 65504 -- outside the range of the fp16-split "
-                "tensor-core LSTM (GNNPN_ERANGE).  Normalise the QoS columns (the reference's data is min-max scaled) "
-                "or set actor.impl = 'ffma' for the strict-fp32 kernels.")
+        if range_flag is not None and not self.defer_range_check:
+            self.raise_if_out_of_range(range_flag)
         idx64 = idx.long()
         self.last = _Last({"idx": idx, "win_logits": win_logits, "win_probs": win_probs, "latent_win": lat,
-                           "enc_buf": enc_out, "enc_layout": layout, "enc_shape": (B, L, self.hidden_size)})
+                           "enc_buf": enc_out, "enc_layout": layout, "enc_shape": (B, L, self.hidden_size),
+                           "range_flag": range_flag})
         if layout == ops.ENC_ROWMAJOR:
             self.last["enc_out"] = enc_out
         if dec_h is not None:
@@ -353,6 +355,15 @@ class PointerNet(nn.Module):
         prev_logits = WindowLogits(K, win_logits, dense_logits)
         return prev_probs, list(idx64.unbind(0)), prev_logits
 
+
+    @staticmethod
+    def raise_if_out_of_range(range_flag):
+        """Reads the device flag ``gnnpn_pn_check_inputs_f32`` wrote (one 4-byte device->host read = one sync)."""
+        if range_flag is not None and int(range_flag.item()):
+            raise ops.GnnpnError(
+                "PointerNet.forward: an input value is NaN / inf or |x| >= 65504 -- outside the range of the fp16-split "
+                "tensor-core LSTM (GNNPN_ERANGE).  Normalise the QoS columns (the reference's data is min-max scaled) "
+                "or set actor.impl = 'ffma' for the strict-fp32 kernels.")
 
     def replay_action_probs(self, inputs, idx, latent_win=None):
         """Differentiable probabilities of the picks ``idx`` [K,B] (REINFORCE needs d log p / d theta).

@@ -80,11 +80,18 @@ def pn_enc_layout(n: int, L: int, F: int, K: int, N: int, has_workspace: bool = 
     return int(lib().gnnpn_pn_enc_layout(n, L, F, K, N, int(bool(has_workspace))))
 
 
+def enc_out_floats(n: int, L: int, hidden: int, layout: int) -> int:
+    """Floats an encodings buffer of this layout holds (the blocked layout pads n to whole groups of 128)."""
+    if layout == ENC_ROWMAJOR:
+        return n * L * hidden
+    return int(lib().gnnpn_pn_enc_out_floats(n, L, hidden, layout))
+
+
 def enc_out_empty(n: int, L: int, hidden: int, layout: int, device) -> torch.Tensor:
     """Encodings buffer for ``lstm_encode``: ``[n, L, H]`` (row-major) or the flat blocked buffer."""
     if layout == ENC_ROWMAJOR:
         return torch.empty(n, L, hidden, device=device, dtype=torch.float32)
-    return torch.empty(int(lib().gnnpn_pn_enc_out_floats(n, L, hidden, layout)), device=device, dtype=torch.float32)
+    return torch.empty(enc_out_floats(n, L, hidden, layout), device=device, dtype=torch.float32)
 
 
 def enc_to_rowmajor(enc_blocked: torch.Tensor, n: int, L: int, hidden: int = 256) -> torch.Tensor:

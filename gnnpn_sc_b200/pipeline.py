@@ -13,6 +13,9 @@ from typing import Iterable, Iterator, Tuple
 import torch
 
 
+NUM_SMS = 148          # B200
+
+
 class GreedyLowHigh:
     def __init__(self, low, high, device=None):
         self.low, self.high = low.eval(), high.eval()
@@ -63,18 +66,52 @@ class GreedyLowHigh:
             slot = cur_slot ^ 1
 
 
-def low_high(low, high, x, side_stream):
+def _own_enc_buffer(actor, n: int, L: int, F: int, device):
+    """Gives ``actor`` a persistent encodings buffer for batches of n rows (kept across calls: a 4.6 GB block per network
+    at n = 18,944 that would otherwise go through the caching allocator -- per stream, with deferred frees for buffers
+    that crossed streams -- on every call).  A caller-set larger buffer is left alone."""
+    from . import ops
+    K, N, H = actor.serCategory, actor.serNumber, actor.hidden_size
+    if actor.embedding_size != 0 or actor.impl == "ffma":
+        return
+    layout = ops.pn_enc_layout(n, L, F, K, N, True) if actor._fast_path(F) else ops.ENC_ROWMAJOR
+    need = ops.enc_out_floats(n, L, H, layout)
+    if actor.enc_buffer is None or actor.enc_buffer.numel() < need:
+        actor.enc_buffer = None                           # release the old block before asking for the larger one
+        actor.enc_buffer = torch.empty(need, device=device, dtype=torch.float32)
+
+
+def low_high(low, high, x, side_stream, own_buffers: bool = True):
     """PNLow greedy -> latent -> PNHigh greedy on the rows ``x`` (trainPNHigh.py:131-144).  The two encoders are independent
     (same rows, different weights): PNHigh's is enqueued on ``side_stream`` and runs concurrently with PNLow's whenever the
     batch leaves SMs free (one encoder occupies ceil(n / 128) SMs); the decoders follow on the current stream.
+    ``own_buffers``: both actors keep their encodings buffer across calls (``actor.last["enc_out"]`` of a call is then only
+    valid until the next call).  The input range flag is read ONCE, after everything is enqueued (no mid-pipeline sync).
     Returns (latent, reward, K-list of picks)."""
     main = torch.cuda.current_stream(x.device)
-    side_stream.wait_stream(main)                         # x is ready on the main stream
-    with torch.cuda.stream(side_stream):
-        enc_hi = high.actor.encode(x)
+    if own_buffers:
+        for m in (low, high):
+            _own_enc_buffer(m.actor, x.shape[0], x.shape[1], x.shape[2], x.device)
+    # two streams only while both encoders fit on the machine together (one CTA per 128 rows, 148 SMs).  At a full wave
+    # the second encoder's CTAs would interleave with PNLow's decoder and delay it: measured 15.5 ms against 14.5 ms
+    # back to back at n = 18,944 (profiles/r02_pn_batch_sweep.jsonl)
+    concurrent = 2 * ((x.shape[0] + 127) // 128) <= NUM_SMS
+    if concurrent:
+        side_stream.wait_stream(main)                     # x is ready on the main stream; last call's decoders are done
+        with torch.cuda.stream(side_stream):
+            enc_hi = high.actor.encode(x)
     enc_lo = low.actor.encode(x)
-    _, _, _, _, latent = low(x, None, sample="greedy", training="SL", encoded=enc_lo)
+    if not concurrent:
+        enc_hi = high.actor.encode(x)
+    deferred = low.actor.defer_range_check
+    low.actor.defer_range_check = True
+    try:
+        _, _, _, _, latent = low(x, None, sample="greedy", training="SL", encoded=enc_lo)
+    finally:
+        low.actor.defer_range_check = deferred
     R, _, _, idx, _ = high(x, None, latent, sample="greedy", training="RL", encoded=enc_hi)
+    if not deferred:
+        low.actor.raise_if_out_of_range(low.actor.last["range_flag"])
     return latent, R, idx
 
 

@@ -11,12 +11,26 @@ from oracle import pn_oracle as po
 from conftest import record_parity
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-5
+import os
+TOL = float(os.environ.get("GNNPN_PARITY_TOL", "1e-5"))      # north_star tolerance; the override only exercises the failure report
 
 
 def _rel(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float((np.abs(a - b) / np.maximum(1.0, np.abs(b))).max())
+
+
+def _redo_state(net, xc):
+    """(initial cell state, packed decoder weights) of a relaunch of ``net``'s decode: the encoder is run again (its final
+    cell state is overwritten by the decode) into a scratch encodings buffer of the same layout."""
+    from gnnpn_sc_b200 import ops
+    a = net.actor
+    enc_w, dec_w = a._packed_weights()
+    n, L, _ = xc.shape
+    lay = a.last["enc_layout"]
+    ws = ops.pn_workspace(n, 256, xc.device)
+    _, c = ops.lstm_encode(xc, enc_w, 256, enc_out=ops.enc_out_empty(n, L, 256, lay, xc.device), workspace=ws, layout=lay)
+    return c, dec_w
 
 
 def _window(dense, N):
@@ -92,7 +106,24 @@ def test_full_wave_sample_matches_oracle(shape, K, N, sample):
         last = net.actor.last
         wl = last["win_logits"].cpu().numpy()[sub]
         wp = last["win_probs"].cpu().numpy()[sub]
-        res[f"logits_{tag}"] = _rel(wl[okm], _window(torch.stack(ref_logits).numpy(), N)[okm])
+        ref_wl = _window(torch.stack(ref_logits).numpy(), N)
+        res[f"logits_{tag}"] = _rel(wl[okm], ref_wl[okm])
+        if res[f"logits_{tag}"] > TOL:                        # say where (and which side moved) before failing
+            with torch.no_grad():                             # the same launch again: is the GPU result reproducible?
+                lat_again = None if tag == "low" else low.actor.last["win_logits"]
+                again = ops.pn_decode_greedy(xc, last["enc_buf"], *_redo_state(net, xc), K, N, latent_win=lat_again,
+                                             workspace=ops.pn_workspace(n, 256, xc.device), enc_layout=last["enc_layout"],
+                                             want_dec_h=False)[2]
+            import platform
+            print(f"  logits_{tag}: GPU relaunch bit-identical to the first launch: {bool(torch.equal(again, last['win_logits']))}; "
+                  f"relaunch vs oracle {_rel(again.cpu().numpy()[sub][okm], ref_wl[okm]):.3e}; host {platform.processor()} "
+                  f"{torch.get_num_threads()} threads; {torch.cuda.get_device_name()}")
+            err = np.abs(wl.astype(np.float64) - ref_wl) / np.maximum(1.0, np.abs(ref_wl))
+            err[~okm] = 0
+            for b, l in list(zip(*np.nonzero(err > TOL)))[:12]:
+                print(f"  logits_{tag}: instance {sub[b]} (row {sub[b] % 128} of CTA {sub[b] // 128}) step {l // N} cand {l % N}: "
+                      f"got {wl[b, l]!r} ref {ref_wl[b, l]!r}; window got {wl[b, l // N * N:(l // N + 1) * N]} ref "
+                      f"{ref_wl[b, l // N * N:(l // N + 1) * N]}")
         res[f"probs_{tag}"] = _rel(wp[okm], _window(torch.stack(ref_probs).numpy(), N)[okm])
         sub_t = torch.from_numpy(sub).cuda()
         # encodings do not depend on picks (PNHigh's encoder reads the raw rows): all sampled instances
