@@ -32,6 +32,8 @@ static std::atomic<int>* option_slot(const char* name) {
   if (!strcmp(name, "scan_groups")) return &o.scan_groups;
   if (!strcmp(name, "persistent")) return &o.persistent;
   if (!strcmp(name, "prof")) return &o.prof;
+  if (!strcmp(name, "spmm_chunk")) return &o.spmm_chunk;
+  if (!strcmp(name, "spmm_dyn")) return &o.spmm_dyn;
   return nullptr;
 }
 int launch_gemm_ffma(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,

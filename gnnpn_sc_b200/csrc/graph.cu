@@ -1,6 +1,7 @@
 // ML stage graph kernels: edge_index -> CSR (+ gcn_norm), CSR segment-reduce aggregation.
 #include <cub/device/device_radix_sort.cuh>
 #include "common.cuh"
+#include "options.cuh"
 
 namespace gnnpn {
 namespace {
@@ -242,11 +243,58 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(
   spmm_finish_row<GROUP, VPL>(acc, row, end - beg, x, ldx, y, ldy, F4, ep, gl);
 }
 
+// Persistent variant used with the split path (graphs with skewed in-degrees): a CTA owns a contiguous range of rows and
+// its lane groups pull the next row from a shared-memory counter when they finish one, so a group that meets a row of
+// 10^2..10^3 edges does not leave the other 31 groups of its CTA (and the 3 of its warp) idle for the rest of the CTA's
+// life.  Per-row arithmetic and order are exactly those of spmm_csr_kernel (bit-identical results).
+template <int GROUP, int VPL, int UNROLL>
+__global__ void __launch_bounds__(256) spmm_csr_dyn_kernel(
+    const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+    const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t n_rows, int F4,
+    const SpmmEpilogue ep, int64_t long_threshold, int64_t rows_per_cta) {
+  constexpr int GROUPS_PER_CTA = 256 / GROUP;
+  __shared__ int32_t s_col[GROUPS_PER_CTA][32];
+  __shared__ float s_val[GROUPS_PER_CTA][32];
+  __shared__ int s_next;
+  const int gl = threadIdx.x % GROUP, grp = threadIdx.x / GROUP;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane / GROUP * GROUP));
+  const int leader = (int)(lane / GROUP * GROUP);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int cnt = (int)min(rows_per_cta, n_rows - r0);
+  if (threadIdx.x == 0) s_next = GROUPS_PER_CTA;      // the first row of every group is its own index
+  __syncthreads();
+  int r = grp;
+  while (r < cnt) {
+    const int64_t row = r0 + r;
+    const int64_t beg = rowptr[row], end = rowptr[row + 1];
+    if (!(long_threshold > 0 && end - beg > long_threshold)) {
+      float4 acc[VPL];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      spmm_accumulate<GROUP, VPL, UNROLL>(acc, beg, end, col, val, x, ldx, F4, s_col[grp], s_val[grp], gl, gmask);
+      spmm_finish_row<GROUP, VPL>(acc, row, end - beg, x, ldx, y, ldy, F4, ep, gl);
+    }
+    int nr = 0;
+    if (gl == 0) nr = atomicAdd(&s_next, 1);
+    r = __shfl_sync(gmask, nr, leader);
+  }
+}
+
 // ---- long-row splitting (hub destinations: a service used by 10^5 compositions would otherwise be ONE group's
 // sequential walk).  Rows with more than T edges are cut into chunks of Tc = T / 8 consecutive edges; every chunk is summed
 // by one group exactly like a short row (sequential in CSR order), the chunk sums are then added in chunk order.
 // Deterministic (fixed order, no atomics in the arithmetic); rows of <= T edges stay bit-identical to index_add_ order,
 // split rows differ from the strictly sequential sum by re-association only (~1e-7 relative; tests bound it by 1e-5).
+// Edges per chunk of a split row of d edges: Tc, raised for hub rows so that no row has more than ~4096 chunks -- the
+// combine walks a row's chunk sums in order (8 loads in flight), so a 7.8M-edge hub cut into 256-edge chunks would be a
+// serial tail of 3,800 dependent L2 round trips (measured: 3 ms of a 12 ms launch)
+constexpr int kMaxChunksPerRow = 4096;
+__host__ __device__ inline int64_t chunk_len_row(int64_t d, int64_t Tc) {
+  if (d <= Tc * kMaxChunksPerRow) return Tc;
+  return ((d + kMaxChunksPerRow - 1) / kMaxChunksPerRow + 31) / 32 * 32;
+}
+
 struct LongRowPlan {
   int* counters;          // [0] number of long rows, [1] number of chunks
   int64_t* row;           // [max_long] row id per slot
@@ -261,7 +309,8 @@ __global__ void find_long_rows_kernel(const int64_t* __restrict__ rowptr, int64_
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
     const int64_t d = rowptr[r + 1] - rowptr[r];
     if (d <= T) continue;
-    const int nch = (int)((d + Tc - 1) / Tc);
+    const int64_t C = chunk_len_row(d, Tc);
+    const int nch = (int)((d + C - 1) / C);
     const int slot = atomicAdd(p.counters, 1);
     const int cb = atomicAdd(p.counters + 1, nch);
     if (slot >= p.max_long || cb + nch > p.max_chunks) continue;        // cannot happen: both bounds follow from nnz / T
@@ -285,8 +334,10 @@ __global__ void __launch_bounds__(256) spmm_chunk_kernel(
   for (int c = blockIdx.x * GROUPS_PER_CTA + grp; c < n_chunks; c += gridDim.x * GROUPS_PER_CTA) {
     const int slot = p.chunk_slot[c];
     const int64_t row = p.row[slot];
-    const int64_t beg = rowptr[row] + (int64_t)(c - p.chunk_base[slot]) * T;
-    const int64_t end = min(beg + T, rowptr[row + 1]);
+    const int64_t rb = rowptr[row], re = rowptr[row + 1];
+    const int64_t C = chunk_len_row(re - rb, T);
+    const int64_t beg = rb + (int64_t)(c - p.chunk_base[slot]) * C;
+    const int64_t end = min(beg + C, re);
     float4 acc[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -309,7 +360,8 @@ __global__ void __launch_bounds__(256) spmm_combine_kernel(
   for (int s = blockIdx.x * GROUPS_PER_CTA + grp; s < n_long; s += gridDim.x * GROUPS_PER_CTA) {
     const int64_t row = p.row[s];
     const int64_t d = rowptr[row + 1] - rowptr[row];
-    const int nch = (int)((d + T - 1) / T), cb = p.chunk_base[s];
+    const int64_t C = chunk_len_row(d, T);
+    const int nch = (int)((d + C - 1) / C), cb = p.chunk_base[s];
     float4 acc[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -367,7 +419,13 @@ __global__ void embed_concat_kernel(const float* __restrict__ x, int64_t n, int 
   }
 }
 
-inline int64_t chunk_len(int64_t T) { return T / 8 < 32 ? 32 : T / 8; }    // edges per chunk of a split row
+inline int64_t chunk_len(int64_t T) {                                       // edges per chunk of a split row
+  const int o = options().spmm_chunk.load(std::memory_order_relaxed);
+  if (o >= 32) return o / 32 * 32;
+  // 256 edges = 8 staging rounds: amortises the chunk's dependent look-ups (slot -> row -> rowptr).  Chunks of 32 made the
+  // chunk pass 3x slower per edge than the short-row kernel (scripts/agg_threshold_probe.py)
+  return T / 8 < 256 ? 256 : T / 8;
+}
 
 template <int GROUP, int VPL, int UNROLL>
 int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* val, const float* x, int64_t ldx,
@@ -383,8 +441,18 @@ int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* val, con
     find_long_rows_kernel<<<(unsigned)(fb < 8 * kNumSMs ? fb : 8 * kNumSMs), 256, 0, st>>>(rowptr, n_rows, T, chunk_len(T), *plan);
     if ((rc = after_launch())) return rc;
   }
-  spmm_csr_kernel<GROUP, VPL, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, ldx, y, ldy, n_rows, F4, ep,
-                                                                       plan ? T : 0);
+  if (plan && options().spmm_dyn.load(std::memory_order_relaxed)) {
+    // persistent CTAs with dynamic row fetching (balanced under skewed in-degrees); at least 4 rows per group
+    int64_t ctas = ceil_div(n_rows, (int64_t)GROUPS_PER_CTA * 4);
+    if (ctas > 8 * kNumSMs) ctas = 8 * kNumSMs;
+    const int64_t rows_per_cta = ceil_div(n_rows, ctas);
+    if (rows_per_cta > 0x7fffffffll) return GNNPN_ERANGE;
+    spmm_csr_dyn_kernel<GROUP, VPL, UNROLL><<<(unsigned)ceil_div(n_rows, rows_per_cta), 256, 0, st>>>(
+        rowptr, col, val, x, ldx, y, ldy, n_rows, F4, ep, T, rows_per_cta);
+  } else {
+    spmm_csr_kernel<GROUP, VPL, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, ldx, y, ldy, n_rows, F4, ep,
+                                                                         plan ? T : 0);
+  }
   if ((rc = after_launch()) || !plan) return rc;
   // persistent grids: they read the chunk / row counts on the device and return at once when there is no long row
   spmm_chunk_kernel<GROUP, VPL, UNROLL><<<8 * kNumSMs, 256, 0, st>>>(rowptr, col, val, x, ldx, F4, chunk_len(T), *plan);

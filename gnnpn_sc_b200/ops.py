@@ -402,16 +402,22 @@ def embed_concat(x: torch.Tensor, table: torch.Tensor, pad_to: int = 4) -> torch
 
 
 SPLIT_MIN_NNZ = 1 << 22          # below this the three extra (tiny) launches of the split path cost more than a hub row
-SPLIT_THRESHOLD = 2048           # rows with more edges are split, into chunks of threshold / 8 = 256 edges (one lane group's
-                                 # sequential walk of 32 rounds of 8 gathers); the QWS co-usage graph's largest row has 1,378 edges
+SPLIT_THRESHOLD = 2048           # rows with more edges are split into chunks of 256 edges (hub rows: at most ~4096 chunks per row);
+                                 # the QWS co-usage graph's largest row has 1,378 edges -> never split, bit-identical to index_add_
+SPLIT_THRESHOLD_NARROW = 256     # F <= 64: 4 / 2 rows share a warp, so a 10^3-edge row idles its warp mates -- split earlier
+                                 # (in-degree-Zipf sweep, F = 32: 0.53 -> 0.59 of the HBM peak, F = 64: 0.68 -> 0.72)
+
+
+def split_threshold(F: int) -> int:
+    return SPLIT_THRESHOLD_NARROW if F <= 64 else SPLIT_THRESHOLD
 
 
 def spmm_csr(rowptr, col, val, x, n_rows: Optional[int] = None, self_scale: float = 0.0, mean: bool = False,
              bias=None, scale=None, shift=None, act=None, out=None, long_row_threshold: Optional[int] = None,
              workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """CSR aggregation.  ``long_row_threshold``: rows with more edges are split into chunks (hub destinations of a skewed
-    graph, ``gnnpn_spmm_csr_split_f32``); None = ``SPLIT_THRESHOLD`` for graphs of at least ``SPLIT_MIN_NNZ`` edges, no splitting below;
-    0 = never."""
+    graph, ``gnnpn_spmm_csr_split_f32``); None = ``split_threshold(F)`` for graphs of at least ``SPLIT_MIN_NNZ`` edges, no
+    splitting below; 0 = never."""
     x = _f32(x, "x")
     F = x.shape[1]
     assert F % 4 == 0, "feature dim must be padded to a multiple of 4"
@@ -419,7 +425,7 @@ def spmm_csr(rowptr, col, val, x, n_rows: Optional[int] = None, self_scale: floa
     y = torch.empty(n_rows, F, device=x.device, dtype=torch.float32) if out is None else out
     nnz = int(col.numel())
     if long_row_threshold is None:
-        long_row_threshold = SPLIT_THRESHOLD if nnz >= SPLIT_MIN_NNZ else 0
+        long_row_threshold = split_threshold(F) if nnz >= SPLIT_MIN_NNZ else 0
     if long_row_threshold:
         need = int(lib().gnnpn_spmm_csr_split_workspace_bytes(nnz, F, int(long_row_threshold)))
         if workspace is None or workspace.numel() < need:

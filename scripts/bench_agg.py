@@ -144,7 +144,7 @@ def main():
                             y = torch.empty(N, F, device=dev)
                             ms = time_point(rowptr, col, val, x, y, iters, flush, args.one_launch)
                             ms0 = time_point(rowptr, col, val, x, y, iters, flush, args.one_launch, long_row_threshold=0)
-                            emit(record(family, E, N, F, weighted, ms, max_in_degree=dmax, long_row_threshold=ops.SPLIT_THRESHOLD,
+                            emit(record(family, E, N, F, weighted, ms, max_in_degree=dmax, long_row_threshold=ops.split_threshold(F),
                                         ms_without_split=ms0))
                         else:
                             rowptr, col, val, E = make_csr(N, d, 1.0 if family == "src_zipf" else 0.0, weighted, dev)
@@ -161,9 +161,9 @@ def main():
             for F in (256,):
                 x = torch.empty(N, F, device=dev).uniform_(-1, 1)
                 y = torch.empty(N, F, device=dev)
-                ms = time_point(rowptr, col, val, x, y, 7, flush, args.one_launch, long_row_threshold=ops.SPLIT_THRESHOLD)
+                ms = time_point(rowptr, col, val, x, y, 7, flush, args.one_launch, long_row_threshold=ops.split_threshold(F))
                 ms0 = time_point(rowptr, col, val, x, y, 7, flush, args.one_launch, long_row_threshold=0)
-                emit(record("qws_cousage", E, N, F, True, ms, max_in_degree=dmax, copies=B, long_row_threshold=ops.SPLIT_THRESHOLD,
+                emit(record("qws_cousage", E, N, F, True, ms, max_in_degree=dmax, copies=B, long_row_threshold=ops.split_threshold(F),
                             ms_without_split=ms0))
 
 

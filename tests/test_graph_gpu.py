@@ -242,13 +242,39 @@ def test_kat_gin_and_segment_mean_on_device():
     assert out.tolist() == kat.MEAN_OUT                                    # empty segments -> 0, not NaN
 
 
+def test_hub_row_with_adaptive_chunk_length():
+    """A hub row of more than 256 * 4096 edges gets longer chunks (at most ~4096 chunk sums per row, so the in-order combine
+    is not a serial tail): same result as the strictly sequential sum to re-association, deterministic, other rows exact."""
+    from gnnpn_sc_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    n, F, T = 500, 8, 256
+    deg = torch.randint(0, 20, (n,), generator=g)
+    deg[3], deg[400] = 1_300_000, 70_000                                   # 1.3M edges -> chunks of 320 edges; 70k -> 256
+    dst = torch.repeat_interleave(torch.arange(n), deg)
+    src = torch.randint(0, n, (dst.numel(),), generator=g)
+    w = torch.rand(dst.numel(), generator=g) + 0.05
+    x = torch.randn(n, F, generator=g)
+    rp, col, val = ops.csr_build(torch.stack([src, dst]).cuda(), w.cuda(), n, ops.CSR_PLAIN)
+    y = ops.spmm_csr(rp, col, val, x.cuda(), long_row_threshold=T).cpu()
+    assert torch.equal(y, ops.spmm_csr(rp, col, val, x.cuda(), long_row_threshold=T).cpu())
+    terms = w.double().view(-1, 1) * x.double()[src]
+    ref64 = torch.zeros(n, F, dtype=torch.float64).index_add_(0, dst, terms)
+    mag = torch.zeros(n, F, dtype=torch.float64).index_add_(0, dst, terms.abs()).clamp(min=1)
+    err = ((y.double() - ref64).abs() / mag).max().item()
+    record_parity("spmm_hub_row_adaptive_chunks", max_err_over_summed_magnitude=err, tolerance=1e-5, max_in_degree=1_300_000)
+    assert err <= 1e-5, err
+    short = deg <= T
+    y0 = ops.spmm_csr(rp, col, val, x.cuda(), long_row_threshold=0).cpu()  # unsplit: strictly sequential
+    assert torch.equal(y[short], y0[short])
+
+
 def test_long_row_split_hub_destinations():
     """Skewed in-degrees (hub rows): rows at or below the threshold are bit-identical to the index_add_ order oracle, split
     rows agree to 1e-5 (re-association of chunk sums only), the result is deterministic, and the fused epilogue (mean,
     bias, ReLU) is applied once per row."""
     from gnnpn_sc_b200 import ops
     g = torch.Generator().manual_seed(5)
-    n, F, T = 3000, 64, 256                                               # rows > 256 edges split into chunks of 32
+    n, F, T = 3000, 64, 256                                               # rows > 256 edges split into chunks of 256
     deg = torch.randint(0, 40, (n,), generator=g)
     deg[7], deg[1500], deg[2999] = 120000, 5000, 257                       # hubs; 257 = just above the threshold
     deg[11] = 256                                                          # exactly at the threshold: not split
