@@ -50,6 +50,11 @@ SIGNATURES = {
     "gnnpn_pn_query_transform_f32": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p]),
     "gnnpn_pn_full_logits_bahdanau_f32": (_i, [_p, _p, _p, _p, _i, _f, _i64, _i, _i, _i, _p, _p]),
     "gnnpn_pn_full_logits_f32": (_i, [_p, _p, _p, _i, _p, _i, _f, _i64, _i, _i, _i, _p, _p]),
+    "gnnpn_pn_anyh_workspace_floats": (C.c_size_t, [_i64, _i, _i]),
+    "gnnpn_lstm_encode_anyh_f32": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "gnnpn_pn_decode_anyh_f32": (_i, [_p, _p, _p, _p, _f, _p, _p, _p, _i, _f, _i64, _i, _i, _i, _i, _i,
+                                      _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "gnnpn_pn_full_logits_anyh_f32": (_i, [_p, _p, _p, _i, _f, _i64, _i, _i, _i, _p, _p]),
     "gnnpn_pn_reward_f32": (_i, [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p]),
     "gnnpn_woa_fitness_f64": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "gnnpn_ml2pn_score_f64": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i, _p, _p, _p, _p]),
@@ -90,7 +95,7 @@ def lib():
                 fn = getattr(h, name)          # AttributeError if the ABI lost a symbol
                 fn.restype = res
                 fn.argtypes = args
-            if h.gnnpn_abi_version() != 6:
+            if h.gnnpn_abi_version() != 7:
                 raise GnnpnError("libgnnpn_b200.so ABI version mismatch")
             _lib = h
     return _lib
@@ -103,7 +108,8 @@ def check(rc: int, what: str = "") -> None:
 
 
 def set_option(name: str, value: int) -> None:
-    """``gnnpn_set_option``: "scan" (-1 auto / 0 CTA-pair / 1 column-split), "scan_groups", "persistent", "prof"."""
+    """``gnnpn_set_option``: "scan" (-1 auto / 0 CTA-pair / 1 column-split), "scan_groups", "persistent", "prof",
+    "spmm_chunk" / "spmm_dyn" (aggregation tuning)."""
     check(lib().gnnpn_set_option(name.encode(), int(value)), f"set_option({name})")
 
 

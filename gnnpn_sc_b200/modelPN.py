@@ -148,8 +148,11 @@ class Attention(nn.Module):
         q = query.detach().float().contiguous()
         none_picked = torch.zeros(1, B, device=ref.device, dtype=torch.int32)
         if self.name == 'Dot':
-            logits = ops.pn_full_logits(refc, q.view(B, 1, H), none_picked, "Dot", None, bool(self.use_tanh),
-                                        float(self.C))[0]
+            if H != 256:                                       # any-hidden-size kernels (strict fp32)
+                logits = ops.pn_full_logits_anyh(refc, q.view(B, 1, H), none_picked, bool(self.use_tanh), float(self.C))[0]
+            else:
+                logits = ops.pn_full_logits(refc, q.view(B, 1, H), none_picked, "Dot", None, bool(self.use_tanh),
+                                            float(self.C))[0]
             return ref.permute(0, 2, 1), logits
         if self.name != 'Bahdanau':
             raise NotImplementedError(self.name)
@@ -226,6 +229,26 @@ class PointerNet(nn.Module):
             self._packed, self._pack_key = (enc, dec), key
         return self._packed
 
+    def _anyh(self) -> bool:
+        """hidden_size other than the shipped 256: the strict-fp32 any-hidden-size kernels (``gnnpn_*_anyh_f32``)."""
+        return self.hidden_size != 256
+
+    def _folded_weights(self):
+        """((w_cat, bias, None), (w_cat, bias, bias0)) of encoder / decoder for the any-hidden-size kernels (cached)."""
+        ps = [self.embedding2.weight, self.embedding2.bias, self.decoder_start_input]
+        for rnn in (self.encoder, self.decoder):
+            ps += [rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0]
+        key = ("anyh",) + tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._pack_key:
+            with torch.no_grad():
+                e, d = self.encoder, self.decoder
+                we, be = self.embedding2.weight, self.embedding2.bias
+                enc = ops.anyh_fold(e.weight_ih_l0, e.weight_hh_l0, e.bias_ih_l0, e.bias_hh_l0, we, be, None)
+                dec = ops.anyh_fold(d.weight_ih_l0, d.weight_hh_l0, d.bias_ih_l0, d.bias_hh_l0, we, be,
+                                    self.decoder_start_input)
+            self._packed, self._pack_key = (enc, dec), key
+        return self._packed
+
     def _kernel_inputs(self, inputs):
         """Raw rows the LSTM kernels consume: with a category embedding (modelPN.py:183-188) column 0 is replaced by
         its ``embedding1`` row (``gnnpn_embed_concat_f32``), giving 20 + 8 = 28 columns."""
@@ -237,7 +260,7 @@ class PointerNet(nn.Module):
 
     def _fast_path(self, F: int) -> bool:
         return (not self.force_general and self.embedding_size == 0 and self.n_glimpses == 0
-                and self.pointer.name == "Dot" and self.serNumber <= 32 and F <= 8)
+                and self.pointer.name == "Dot" and self.serNumber <= 32 and F <= 8 and not self._anyh())
 
     def encode(self, inputs):
         """The encoder half of ``forward`` (modelPN.py:183-191: embedding + encoder LSTM), enqueued on the CURRENT stream.
@@ -250,6 +273,16 @@ class PointerNet(nn.Module):
             raise RuntimeError("PointerNet.forward needs CUDA tensors: the B200 path has no CPU fallback")
         K, N = self.serCategory, self.serNumber
         x = self._kernel_inputs(inputs)
+        if self._anyh():
+            if self.n_glimpses != 0 or self.pointer.name != "Dot" or N > 32:
+                raise NotImplementedError(
+                    f"hidden_size = {self.hidden_size}: the any-hidden-size kernels cover Dot attention without glimpses and "
+                    "windows of at most 32 candidates (Bahdanau / glimpses / wider windows need hidden_size = 256)")
+            (w_cat, bias, _), _ = self._folded_weights()
+            with torch.no_grad():
+                enc_out, c = ops.lstm_encode_anyh(x, w_cat, bias, self.hidden_size)
+            return {"x": x, "ws": None, "layout": ops.ENC_ROWMAJOR, "enc_out": enc_out, "c": c, "range_flag": None,
+                    "fast": False, "anyh": True, "stream": torch.cuda.current_stream(x.device)}
         range_flag = ops.pn_check_inputs(x) if (self.check_inputs and self.impl != "ffma") else None
         fast = self._fast_path(x.shape[2])
         enc_w, _ = self._packed_weights()
@@ -289,7 +322,8 @@ class PointerNet(nn.Module):
                         t.record_stream(cur)
         x, ws, layout, enc_out, c = (encoded[k] for k in ("x", "ws", "layout", "enc_out", "c"))
         range_flag, fast = encoded["range_flag"], encoded["fast"]
-        _, dec_w = self._packed_weights()
+        anyh = bool(encoded.get("anyh"))
+        dec_w = None if anyh else self._packed_weights()[1]
         use_tanh, C = bool(self.pointer.use_tanh), float(self.pointer.C)
         att = self.pointer.name
         with torch.no_grad():
@@ -299,7 +333,13 @@ class PointerNet(nn.Module):
             uniform = None if sample == "greedy" else torch.rand(K, B, device=x.device, generator=self.generator)
             ptr_blk = qw = None
             replay = None
-            if fast:
+            if anyh:
+                _, (w_cat, bias, bias0) = self._folded_weights()
+                dec_h, idx, win_logits, win_probs = ops.pn_decode_anyh(
+                    x, enc_out, c, w_cat, bias, bias0, K, N, latent_win=lat, alpha=float(self.alpha), use_tanh=use_tanh, C=C,
+                    forced_idx=forced, sample_uniform=uniform)
+                dec_q = dec_h
+            elif fast:
                 lazy_h = layout == ops.ENC_BLOCKED128          # fused decoder: hidden states stay on chip
                 c_enc = c.clone() if lazy_h else None
                 kw = dict(latent_win=lat, alpha=float(self.alpha), attention="Dot", use_tanh=use_tanh, C=C,
@@ -340,6 +380,8 @@ class PointerNet(nn.Module):
         fed = idx if forced is None else forced.contiguous()     # the picks the visited mask follows
 
         def dense_logits():
+            if anyh:
+                return ops.pn_full_logits_anyh(last["enc_out"], last["dec_h"], fed, use_tanh, C)
             if att == "Dot":
                 return ops.pn_full_logits(last["enc_out"], last["dec_q"], fed, "Dot", None, use_tanh, C)
             return ops.pn_full_logits_bahdanau(ops.pn_ref_transform(last["enc_out"], ptr_blk), qw, ptr_blk, fed,

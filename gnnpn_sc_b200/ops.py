@@ -152,6 +152,70 @@ def pn_decode_greedy(inputs, enc_out, c_state, packed_dec, K: int, N: int, laten
     return dec_h, idx, wl, wp
 
 
+# ------------------------------------------------------------------ any hidden size (strict fp32, per-step launches)
+def anyh_fold(w_ih, w_hh, b_ih, b_hh, w_embed, b_embed, start_input=None):
+    """Folded weights of the any-hidden-size kernels: ``w_cat [4H, H+F] = [W_hh | W_ih . W_emb]``, ``bias = b_ih + b_hh +
+    W_ih . b_emb`` and, for a decoder, ``bias0 = b_ih + b_hh + W_ih . start``.  float64 products (as the H = 256 packer)."""
+    wi, we = w_ih.detach().double(), w_embed.detach().double()
+    b = b_ih.detach().double() + b_hh.detach().double()
+    w_cat = torch.cat([w_hh.detach().double(), wi @ we], 1).float().contiguous()
+    bias = (b + wi @ b_embed.detach().double()).float().contiguous()
+    bias0 = None if start_input is None else (b + wi @ start_input.detach().double()).float().contiguous()
+    return w_cat, bias, bias0
+
+
+def _anyh_ws(n, H, F, device):
+    return torch.empty(int(lib().gnnpn_pn_anyh_workspace_floats(n, H, F)), device=device, dtype=torch.float32)
+
+
+def lstm_encode_anyh(inputs, w_cat, bias, hidden: int):
+    x = _f32(inputs, "inputs")
+    n, L, F = x.shape
+    enc_out = torch.empty(n, L, hidden, device=x.device, dtype=torch.float32)
+    c = torch.empty(n, hidden, device=x.device, dtype=torch.float32)
+    ws = _anyh_ws(n, hidden, F, x.device)
+    check(lib().gnnpn_lstm_encode_anyh_f32(x.data_ptr(), n, L, F, hidden, w_cat.data_ptr(), bias.data_ptr(), enc_out.data_ptr(),
+                                           c.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "lstm_encode_anyh")
+    return enc_out, c
+
+
+def pn_decode_anyh(inputs, enc_out, c_state, w_cat, bias, bias0, K: int, N: int, latent_win=None, alpha: float = 1.0,
+                   use_tanh: bool = True, C: float = 10.0, forced_idx=None, sample_uniform=None):
+    """-> (dec_h [n,K,H], idx int32 [K,n], win_logits [n,L], win_probs [n,L]); ``c_state`` is updated in place."""
+    x = _f32(inputs, "inputs")
+    n, L, F = x.shape
+    H = enc_out.shape[2]
+    dev = x.device
+    dec_h = torch.empty(n, K, H, device=dev, dtype=torch.float32)
+    idx = torch.empty(K, n, device=dev, dtype=torch.int32)
+    wl = torch.empty(n, L, device=dev, dtype=torch.float32)
+    wp = torch.empty(n, L, device=dev, dtype=torch.float32)
+    if latent_win is not None:
+        latent_win = _f32(latent_win, "latent_win")
+        assert latent_win.shape == (n, L)
+    if forced_idx is not None:
+        forced_idx = forced_idx.to(torch.int32).contiguous()
+    if sample_uniform is not None:
+        sample_uniform = _f32(sample_uniform, "sample_uniform")
+    ws = _anyh_ws(n, H, F, dev)
+    check(lib().gnnpn_pn_decode_anyh_f32(x.data_ptr(), enc_out.data_ptr(), c_state.data_ptr(), _ptr(latent_win), float(alpha),
+                                         w_cat.data_ptr(), bias.data_ptr(), bias0.data_ptr(), int(bool(use_tanh)), float(C),
+                                         n, L, F, H, K, N, dec_h.data_ptr(), idx.data_ptr(), wl.data_ptr(), wp.data_ptr(),
+                                         _ptr(forced_idx), _ptr(sample_uniform), ws.data_ptr(), ws.numel(), _stream()),
+          "pn_decode_anyh")
+    return dec_h, idx, wl, wp
+
+
+def pn_full_logits_anyh(enc_out, dec_h, idx, use_tanh: bool = True, C: float = 10.0) -> torch.Tensor:
+    n, L, H = enc_out.shape
+    K = dec_h.shape[1]
+    out = torch.empty(K, n, L, device=enc_out.device, dtype=torch.float32)
+    check(lib().gnnpn_pn_full_logits_anyh_f32(enc_out.data_ptr(), dec_h.data_ptr(), idx.contiguous().data_ptr(),
+                                              int(bool(use_tanh)), float(C), n, L, H, K, out.data_ptr(), _stream()),
+          "pn_full_logits_anyh")
+    return out
+
+
 def pn_train_forward(inputs, packed_enc, packed_dec, idx, K: int, N: int, latent_win=None, alpha: float = 1.0,
                      use_tanh: bool = True, C: float = 10.0, hidden: int = 256):
     """Differentiable replay, forward half (``gnnpn_pn_train_forward_f32``).  Returns the dict of saved tensors."""

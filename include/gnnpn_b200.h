@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNNPN_ABI_VERSION 6
+#define GNNPN_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define GNNPN_API __attribute__((visibility("default")))
@@ -217,6 +217,26 @@ GNNPN_API int gnnpn_pn_query_transform_f32(const float* q, int64_t q_ld, const f
 GNNPN_API int gnnpn_pn_full_logits_bahdanau_f32(const float* E, const float* qw, const float* att_block,
                                       const int32_t* idx, int use_tanh, float C, int64_t n, int L, int hidden,
                                       int K, float* logits_full, void* stream);
+
+/* ---- any hidden size (the ini's hidden_size is free: src/models/trainPNLow.py:204, environment.ini:24,39; the kernels above
+ * are specialised for the shipped value 256 and return GNNPN_ESHAPE otherwise).  Strict fp32, one GEMM + one cell launch per
+ * recurrence step, one pointer-step launch per decode step (Dot attention, no glimpses, N <= 32, in_features <= 32).
+ *   w_cat  fp32 [4H, H + F]   rows in torch gate order (i, f, g, o blocks of H); columns [W_hh | W_ih . W_emb]
+ *   bias   fp32 [4H]          b_ih + b_hh + W_ih . b_emb;   bias0 (decoder step 0): b_ih + b_hh + W_ih . decoder_start_input
+ *   workspace: gnnpn_pn_anyh_workspace_floats(n, H, F) floats.  Encodings are row-major [n, L, H]; dec_h [n, K, H] is required.
+ * Same meaning of every other argument as gnnpn_lstm_encode_f32 / gnnpn_pn_decode_greedy_f32 / gnnpn_pn_full_logits_f32
+ * (modelPN.py:183-239). */
+GNNPN_API size_t gnnpn_pn_anyh_workspace_floats(int64_t n, int hidden, int in_features);
+GNNPN_API int gnnpn_lstm_encode_anyh_f32(const float* inputs, int64_t n, int L, int in_features, int hidden,
+                               const float* w_cat, const float* bias, float* enc_out, float* c_state,
+                               float* workspace, size_t workspace_floats, void* stream);
+GNNPN_API int gnnpn_pn_decode_anyh_f32(const float* inputs, const float* enc_out, float* c_state, const float* latent_win,
+                             float alpha, const float* w_cat, const float* bias, const float* bias0, int use_tanh,
+                             float C, int64_t n, int L, int in_features, int hidden, int K, int N, float* dec_h,
+                             int32_t* idx_out, float* win_logits, float* win_probs, const int32_t* forced_idx,
+                             const float* sample_uniform, float* workspace, size_t workspace_floats, void* stream);
+GNNPN_API int gnnpn_pn_full_logits_anyh_f32(const float* enc_out, const float* dec_h, const int32_t* idx, int use_tanh,
+                                  float C, int64_t n, int L, int hidden, int K, float* logits_full, void* stream);
 
 /* Interface-faithful materialisation of PointerNet.forward's prev_logits (modelPN.py:213-214,239):
  *   logits_full fp32 [K, n, L] = C*tanh(<enc_out[b,l,:], dec_h[b,k,:]>) with -inf at the positions

@@ -11,7 +11,7 @@ flush = torch.zeros(64 << 20, device=dev)
 E_t = 1 << int(os.environ.get("LOG2E", "28"))
 N = E_t // 16
 pk = peak()
-for F in (32, 64, 128, 256):
+for F in (32, 64, 128):
     x = torch.empty(N, F, device=dev).uniform_(-1, 1)
     y = torch.empty(N, F, device=dev)
     rowptr, col, val, E = make_csr(N, 16, 0.0, True, dev)
@@ -26,13 +26,16 @@ for F in (32, 64, 128, 256):
     ms = time_point(rowptr, col, val, x, y, 3, flush, False, long_row_threshold=0)
     print(json.dumps({"family": "uniform_d8", "F": F, "E": E, "ms": ms, "frac": alg / ms / 1e6 / pk}), flush=True)
     del rowptr, col, val
-    rowptr, col, val, E, dmax = make_csr_indegree_zipf(N, E_t, True, dev, floor=8)
-    alg = E * (8 + 4 * F) + N * 4 * F + (N + 1) * 8
-    for T, C, dyn in ((2048, 0, 0), (256, 256, 0), (1024, 256, 0)):
-        ops.set_option("spmm_chunk", C); ops.set_option("spmm_dyn", dyn)
-        ms = time_point(rowptr, col, val, x, y, 3, flush, False, long_row_threshold=T)
-        print(json.dumps({"family": "indeg_zipf", "F": F, "E": E, "T": T, "chunk": C, "dyn": dyn, "ms": ms,
-                          "frac": alg / ms / 1e6 / pk, "dmax": dmax}), flush=True)
-    ops.set_option("spmm_chunk", 0); ops.set_option("spmm_dyn", 0)
+    for fam, floor in (("indeg_zipf", 8), ("indeg_zipf_pure", 0)):
+        rowptr, col, val, E, dmax = make_csr_indegree_zipf(N, E_t, True, dev, floor=floor)
+        alg = E * (8 + 4 * F) + N * 4 * F + (N + 1) * 8
+        for T, C, dyn in ((32, 256, 0), (64, 256, 0), (128, 256, 0), (256, 256, 0), (2048, 256, 0)):
+            ops.set_option("spmm_chunk", C); ops.set_option("spmm_dyn", dyn)
+            ms = time_point(rowptr, col, val, x, y, 3, flush, False, long_row_threshold=T)
+            print(json.dumps({"family": fam, "F": F, "E": E, "T": T, "chunk": C, "dyn": dyn, "ms": ms,
+                              "frac": alg / ms / 1e6 / pk, "dmax": dmax}), flush=True)
+        ops.set_option("spmm_chunk", 0); ops.set_option("spmm_dyn", 0)
+        del rowptr, col, val
+    rowptr = col = val = None
     del rowptr, col, val, x, y
     torch.cuda.empty_cache()

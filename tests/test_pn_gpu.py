@@ -391,3 +391,73 @@ def test_column_split_scan_equals_cta_pair_scan_bitwise(n, K, N):
     for key in ("cs1", "cs2"):
         for a, b in zip(outs[key], outs["pair"]):
             assert torch.equal(a, b), key
+
+
+# ----------------------------------------------------------------------------- any hidden size
+@pytest.mark.parametrize("H,n,K,N,emb", [(64, 37, 6, 4, 0), (128, 130, 12, 5, 0), (200, 9, 5, 7, 0), (512, 16, 4, 3, 0),
+                                         (96, 20, 6, 4, 20)])
+def test_any_hidden_size_matches_oracle(H, n, K, N, emb):
+    """hidden_size is a free ini parameter (trainPNLow.py:204): sizes other than the shipped 256 run on the strict-fp32
+    any-hidden-size kernels (gnnpn_*_anyh_f32).  PNLow -> PNHigh greedy against the oracle: picks exact (a flip must sit on
+    a reference margin below the tolerance), window logits / probabilities / encodings / decoder states within 1e-5, the
+    -inf pattern of the dense logits exact, reward exact; then a teacher-forced sampled decode."""
+    from gnnpn_sc_b200 import modelPN as M
+    L = K * N
+    cfg = po.PNConfig(hidden_size=H, seq_len=L, s_number=N, s_category=K, embedding_size=emb)
+    g = torch.Generator().manual_seed(H + n)
+    x = torch.rand(n, L, 8, generator=g)
+    if emb:
+        x = torch.cat([torch.arange(L).div(N, rounding_mode="floor").float().view(1, L, 1).expand(n, L, 1), x], 2)
+    sds = [po.make_state_dict(cfg, 11), po.make_state_dict(cfg, 12)]
+    nets = []
+    for level, sd in zip(("Low", "High"), sds):
+        m = M.CombinatorialRL(emb, H, L, 0, 10, 1, M.reward, "Dot", N, K, level=level)
+        m.load_state_dict(sd, strict=True)
+        nets.append(m.cuda().eval())
+    xc = x.cuda()
+    with torch.no_grad():
+        _, _, _, idx_lo, lat = nets[0](xc, None, sample="greedy", training="SL")
+        R, _, _, idx_hi, lg_hi = nets[1](xc, None, lat, sample="greedy", training="RL")
+        p_lo, i_lo, l_lo, int_lo = po.pointer_forward(sds[0], cfg, x, None, "greedy", return_internals=True)
+        p_hi, i_hi, l_hi, int_hi = po.pointer_forward(sds[1], cfg, x, l_lo, "greedy", return_internals=True)
+    assert torch.equal(torch.stack(idx_lo).cpu(), torch.stack(i_lo)), "PNLow picks"
+    assert torch.equal(torch.stack(idx_hi).cpu(), torch.stack(i_hi)), "PNHigh picks"
+    worst = {}
+    for tag, net, ref_l, ref_p, internals in (("low", nets[0], l_lo, p_lo, int_lo), ("high", nets[1], l_hi, p_hi, int_hi)):
+        last = net.actor.last
+        dense = torch.stack(ref_l)                                     # [K, n, L]
+        win = dense.view(K, n, K, N).diagonal(dim1=0, dim2=2).permute(0, 2, 1).reshape(n, L)
+        winp = torch.stack(ref_p).view(K, n, K, N).diagonal(dim1=0, dim2=2).permute(0, 2, 1).reshape(n, L)
+        rel = lambda a, b: float(((a - b).abs() / b.abs().clamp(min=1)).max())
+        worst[f"logits_{tag}"] = rel(last["win_logits"].cpu(), win)
+        worst[f"probs_{tag}"] = rel(last["win_probs"].cpu(), winp)
+        worst[f"enc_out_{tag}"] = rel(last["enc_out"].cpu(), internals["enc_out"])
+        worst[f"dec_h_{tag}"] = rel(last["dec_h"].cpu(), torch.stack(internals["queries"], 1))
+    got_dense = torch.stack([lg_hi[k] for k in range(K)]).cpu()
+    ref_dense = torch.stack(l_hi)
+    assert torch.equal(torch.isinf(got_dense), torch.isinf(ref_dense)), "-inf pattern of the dense logits"
+    fin = torch.isfinite(ref_dense)
+    worst["dense_logits_high"] = float(((got_dense[fin] - ref_dense[fin]).abs() / ref_dense[fin].abs().clamp(min=1)).max())
+    record_parity(f"any_hidden_size_H{H}_n{n}_K{K}_N{N}_emb{emb}", tolerance=LOGIT_TOL, **worst)
+    for k, v in worst.items():
+        assert v <= LOGIT_TOL, (k, v)
+    rows = torch.arange(n)
+    R_ref = po.reward([x[rows, a, :] for a in i_hi], None, K, "High", emb)
+    assert torch.equal(R.cpu(), R_ref)
+    # sampled decode, teacher-forced on an arbitrary in-window sequence: probabilities of every step against the oracle
+    forced = [(k * N + torch.randint(0, N, (n,), generator=g)) for k in range(K)]
+    with torch.no_grad():
+        probs, _, _ = nets[0].actor(xc, None, sample="sample", forced_idxs=[f.cuda() for f in forced])
+        p_ref, _, _ = po.pointer_forward(sds[0], cfg, x, None, "sample", forced_idxs=forced)
+    winp = torch.stack(p_ref).view(K, n, K, N).diagonal(dim1=0, dim2=2).permute(0, 2, 1).reshape(n, L)
+    assert float((probs.window.cpu() - winp).abs().max()) <= LOGIT_TOL
+
+
+def test_any_hidden_size_unsupported_variants_raise():
+    """Bahdanau / glimpses / windows wider than 32 exist only for hidden_size = 256: a clear error, not garbage."""
+    from gnnpn_sc_b200 import modelPN as M
+    x = torch.rand(4, 12, 8).cuda()
+    for kw in (dict(att="Bahdanau", gl=0), dict(att="Dot", gl=1)):
+        m = M.CombinatorialRL(0, 128, 12, kw["gl"], 10, 1, M.reward, kw["att"], 4, 3, level="Low").cuda().eval()
+        with pytest.raises(NotImplementedError):
+            m(x, None, sample="greedy", training="SL")

@@ -12,10 +12,10 @@ from oracle import pn_oracle as po
 pytestmark = pytest.mark.gpu
 
 
-def _model(K, N, level="Low", seed=1):
+def _model(K, N, level="Low", seed=1, H=256):
     from gnnpn_sc_b200 import modelPN as M
-    cfg = po.PNConfig(seq_len=K * N, s_number=N, s_category=K)
-    m = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level=level)
+    cfg = po.PNConfig(hidden_size=H, seq_len=K * N, s_number=N, s_category=K)
+    m = M.CombinatorialRL(0, H, K * N, 0, 10, 1, M.reward, "Dot", N, K, level=level)
     sd = po.make_state_dict(cfg, seed)
     m.load_state_dict(sd)
     return cfg, sd, m.cuda()
@@ -72,6 +72,25 @@ def test_replay_gradient_equals_oracle_autograd(impl, K, N, B, high):
     print(f"replay gradient [{impl}, K={K}, N={N}, B={B}, high={high}] max relative deviation vs oracle autograd: {worst:.2e}")
     record_parity(f"reinforce_gradient_{impl}_K{K}_N{N}_B{B}_{'high' if high else 'low'}", max_rel_dev=worst, tolerance=1e-4)
     assert worst < 1e-4
+
+
+def test_reinforce_gradient_other_hidden_size():
+    """hidden_size = 128: the sampled decode runs on the any-hidden-size kernels, the gradient on the torch replay; it
+    equals autograd through the oracle's graph on the same picks."""
+    from gnnpn_sc_b200.synth import pn_instances
+    K, N, B = 6, 4, 12
+    cfg, sd, m = _model(K, N, seed=4, H=128)
+    x = pn_instances(B, K, N, seed=8)
+    m.train()
+    R, ap, _, idx, _ = m(x.cuda(), None, sample="sample", training="RL")
+    idx_cpu = [t.cpu() for t in idx]
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    probs, _, _ = po.pointer_forward(sd_g, cfg, x, None, "greedy", forced_idxs=idx_cpu)
+    sum(torch.log(p[torch.arange(B), a]) for p, a in zip(probs, idx_cpu)).sum().backward()
+    sum(torch.log(p) for p in ap).sum().backward()
+    worst = max(float((p.grad.cpu() - sd_g[name].grad).abs().max() / sd_g[name].grad.abs().max().clamp(min=1e-3))
+                for name, p in m.named_parameters())
+    assert worst < 1e-4, worst
 
 
 def _toy_pn_data(n, K, N, seed=0):
