@@ -503,6 +503,39 @@ int gnnpn_pn_train_forward_f32(const float* inputs, const float* packed_enc, con
   return GNNPN_OK;
 }
 
+int gnnpn_pn_train_forward_tc_f32(const float* inputs, const float* packed_enc, const float* packed_dec,
+                                  const int32_t* forced_idx, const float* sample_uniform, const float* latent_win,
+                                  float alpha, int use_tanh, float C, int64_t n, int L, int in_features, int hidden, int K,
+                                  int N, float* enc_out, float* gates_e, float* c_e, float* dec_h, float* gates_d,
+                                  float* c_d, float* win_logits, float* win_probs, int32_t* idx_out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  GNNPN_REQUIRE(inputs && packed_enc && packed_dec && enc_out && gates_e && c_e && dec_h && gates_d && c_d && win_logits &&
+                    win_probs && idx_out && workspace, GNNPN_ENULL);
+  GNNPN_REQUIRE(hidden == kH && in_features >= 1 && in_features <= 8 && K >= 1 && N >= 1 && N <= kMaxWindow &&
+                    (int64_t)K * N == L && n >= 0 && n < (1ll << 31), GNNPN_ESHAPE);
+  GNNPN_REQUIRE(aligned16(enc_out) && aligned16(dec_h) && aligned16(gates_e) && aligned16(gates_d) && aligned16(c_e) &&
+                    aligned16(c_d), GNNPN_EALIGN);
+  GNNPN_REQUIRE(workspace_bytes >= tc_lstm_workspace_bytes(n), GNNPN_EWORKSPACE);
+  // the column-split cluster scan only (training batches: the reference's is 128); larger batches use the FFMA replay
+  GNNPN_REQUIRE(tc_colsplit_wanted(n) && tc_colsplit_wanted_encode(n), GNNPN_EUNSUPPORTED);
+  if (n == 0) return GNNPN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* scr = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  const size_t nh = (size_t)n * kH;
+  float* c_last_e = c_e + (size_t)(L - 1) * nh;          // the encoder's final cell state = its last save
+  float* c_last_d = c_d + (size_t)(K - 1) * nh;          // decoder: in (copy of c_last_e) / out (= its last save)
+  SeqEncodeArgs ea{inputs, n, L, in_features, packed_enc, enc_out, c_last_e, scr, GNNPN_ENC_ROWMAJOR};
+  ea.save_gates = gates_e; ea.save_c = c_e;
+  int rc = tc_colsplit_encode(ea, scr, st);
+  if (rc) return rc;
+  cudaError_t ce = cudaMemcpyAsync(c_last_d, c_last_e, nh * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (ce != cudaSuccess) return (int)ce;
+  SeqDecodeArgs da{inputs, enc_out, c_last_d, latent_win, alpha, packed_dec, use_tanh, C, n, L, in_features, K, N, dec_h,
+                   idx_out, win_logits, win_probs, forced_idx, sample_uniform, scr, GNNPN_ENC_ROWMAJOR};
+  da.save_gates = gates_d; da.save_c = c_d;
+  return tc_colsplit_decode(da, scr, st);
+}
+
 int gnnpn_pn_full_logits_f32(const float* enc_out, const float* dec_h, const int32_t* idx,
                              int attention, const float* att_params, int use_tanh, float C,
                              int64_t n, int L, int hidden, int K, float* logits_full, void* stream) {

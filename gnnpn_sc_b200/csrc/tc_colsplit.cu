@@ -75,6 +75,8 @@ struct Params {
   __half* scratch;         // [groups][parity 2][hi|lo][128][kH] halfs
   PointerStepArgs pa;      // decoder only
   unsigned long long* prof;
+  float* save_gates;       // training: [steps, n, kG] post-activation gates (columns 4j + {i,f,g,o}) or nullptr
+  float* save_c;           // training: [steps, n, kH] cell state after every step or nullptr
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -392,7 +394,18 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(g));                         // accumulator is in registers
         float cn[8], hn[8];
-        lstm_cell8(v, bias4, c[g], cn, hn);
+        if (p.save_gates) {
+          // training forward: the BPTT's saves (gnnpn_pn_train_backward_f32) -- 128 + 32 contiguous bytes per thread
+          lstm_cell8_gates(v, bias4, c[g], cn, hn, v);
+          if (ok) {
+            float* gd = p.save_gates + ((int64_t)t * p.n + m) * kG + 4 * u0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) stg256(gd + 8 * i, v + 8 * i);
+            stg256(p.save_c + ((int64_t)t * p.n + m) * kH + u0, cn);
+          }
+        } else {
+          lstm_cell8(v, bias4, c[g], cn, hn);
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) c[g][u] = cn[u];
         const long long t3 = prof ? clock64() : 0;
@@ -623,6 +636,7 @@ int tc_colsplit_encode(const SeqEncodeArgs& a, void* scratch, cudaStream_t st) {
   p.bias0 = p.bias = a.packed + kOffBias;
   p.c = a.c_state;
   p.h_out = a.enc_out; p.h_out_inst_ld = (int64_t)a.L * kH;
+  p.save_gates = a.save_gates; p.save_c = a.save_c;
   return colsplit_groups_per_cluster(a.n) == 2 ? cs::launch<false, 2>(a.packed, p, scratch, st)
                                                : cs::launch<false, 1>(a.packed, p, scratch, st);
 }
@@ -640,6 +654,7 @@ int tc_colsplit_decode(const SeqDecodeArgs& a, void* scratch, cudaStream_t st) {
   p.pa.alpha = a.alpha; p.pa.use_tanh = a.use_tanh; p.pa.C = a.C; p.pa.n = a.n; p.pa.L = a.L;
   p.pa.N = a.N; p.pa.idx_out = a.idx_out; p.pa.win_logits = a.win_logits; p.pa.win_probs = a.win_probs;
   p.pa.forced = a.forced_idx; p.pa.uniform = a.sample_uniform;
+  p.save_gates = a.save_gates; p.save_c = a.save_c;
   return cs::launch<true, 1>(a.packed, p, scratch, st);
 }
 

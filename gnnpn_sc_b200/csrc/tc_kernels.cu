@@ -13,6 +13,7 @@
 // smem ring: STAGES x { A_hi, A_lo [128 x 32 f32], B_hi, B_lo [BN x 32 f32] }, 128B-swizzled K-major tiles
 // written by TMA and read by tcgen05.mma through UMMA descriptors.
 #include <stdlib.h>
+#include <algorithm>
 #include "tc_common.cuh"
 #include "common.cuh"
 #include "lstm_step.cuh"
@@ -37,6 +38,7 @@ constexpr int TMEM_COLS = 512;
 struct GemmEpilogueParams {
   const float* bias; const float* scale; const float* shift; int act;
   float* C; int64_t ldc; int N;
+  int64_t split_stride;     // split-K: floats between the partial outputs of consecutive k-splits (blockIdx.y), else 0
 };
 
 struct LstmEpilogueParams {
@@ -61,6 +63,7 @@ struct MainloopParams {
   int k_blocks;             // K / 32
   int last_block_ksteps;    // k-steps (of 8) actually non-zero in the last k block (1..4)
   int dbg;                  // profiling experiments only (GNNPN_TC_DBG): 1 = hi.hi MMA only, 2 = epilogue skips math
+  int kb_per_split;         // split-K: k blocks per blockIdx.y (>= k_blocks: no split)
 };
 
 // Operand flavour of the mainloop: every smem tile row is 128 bytes either way.
@@ -113,6 +116,9 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   constexpr int BKE = Kind<F16>::BKE;                 // elements per 128-byte k-block row
+  // split-K (weight-gradient GEMMs: few output tiles, very long K): blockIdx.y owns the k blocks [kb0, kb1)
+  const int kb0 = (int)blockIdx.y * mp.kb_per_split;
+  const int kb1 = min(mp.k_blocks, kb0 + mp.kb_per_split);
   const uint32_t stage_tx = 2u * A_TILE_BYTES + 2u * (uint32_t)mp.bn * 128u;
 
   if (warp == 0) {
@@ -120,7 +126,7 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int nt = 0; nt < mp.n_tiles; ++nt) {
-        for (int kb = 0; kb < mp.k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_arrive_expect_tx(full_bar(s), stage_tx);
           const uint32_t st = smem_base + s * STAGE_BYTES;
@@ -143,7 +149,7 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         mbar_wait(tmem_empty_bar(buf), (use & 1u) ^ 1u);    // epilogue has drained it (passes on first use)
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(buf * BN_MAX);
-        for (int kb = 0; kb < mp.k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t st = smem_base + s * STAGE_BYTES;
@@ -153,7 +159,7 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           const int ksteps = (kb == mp.k_blocks - 1) ? mp.last_block_ksteps : 4;
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t adv = (uint64_t)(ks * 2);            // +32 B per k-step inside the 128-byte swizzle row
-            const uint32_t acc0 = (kb | ks) != 0;
+            const uint32_t acc0 = ((kb - kb0) | ks) != 0;
             if (mp.dbg != 1) {
               Kind<F16>::mma(d, a_lo + adv, b_hi + adv, idesc, acc0);
               Kind<F16>::mma(d, a_hi + adv, b_lo + adv, idesc, 1u);
@@ -163,7 +169,7 @@ tc_mainloop_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             }
           }
           mma_commit(empty_bar(s));                 // smem slot reusable once these MMAs retire
-          if (kb == mp.k_blocks - 1) mma_commit(tmem_full_bar(buf));
+          if (kb == kb1 - 1) mma_commit(tmem_full_bar(buf));
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -219,7 +225,7 @@ struct GemmEpilogue {
   __device__ void prefetch(int, int) {}
   __device__ void chunk(int, int col0, int ncols, const float* v) {
     if (!ok) return;
-    float* out = p.C + row * p.ldc;
+    float* out = p.C + (int64_t)blockIdx.y * p.split_stride + row * p.ldc;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int n = col0 + j;
@@ -375,7 +381,7 @@ int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, in
 }
 
 template <class Epi, class EpiParams, bool F16>
-int launch_mainloop(const CUtensorMap maps[4], const MainloopParams& mp, const EpiParams& ep, cudaStream_t st) {
+int launch_mainloop(const CUtensorMap maps[4], const MainloopParams& mp, const EpiParams& ep, cudaStream_t st, int splits = 1) {
   auto kern = tc_mainloop_kernel<Epi, EpiParams, F16>;
   static bool configured = false;
   if (!configured) {
@@ -387,7 +393,8 @@ int launch_mainloop(const CUtensorMap maps[4], const MainloopParams& mp, const E
   static const int dbg = getenv("GNNPN_TC_DBG") ? atoi(getenv("GNNPN_TC_DBG")) : 0;
   MainloopParams mpd = mp;
   mpd.dbg = dbg;
-  kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], mpd, ep);
+  if (mpd.kb_per_split <= 0) mpd.kb_per_split = mpd.k_blocks;
+  kern<<<dim3(grid, (unsigned)splits), THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], mpd, ep);
   return after_launch();
 }
 
@@ -395,10 +402,45 @@ int launch_mainloop(const CUtensorMap maps[4], const MainloopParams& mp, const E
 
 // ------------------------------------------------------------------------------------------------
 // node transform through tcgen05.  Workspace holds the tf32 splits of A and W.
+// split-K factor of the GEMM: only when the output has few row tiles and K is long (weight gradients of the REINFORCE
+// replay: [4H, T*n] x [T*n, H+16] = 8 row tiles, 940 k blocks of 32).  Two reasons: (1) 8 CTAs on 148 SMs; (2) the tensor
+// cores' fp32 accumulation loses ~0.5 ulp per MMA, so one 11,000-MMA chain is 1e-4 off where the element-wise bound of
+// this entry is 1e-5 -- chains of 8 k blocks (96 MMAs) summed by fp32 adds in split order stay inside it.  The partial
+// outputs are capped at 256 MB.
+static int tc_gemm_splits(int64_t M, int N, int K) {
+  const int64_t row_tiles = ceil_div(M, tc::BM);
+  const int k_blocks = round_up(K, tc::BK) / tc::BK;
+  if (row_tiles * 2 > kNumSMs || k_blocks < 64) return 1;
+  int64_t s_max = (256ll << 20) / (M * (int64_t)N * 4);
+  if (s_max > 128) s_max = 128;
+  if (s_max < 2) return 1;
+  const int kps = (int)std::max<int64_t>(8, ceil_div(k_blocks, s_max));
+  return (int)ceil_div(k_blocks, kps);
+}
+
 size_t tc_gemm_workspace_bytes(int64_t M, int N, int K) {
   const int64_t Kp = round_up(K, tc::BK);
-  return (size_t)(2 * (M + N) * Kp) * sizeof(float) + 1024;
+  const int S = tc_gemm_splits(M, N, K);
+  return (size_t)(2 * (M + N) * Kp) * sizeof(float) + 1024 + (S > 1 ? (size_t)S * M * N * sizeof(float) + 256 : 0);
 }
+
+namespace {
+// C = epilogue(sum over the k-splits, in split order): deterministic
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int S, int64_t M, int N, const float* __restrict__ bias,
+                                     const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                     float* __restrict__ C, int64_t ldc) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= M * N) return;
+  const int n = (int)(e % N);
+  float r = part[e];
+  for (int s = 1; s < S; ++s) r += part[(int64_t)s * M * N + e];
+  if (bias) r += __ldg(bias + n);
+  if (scale) r = fmaf(r, __ldg(scale + n), __ldg(shift + n));
+  if (act == GNNPN_ACT_RELU) r = fmaxf(r, 0.f);
+  else if (act == GNNPN_ACT_SIGMOID) r = sigmoid_accurate(r);
+  C[(e / N) * ldc + n] = r;
+}
+}  // namespace
 
 int launch_gemm_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* scale,
                    const float* shift, int act, float* C, int64_t ldc, int64_t M, int N, int K, void* workspace,
@@ -422,8 +464,20 @@ int launch_gemm_tc(const float* A, int64_t lda, const float* W, int64_t ldw, con
   if ((rc = make_map_2d(&maps[1], a_lo, M, Kp, Kp, BM))) return rc;
   if ((rc = make_map_2d(&maps[2], w_hi, N, Kp, Kp, bn))) return rc;
   if ((rc = make_map_2d(&maps[3], w_lo, N, Kp, Kp, bn))) return rc;
-  MainloopParams mp{(int)M, n_tiles, bn, Kp / BK, BK / 8, 0};
-  GemmEpilogueParams ep{bias, scale, shift, act, C, ldc, N};
+  const int S = tc_gemm_splits(M, N, K);
+  if (S > 1) {
+    float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(w_lo + (int64_t)N * Kp) + 255) & ~uintptr_t(255));
+    const int kps = (int)ceil_div(Kp / BK, S);
+    const int S_eff = (int)ceil_div(Kp / BK, kps);               // every split owns at least one k block (S_eff <= S)
+    MainloopParams mp{(int)M, n_tiles, bn, Kp / BK, BK / 8, 0, kps};
+    GemmEpilogueParams ep{nullptr, nullptr, nullptr, GNNPN_ACT_NONE, part, N, N, (int64_t)M * N};
+    if ((rc = launch_mainloop<GemmEpilogue, GemmEpilogueParams, false>(maps, mp, ep, st, S_eff))) return rc;
+    splitk_reduce_kernel<<<(unsigned)ceil_div(M * (int64_t)N, 256), 256, 0, st>>>(part, S_eff, M, N, bias, scale, shift, act, C,
+                                                                               ldc);
+    return after_launch();
+  }
+  MainloopParams mp{(int)M, n_tiles, bn, Kp / BK, BK / 8, 0, Kp / BK};
+  GemmEpilogueParams ep{bias, scale, shift, act, C, ldc, N, 0};
   return launch_mainloop<GemmEpilogue, GemmEpilogueParams, false>(maps, mp, ep, st);
 }
 
@@ -549,6 +603,7 @@ int tc_lstm_step(const TcLstmPlan& plan, const TcLstmStep& s, cudaStream_t st) {
   mp.k_blocks = kH / bke + (s.use_x ? 1 : 0);
   mp.last_block_ksteps = s.use_x ? (s.F + (bke / 4) - 1) / (bke / 4) : 4;
   mp.dbg = 0;
+  mp.kb_per_split = mp.k_blocks;
   LstmEpilogueParams ep;
   ep.bias = s.bias; ep.c = s.c; ep.h_out = s.h_out; ep.h_out_ld = s.h_out_ld;
   ep.a_hi_next = (float*)plan.hi[s.cur ^ 1]; ep.a_lo_next = (float*)plan.lo[s.cur ^ 1]; ep.a_ld = plan.ld;

@@ -23,6 +23,9 @@ struct SeqEncodeArgs {
   float* c_state;          // [n, kH] out
   float* c_scratch;        // tc_seq_scratch_floats(n) floats
   int enc_layout;          // GNNPN_ENC_ROWMAJOR / GNNPN_ENC_BLOCKED128 (CTA-pair scan only)
+  // training (column-split scan only): per-step saves for the BPTT, or nullptr
+  float* save_gates;       // [L, n, 4H] post-activation gates, columns 4j + {i,f,g,o}
+  float* save_c;           // [L, n, H] cell state after every step
 };
 // returns GNNPN_EUNSUPPORTED when the shape is outside what the persistent kernel covers
 int tc_seq_encode(const SeqEncodeArgs& a, cudaStream_t st);
@@ -56,6 +59,8 @@ struct SeqDecodeArgs {
   const float* sample_uniform;   // [K, n] or nullptr
   float* c_scratch;              // tc_seq_scratch_floats(n) floats
   int enc_layout;                // layout of enc_out
+  float* save_gates;             // training (column-split scan only): [K, n, 4H] post-activation gates, or nullptr
+  float* save_c;                 // [K, n, H] cell state after every step, or nullptr
 };
 bool tc_seq_fused_decode_supported(int N);     // blocked-layout decoder (pointer dots fused into the cell epilogue)
 int tc_seq_decode(const SeqDecodeArgs& a, cudaStream_t st);

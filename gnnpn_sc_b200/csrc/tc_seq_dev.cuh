@@ -178,5 +178,32 @@ __device__ __forceinline__ void lstm_cell8(const float* v, const float4* bias4, 
   }
 }
 
+// Same cell, also returning the post-activation gates (training saves: the BPTT reads sigm(i), sigm(f), tanh(g), sigm(o)):
+//   sigm(i) = d g r, sigm(f) = a g r, tanh(g) = (1 - Eg) a d r, sigm(o) = (1 + Ec) r2     (r, r2 as above)
+__device__ __forceinline__ void lstm_cell8_gates(const float* v, const float4* bias4, const float* c_old, float* c_new,
+                                                 float* h_new, float* gates) {
+  constexpr float S1 = -kLog2e / kW16Scale, S2 = -2.0f * kLog2e / kW16Scale;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float4 b = bias4[u];
+    const float Ei = ex2_approx(fminf(fmaf(v[4 * u + 0], S1, b.x), kClampT));
+    const float Ef = ex2_approx(fminf(fmaf(v[4 * u + 1], S1, b.y), kClampT));
+    const float Eg = ex2_approx(fminf(fmaf(v[4 * u + 2], S2, b.z), kClampT));
+    const float Eo = ex2_approx(fminf(fmaf(v[4 * u + 3], S1, b.w), kClampT));
+    const float a = 1.0f + Ei, d = 1.0f + Ef, g = 1.0f + Eg;
+    const float ag = a * g;
+    const float r = rcp_refined(ag * d);
+    const float cn = fmaf(1.0f - Eg, d, c_old[u] * ag) * r;
+    const float Ec = ex2_approx(fminf(cn * (-2.0f * kLog2e), kClampT));
+    const float r2 = rcp_refined((1.0f + Eo) * (1.0f + Ec));
+    c_new[u] = cn;
+    h_new[u] = (1.0f - Ec) * r2;
+    gates[4 * u + 0] = d * g * r;
+    gates[4 * u + 1] = ag * r;
+    gates[4 * u + 2] = (1.0f - Eg) * (a * d) * r;
+    gates[4 * u + 3] = (1.0f + Ec) * r2;
+  }
+}
+
 }  // namespace seq
 }  // namespace gnnpn

@@ -212,6 +212,7 @@ class PointerNet(nn.Module):
         self.defer_range_check = False            # True: forward leaves the range flag in ``last["range_flag"]`` (no sync);
                                                   # the caller reads it with ``raise_if_out_of_range`` when convenient
         self.replay_impl = "own"                  # REINFORCE gradient: "own" = library kernels (fast configuration), "torch"
+        self._train_saves = None                  # (saves, inputs, latent window) of a training-mode forward, consumed by the replay
 
     # -- packed weights are a cache over the parameters; rebuilt when any of them changes
     def _packed_weights(self):
@@ -304,6 +305,23 @@ class PointerNet(nn.Module):
         return {"x": x, "ws": ws, "layout": layout, "enc_out": enc_out, "c": c, "range_flag": range_flag, "fast": fast,
                 "stream": torch.cuda.current_stream(x.device)}
 
+    def _train_forward(self, inputs, lat, uniform, use_tanh, C):
+        """Free-running decode (greedy, or sampled with ``uniform``) on ``gnnpn_pn_train_forward_tc_f32``: the picks plus
+        every per-step save of the BPTT.  Returns (saves, encode-handle) or (None, None) when the batch does not fit the
+        column-split cluster scan."""
+        x = self._kernel_inputs(inputs)
+        range_flag = ops.pn_check_inputs(x) if self.check_inputs else None
+        enc_w, dec_w = self._packed_weights()
+        K, N = self.serCategory, self.serNumber
+        with torch.no_grad():
+            try:
+                sv = ops.pn_train_forward(x, enc_w, dec_w, None, K, N, latent_win=lat, alpha=float(self.alpha),
+                                          use_tanh=use_tanh, C=C, hidden=self.hidden_size, impl="tc", sample_uniform=uniform)
+            except ops.GnnpnError:
+                return None, None
+        return sv, {"x": x, "ws": None, "layout": ops.ENC_ROWMAJOR, "enc_out": sv["enc_out"], "c": None,
+                    "range_flag": range_flag, "fast": True, "stream": torch.cuda.current_stream(x.device)}
+
     def forward(self, inputs, latent, sample="sample", forced_idxs=None, encoded=None):
         """inputs [B, L, F] -> (prev_probs, prev_idxs, prev_logits), K-long each (modelPN.py:241)."""
         B, L, _ = inputs.shape
@@ -311,8 +329,22 @@ class PointerNet(nn.Module):
         if self.pointer.name not in ("Dot", "Bahdanau"):
             raise NotImplementedError(self.pointer.name)
         K, N = self.serCategory, self.serNumber
+        use_tanh, C = bool(self.pointer.use_tanh), float(self.pointer.C)
+        with torch.no_grad():
+            lat = _window_of(latent, K, N) if latent else None
+            forced = None if forced_idxs is None else torch.stack([t.to(torch.int32) for t in forced_idxs])
+            # sample != "greedy": multinomial draw per step (modelPN.py:227-228) as an inverse-CDF pick in the kernel
+            uniform = None if sample == "greedy" else torch.rand(K, B, device=inputs.device, generator=self.generator)
+        train_sv = None
+        self._train_saves = None
         if encoded is None:
-            encoded = self.encode(inputs)
+            if (forced is None and self.training and torch.is_grad_enabled() and self.replay_impl != "torch"
+                    and self.impl != "ffma" and inputs.is_cuda and self._fast_path(inputs.shape[2])):
+                # REINFORCE: the decode itself runs with the BPTT's saves enabled (tensor-core column-split scan), so
+                # replay_action_probs needs no second forward; batches outside that scan decode normally and replay
+                train_sv, encoded = self._train_forward(inputs, lat, uniform, use_tanh, C)
+            if encoded is None:
+                encoded = self.encode(inputs)
         else:
             cur = torch.cuda.current_stream(inputs.device)
             if encoded["stream"] != cur:                   # encoded on a side stream: order after it, keep its buffers alive
@@ -324,16 +356,15 @@ class PointerNet(nn.Module):
         range_flag, fast = encoded["range_flag"], encoded["fast"]
         anyh = bool(encoded.get("anyh"))
         dec_w = None if anyh else self._packed_weights()[1]
-        use_tanh, C = bool(self.pointer.use_tanh), float(self.pointer.C)
         att = self.pointer.name
         with torch.no_grad():
-            lat = _window_of(latent, K, N) if latent else None
-            forced = None if forced_idxs is None else torch.stack([t.to(torch.int32) for t in forced_idxs])
-            # sample != "greedy": multinomial draw per step (modelPN.py:227-228) as an inverse-CDF pick in the kernel
-            uniform = None if sample == "greedy" else torch.rand(K, B, device=x.device, generator=self.generator)
             ptr_blk = qw = None
             replay = None
-            if anyh:
+            if train_sv is not None:
+                dec_h = dec_q = train_sv["dec_h"]
+                idx, win_logits, win_probs = train_sv["idx"], train_sv["win_logits"], train_sv["win_probs"]
+                self._train_saves = (train_sv, inputs, lat)
+            elif anyh:
                 _, (w_cat, bias, bias0) = self._folded_weights()
                 dec_h, idx, win_logits, win_probs = ops.pn_decode_anyh(
                     x, enc_out, c, w_cat, bias, bias0, K, N, latent_win=lat, alpha=float(self.alpha), use_tanh=use_tanh, C=C,
@@ -414,11 +445,14 @@ class PointerNet(nn.Module):
         the windows -- outside window k the reference's probabilities are exactly 0 and carry no gradient
         (modelPN.py:220-224) -- so the gradient equals the reference's.  Encoder via nn.LSTM (cuDNN), K cell steps;
         glimpses (when configured) attend over all positions with the cumulative visited mask as in modelPN.py:208-211."""
+        saves, self._train_saves = self._train_saves, None
         if self.replay_impl != "torch" and self._fast_path(inputs.shape[2]):
-            # the library's own forward-with-saves + BPTT kernels (Dot attention, no glimpse, embedding_size = 0)
+            # the library's own forward-with-saves + BPTT kernels (Dot attention, no glimpse, embedding_size = 0).  When the
+            # forward of THIS batch already ran with the saves enabled (same inputs / latent objects) they are used as is
+            sv = saves[0] if (saves is not None and saves[1] is inputs and saves[2] is latent_win) else None
             e, d = self.encoder, self.decoder
             probs = _ReplayFn.apply(self, inputs.detach().float().contiguous(), idx.to(torch.int32).contiguous(),
-                                    latent_win, self.embedding2.weight, self.embedding2.bias, self.decoder_start_input,
+                                    latent_win, sv, self.embedding2.weight, self.embedding2.bias, self.decoder_start_input,
                                     e.weight_ih_l0, e.weight_hh_l0, e.bias_ih_l0, e.bias_hh_l0,
                                     d.weight_ih_l0, d.weight_hh_l0, d.bias_ih_l0, d.bias_hh_l0)
             return list(probs.unbind(0))
@@ -461,12 +495,13 @@ class _ReplayFn(torch.autograd.Function):
     Layout shuffles (transposes, shifts) are torch copy kernels; every contraction and the BPTT run in the library."""
 
     @staticmethod
-    def forward(ctx, actor, x, idx, latent_win, emb_w, emb_b, start, e_ih, e_hh, e_bih, e_bhh, d_ih, d_hh, d_bih, d_bhh):
+    def forward(ctx, actor, x, idx, latent_win, sv, emb_w, emb_b, start, e_ih, e_hh, e_bih, e_bhh, d_ih, d_hh, d_bih, d_bhh):
         K, N = actor.serCategory, actor.serNumber
-        enc_w, dec_w = actor._packed_weights()
         use_tanh, C = bool(actor.pointer.use_tanh), float(actor.pointer.C)
-        sv = ops.pn_train_forward(x, enc_w, dec_w, idx, K, N, latent_win=latent_win, alpha=float(actor.alpha),
-                                  use_tanh=use_tanh, C=C, hidden=actor.hidden_size)
+        if sv is None:                             # teacher-forced replay of the picks (no saves from the decode itself)
+            enc_w, dec_w = actor._packed_weights()
+            sv = ops.pn_train_forward(x, enc_w, dec_w, idx, K, N, latent_win=latent_win, alpha=float(actor.alpha),
+                                      use_tanh=use_tanh, C=C, hidden=actor.hidden_size, impl=actor.impl)
         ctx.sv, ctx.x, ctx.cfg = sv, x, (K, N, use_tanh, C)
         ctx.save_for_backward(emb_w, emb_b, start, e_ih, e_hh, d_ih, d_hh)
         return sv["win_probs"].gather(1, idx.t().long()).t().contiguous()            # [K, B]
@@ -510,7 +545,7 @@ class _ReplayFn(torch.autograd.Function):
         d_emb_w = mm(e_ih_t, dM_e.t().contiguous()) + mm(d_ih_t, dM_d.t().contiguous())
         d_emb_b = (mm(e_ih_t, db_e.view(1, -1)) + mm(d_ih_t, db_d.view(1, -1))).view(-1)
         d_start = mm(d_ih_t, s0.view(1, -1)).view(-1)
-        return (None, None, None, None, d_emb_w, d_emb_b, d_start, dWih_e, dWhh_e, db_e, db_e, dWih_d, dWhh_d, db_dec, db_dec)
+        return (None, None, None, None, None, d_emb_w, d_emb_b, d_start, dWih_e, dWhh_e, db_e, db_e, dWih_d, dWhh_d, db_dec, db_dec)
 
 
 # --------------------------------------------------------------------------- CombinatorialRL

@@ -174,6 +174,18 @@ GNNPN_API int gnnpn_pn_train_forward_f32(const float* inputs, const float* packe
                                int64_t n, int L, int in_features, int hidden, int K, int N, float* enc_out,
                                float* gates_e, float* c_e, float* dec_h, float* gates_d, float* c_d,
                                float* win_logits, float* win_probs, int32_t* idx_free, void* stream);
+/* The same forward on the tensor-core column-split cluster scan (tcgen05, 3xFP16 split: the kernels of the small-batch
+ * inference path with the per-step saves enabled), for batches that scan takes (n <= ~3,840 on a B200; the reference trains
+ * with 128) -- else GNNPN_EUNSUPPORTED and the caller uses gnnpn_pn_train_forward_f32.  forced_idx != NULL: teacher-forced
+ * replay of those picks; forced_idx == NULL with sample_uniform: the SAMPLED decode itself (modelPN.py:227-228) saving what
+ * the BPTT needs, so no replay forward is required at all; idx_out [K, n] receives the (free) picks.
+ * workspace: gnnpn_pn_workspace_bytes(n, hidden). */
+GNNPN_API int gnnpn_pn_train_forward_tc_f32(const float* inputs, const float* packed_encoder, const float* packed_decoder,
+                                  const int32_t* forced_idx, const float* sample_uniform, const float* latent_win,
+                                  float alpha, int use_tanh, float C, int64_t n, int L, int in_features, int hidden,
+                                  int K, int N, float* enc_out, float* gates_e, float* c_e, float* dec_h, float* gates_d,
+                                  float* c_d, float* win_logits, float* win_probs, int32_t* idx_out, void* workspace,
+                                  size_t workspace_bytes, void* stream);
 GNNPN_API size_t gnnpn_pn_train_backward_workspace_floats(int64_t n, int L, int K, int hidden);
 GNNPN_API int gnnpn_pn_train_backward_f32(const float* enc_out, const float* gates_e, const float* c_e, const float* dec_h,
                                 const float* gates_d, const float* c_d, const float* win_logits,

@@ -121,7 +121,8 @@ def test_gcn_layer_epilogue():
 @pytest.mark.parametrize("impl", ["tc", "ffma"])
 @pytest.mark.parametrize("M,N,K", [(1, 128, 128), (97, 256, 28), (5014, 256, 24), (1000, 128, 256), (130, 2507, 128),
                                    (5014, 256, 256), (200000, 256, 256), (257, 48, 4), (300, 16, 60),
-                                   (70000, 128, 136), (40000, 240, 252)])
+                                   (70000, 128, 136), (40000, 240, 252),
+                                   (1024, 272, 30080), (300, 48, 9004), (640, 272, 2100)])     # long K, few row tiles: split-K
 def test_node_transform_gemm(M, N, K, impl):
     """tcgen05 (persistent 3xFP16-split kernel for K, N <= 256; 3xTF32 mainloop otherwise) and FFMA node transforms
     against an fp64 evaluation on the CPU, ELEMENT-WISE: |y - ref| <= 1e-5 * max(1, |ref|) for every entry."""
@@ -132,9 +133,13 @@ def test_node_transform_gemm(M, N, K, impl):
     ref = torch.relu(torch.nn.functional.linear(a.double(), w.double(), b.double()) * scale.double() + shift.double())
     y = ops.gemm_bias_act(a.cuda(), w.cuda(), bias=b.cuda(), scale=scale.cuda(), shift=shift.cuda(), act="relu", impl=impl)
     err = ((y.cpu().double() - ref).abs() / ref.abs().clamp(min=1)).max().item()
-    print(f"gemm[{impl}] M={M} N={N} K={K}: max element-wise |err| / max(1,|ref|) {err:.2e}")
-    record_parity(f"gemm_{impl}_M{M}_N{N}_K{K}", max_elementwise_rel=err, tolerance=1e-5)
-    assert err <= 1e-5, err
+    # strict-fp32 FFMA accumulates the K terms sequentially in fp32: beyond K ~ 1,700 its own rounding (~ sqrt(K) * 2^-24 per
+    # unit of summed magnitude, any fp32 GEMM has it) passes 1e-5, so that path is held to 4 * sqrt(K) * 2^-24 there.  The
+    # tensor-core path (split-K chains of 8 k blocks, fp32 adds in split order) is held to 1e-5 at every K.
+    tol = 1e-5 if impl == "tc" else max(1e-5, 4.0 * K ** 0.5 * 2.0 ** -24)
+    print(f"gemm[{impl}] M={M} N={N} K={K}: max element-wise |err| / max(1,|ref|) {err:.2e} (bound {tol:.1e})")
+    record_parity(f"gemm_{impl}_M{M}_N{N}_K{K}", max_elementwise_rel=err, tolerance=tol)
+    assert err <= tol, err
 
 
 @pytest.mark.parametrize("mag", [1.0e4, 1.0e6])
