@@ -21,6 +21,7 @@ Options& options() {
     env_int("GNNPN_COLSPLIT_G", x->scan_groups);
     env_int("GNNPN_SEQ", x->persistent);
     env_int("GNNPN_SEQ_PROF", x->prof);
+    env_int("GNNPN_BPTT", x->bptt);
     return x;
   }();
   return *o;
@@ -32,6 +33,7 @@ static std::atomic<int>* option_slot(const char* name) {
   if (!strcmp(name, "scan_groups")) return &o.scan_groups;
   if (!strcmp(name, "persistent")) return &o.persistent;
   if (!strcmp(name, "prof")) return &o.prof;
+  if (!strcmp(name, "bptt")) return &o.bptt;
   if (!strcmp(name, "spmm_chunk")) return &o.spmm_chunk;
   if (!strcmp(name, "spmm_dyn")) return &o.spmm_dyn;
   return nullptr;

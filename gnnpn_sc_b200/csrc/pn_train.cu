@@ -12,11 +12,15 @@
 #include <math.h>
 #include "lstm_step.cuh"
 #include "pointer.cuh"
+#include "options.cuh"
 
 namespace gnnpn {
 int launch_gemm_ffma(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                      const float* scale, const float* shift, int act, float* C, int64_t ldc, int64_t M, int N,
                      int K, cudaStream_t st);
+int launch_bptt_scan(const float* gates, const float* c, const float* c_init, const float* dh_ext, int64_t dh_ld_m,
+                     const float* dh_init, const float* dc_init, const float* w_hh, float* dG_T, float* dh_out,
+                     float* dc_out, int64_t n, int T, cudaStream_t st);
 namespace {
 
 // split-K of dh(t-1) = dG(t) . W_hh (dh_splitk_kernel): 16 chunks of 64 gate rows
@@ -231,6 +235,18 @@ int gnnpn_pn_train_backward_f32(const float* enc_out, const float* gates_e, cons
   attention_bwd_kernel<<<(unsigned)ceil_div(n * K, 8), 256, 0, st>>>(enc_out, dec_h, win_logits, win_probs, idx, grad_p,
                                                                     use_tanh, C, n, L, K, N, dq, d_enc);
   if ((rc = after_launch())) return rc;
+  if (options().bptt.load(std::memory_order_relaxed)) {
+    // ---- persistent cluster scans (pn_bptt.cu): one launch per LSTM instead of two per step.  The decoder started from the
+    // encoder's last state: its dh / dc w.r.t. that state enter the encoder scan at t = L-1
+    float* dh0 = dh_rec[0];
+    float* dc0 = dc[0];
+    if ((rc = launch_bptt_scan(gates_d, c_d, c_e + (size_t)(L - 1) * n * kH, dq, (int64_t)K * kH, nullptr, nullptr, w_hh_dec,
+                               dG_dec_T, dh0, dc0, n, K, st)))
+      return rc;
+    return launch_bptt_scan(gates_e, c_e, nullptr, d_enc, (int64_t)L * kH, dh0, dc0, w_hh_enc, dG_enc_T, nullptr, nullptr, n,
+                            L, st);
+  }
+  // ---- per-step kernels (option "bptt" = 0; kept as the A/B reference of the scan)
   // ---- decoder BPTT, k = K-1 .. 0;  c_prev of step 0 is the encoder's final cell state c_e[L-1]
   int cur = 0;
   for (int k = K - 1; k >= 0; --k) {

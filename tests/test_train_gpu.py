@@ -74,6 +74,36 @@ def test_replay_gradient_equals_oracle_autograd(impl, K, N, B, high):
     assert worst < 1e-4
 
 
+@pytest.mark.parametrize("B,K,N", [(128, 47, 5), (37, 6, 4), (16, 3, 2), (130, 5, 10)])
+def test_bptt_cluster_scan_equals_per_step_kernels(B, K, N):
+    """The persistent cluster BPTT (pn_bptt.cu, option bptt = 1) against the per-step kernels it replaces (bptt = 0) on the
+    same saves: gate gradients of every (step, instance, gate row) agree to fp32 re-association (the dh GEMM sums its k
+    chunks in a different fixed order), ragged batches included; the scan is deterministic."""
+    from gnnpn_sc_b200 import ops
+    from gnnpn_sc_b200.synth import pn_instances
+    cfg, sd, m = _model(K, N, seed=6)
+    x = pn_instances(B, K, N, seed=3).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    idx = (torch.arange(K, device="cuda").view(K, 1) * N + torch.randint(0, N, (K, B), device="cuda", generator=g)).to(torch.int32)
+    enc_w, dec_w = m.actor._packed_weights()
+    sv = ops.pn_train_forward(x, enc_w, dec_w, idx, K, N)
+    gp = torch.rand(K, B, device="cuda", generator=g) - 0.4
+    whe, whd = m.actor.encoder.weight_hh_l0.detach(), m.actor.decoder.weight_hh_l0.detach()
+    try:
+        ops.set_option("bptt", 0)
+        ref_e, ref_d = [t.clone() for t in ops.pn_train_backward(sv, gp, whe, whd, K, N)]
+        ops.set_option("bptt", 1)
+        got_e, got_d = [t.clone() for t in ops.pn_train_backward(sv, gp, whe, whd, K, N)]
+        again_e, again_d = ops.pn_train_backward(sv, gp, whe, whd, K, N)
+    finally:
+        ops.set_option("bptt", 1)
+    assert torch.equal(got_e, again_e) and torch.equal(got_d, again_d)
+    for got, ref in ((got_e, ref_e), (got_d, ref_d)):
+        scale = float(ref.abs().max())
+        assert scale > 0
+        assert float((got - ref).abs().max()) <= 2e-6 * scale, float((got - ref).abs().max()) / scale
+
+
 def test_reinforce_gradient_other_hidden_size():
     """hidden_size = 128: the sampled decode runs on the any-hidden-size kernels, the gradient on the torch replay; it
     equals autograd through the oracle's graph on the same picks."""
