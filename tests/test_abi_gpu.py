@@ -105,3 +105,53 @@ def test_host_buffer_entry_point_equals_module_path():
     assert np.array_equal(idx_hi, torch.stack(i_hi).cpu().numpy())
     # instances whose every category is neutral have no service with q0 > 0: 0/0 = nan in the reference's calc() too
     assert np.array_equal(rew, R.cpu().numpy(), equal_nan=True)
+
+
+def test_argument_errors_of_the_round_2_entry_points():
+    """Any-hidden-size kernels and the tensor-core training forward: negative codes before any launch, n = 0 is a no-op."""
+    from gnnpn_sc_b200 import _lib
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    n, Hh = 5, 96
+    x = torch.zeros(n, L, F, device="cuda")
+    w = torch.zeros(4 * Hh, Hh + F, device="cuda")
+    b = torch.zeros(4 * Hh, device="cuda")
+    enc = torch.empty(n, L, Hh, device="cuda")
+    c = torch.empty(n, Hh, device="cuda")
+    wsf = lib.gnnpn_pn_anyh_workspace_floats(n, Hh, F)
+    assert wsf == n * (Hh + F) + n * 4 * Hh
+    ws = torch.empty(wsf, device="cuda")
+    enc_p, dec_p = _packed()                                     # (two pack launches: before the counter is sampled)
+    before = lib.gnnpn_launch_count()
+    enc_call = lambda **kw: lib.gnnpn_lstm_encode_anyh_f32(
+        kw.get("x", x.data_ptr()), kw.get("n", n), L, kw.get("F", F), kw.get("H", Hh), w.data_ptr(), b.data_ptr(),
+        enc.data_ptr(), c.data_ptr(), ws.data_ptr(), kw.get("wsf", wsf), st)
+    assert enc_call(x=None) == -1
+    assert enc_call(H=0) == -2 and enc_call(F=33) == -2
+    assert enc_call(wsf=8) == -4
+    assert enc_call(n=0) == 0
+    dec_h = torch.empty(n, K, Hh, device="cuda")
+    idx = torch.empty(K, n, dtype=torch.int32, device="cuda")
+    wl, wp = torch.empty(n, L, device="cuda"), torch.empty(n, L, device="cuda")
+    dec_call = lambda **kw: lib.gnnpn_pn_decode_anyh_f32(
+        x.data_ptr(), enc.data_ptr(), c.data_ptr(), None, C.c_float(1.0), w.data_ptr(), b.data_ptr(), kw.get("b0", b.data_ptr()),
+        1, C.c_float(10.0), n, kw.get("L", L), F, Hh, kw.get("K", K), kw.get("N", N), dec_h.data_ptr(), idx.data_ptr(),
+        wl.data_ptr(), wp.data_ptr(), None, None, ws.data_ptr(), wsf, st)
+    assert dec_call(b0=None) == -1
+    assert dec_call(K=1, N=40, L=40) == -2                       # windows wider than 32 need hidden_size = 256
+    assert dec_call(K=5) == -2                                   # K * N != L
+    assert lib.gnnpn_pn_full_logits_anyh_f32(enc.data_ptr(), dec_h.data_ptr(), None, 1, C.c_float(10.0), n, L, Hh, K,
+                                             wl.data_ptr(), st) == -1
+    # tensor-core training forward: a batch beyond the column-split scan is refused (the caller replays on the FFMA kernels)
+    big = 8192
+    dummy = torch.empty(16, device="cuda")
+    wsb = lib.gnnpn_pn_workspace_bytes(big, H)
+    p = dummy.data_ptr()
+    rc = lib.gnnpn_pn_train_forward_tc_f32(p, enc_p.data_ptr(), dec_p.data_ptr(), None, None, None, C.c_float(1.0), 1,
+                                           C.c_float(10.0), big, L, F, H, K, N, p, p, p, p, p, p, p, p, p, p, wsb, st)
+    assert rc == -6                                              # GNNPN_EUNSUPPORTED
+    rc = lib.gnnpn_pn_train_forward_tc_f32(p, enc_p.data_ptr(), dec_p.data_ptr(), None, None, None, C.c_float(1.0), 1,
+                                           C.c_float(10.0), 64, L, F, 128, K, N, p, p, p, p, p, p, p, p, p, p, wsb, st)
+    assert rc == -2                                              # hidden_size != 256
+    assert lib.gnnpn_launch_count() == before
+    torch.cuda.synchronize()
