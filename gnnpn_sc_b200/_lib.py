@@ -111,7 +111,7 @@ def check(rc: int, what: str = "") -> None:
 
 def set_option(name: str, value: int) -> None:
     """``gnnpn_set_option``: "scan" (-1 auto / 0 CTA-pair / 1 column-split), "scan_groups", "persistent", "prof",
-    "spmm_chunk" / "spmm_dyn" (aggregation tuning)."""
+    "bptt" (0: per-step BPTT kernels), "spmm_chunk" (aggregation tuning)."""
     check(lib().gnnpn_set_option(name.encode(), int(value)), f"set_option({name})")
 
 

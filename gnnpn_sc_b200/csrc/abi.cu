@@ -35,7 +35,6 @@ static std::atomic<int>* option_slot(const char* name) {
   if (!strcmp(name, "prof")) return &o.prof;
   if (!strcmp(name, "bptt")) return &o.bptt;
   if (!strcmp(name, "spmm_chunk")) return &o.spmm_chunk;
-  if (!strcmp(name, "spmm_dyn")) return &o.spmm_dyn;
   return nullptr;
 }
 int launch_gemm_ffma(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,

@@ -129,7 +129,10 @@ CsrWorkspace csr_layout(int64_t Nn, int64_t E, int mode) {
 // GROUP lanes own one destination row; lane g of the group owns float4 columns g, g+GROUP, ...
 // Neighbour (col,val) pairs are staged 32 at a time per group through shared memory, gathers are
 // issued UNROLL rows ahead, accumulation is strictly sequential in CSR order per feature
-// (mul_rn then add_rn: bit-identical to the CPU index_add_ oracle).
+// (mul_rn then add_rn: bit-identical to the CPU index_add_ oracle).  Latency is hidden by occupancy (~60 registers, 4 CTAs of
+// 8 warps per SM), not by per-thread pipelining: a variant that requested the next round of gathers and the next batch of
+// (col, val) pairs ahead of the accumulation needed 104-128 registers and was slower everywhere (uniform F = 32: 0.91 ->
+// 0.80 of the HBM peak, in-degree 8: 0.83 -> 0.55).
 // --- shared pieces: one group's accumulation over the edge range [beg, end), and the row epilogue
 template <int GROUP, int VPL, int UNROLL>
 __device__ __forceinline__ void spmm_accumulate(float4 (&acc)[VPL], int64_t beg, int64_t end, const int32_t* __restrict__ col,
@@ -241,44 +244,6 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(
   for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   spmm_accumulate<GROUP, VPL, UNROLL>(acc, beg, end, col, val, x, ldx, F4, s_col[grp], s_val[grp], gl, gmask);
   spmm_finish_row<GROUP, VPL>(acc, row, end - beg, x, ldx, y, ldy, F4, ep, gl);
-}
-
-// Persistent variant used with the split path (graphs with skewed in-degrees): a CTA owns a contiguous range of rows and
-// its lane groups pull the next row from a shared-memory counter when they finish one, so a group that meets a row of
-// 10^2..10^3 edges does not leave the other 31 groups of its CTA (and the 3 of its warp) idle for the rest of the CTA's
-// life.  Per-row arithmetic and order are exactly those of spmm_csr_kernel (bit-identical results).
-template <int GROUP, int VPL, int UNROLL>
-__global__ void __launch_bounds__(256) spmm_csr_dyn_kernel(
-    const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
-    const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t n_rows, int F4,
-    const SpmmEpilogue ep, int64_t long_threshold, int64_t rows_per_cta) {
-  constexpr int GROUPS_PER_CTA = 256 / GROUP;
-  __shared__ int32_t s_col[GROUPS_PER_CTA][32];
-  __shared__ float s_val[GROUPS_PER_CTA][32];
-  __shared__ int s_next;
-  const int gl = threadIdx.x % GROUP, grp = threadIdx.x / GROUP;
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane / GROUP * GROUP));
-  const int leader = (int)(lane / GROUP * GROUP);
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-  const int cnt = (int)min(rows_per_cta, n_rows - r0);
-  if (threadIdx.x == 0) s_next = GROUPS_PER_CTA;      // the first row of every group is its own index
-  __syncthreads();
-  int r = grp;
-  while (r < cnt) {
-    const int64_t row = r0 + r;
-    const int64_t beg = rowptr[row], end = rowptr[row + 1];
-    if (!(long_threshold > 0 && end - beg > long_threshold)) {
-      float4 acc[VPL];
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      spmm_accumulate<GROUP, VPL, UNROLL>(acc, beg, end, col, val, x, ldx, F4, s_col[grp], s_val[grp], gl, gmask);
-      spmm_finish_row<GROUP, VPL>(acc, row, end - beg, x, ldx, y, ldy, F4, ep, gl);
-    }
-    int nr = 0;
-    if (gl == 0) nr = atomicAdd(&s_next, 1);
-    r = __shfl_sync(gmask, nr, leader);
-  }
 }
 
 // ---- long-row splitting (hub destinations: a service used by 10^5 compositions would otherwise be ONE group's
@@ -441,21 +406,21 @@ int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* val, con
     find_long_rows_kernel<<<(unsigned)(fb < 8 * kNumSMs ? fb : 8 * kNumSMs), 256, 0, st>>>(rowptr, n_rows, T, chunk_len(T), *plan);
     if ((rc = after_launch())) return rc;
   }
-  if (plan && options().spmm_dyn.load(std::memory_order_relaxed)) {
-    // persistent CTAs with dynamic row fetching (balanced under skewed in-degrees); at least 4 rows per group
-    int64_t ctas = ceil_div(n_rows, (int64_t)GROUPS_PER_CTA * 4);
-    if (ctas > 8 * kNumSMs) ctas = 8 * kNumSMs;
-    const int64_t rows_per_cta = ceil_div(n_rows, ctas);
-    if (rows_per_cta > 0x7fffffffll) return GNNPN_ERANGE;
-    spmm_csr_dyn_kernel<GROUP, VPL, UNROLL><<<(unsigned)ceil_div(n_rows, rows_per_cta), 256, 0, st>>>(
-        rowptr, col, val, x, ldx, y, ldy, n_rows, F4, ep, T, rows_per_cta);
-  } else {
-    spmm_csr_kernel<GROUP, VPL, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, ldx, y, ldy, n_rows, F4, ep,
-                                                                         plan ? T : 0);
-  }
+  spmm_csr_kernel<GROUP, VPL, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, ldx, y, ldy, n_rows, F4, ep,
+                                                                       plan ? T : 0);
   if ((rc = after_launch()) || !plan) return rc;
-  // persistent grids: they read the chunk / row counts on the device and return at once when there is no long row
-  spmm_chunk_kernel<GROUP, VPL, UNROLL><<<8 * kNumSMs, 256, 0, st>>>(rowptr, col, val, x, ldx, F4, chunk_len(T), *plan);
+  // persistent grids: they read the chunk / row counts on the device and return at once when there is no long row.  The
+  // chunk grid is exactly one resident wave (the static stride gives every CTA the same share: CTAs that only start when
+  // others finish -- 8 per SM were launched where 5-6 fit -- ran a second, mostly empty pass: 0.59 -> 0.8 of the HBM peak)
+  static const int chunk_ctas_per_sm = [] {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmm_chunk_kernel<GROUP, VPL, UNROLL>, 256, 0) != cudaSuccess || nb < 1) {
+      cudaGetLastError();
+      nb = 4;
+    }
+    return nb;
+  }();
+  spmm_chunk_kernel<GROUP, VPL, UNROLL><<<chunk_ctas_per_sm * kNumSMs, 256, 0, st>>>(rowptr, col, val, x, ldx, F4, chunk_len(T), *plan);
   if ((rc = after_launch())) return rc;
   spmm_combine_kernel<GROUP, VPL><<<kNumSMs, 256, 0, st>>>(rowptr, x, ldx, y, ldy, F4, chunk_len(T), ep, *plan);
   return after_launch();

@@ -11,7 +11,6 @@ struct Options {
   std::atomic<int> scan_groups{0};   // "scan_groups": 0 auto, 1 / 2 instance groups per column-split cluster            [GNNPN_COLSPLIT_G]
   std::atomic<int> persistent{3};    // "persistent": bit 0 encoder, bit 1 decoder run as ONE persistent launch           [GNNPN_SEQ]
   std::atomic<int> spmm_chunk{0};    // "spmm_chunk": edges per chunk of a split row, 0 = auto (threshold / 8, at least 32)   (tuning)
-  std::atomic<int> spmm_dyn{0};      // "spmm_dyn": 1 = persistent main kernel with dynamic row fetching in the split path     (tuning)
   std::atomic<int> bptt{1};          // "bptt": 1 = REINFORCE backward as two persistent cluster scans, 0 = two launches per step   [GNNPN_BPTT]
   std::atomic<int> prof{0};          // "prof": in-kernel wait-cycle counters, printed to stderr (debug, synchronous)     [GNNPN_SEQ_PROF]
 };
