@@ -28,6 +28,7 @@ class GreedyLowHigh:
         self._stage = [None, None]            # device staging buffers (double buffer)
         self._ready = [torch.cuda.Event(), torch.cuda.Event()]
         self._consumed = [None, None]
+        self._out = [None, None]              # pinned result buffers (double buffer)
 
     def _upload(self, slot: int, x_host: torch.Tensor) -> None:
         buf = self._stage[slot]
@@ -43,13 +44,25 @@ class GreedyLowHigh:
 
     @torch.no_grad()
     def run(self, host_batches: Iterable[torch.Tensor]) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
-        """Yields ``(idx_high int32 [K, n] (cpu), reward fp32 [n] (cpu))`` per host batch ``fp32 [n, L, F]``."""
+        """Yields ``(idx_high int32 [K, n] (cpu), reward fp32 [n] (cpu))`` per host batch ``fp32 [n, L, F]``, in order.
+        Software-pipelined by one batch: the kernels of batch i+1 are enqueued before the host waits for the results of
+        batch i (asynchronous device->host copies into pinned buffers + an event), so the GPU never idles while the host
+        prepares the next launches; the input range flag travels with the results (no mid-batch sync)."""
         it = iter(host_batches)
         nxt = next(it, None)
         slot = 0
         if nxt is not None:
             self._upload(slot, nxt)
         main = torch.cuda.current_stream(self.device)
+        pending = None                                    # (pinned idx, pinned reward, pinned flag, event) of the previous batch
+
+        def finish(p):
+            idx_pin, r_pin, flag_pin, ev = p
+            ev.synchronize()
+            if flag_pin is not None and int(flag_pin[0]):
+                self.low.actor.raise_if_out_of_range(flag_pin)
+            return idx_pin.clone(), r_pin.clone()         # the pinned buffers are reused two batches later
+
         while nxt is not None:
             cur_slot = slot
             nxt = next(it, None)
@@ -57,13 +70,26 @@ class GreedyLowHigh:
                 self._upload(cur_slot ^ 1, nxt)
             main.wait_event(self._ready[cur_slot])
             x = self._stage[cur_slot]
-            latent, R, idx = low_high(self.low, self.high, x, self._side)
+            latent, R, idx, flag = low_high(self.low, self.high, x, self._side, check="defer")
             idx32 = torch.stack(idx).to(torch.int32)
+            out = self._out[cur_slot]
+            if out is None or out[0].shape != idx32.shape:
+                out = self._out[cur_slot] = (torch.empty(idx32.shape, dtype=torch.int32).pin_memory(),
+                                             torch.empty(R.shape, dtype=torch.float32).pin_memory(),
+                                             torch.zeros(1, dtype=torch.int32).pin_memory())
+            out[0].copy_(idx32, non_blocking=True)
+            out[1].copy_(R, non_blocking=True)
+            if flag is not None:
+                out[2].copy_(flag, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(main)
             self._consumed[cur_slot] = ev
-            yield idx32.cpu(), R.cpu()                    # device->host reads synchronise this batch
+            if pending is not None:
+                yield finish(pending)
+            pending = (out[0], out[1], out[2] if flag is not None else None, ev)
             slot = cur_slot ^ 1
+        if pending is not None:
+            yield finish(pending)
 
 
 def _own_enc_buffer(actor, n: int, L: int, F: int, device):
@@ -81,12 +107,13 @@ def _own_enc_buffer(actor, n: int, L: int, F: int, device):
         actor.enc_buffer = torch.empty(need, device=device, dtype=torch.float32)
 
 
-def low_high(low, high, x, side_stream, own_buffers: bool = True):
+def low_high(low, high, x, side_stream, own_buffers: bool = True, check: str = "now"):
     """PNLow greedy -> latent -> PNHigh greedy on the rows ``x`` (trainPNHigh.py:131-144).  The two encoders are independent
     (same rows, different weights): PNHigh's is enqueued on ``side_stream`` and runs concurrently with PNLow's whenever the
     batch leaves SMs free (one encoder occupies ceil(n / 128) SMs); the decoders follow on the current stream.
     ``own_buffers``: both actors keep their encodings buffer across calls (``actor.last["enc_out"]`` of a call is then only
-    valid until the next call).  The input range flag is read ONCE, after everything is enqueued (no mid-pipeline sync).
+    valid until the next call).  The input range flag is read ONCE, after everything is enqueued (no mid-pipeline sync);
+    ``check="defer"`` does not read it at all and returns it as a fourth value (device int32 [1] or None) for the caller.
     Returns (latent, reward, K-list of picks)."""
     main = torch.cuda.current_stream(x.device)
     if own_buffers:
@@ -110,8 +137,11 @@ def low_high(low, high, x, side_stream, own_buffers: bool = True):
     finally:
         low.actor.defer_range_check = deferred
     R, _, _, idx, _ = high(x, None, latent, sample="greedy", training="RL", encoded=enc_hi)
+    flag = low.actor.last["range_flag"]
+    if check == "defer":
+        return latent, R, idx, flag
     if not deferred:
-        low.actor.raise_if_out_of_range(low.actor.last["range_flag"])
+        low.actor.raise_if_out_of_range(flag)
     return latent, R, idx
 
 
