@@ -247,10 +247,12 @@ def pipeline_block(dev, shape: str, n: int, steps: int, warmup: int):
     def device_step():
         out.update(pipe.compose(batch, *cons))
 
-    def e2e_step():
-        b, c = upload()
-        r = pipe.compose(b, *c)
-        return r["services"].to(torch.int32).cpu(), r["objective"].cpu()
+    def e2e_steps(k):
+        # the public host-batch API: every step uploads its request graphs + constraint tensors from pinned host memory (copy
+        # stream, under the previous step's kernels) and reads the chosen services + objective back to the host
+        for res in pipe.run((host, *cons_host) for _ in range(k)):
+            pass
+        return res
 
     def timed(fn, k):
         torch.cuda.synchronize()
@@ -275,8 +277,9 @@ def pipeline_block(dev, shape: str, n: int, steps: int, warmup: int):
         runs.append(evs)
     torch.cuda.synchronize()
     stage = {k: sum(evs[i].elapsed_time(evs[i + 1]) for evs in runs[1:]) / steps for i, k in enumerate(names)}
-    e2e_step()
-    e2e_ms = timed(e2e_step, max(2, steps // 2))
+    e2e_steps(2)
+    k_e2e = max(6, 2 * steps)                            # the first upload of a run is not overlapped: amortise it
+    e2e_ms = timed(lambda: e2e_steps(k_e2e), 1) / k_e2e
     d2h = n * K * 4 + n * 4
     return {"workload": f"ml2pn_pipeline_{shape}", "K": K, "N": N, "L": K * N, "S": S, "gcn_layers": cfg["gcn"],
             "instances": n, "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "instances/s", "stage_ms": stage,

@@ -197,9 +197,65 @@ class ML2PN:
         self.N = low.sNumber
         self.service_enc = net.service_encodings(service_sample)          # static: encoded once
         self._side = torch.cuda.Stream(self.device)
+        self._copy = torch.cuda.Stream(self.device)                       # host->device uploads of run()
 
     @torch.no_grad()
-    def compose(self, request_batch, local_bounds, used, global_bounds, stage_events=None):
+    def run(self, host_batches):
+        """The pipeline from HOST batches: every item is ``(request_batch, local_bounds, used, global_bounds)`` with pinned
+        host tensors (``trainML.collate_requests(..., pin=True)``, ``constraint_arrays``).  Yields, in order,
+        ``(services int32 [n, K] (cpu), objective fp32 [n] (cpu))``.  The upload of batch i+1 runs on a copy stream under the
+        kernels of batch i, and the results of batch i are waited for only after batch i+1 has been enqueued."""
+        main = torch.cuda.current_stream(self.device)
+
+        def upload(item):
+            rb, lb, us, gb = item
+            with torch.cuda.stream(self._copy):
+                dev = type(rb)(x=rb.x.to(self.device, non_blocking=True), edge_index=rb.edge_index.to(self.device, non_blocking=True),
+                               batch=rb.batch.to(self.device, non_blocking=True), num_graphs=rb.num_graphs)
+                cons = [t.to(self.device, non_blocking=True) for t in (lb, us, gb)]
+                ev = torch.cuda.Event()
+                ev.record(self._copy)
+            return dev, cons, ev
+
+        def finish(p):
+            svc_pin, obj_pin, flag_pin, ev, keep = p
+            ev.synchronize()
+            if flag_pin is not None and int(flag_pin[0]):
+                self.low.actor.raise_if_out_of_range(flag_pin)
+            return svc_pin.clone(), obj_pin.clone()
+
+        it = iter(host_batches)
+        nxt = next(it, None)
+        up = upload(nxt) if nxt is not None else None
+        pending, out, slot = None, [None, None], 0
+        while up is not None:
+            dev, cons, ev_up = up
+            nxt = next(it, None)
+            up = upload(nxt) if nxt is not None else None    # next upload overlaps this batch's kernels
+            main.wait_event(ev_up)
+            for t in (dev.x, dev.edge_index, dev.batch, *cons):
+                t.record_stream(main)                        # allocated on the copy stream, consumed on the main one
+            r = self.compose(dev, *cons, defer_check=True)
+            svc, obj, flag = r["services"].to(torch.int32), r["objective"], r["range_flag"]
+            if out[slot] is None or out[slot][0].shape != svc.shape:
+                out[slot] = (torch.empty(svc.shape, dtype=torch.int32).pin_memory(),
+                             torch.empty(obj.shape, dtype=torch.float32).pin_memory(),
+                             torch.zeros(1, dtype=torch.int32).pin_memory())
+            out[slot][0].copy_(svc, non_blocking=True)
+            out[slot][1].copy_(obj, non_blocking=True)
+            if flag is not None:
+                out[slot][2].copy_(flag, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            if pending is not None:
+                yield finish(pending)
+            pending = (out[slot][0], out[slot][1], out[slot][2] if flag is not None else None, ev, (dev, cons))
+            slot ^= 1
+        if pending is not None:
+            yield finish(pending)
+
+    @torch.no_grad()
+    def compose(self, request_batch, local_bounds, used, global_bounds, stage_events=None, defer_check: bool = False):
         """``request_batch``: collated request graphs (x, edge_index, batch) on the device; constraint tensors from
         ``constraint_arrays``.  Returns scores, PN rows, picked service ids per row, PNHigh picks and objective.
         ``stage_events``: optional list that receives five CUDA events recorded on the current stream at the stage
@@ -218,11 +274,14 @@ class ML2PN:
         rows, picked = ops.select_candidates(scores, self.svc_qos, self.cat_ptr, local_bounds, used, global_bounds,
                                              self.N, with_category=False, return_picked=True)  # [B, K*N, 8]
         mark()
-        latent, R, idx = low_high(self.low, self.high, rows, self._side)
+        # defer_check: the input range flag is returned (``range_flag``) instead of being read here (one host sync less)
+        latent, R, idx, flag = low_high(self.low, self.high, rows, self._side, check="defer")
+        if not defer_check:
+            self.low.actor.raise_if_out_of_range(flag)
         idx = torch.stack(idx)                                                                # [K, B]
         services = picked.gather(1, idx.t())                                                  # chosen service per task (-1: unused)
         mark()
         viol, obj, _ = ops.pn_reward(rows, idx.to(torch.int32))
         mark()
         return {"scores": scores, "rows": rows, "picked": picked, "idx_high": idx, "services": services,
-                "reward": R, "violations": viol, "objective": obj}
+                "reward": R, "violations": viol, "objective": obj, "range_flag": flag}

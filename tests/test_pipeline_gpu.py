@@ -100,3 +100,31 @@ def test_ml2pn_pipeline_equals_stage_by_stage():
         for k in range(K):
             if svc[b, k] >= 0:
                 assert ptr[k] <= svc[b, k] < ptr[k + 1]
+
+
+def test_ml2pn_run_from_host_batches_equals_compose():
+    """ML2PN.run (pinned host batches, uploads on a copy stream, results pipelined by one batch) yields, in order, exactly
+    what compose() gives on the same batches -- including a last batch of another size."""
+    from gnnpn_sc_b200 import modelPN as M, trainML
+    from gnnpn_sc_b200.pipeline import ML2PN, constraint_arrays
+    K, S, N, n = 10, 200, 4, 12
+    ds, samples, net = _dataset(K, S, n, seed=6)
+    cfg = po.PNConfig(seq_len=K * N, s_number=N, s_category=K)
+    nets = []
+    for level, seed in (("Low", 3), ("High", 4)):
+        m = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level=level)
+        m.load_state_dict(po.make_state_dict(cfg, seed))
+        nets.append(m.cuda().eval())
+    dev_sample = type(samples[0])(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in vars(samples[0]).items()})
+    pipe = ML2PN(net, nets[0], nets[1], dev_sample, ds["serviceFeature"], "cuda")
+    cons = constraint_arrays(ds["nodefeatures"], K)
+    parts = [(0, 5), (5, 10), (10, 12)]                      # three batches, the last one smaller
+    host = [(trainML.collate_requests(samples[a:b], pin=True), *[torch.from_numpy(c[a:b]).pin_memory() for c in cons])
+            for a, b in parts]
+    got = list(pipe.run(host))
+    assert len(got) == len(parts)
+    for (a, b), (svc, obj) in zip(parts, got):
+        rb = trainML.collate_requests(samples[a:b], device="cuda")
+        want = pipe.compose(rb, *[torch.from_numpy(c[a:b]).cuda() for c in cons])
+        assert torch.equal(svc, want["services"].to(torch.int32).cpu())
+        assert torch.equal(obj, want["objective"].cpu(), ) or torch.allclose(obj, want["objective"].cpu(), equal_nan=True)
