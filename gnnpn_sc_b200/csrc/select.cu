@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(
 // category), two entries per lane, bitonic network through register shuffles -- no shared memory, no block barriers
 // (the block version above spends its time in 21 __syncthreads stages with a quarter of its threads active).
 constexpr int kSelWarps = 4;
+constexpr int kSelTopN = 8;          // N at or below this: top-N selection rounds instead of the full sorting network
 
 __device__ __forceinline__ void sel_cex(float& k, int& id, float ok, int oid, bool keep_first) {
   const bool mine_first = sel_before(k, id, ok, oid);
@@ -136,6 +137,29 @@ __global__ void __launch_bounds__(32 * kSelWarps) select_candidates_warp_kernel(
     }
   }
   const int count = __popc(__ballot_sync(0xffffffffu, id[0] != 0x7fffffff)) + __popc(__ballot_sync(0xffffffffu, id[1] != 0x7fffffff));
+  const int rounds = min(N, count);                       // sorted positions the rows can refer to (row j -> j % count)
+  int sorted_id = 0x7fffffff;                             // lane r: id at sorted position r (selection path)
+  if (N <= kSelTopN) {
+    // Only the first min(N, count) positions of the order are needed (N = 5 for the QWS sections): `rounds` warp-wide
+    // arg-best reductions instead of the full 21-stage sorting network -- same total order (score desc, id asc; ids are
+    // unique), so the same rows; about half the instructions at N = 5.
+    if (sel_before(k[1], id[1], k[0], id[0])) {            // the lane's better entry first
+      const float tk = k[0]; const int ti = id[0];
+      k[0] = k[1]; id[0] = id[1]; k[1] = tk; id[1] = ti;
+    }
+    for (int r = 0; r < rounds; ++r) {
+      float bk = k[0];
+      int bi = id[0];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, bk, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (sel_before(ok, oi, bk, bi)) { bk = ok; bi = oi; }
+      }
+      if (lane == r) sorted_id = bi;
+      if (id[0] == bi) { k[0] = k[1]; id[0] = id[1]; k[1] = -INFINITY; id[1] = 0x7fffffff; }   // consume the winner
+    }
+  } else {
   // bitonic sort of the 64 entries e = lane + 32 h, best first
 #pragma unroll
   for (int size = 2; size <= 64; size <<= 1) {
@@ -158,6 +182,7 @@ __global__ void __launch_bounds__(32 * kSelWarps) select_candidates_warp_kernel(
       }
     }
   }
+  }
   const int F = 8 + (with_category ? 1 : 0);
   float tail[4] = {0.f, 0.f, 0.f, 0.f};
   if (c == 0) {
@@ -166,13 +191,14 @@ __global__ void __launch_bounds__(32 * kSelWarps) select_candidates_warp_kernel(
   }
   // row j takes the entry at sorted position j % count (self-duplication padding = cyclic repetition)
   const int pos = count > 0 ? lane % count : 0;
+  const int vs = __shfl_sync(0xffffffffu, sorted_id, pos & 31);
   const int v0 = __shfl_sync(0xffffffffu, id[0], pos & 31), v1 = __shfl_sync(0xffffffffu, id[1], pos & 31);
   if (lane < N) {
     float* r = rows + ((b * K + c) * (int64_t)N + lane) * F;
     int sid = -1;
     float4 q = make_float4(0.f, 1.f, 1.f, 1.f);           // neutral row (loadData.py:148)
     if (count > 0) {
-      sid = pos < 32 ? v0 : v1;
+      sid = N <= kSelTopN ? vs : (pos < 32 ? v0 : v1);
       q = __ldg(reinterpret_cast<const float4*>(svc_qos) + sid);
     }
     if (with_category) *r++ = (float)c;

@@ -433,16 +433,18 @@ def woa_search(qos, base, size, klen, bounds, pops, best_fit, best_ref, best_vec
 
 
 def select_candidates(scores, svc_qos, cat_ptr, local_bounds, used, global_bounds, N: int, with_category: bool = False,
-                      return_picked: bool = False):
-    """ML scores ``[n, S]`` -> PN input rows ``[n, K*N, 8(+1)]`` (see ``gnnpn_select_candidates_f32``)."""
+                      return_picked: bool = False, max_category_size: Optional[int] = None):
+    """ML scores ``[n, S]`` -> PN input rows ``[n, K*N, 8(+1)]`` (see ``gnnpn_select_candidates_f32``).
+    ``max_category_size``: the largest category (static per dataset); None reads it from ``cat_ptr`` -- one host sync."""
     scores = _f32(scores, "scores")
     n, S = scores.shape
     K = cat_ptr.numel() - 1
     svc_qos = _f32(svc_qos, "svc_qos")
     assert svc_qos.shape == (S, 4) and local_bounds.shape == (n, K, 4) and used.shape == (n, K)
     cat_ptr = cat_ptr.to(torch.int32).contiguous()
-    sizes = cat_ptr[1:] - cat_ptr[:-1]
-    max_size = int(sizes.max().item())
+    if max_category_size is None:
+        max_category_size = int((cat_ptr[1:] - cat_ptr[:-1]).max().item())
+    max_size = int(max_category_size)
     rows = torch.empty(n, K * N, 9 if with_category else 8, device=scores.device, dtype=torch.float32)
     picked = torch.empty(n, K * N, device=scores.device, dtype=torch.int32) if return_picked else None
     check(lib().gnnpn_select_candidates_f32(
@@ -474,7 +476,10 @@ def csr_build(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], n_n
     ws = torch.empty(nbytes.value, device=dev, dtype=torch.uint8)
     check(lib().gnnpn_csr_build(ei.data_ptr(), _ptr(w), E, n_nodes, mode, rowptr.data_ptr(), col.data_ptr(),
                                 _ptr(val), nnz.data_ptr(), ws.data_ptr(), nbytes.value, _stream()), "csr_build")
-    total = int(nnz.item())
+    # plain mode adds nothing (no self loops): every valid edge is one entry, and entries with an out-of-range endpoint sort
+    # behind rowptr[n] where no kernel reads them -- the count is E without asking the device.  gcn_norm's count depends on
+    # the self loops already present: one 8-byte read (the static service graph is built once and cached).
+    total = E if mode == CSR_PLAIN else int(nnz.item())
     return rowptr, col[:total], (None if val is None else val[:total])
 
 

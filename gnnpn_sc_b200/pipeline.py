@@ -193,6 +193,7 @@ class ML2PN:
         qos, ptr = service_arrays(serviceFeature)
         self.svc_qos = torch.from_numpy(qos).to(self.device)
         self.cat_ptr = torch.from_numpy(ptr).to(self.device)
+        self.max_category_size = int((ptr[1:] - ptr[:-1]).max())         # static: no device read per call
         self.K = len(ptr) - 1
         self.N = low.sNumber
         self.service_enc = net.service_encodings(service_sample)          # static: encoded once
@@ -272,7 +273,8 @@ class ML2PN:
         scores = self.net.score_requests(request_batch, self.service_enc)                     # [B, S]
         mark()
         rows, picked = ops.select_candidates(scores, self.svc_qos, self.cat_ptr, local_bounds, used, global_bounds,
-                                             self.N, with_category=False, return_picked=True)  # [B, K*N, 8]
+                                             self.N, with_category=False, return_picked=True,
+                                             max_category_size=self.max_category_size)          # [B, K*N, 8]
         mark()
         # defer_check: the input range flag is returned (``range_flag``) instead of being read here (one host sync less)
         latent, R, idx, flag = low_high(self.low, self.high, rows, self._side, check="defer")
