@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kSelThreads) select_candidates_kernel(
 // category), two entries per lane, bitonic network through register shuffles -- no shared memory, no block barriers
 // (the block version above spends its time in 21 __syncthreads stages with a quarter of its threads active).
 constexpr int kSelWarps = 4;
-constexpr int kSelTopN = 8;          // N at or below this: top-N selection rounds instead of the full sorting network
+constexpr int kSelTopN = 16;         // N at or below this: top-N selection rounds instead of the full sorting network
 
 __device__ __forceinline__ void sel_cex(float& k, int& id, float ok, int oid, bool keep_first) {
   const bool mine_first = sel_before(k, id, ok, oid);

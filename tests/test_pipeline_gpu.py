@@ -32,7 +32,7 @@ def _mirror_rows(ds, rankings, N):
                        for nf, rk in zip(ds["nodefeatures"], rankings)], dtype=np.float32)
 
 
-@pytest.mark.parametrize("K,S,N", [(12, 300, 5), (47, 2507, 5), (6, 40, 10), (3, 3000, 1000), (8, 400, 8), (5, 300, 3), (9, 500, 9)])
+@pytest.mark.parametrize("K,S,N", [(12, 300, 5), (47, 2507, 5), (6, 40, 10), (3, 3000, 1000), (8, 400, 8), (5, 300, 3), (9, 500, 16), (7, 420, 17), (4, 240, 32)])
 def test_select_candidates_matches_loaddatapn(K, S, N):
     from gnnpn_sc_b200 import ops
     from gnnpn_sc_b200.pipeline import constraint_arrays, service_arrays
