@@ -226,16 +226,33 @@ struct GemmEpilogue {
   __device__ void chunk(int, int col0, int ncols, const float* v) {
     if (!ok) return;
     float* out = p.C + (int64_t)blockIdx.y * p.split_stride + row * p.ldc;
+    // a thread owns 32 consecutive columns of ONE row: with 8-float-aligned rows it writes whole 32-byte sectors (one
+    // 256-bit store per 8 columns); scalar stores put 32 different rows into every warp-wide store instruction -- 8x the
+    // L2 write transactions (the [18,944 x 2,507] readout of the ML stage: 0.43 -> 0.1x ms)
+    const bool vec = (p.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 31u) == 0 && (p.split_stride & 7) == 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int n = col0 + j;
-      if (j < ncols && n < p.N) {
-        float r = v[j];
-        if (p.bias) r += __ldg(p.bias + n);
-        if (p.scale) r = fmaf(r, __ldg(p.scale + n), __ldg(p.shift + n));
-        if (p.act == GNNPN_ACT_RELU) r = fmaxf(r, 0.f);
-        else if (p.act == GNNPN_ACT_SIGMOID) r = sigmoid_accurate(r);
-        out[n] = r;
+    for (int j0 = 0; j0 < 32; j0 += 8) {
+      float r8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = col0 + j0 + j;
+        float r = v[j0 + j];
+        if (j0 + j < ncols && n < p.N) {
+          if (p.bias) r += __ldg(p.bias + n);
+          if (p.scale) r = fmaf(r, __ldg(p.scale + n), __ldg(p.shift + n));
+          if (p.act == GNNPN_ACT_RELU) r = fmaxf(r, 0.f);
+          else if (p.act == GNNPN_ACT_SIGMOID) r = sigmoid_accurate(r);
+        }
+        r8[j] = r;
+      }
+      const int n0 = col0 + j0;
+      if (vec && j0 + 8 <= ncols && n0 + 8 <= p.N) {
+        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out + n0), "f"(r8[0]), "f"(r8[1]), "f"(r8[2]),
+                     "f"(r8[3]), "f"(r8[4]), "f"(r8[5]), "f"(r8[6]), "f"(r8[7]) : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j0 + j < ncols && n0 + j < p.N) out[n0 + j] = r8[j];
       }
     }
   }

@@ -360,7 +360,7 @@ class Net(nn.Module):
         """sigmoid(x_req . service_enc^T) ``[B, S]`` for a collated batch of request graphs (``data.x``,
         ``data.edge_index``, ``data.batch``) against cached ``service_encodings``."""
         x, _ = self._encode_requests(data)
-        return ops.gemm_bias_act(x, service_enc, act="sigmoid")
+        return ops.gemm_bias_act(x, service_enc, act="sigmoid", pad_ld=True)       # [B, S] view of rows padded to 8 floats
 
     def _fold(self, bn: BatchNorm1d):
         if self.training:

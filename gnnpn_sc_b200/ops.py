@@ -436,7 +436,8 @@ def select_candidates(scores, svc_qos, cat_ptr, local_bounds, used, global_bound
                       return_picked: bool = False, max_category_size: Optional[int] = None):
     """ML scores ``[n, S]`` -> PN input rows ``[n, K*N, 8(+1)]`` (see ``gnnpn_select_candidates_f32``).
     ``max_category_size``: the largest category (static per dataset); None reads it from ``cat_ptr`` -- one host sync."""
-    scores = _f32(scores, "scores")
+    if not (scores.is_cuda and scores.dtype == torch.float32 and scores.stride(1) == 1):
+        scores = _f32(scores, "scores")                    # rows may be padded (stride(0) > S): no copy then
     n, S = scores.shape
     K = cat_ptr.numel() - 1
     svc_qos = _f32(svc_qos, "svc_qos")
@@ -536,16 +537,24 @@ def spmm_csr(rowptr, col, val, x, n_rows: Optional[int] = None, self_scale: floa
     return y
 
 
-def gemm_bias_act(a, w, bias=None, scale=None, shift=None, act=None, out=None, impl: Optional[str] = None) -> torch.Tensor:
+def gemm_bias_act(a, w, bias=None, scale=None, shift=None, act=None, out=None, impl: Optional[str] = None,
+                  pad_ld: bool = False) -> torch.Tensor:
     """``act((a @ w.T + bias) * scale + shift)`` with ``w`` in nn.Linear layout [N,K].
 
-    ``impl="tc"`` (default for M >= TC_GEMM_MIN_ROWS): tcgen05 3xTF32; ``"ffma"``: strict fp32 CUDA cores."""
+    ``impl="tc"`` (default for M >= TC_GEMM_MIN_ROWS): tcgen05 3xTF32; ``"ffma"``: strict fp32 CUDA cores.
+    ``pad_ld``: allocate the result with rows padded to a multiple of 8 floats and return the ``[:, :N]`` view (row stride
+    != N): the tensor-core epilogue then writes whole 32-byte sectors -- for wide outputs whose N is not a multiple of 8."""
     a = _f32(a, "a")
     w = _f32(w, "w")
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K
-    c = torch.empty(M, N, device=a.device, dtype=torch.float32) if out is None else out
+    if out is not None:
+        c = out
+    elif pad_ld and N % 8:
+        c = torch.empty(M, (N + 7) // 8 * 8, device=a.device, dtype=torch.float32)[:, :N]
+    else:
+        c = torch.empty(M, N, device=a.device, dtype=torch.float32)
     impl = impl or (DEFAULT_IMPL if M >= TC_GEMM_MIN_ROWS else "ffma")
     ws = None
     if impl == "tc":

@@ -142,6 +142,21 @@ def test_node_transform_gemm(M, N, K, impl):
     assert err <= tol, err
 
 
+def test_gemm_padded_rows_equal_dense_rows():
+    """``pad_ld=True`` (rows padded to 8 floats so the tensor-core epilogue stores whole sectors: the ML stage's
+    [B, 2507] readout) returns a strided view with exactly the values of the dense result."""
+    from gnnpn_sc_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for M, N, K in ((5000, 2507, 128), (700, 331, 300)):
+        a, w, b = torch.randn(M, K, generator=g).cuda(), (torch.randn(N, K, generator=g) / K ** 0.5).cuda(), torch.randn(N, generator=g).cuda()
+        dense = ops.gemm_bias_act(a, w, bias=b, act="sigmoid", impl="tc")
+        padded = ops.gemm_bias_act(a, w, bias=b, act="sigmoid", impl="tc", pad_ld=True)
+        assert padded.shape == dense.shape and padded.stride(0) % 8 == 0 and padded.stride(0) >= N
+        assert torch.equal(padded, dense)
+        ref = torch.sigmoid(torch.nn.functional.linear(a.double(), w.double(), b.double()))
+        assert float((dense.double() - ref).abs().max()) <= 1e-5
+
+
 @pytest.mark.parametrize("mag", [1.0e4, 1.0e6])
 def test_node_transform_out_of_range_inputs_fall_back(mag):
     """|a| * 2^4 >= 65504 overflows the fp16 split: the converters raise the workspace flag and the guarded strict-fp32
