@@ -57,9 +57,12 @@ template <int G> struct Layout {
   static constexpr uint32_t OFF_RING = OFF_AX + G * AX_BYTES;
   static constexpr uint32_t OFF_BIAS = OFF_RING + NSLOT * BLK_BYTES;
   static constexpr uint32_t OFF_BAR = OFF_BIAS + 2 * TILE_N * 4;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int BAR_BYTES = G <= 2 ? 256 : 512;
+  static constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = G * TILE_N <= 128 ? 128 : (G * TILE_N <= 256 ? 256 : 512);    // power of two
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
-  static_assert(8 * (1 + 2 * NSLOT + G * (3 + 2 * KB_H)) + 4 <= 256, "barrier block overflow");
+  static_assert(8 * (1 + 2 * NSLOT + G * (3 + 2 * KB_H)) + 4 <= BAR_BYTES, "barrier block overflow");
+  static_assert(G * TILE_N <= 512, "accumulators exceed TMEM");
 };
 constexpr uint32_t W_BYTES = 2 * KB_H * BLK_BYTES + 2 * TILE_N * XROW_BYTES;
 
@@ -140,7 +143,7 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, G * TILE_N);
+  if (warp == 2) tmem_alloc(tmem_slot, LY::TMEM_COLS);
   // transformed biases of this CTA's 128 gate columns (two sets: step 0, steps >= 1): (i,f,o) * -log2e, g * -2log2e
   for (int i = threadIdx.x; i < 2 * TILE_N; i += THREADS) {
     const int col = i & (TILE_N - 1);
@@ -482,7 +485,7 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
   __syncwarp();
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 2) tmem_dealloc(tmem_base, G * TILE_N);
+  if (warp == 2) tmem_dealloc(tmem_base, LY::TMEM_COLS);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -503,7 +506,7 @@ static EncodeTiledFn encode_fn() {
 }  // namespace cs
 
 size_t tc_colsplit_scratch_bytes(int64_t n) {
-  const int64_t groups = (ceil_div(n, cs::BM) + 1) & ~int64_t(1);          // two-group clusters round the group count up to even
+  const int64_t groups = ceil_div(ceil_div(n, cs::BM), 6) * 6;             // 1 / 2 / 3 groups per cluster: whole clusters either way
   return (size_t)groups * 2 * 2 * cs::BM * kH * sizeof(__half);
 }
 
@@ -527,8 +530,9 @@ static int max_active_clusters() {
 }
 int tc_colsplit_max_active_clusters() { return max_active_clusters(); }
 
-// GNNPN_COLSPLIT: -1 (default) = automatic, 0 = never, 1 = always; GNNPN_COLSPLIT_G = 1 / 2 forces the groups per cluster of
-// the encoder (default: 2 as soon as one-group clusters would need a second wave).  Automatic (measured on a B200 with 15
+// GNNPN_COLSPLIT: -1 (default) = automatic, 0 = never, 1 = always; GNNPN_COLSPLIT_G = 1 / 2 / 3 forces the groups per cluster of
+// the encoder (default: 2 as soon as one-group clusters would need a second wave; 3 is chosen by pipeline.low_high for
+// 16..21 groups so that PNLow's and PNHigh's encoders -- 7 clusters each -- run side by side on the 15 cluster slots).  Automatic (measured on a B200 with 15
 // co-resident clusters, profiles/r01_colsplit_timing.jsonl, r01_pn_batch_sweep.jsonl): a step of the column-split scan
 // costs ~6.6 us per wave (~7 us with two groups per cluster) against ~16.7 us (encoder) / ~37 us (fused decoder) for
 // the CTA-pair scan at any batch up to 18,944.  Encoder: one-group clusters up to 15 groups of 128, two-group clusters up to
@@ -548,7 +552,7 @@ bool tc_colsplit_wanted_encode(int64_t n) {
 }
 static int colsplit_groups_per_cluster(int64_t n) {
   const int g = options().scan_groups.load(std::memory_order_relaxed);
-  if (g == 1 || g == 2) return g;
+  if (g >= 1 && g <= 3) return g;
   return ceil_div(n, cs::BM) > (int64_t)max_active_clusters() ? 2 : 1;
 }
 
@@ -637,8 +641,11 @@ int tc_colsplit_encode(const SeqEncodeArgs& a, void* scratch, cudaStream_t st) {
   p.c = a.c_state;
   p.h_out = a.enc_out; p.h_out_inst_ld = (int64_t)a.L * kH;
   p.save_gates = a.save_gates; p.save_c = a.save_c;
-  return colsplit_groups_per_cluster(a.n) == 2 ? cs::launch<false, 2>(a.packed, p, scratch, st)
-                                               : cs::launch<false, 1>(a.packed, p, scratch, st);
+  switch (colsplit_groups_per_cluster(a.n)) {
+    case 3: return cs::launch<false, 3>(a.packed, p, scratch, st);
+    case 2: return cs::launch<false, 2>(a.packed, p, scratch, st);
+    default: return cs::launch<false, 1>(a.packed, p, scratch, st);
+  }
 }
 
 int tc_colsplit_decode(const SeqDecodeArgs& a, void* scratch, cudaStream_t st) {

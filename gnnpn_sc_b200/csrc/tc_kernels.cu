@@ -550,10 +550,11 @@ int tc_lstm_default_f16() {
 
 // sized for the larger (tf32) layout so one query serves both operand kinds
 // (also covers the persistent kernels' blocked cell-state scratch, tc_seq_scratch_floats(n))
+size_t tc_colsplit_scratch_bytes(int64_t n);
 size_t tc_lstm_workspace_bytes(int64_t n) {
   const size_t step = (size_t)4 * n * kKp * sizeof(float) + 1024;
   const size_t seq = (size_t)((n + 255) / 256) * 256 * kH * sizeof(float) + 1024;
-  const size_t colsplit = (size_t)((((n + 127) / 128) + 1) & ~int64_t(1)) * 4 * 128 * kH * 2 + 1024;   // tc_colsplit_scratch_bytes(n)
+  const size_t colsplit = tc_colsplit_scratch_bytes(n) + 1024;
   const size_t m = step > seq ? step : seq;
   return m > colsplit ? m : colsplit;
 }

@@ -115,6 +115,7 @@ def low_high(low, high, x, side_stream, own_buffers: bool = True, check: str = "
     valid until the next call).  The input range flag is read ONCE, after everything is enqueued (no mid-pipeline sync);
     ``check="defer"`` does not read it at all and returns it as a fourth value (device int32 [1] or None) for the caller.
     Returns (latent, reward, K-list of picks)."""
+    from . import ops
     main = torch.cuda.current_stream(x.device)
     if own_buffers:
         for m in (low, high):
@@ -122,14 +123,29 @@ def low_high(low, high, x, side_stream, own_buffers: bool = True, check: str = "
     # two streams only while both encoders fit on the machine together (one CTA per 128 rows, 148 SMs).  At a full wave
     # the second encoder's CTAs would interleave with PNLow's decoder and delay it: measured 15.5 ms against 14.5 ms
     # back to back at n = 18,944 (profiles/r02_pn_batch_sweep.jsonl)
-    concurrent = 2 * ((x.shape[0] + 127) // 128) <= NUM_SMS
-    if concurrent:
-        side_stream.wait_stream(main)                     # x is ready on the main stream; last call's decoders are done
-        with torch.cuda.stream(side_stream):
+    groups = (x.shape[0] + 127) // 128
+    concurrent = 2 * groups <= NUM_SMS
+    # Column-split encoders (<= 30 groups): a B200 holds 15 of their 8-CTA clusters at a time.  Both networks' encoders run side
+    # by side only if together they need at most 15 clusters, so the groups per cluster are chosen for that: 8..14 groups ->
+    # two per cluster (<= 7 clusters each, 9.1 us per step instead of two sequential scans at 6.6 us), 15..21 -> three per
+    # cluster (<= 7 each, ~12.5 us per step); above that the automatic choice (two per cluster, one encoder after the other).
+    g_opt = 0
+    if ops.get_option("scan") == -1 and ops.get_option("scan_groups") == 0:
+        g_opt = 2 if 8 <= groups <= 14 else (3 if 15 <= groups <= 21 else 0)
+    three = g_opt != 0
+    if three:
+        ops.set_option("scan_groups", g_opt)              # read by the dispatcher at launch time (host side)
+    try:
+        if concurrent:
+            side_stream.wait_stream(main)                 # x is ready on the main stream; last call's decoders are done
+            with torch.cuda.stream(side_stream):
+                enc_hi = high.actor.encode(x)
+        enc_lo = low.actor.encode(x)
+        if not concurrent:
             enc_hi = high.actor.encode(x)
-    enc_lo = low.actor.encode(x)
-    if not concurrent:
-        enc_hi = high.actor.encode(x)
+    finally:
+        if three:
+            ops.set_option("scan_groups", 0)
     deferred = low.actor.defer_range_check
     low.actor.defer_range_check = True
     try:

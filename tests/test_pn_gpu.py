@@ -376,9 +376,9 @@ def test_column_split_scan_equals_cta_pair_scan_bitwise(n, K, N):
     m = m.cuda().eval()
     lat = [torch.randn(n, K * N, device="cuda") for _ in range(K)]
     outs = {}
-    # options (scan, scan_groups): column-split with one / two instance groups per cluster (encoder), CTA-pair scan
+    # options (scan, scan_groups): column-split with one / two / three instance groups per cluster (encoder), CTA-pair scan
     from gnnpn_sc_b200 import ops
-    for key, (mode, g) in {"cs1": (1, 1), "cs2": (1, 2), "pair": (0, 0)}.items():
+    for key, (mode, g) in {"cs1": (1, 1), "cs2": (1, 2), "cs3": (1, 3), "pair": (0, 0)}.items():
         ops.set_option("scan", mode)
         ops.set_option("scan_groups", g)
         with torch.no_grad():
@@ -388,7 +388,7 @@ def test_column_split_scan_equals_cta_pair_scan_bitwise(n, K, N):
         outs[key] = [torch.stack(idx).clone()] + [last[k].clone() for k in ("enc_out", "dec_h", "win_logits", "win_probs")]
         # the pair scan keeps blocked encodings / fused pointer dots for windows of up to 10 candidates
         assert last["enc_layout"] == (ops.ENC_BLOCKED128 if key == "pair" and N <= 10 else ops.ENC_ROWMAJOR)
-    for key in ("cs1", "cs2"):
+    for key in ("cs1", "cs2", "cs3"):
         for a, b in zip(outs[key], outs["pair"]):
             assert torch.equal(a, b), key
 
