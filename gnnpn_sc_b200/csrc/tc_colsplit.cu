@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid_constant__ CUtensorMap map_wh_lo,
                      const __grid_constant__ CUtensorMap map_wx_hi, const __grid_constant__ CUtensorMap map_wx_lo,
                      const __grid_constant__ CUtensorMap map_scr, const __grid_constant__ Params p) {
-  static_assert(!DEC || G == 1, "the fused decoder runs one group per cluster");
+  static_assert(!DEC || G <= 2, "the fused decoder runs one or two groups per cluster");
   using LY = Layout<G>;
   constexpr int NSLOT = LY::NSLOT;
   constexpr int SET_WARPS = EPI_WARPS;                 // every epilogue warp serves every group
@@ -356,21 +356,24 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
     };
     float c[G][8];
     if (DEC) {
-      const int64_t m = row_of(0);
-      const bool ok = m < p.n;
-      if (ok) ldg256(p.c + m * kH + u0, c[0]);
-      else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) c[0][u] = 0.f;
-      }
-      float h0v[8];
-      if (ok) ldg256(p.h0 + m * p.h0_ld + u0, h0v);
-      else {
+      for (int g = 0; g < G; ++g) {
+        const int64_t m = row_of(g);
+        const bool ok = m < p.n;
+        if (ok) ldg256(p.c + m * kH + u0, c[g]);
+        else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) h0v[u] = 0.f;
+          for (int u = 0; u < 8; ++u) c[g][u] = 0.f;
+        }
+        float h0v[8];
+        if (ok) ldg256(p.h0 + m * p.h0_ld + u0, h0v);
+        else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) h0v[u] = 0.f;
+        }
+        stage(g, h0v, 0);
+        publish(g, 0);
       }
-      stage(0, h0v, 0);
-      publish(0, 0);
     } else {
 #pragma unroll
       for (int g = 0; g < G; ++g)
@@ -416,17 +419,17 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
         if (DEC) {
           // the query of this step's pointer phase: fp32 h'(t) to dec_h BEFORE the publish (read by other CTAs after it)
           if (ok) stg256(h_dst, hn);
-          stage(0, hn, t + 1);
-          publish(0, t + 1);
+          stage(g, hn, t + 1);
+          publish(g, t + 1);
           if (prof) d_pub += clock64() - t3;
           // ---- pointer step k = t for instance row 16 * rank + (warp - 4) of the group; the pick's raw row becomes the
           // x block row of ALL 8 CTAs for step t+1
           const long long t4 = prof ? clock64() : 0;
           const int pj = t + 1;
 #pragma unroll
-          for (int kb = 0; kb < KB_H; ++kb) mbar_wait_cluster(a_rdy(0, pj & 1, kb), (uint32_t)(pj >> 1) & 1u);   // all of h'(t) is in dec_h
+          for (int kb = 0; kb < KB_H; ++kb) mbar_wait_cluster(a_rdy(g, pj & 1, kb), (uint32_t)(pj >> 1) & 1u);   // all of h'(t) is in dec_h
           const int prow = (int)rank * (BM / CL) + (warp - 4);
-          const int64_t b = group0 * BM + prow;
+          const int64_t b = (group0 + g) * BM + prow;
           int fed = 0;
           if (b < p.n) {                                                        // warp-uniform
             float4 q0, q1;
@@ -447,14 +450,14 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
                 lo[i] = pack_h2(xv[2 * i] - bk.x, xv[2 * i + 1] - bk.y);
               }
               const uint32_t o = (uint32_t)prow * XROW_BYTES;
-              const uint32_t dhi = mapa_rank(ax_hi_off(0) + o, (uint32_t)lane);
-              const uint32_t dlo = mapa_rank(ax_lo_off(0) + o, (uint32_t)lane);
+              const uint32_t dhi = mapa_rank(ax_hi_off(g) + o, (uint32_t)lane);
+              const uint32_t dlo = mapa_rank(ax_lo_off(g) + o, (uint32_t)lane);
               st_cluster_v4(dhi, hi[0], hi[1], hi[2], hi[3]);
               st_cluster_v4(dhi + 16, hi[0], hi[1], hi[2], hi[3]);
               st_cluster_v4(dlo, lo[0], lo[1], lo[2], lo[3]);
               st_cluster_v4(dlo + 16, lo[0], lo[1], lo[2], lo[3]);
               fence_proxy_async_all();
-              mbar_arrive_release_cluster(mapa_rank(x_rdy(0), (uint32_t)lane));
+              mbar_arrive_release_cluster(mapa_rank(x_rdy(g), (uint32_t)lane));
             }
             __syncwarp();
           }
@@ -662,7 +665,9 @@ int tc_colsplit_decode(const SeqDecodeArgs& a, void* scratch, cudaStream_t st) {
   p.pa.N = a.N; p.pa.idx_out = a.idx_out; p.pa.win_logits = a.win_logits; p.pa.win_probs = a.win_probs;
   p.pa.forced = a.forced_idx; p.pa.uniform = a.sample_uniform;
   p.save_gates = a.save_gates; p.save_c = a.save_c;
-  return cs::launch<true, 1>(a.packed, p, scratch, st);
+  // two groups per cluster as soon as one-group clusters would need a second wave (16..30 groups): one wave of 8..15 clusters
+  return colsplit_groups_per_cluster(a.n) >= 2 ? cs::launch<true, 2>(a.packed, p, scratch, st)
+                                                : cs::launch<true, 1>(a.packed, p, scratch, st);
 }
 
 }  // namespace gnnpn
