@@ -395,30 +395,25 @@ def run_ours(args):
     e2e_ms = timed(lambda: e2e_steps(args.steps), 1)
     clocks = sampler.stop() if rank == 0 else None
 
-    # latency of ONE reference-sized batch (B = 128, trainPNLow.py:221) through the same kernels' entry points: the
-    # dispatcher runs the column-split cluster scan there; GNNPN_COLSPLIT=0 forces the CTA-pair scan for comparison
+    # latency of ONE reference-sized batch (B = 128, trainPNLow.py:221) through the public pipeline call (low_high: the two
+    # encoders side by side on two streams, then the decoders): the dispatcher runs the column-split cluster scan there;
+    # option scan = 0 forces the CTA-pair scan for comparison
     small = None
     if rank == 0:
+        from gnnpn_sc_b200.pipeline import low_high
         nb = 128
         xs = x[:nb].contiguous()
-        c_s = torch.empty(nb, HID, device=dev)
-        bufs_s = [(torch.empty(nb, K_TASKS, HID, device=dev), torch.empty(K_TASKS, nb, device=dev, dtype=torch.int32),
-                   torch.empty(nb, L_SEQ, device=dev), torch.empty(nb, L_SEQ, device=dev)) for _ in range(2)]
-        ws_s = ops.pn_workspace(nb, HID, dev, args.kernel)
+        side_s = torch.cuda.Stream(dev)
+        chk = low.actor.check_inputs, high.actor.check_inputs
+        low.actor.check_inputs = high.actor.check_inputs = False          # no host sync inside the timed loop
 
         def small_step():
-            lat = None
-            for lvl, (ew, dw) in enumerate(((enc_w_lo, dec_w_lo), (enc_w_hi, dec_w_hi))):
-                ops.lstm_encode(xs, ew, HID, enc_s, c_s, workspace=ws_s, layout=lay_s)
-                _, idx_s, lat, _ = ops.pn_decode_greedy(xs, enc_s, c_s, dw, K_TASKS, N_CAND, latent_win=lat,
-                                                        out=bufs_s[lvl], workspace=ws_s, enc_layout=lay_s)
-            return ops.pn_reward(xs, idx_s)[2]
+            with torch.no_grad():
+                return low_high(low, high, xs, side_s, own_buffers=False)[1]
 
         small = {"instances": nb}
         for key, mode in (("ms", -1), ("ms_cta_pair_scan", 0)):
             ops.set_option("scan", mode)
-            lay_s = ops.pn_enc_layout(nb, L_SEQ, FEAT, K_TASKS, N_CAND, ws_s is not None)
-            enc_s = ops.enc_out_empty(nb, L_SEQ, HID, lay_s, dev)
             for _ in range(3):
                 small_step()
             torch.cuda.synchronize()
@@ -430,6 +425,8 @@ def run_ours(args):
             torch.cuda.synchronize()
             small[key] = t0.elapsed_time(t1) / 10
         ops.set_option("scan", -1)
+        low.actor.check_inputs, high.actor.check_inputs = chk
+        low.actor.last = high.actor.last = None
         small["instances_per_s"] = nb / (small["ms"] * 1e-3)
 
     # second half of BASELINE.json's metric: CSR aggregation GB/s against the HBM peak (one point of the sweep in
