@@ -400,18 +400,18 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(g));                         // accumulator is in registers
         float cn[8], hn[8];
-        if (p.save_gates) {
-          // training forward: the BPTT's saves (gnnpn_pn_train_backward_f32) -- 128 + 32 contiguous bytes per thread
-          lstm_cell8_gates(v, bias4, c[g], cn, hn, v);
-          if (ok) {
+        // training forward: v becomes the post-activation gates; they are stored AFTER the publish (off the step's critical path)
+        if (p.save_gates) lstm_cell8_gates(v, bias4, c[g], cn, hn, v);
+        else lstm_cell8(v, bias4, c[g], cn, hn);
+        auto save_step = [&]() {
+          // the BPTT's saves (gnnpn_pn_train_backward_f32): 128 + 32 contiguous bytes per thread
+          if (p.save_gates && ok) {
             float* gd = p.save_gates + ((int64_t)t * p.n + m) * kG + 4 * u0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) stg256(gd + 8 * i, v + 8 * i);
             stg256(p.save_c + ((int64_t)t * p.n + m) * kH + u0, cn);
           }
-        } else {
-          lstm_cell8(v, bias4, c[g], cn, hn);
-        }
+        };
 #pragma unroll
         for (int u = 0; u < 8; ++u) c[g][u] = cn[u];
         const long long t3 = prof ? clock64() : 0;
@@ -421,6 +421,7 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
           if (ok) stg256(h_dst, hn);
           stage(g, hn, t + 1);
           publish(g, t + 1);
+          save_step();
           if (prof) d_pub += clock64() - t3;
           // ---- pointer step k = t for instance row 16 * rank + (warp - 4) of the group; the pick's raw row becomes the
           // x block row of ALL 8 CTAs for step t+1
@@ -470,6 +471,7 @@ lstm_colsplit_kernel(const __grid_constant__ CUtensorMap map_wh_hi, const __grid
           if (prof && g == 0) d_pub += clock64() - t3;
           const long long t4 = prof ? clock64() : 0;
           if (ok) stg256(h_dst, hn);
+          save_step();
           if (prof && g == 0) d_out += clock64() - t4;
         }
       }
