@@ -98,7 +98,7 @@ def _own_enc_buffer(actor, n: int, L: int, F: int, device):
     that crossed streams -- on every call).  A caller-set larger buffer is left alone."""
     from . import ops
     K, N, H = actor.serCategory, actor.serNumber, actor.hidden_size
-    if actor.embedding_size != 0 or actor.impl == "ffma":
+    if actor.embedding_size != 0 or actor.impl == "ffma" or actor._anyh():
         return
     layout = ops.pn_enc_layout(n, L, F, K, N, True) if actor._fast_path(F) else ops.ENC_ROWMAJOR
     need = ops.enc_out_floats(n, L, H, layout)
@@ -132,8 +132,7 @@ def low_high(low, high, x, side_stream, own_buffers: bool = True, check: str = "
     g_opt = 0
     if ops.get_option("scan") == -1 and ops.get_option("scan_groups") == 0:
         g_opt = 2 if 8 <= groups <= 14 else (3 if 15 <= groups <= 21 else 0)
-    three = g_opt != 0
-    if three:
+    if g_opt:
         ops.set_option("scan_groups", g_opt)              # read by the dispatcher at launch time (host side)
     try:
         if concurrent:
@@ -144,7 +143,7 @@ def low_high(low, high, x, side_stream, own_buffers: bool = True, check: str = "
         if not concurrent:
             enc_hi = high.actor.encode(x)
     finally:
-        if three:
+        if g_opt:
             ops.set_option("scan_groups", 0)
     deferred = low.actor.defer_range_check
     low.actor.defer_range_check = True
