@@ -117,3 +117,33 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == ("reference" if installed else "port")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"] == "qws_greedy_pnlow_pnhigh_decode"
+
+
+def test_anyh_fold_reproduces_the_lstm_preactivations():
+    """Host-side folding for the any-hidden-size kernels (ops.anyh_fold): [h | x_raw] . w_cat^T + bias equals
+    W_ih . (W_emb x_raw + b_emb) + b_ih + W_hh h + b_hh, and bias0 carries the decoder's start token (modelPN.py:155-163,
+    190-191, 205).  Pure torch: runs on the CPU."""
+    import torch
+    from gnnpn_sc_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    H, F, n = 48, 8, 5
+    w_ih, w_hh = torch.randn(4 * H, H, generator=g), torch.randn(4 * H, H, generator=g)
+    b_ih, b_hh = torch.randn(4 * H, generator=g), torch.randn(4 * H, generator=g)
+    w_emb, b_emb, start = torch.randn(H, F, generator=g), torch.randn(H, generator=g), torch.randn(H, generator=g)
+    w_cat, bias, bias0 = ops.anyh_fold(w_ih, w_hh, b_ih, b_hh, w_emb, b_emb, start)
+    assert w_cat.shape == (4 * H, H + F) and bias.shape == (4 * H,) and bias0.shape == (4 * H,)
+    h, x = torch.randn(n, H, generator=g).double(), torch.rand(n, F, generator=g).double()
+    emb = x @ w_emb.double().T + b_emb.double()
+    want = emb @ w_ih.double().T + b_ih.double() + h @ w_hh.double().T + b_hh.double()
+    got = torch.cat([h, x], 1) @ w_cat.double().T + bias.double()
+    assert float((got - want).abs().max()) < 1e-4 * float(want.abs().max())
+    want0 = start.double() @ w_ih.double().T + b_ih.double() + h @ w_hh.double().T + b_hh.double()
+    got0 = torch.cat([h, torch.zeros_like(x)], 1) @ w_cat.double().T + bias0.double()
+    assert float((got0 - want0).abs().max()) < 1e-4 * float(want0.abs().max())
+    assert ops.anyh_fold(w_ih, w_hh, b_ih, b_hh, w_emb, b_emb)[2] is None          # an encoder has no start token
+
+
+def test_split_threshold_policy():
+    from gnnpn_sc_b200 import ops
+    assert ops.split_threshold(32) == ops.SPLIT_THRESHOLD_NARROW and ops.split_threshold(64) == ops.SPLIT_THRESHOLD_NARROW
+    assert ops.split_threshold(128) == ops.SPLIT_THRESHOLD and ops.SPLIT_THRESHOLD_NARROW < ops.SPLIT_THRESHOLD
