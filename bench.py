@@ -451,6 +451,33 @@ def run_ours(args):
                "GBps": bytes_a / ms_a / 1e6, "frac_of_hbm_peak": bytes_a / ms_a / 1e6 / peaks()["hbm_gbs"]}
         del rowptr, col, val, xa, ya
 
+    # the attention of the decode loop ALONE (no LSTM step in the launches): the stand-alone pointer kernel over all K steps on
+    # row-major encodings and the decoder states of a real decode -- the HBM roofline point of north_star's "attention"
+    attention = None
+    if rank == 0 and world == 1 and not args.no_attention and layout == ops.ENC_BLOCKED128:
+        ops.lstm_encode(x, enc_w_hi, HID, enc_out, c, workspace=ws, layout=layout)
+        dec_h_a = torch.empty(n, K_TASKS, HID, device=dev)
+        ops.pn_decode_greedy(x, enc_out, c, dec_w_hi, K_TASKS, N_CAND, out=(dec_h_a,) + tuple(bufs[1][1:]), workspace=ws,
+                             enc_layout=layout)
+        enc_rm = ops.enc_to_rowmajor(enc_out, n, L_SEQ, HID)
+        out_a = (torch.empty(K_TASKS, n, device=dev, dtype=torch.int32), torch.empty(n, L_SEQ, device=dev),
+                 torch.empty(n, L_SEQ, device=dev))
+        for _ in range(3):
+            ops.pn_attention_windows(enc_rm, dec_h_a, N_CAND, out=out_a)
+        ts = []
+        for _ in range(5):
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(); ops.pn_attention_windows(enc_rm, dec_h_a, N_CAND, out=out_a); t1.record(); torch.cuda.synchronize()
+            ts.append(t0.elapsed_time(t1))
+        ms_at = sorted(ts)[len(ts) // 2]
+        same = bool(torch.equal(out_a[1], bufs[1][2]) and torch.equal(out_a[0], bufs[1][1]))
+        bytes_at = n * (L_SEQ * HID * 4 + K_TASKS * HID * 4 + 2 * L_SEQ * 4 + K_TASKS * 4)
+        attention = {"kernel": "pointer_step_dot_kernel x K (stand-alone attention over the windows, row-major encodings)",
+                     "ms": ms_at, "algorithmic_bytes": bytes_at, "GBps": bytes_at / ms_at / 1e6,
+                     "frac_of_hbm_peak": bytes_at / ms_at / 1e6 / peaks()["hbm_gbs"],
+                     "bitwise_equal_to_fused_decoder": same}
+        del enc_rm, dec_h_a, out_a
+
     pipeline = None
     if rank == 0 and world == 1 and not args.no_pipeline:
         del enc_out, bufs                                    # the pipeline allocates its own encodings (2 x 9.7 GB at Normal)
@@ -504,7 +531,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": K_TASKS * n * 4 + n * 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(lt.item()), "clocks": clocks,
-            "small_batch": small, "aggregation": agg, "pipeline": pipeline,
+            "small_batch": small, "aggregation": agg, "roofline_attention": attention, "pipeline": pipeline,
         }
         print(json.dumps(line))
     if world > 1:
@@ -619,6 +646,7 @@ def main():
     ap.add_argument("--cpu-batches", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aggregation", action="store_true", help="skip the CSR aggregation GB/s point")
+    ap.add_argument("--no-attention", action="store_true", help="skip the attention-only (stand-alone pointer kernel) roofline point")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the full ML+2PN pipeline block (BASELINE config 3)")
     ap.add_argument("--kernel", default="tc", choices=["tc", "ffma"],
                     help="recurrence kernel: tcgen05 3xTF32 (default) or strict-fp32 FFMA")

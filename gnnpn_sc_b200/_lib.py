@@ -57,6 +57,7 @@ SIGNATURES = {
     "gnnpn_pn_decode_anyh_f32": (_i, [_p, _p, _p, _p, _f, _p, _p, _p, _i, _f, _i64, _i, _i, _i, _i, _i,
                                       _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "gnnpn_pn_full_logits_anyh_f32": (_i, [_p, _p, _p, _i, _f, _i64, _i, _i, _i, _p, _p]),
+    "gnnpn_pn_attention_windows_f32": (_i, [_p, _p, _p, _f, _i, _f, _i64, _i, _i, _i, _i, _p, _p, _p, _p]),
     "gnnpn_pn_reward_f32": (_i, [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p]),
     "gnnpn_woa_fitness_f64": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "gnnpn_ml2pn_score_f64": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i, _p, _p, _p, _p]),

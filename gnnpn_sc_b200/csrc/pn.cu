@@ -503,6 +503,31 @@ int gnnpn_pn_train_forward_f32(const float* inputs, const float* packed_enc, con
   return GNNPN_OK;
 }
 
+// The attention of the decode loop alone (modelPN.py:213-228 restricted to the windows): for given decoder states
+// dec_h [n, K, H] every step's window logits / probabilities / first-max picks.  One launch of the stand-alone pointer
+// kernel per step; reads every encoding row exactly once.  Used to re-derive window logits for saved states and as the
+// attention-only roofline point of bench.py (no LSTM step in the launches).
+int gnnpn_pn_attention_windows_f32(const float* enc_out, const float* dec_h, const float* latent_win, float alpha,
+                                   int use_tanh, float C, int64_t n, int L, int hidden, int K, int N, int32_t* idx_out,
+                                   float* win_logits, float* win_probs, void* stream) {
+  GNNPN_REQUIRE(enc_out && dec_h && idx_out && win_logits && win_probs, GNNPN_ENULL);
+  GNNPN_REQUIRE(hidden == kH && K >= 1 && N >= 1 && N <= kMaxWindow && (int64_t)K * N == L && n >= 0, GNNPN_ESHAPE);
+  GNNPN_REQUIRE(aligned16(enc_out) && aligned16(dec_h), GNNPN_EALIGN);
+  if (n == 0) return GNNPN_OK;
+  PointerStepArgs pa;
+  pa.enc_out = enc_out; pa.enc_inst_ld = (int64_t)L * kH; pa.latent_win = latent_win; pa.alpha = alpha;
+  pa.use_tanh = use_tanh; pa.C = C; pa.n = n; pa.L = L; pa.N = N;
+  pa.idx_out = idx_out; pa.win_logits = win_logits; pa.win_probs = win_probs;
+  pa.forced = nullptr; pa.uniform = nullptr;
+  for (int k = 0; k < K; ++k) {
+    pointer_step_dot_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(
+        pa, k, dec_h + (int64_t)k * kH, (int64_t)K * kH, nullptr, 0, nullptr, nullptr, 0, 0);
+    const int rc = after_launch();
+    if (rc) return rc;
+  }
+  return GNNPN_OK;
+}
+
 int gnnpn_pn_train_forward_tc_f32(const float* inputs, const float* packed_enc, const float* packed_dec,
                                   const int32_t* forced_idx, const float* sample_uniform, const float* latent_win,
                                   float alpha, int use_tanh, float C, int64_t n, int L, int in_features, int hidden, int K,

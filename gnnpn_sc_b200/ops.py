@@ -364,6 +364,23 @@ def pn_full_logits(enc_out, dec_h, idx, attention: str = "Dot", att_params=None,
     return out
 
 
+def pn_attention_windows(enc_out, dec_h, N: int, latent_win=None, alpha: float = 1.0, use_tanh: bool = True, C: float = 10.0,
+                         out=None):
+    """Window logits / probabilities / first-max picks of every decode step for GIVEN decoder states (row-major encodings
+    ``[n, L, H]``, ``dec_h [n, K, H]``): ``gnnpn_pn_attention_windows_f32``.  Returns (idx int32 [K, n], win_logits, win_probs)."""
+    n, L, H = enc_out.shape
+    K = dec_h.shape[1]
+    if out is None:
+        out = (torch.empty(K, n, device=enc_out.device, dtype=torch.int32), torch.empty(n, L, device=enc_out.device),
+               torch.empty(n, L, device=enc_out.device))
+    idx, wl, wp = out
+    lat = None if latent_win is None else _f32(latent_win, "latent_win")
+    check(lib().gnnpn_pn_attention_windows_f32(enc_out.data_ptr(), dec_h.data_ptr(), _ptr(lat), float(alpha), int(bool(use_tanh)),
+                                               float(C), n, L, H, K, N, idx.data_ptr(), wl.data_ptr(), wp.data_ptr(), _stream()),
+          "pn_attention_windows")
+    return idx, wl, wp
+
+
 def pn_reward(inputs, idx, tag: int = 0):
     """(violations int32 [n], objFunc fp32 [n], round(viol+obj,5) fp32 [n]) for picks ``idx`` int32 [K,n]."""
     x = _f32(inputs, "inputs")

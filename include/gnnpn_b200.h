@@ -250,6 +250,14 @@ GNNPN_API int gnnpn_pn_decode_anyh_f32(const float* inputs, const float* enc_out
 GNNPN_API int gnnpn_pn_full_logits_anyh_f32(const float* enc_out, const float* dec_h, const int32_t* idx, int use_tanh,
                                   float C, int64_t n, int L, int hidden, int K, float* logits_full, void* stream);
 
+/* The attention of the decode loop alone (modelPN.py:213-228 restricted to the windows) for GIVEN decoder states:
+ *   enc_out fp32 [n, L, H] row-major, dec_h fp32 [n, K, H]  ->  win_logits / win_probs [n, L], idx_out int32 [K, n]
+ * (first-max pick of every window; latent_win / alpha / use_tanh / C as in gnnpn_pn_decode_greedy_f32).  K launches of the
+ * stand-alone pointer kernel, every encoding row read once: the attention-only roofline point of bench.py. */
+GNNPN_API int gnnpn_pn_attention_windows_f32(const float* enc_out, const float* dec_h, const float* latent_win, float alpha,
+                                   int use_tanh, float C, int64_t n, int L, int hidden, int K, int N, int32_t* idx_out,
+                                   float* win_logits, float* win_probs, void* stream);
+
 /* Interface-faithful materialisation of PointerNet.forward's prev_logits (modelPN.py:213-214,239):
  *   logits_full fp32 [K, n, L] = C*tanh(<enc_out[b,l,:], dec_h[b,k,:]>) with -inf at the positions
  *   chosen at steps < k (the cumulative visited mask, modelPN.py:165-173). */

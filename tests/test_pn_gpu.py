@@ -393,6 +393,27 @@ def test_column_split_scan_equals_cta_pair_scan_bitwise(n, K, N):
             assert torch.equal(a, b), key
 
 
+@pytest.mark.parametrize("n,K,N,with_latent", [(300, 47, 5, False), (130, 12, 10, True), (5, 3, 32, True)])
+def test_attention_windows_entry_equals_the_decode(n, K, N, with_latent):
+    """gnnpn_pn_attention_windows_f32 (the decode loop's attention alone, for given decoder states) reproduces the window
+    logits / probabilities / picks of the decode those states came from, bit for bit (canonical dot order)."""
+    from gnnpn_sc_b200 import modelPN as M, ops
+    from gnnpn_sc_b200.synth import pn_instances
+    from gnnpn_sc_b200.weights import reference_shaped_state_dict
+    x = pn_instances(n, K, N, seed=11).cuda()
+    m = M.CombinatorialRL(0, 256, K * N, 0, 10, 1, M.reward, "Dot", N, K, level="High")
+    m.load_state_dict(reference_shaped_state_dict(256, 8, 5))
+    m = m.cuda().eval()
+    lat = [torch.randn(n, K * N, device="cuda") for _ in range(K)] if with_latent else None
+    with torch.no_grad():
+        _, idx, _ = m.actor(x, lat, sample="greedy")
+    last = m.actor.last
+    got_idx, wl, wp = ops.pn_attention_windows(last["enc_out"], last["dec_h"], N, latent_win=last["latent_win"],
+                                               alpha=float(m.actor.alpha))
+    assert torch.equal(wl, last["win_logits"]) and torch.equal(wp, last["win_probs"])
+    assert torch.equal(got_idx, last["idx"])
+
+
 # ----------------------------------------------------------------------------- any hidden size
 @pytest.mark.parametrize("H,n,K,N,emb", [(64, 37, 6, 4, 0), (128, 130, 12, 5, 0), (200, 9, 5, 7, 0), (512, 16, 4, 3, 0),
                                          (96, 20, 6, 4, 20)])
