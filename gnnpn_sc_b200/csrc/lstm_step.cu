@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(TPB, 2) lstm_step_ffma_kernel(const LstmStepAr
       const float gf = acc[i][u * 4 + 1] + bb.y;
       const float gg = acc[i][u * 4 + 2] + bb.z;
       const float go = acc[i][u * 4 + 3] + bb.w;
-      const float c_old = a.first ? 0.f : crow[j];
+      const float c_old = a.first ? 0.f : cin[j];        // training replay: the previous step's saved slot (c_in), not this step's
       const float si = sigmoid_accurate(gi), sf = sigmoid_accurate(gf), tg = tanhf(gg), so = sigmoid_accurate(go);
       const float c_new = sf * c_old + si * tg;
       crow[j] = c_new;

@@ -27,6 +27,7 @@ def test_sampled_decode_follows_the_window_distribution():
     cfg, sd, m = _model(K, N)
     x = pn_instances(1, K, N, seed=3).repeat(20000, 1, 1).cuda()         # same instance 20k times
     m.eval()
+    m.actor.generator = torch.Generator(device="cuda").manual_seed(5)      # fixed draws
     with torch.no_grad():
         probs, idx, _ = m.actor(x, None, sample="sample")
     idx = torch.stack(idx)
@@ -104,6 +105,29 @@ def test_bptt_cluster_scan_equals_per_step_kernels(B, K, N):
         assert float((got - ref).abs().max()) <= 2e-6 * scale, float((got - ref).abs().max()) / scale
 
 
+def test_training_batch_outside_the_column_split_scan_falls_back_to_the_replay():
+    """A training batch the column-split scan does not take (> 30 groups of 128) decodes on the CTA-pair scan and replays
+    teacher-forced on the strict-fp32 kernels; its gradient equals the sum over two half batches, which DO take the fused
+    decode-with-saves path -- to the difference between the tensor-core and the FFMA forward arithmetic."""
+    from gnnpn_sc_b200.synth import pn_instances
+    K, N, B = 6, 4, 3968
+    cfg, sd, m = _model(K, N, seed=8)
+    x = pn_instances(B, K, N, seed=12).cuda()
+    m.train()
+    m.actor.generator = torch.Generator(device="cuda").manual_seed(3)
+    R, ap, _, idx, _ = m(x, None, sample="greedy", training="RL")
+    assert m.actor._train_saves is None                                    # the fused path refused this batch
+    sum(torch.log(p) for p in ap).sum().backward()
+    g_full = {n_: p.grad.clone() for n_, p in m.named_parameters()}
+    m.zero_grad()
+    for lo, hi in ((0, B // 2), (B // 2, B)):
+        _, ap_h, _, idx_h, _ = m(x[lo:hi].contiguous(), None, sample="greedy", training="RL")
+        assert torch.equal(torch.stack(idx_h), torch.stack(idx)[:, lo:hi])   # same picks on both scans (bit-identical decodes)
+        sum(torch.log(p) for p in ap_h).sum().backward()
+    worst = max(float((p.grad - g_full[n_]).abs().max() / g_full[n_].abs().max().clamp(min=1e-3)) for n_, p in m.named_parameters())
+    assert worst < 1e-4, worst
+
+
 def test_reinforce_gradient_other_hidden_size():
     """hidden_size = 128: the sampled decode runs on the any-hidden-size kernels, the gradient on the torch replay; it
     equals autograd through the oracle's graph on the same picks."""
@@ -112,6 +136,7 @@ def test_reinforce_gradient_other_hidden_size():
     cfg, sd, m = _model(K, N, seed=4, H=128)
     x = pn_instances(B, K, N, seed=8)
     m.train()
+    m.actor.generator = torch.Generator(device="cuda").manual_seed(17)      # fixed draws: the test must not depend on what ran before
     R, ap, _, idx, _ = m(x.cuda(), None, sample="sample", training="RL")
     idx_cpu = [t.cpu() for t in idx]
     sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
