@@ -360,7 +360,7 @@ def test_bahdanau_attention_module_against_oracle():
     assert _close(lg.cpu().numpy(), lg_o.numpy()).all()
 
 
-@pytest.mark.parametrize("n,K,N", [(1, 3, 2), (130, 12, 32), (300, 47, 5), (2100, 20, 5)])
+@pytest.mark.parametrize("n,K,N", [(1, 3, 2), (130, 12, 32), (300, 47, 5), (2100, 20, 5), (260, 9, 7), (140, 6, 10), (200, 5, 12)])
 def test_column_split_scan_equals_cta_pair_scan_bitwise(n, K, N):
     """The small-batch cluster scan (tc_colsplit.cu) issues the same MMA sequence and the same cell / pointer
     arithmetic as the CTA-pair scan (tc_seq.cu): encodings, decoder states, logits, probabilities and picks are
